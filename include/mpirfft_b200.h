@@ -1,0 +1,204 @@
+/* mpirfft_b200.h -- public C ABI of libmpirfft_b200.so
+ *
+ * A B200-native (sm_100a) implementation of the Schoenhage-Strassen multiplication path of
+ * wbhart/mpir-fft, behind the reference's own C entry points.  The "plugin interface" of the
+ * reference is simply the external linkage of mul_fft.c (every function is a global C symbol;
+ * mul_fft.h:73-79 declares two of them).  Part 1 of this header re-declares those symbols with
+ * byte-identical signatures, each citing the reference definition it replaces; linking a driver
+ * against this library instead of mul_fft.o is the drop-in.  Part 2 is the device-resident
+ * API the drop-in symbols are built on (operands and slabs stay in HBM between stages).
+ *
+ * Types: mp_limb_t = unsigned long (64-bit), mp_size_t = long, mp_bitcnt_t = unsigned long,
+ * exactly as MPIR 2.4.0 defines them on LP64.  A coefficient block is (l+1) limbs: l limbs
+ * of body and one signed two's-complement carry limb (README:54), value taken mod 2^(64 l)+1.
+ *
+ * Error behaviour: the reference has no error channel (void returns; illegal parameters
+ * "will just segfault", mul_fft.c:3186-3187).  The drop-in symbols validate their parameters and
+ * the device state and abort() with a diagnostic on stderr.  There is NO CPU fallback: without
+ * a CUDA device every entry point that computes aborts (part 1) or returns an error (part 2).
+ */
+#ifndef MPIRFFT_B200_H
+#define MPIRFFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef MPIRFFT_HAVE_MP_TYPES
+typedef unsigned long mp_limb_t;
+typedef long          mp_size_t;
+typedef unsigned long mp_bitcnt_t;
+#endif
+
+/* ============================ Part 1: reference entry points ============================ */
+
+/* mul_fft.c:3190  r1[0..n1+n2) = {i1,n1} * {i2,n2}; n = 2^depth, p = 2^(n w)+1.
+ * (Implements the corrected row selection depth+1-depth/2 of mul_fft.c:3246.) */
+void new_mpn_mul(mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2,
+                 mp_bitcnt_t depth, mp_bitcnt_t w);
+
+/* mul_fft.c:41, 3119  r = i1*i2 mod 2^bits+1; c bit0 <=> i1 == 2^bits, bit1 <=> i2 == 2^bits;
+ * returns 1 iff the result is 2^bits.  tt (2*(bits/64+1) limbs) is accepted and unused. */
+mp_limb_t new_mpn_mulmod_2expp1(mp_limb_t *r, mp_limb_t *i1, mp_limb_t *i2, mp_limb_t c,
+                                mp_limb_t bits, mp_limb_t *tt);
+
+/* mul_fft.c:3125  r = i1*i2 mod 2^(n w)+1 on (n w/64 + 1)-limb blocks; returns the top bit
+ * (the reference always returns 0 above 250 limbs, TODO:213-221; this returns the true bit). */
+mp_limb_t fft_mulmod_2expp1(mp_limb_t *r, mp_limb_t *i1, mp_limb_t *i2, mp_size_t n, mp_size_t w,
+                            mp_limb_t *tt);
+
+/* mul_fft.c:2998  r1[0..r_limbs] = i1*i2 mod 2^(64 r_limbs)+1 for r_limbs-limb operands */
+void FFT_mulmod_2expp1(mp_limb_t *r1, mp_limb_t *i1, mp_limb_t *i2, mp_size_t r_limbs,
+                       mp_bitcnt_t depth, mp_bitcnt_t w);
+
+/* mul_fft.c:2021 / 2411  length-2n MFA transform on n2 = 2n/n1 rows of n1 columns */
+void FFT_radix2_mfa(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                    mp_limb_t **temp, mp_size_t n1);
+void IFFT_radix2_mfa(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                     mp_limb_t **temp, mp_size_t n1);
+/* mul_fft.c:2357 / 2925  truncated MFA (trunc a multiple of 2*n1) */
+void FFT_radix2_mfa_truncate(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                             mp_limb_t **t2, mp_limb_t **temp, mp_size_t n1, mp_size_t trunc);
+void IFFT_radix2_mfa_truncate(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                              mp_limb_t **t2, mp_limb_t **temp, mp_size_t n1, mp_size_t trunc);
+
+/* mul_fft.c:786 / 1444  length-2n radix-2 FFT (output bit-reversed) and its inverse (unscaled) */
+void FFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
+void IFFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                 mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
+/* mul_fft.c:1128, 1028, 1674, 1538  truncated variants (rr == ii, rs == 1 as in every caller) */
+void FFT_radix2_truncate(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                         mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
+void FFT_radix2_truncate1(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                          mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
+void IFFT_radix2_truncate(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                          mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
+void IFFT_radix2_truncate1(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                           mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
+/* mul_fft.c:1397, 1964 (mul_fft.h:73-79), 1179, 1076, 1733, 1604  strided + twisted variants */
+void FFT_radix2_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                        mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c,
+                        mp_size_t rs);
+void IFFT_radix2_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                         mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c,
+                         mp_size_t rs);
+void FFT_radix2_truncate_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w,
+                                 mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws,
+                                 mp_size_t r, mp_size_t c, mp_size_t rs, mp_size_t trunc);
+void FFT_radix2_truncate1_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w,
+                                  mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws,
+                                  mp_size_t r, mp_size_t c, mp_size_t rs, mp_size_t trunc);
+void IFFT_radix2_truncate_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w,
+                                  mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws,
+                                  mp_size_t r, mp_size_t c, mp_size_t rs, mp_size_t trunc);
+void IFFT_radix2_truncate1_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w,
+                                   mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws,
+                                   mp_size_t r, mp_size_t c, mp_size_t rs, mp_size_t trunc);
+/* mul_fft.c:1290, 1861  negacyclic transforms (even w; the odd-w sqrt2 path is out of scope) */
+void FFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                           mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
+void IFFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n,
+                            mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
+
+/* mul_fft.c:553, 639, 517, 721, 926  single butterflies / twiddle (outputs must not alias inputs) */
+void FFT_radix2_butterfly(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2, mp_size_t i,
+                          mp_size_t n, mp_bitcnt_t w);
+void FFT_radix2_inverse_butterfly(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2,
+                                  mp_size_t i, mp_size_t n, mp_bitcnt_t w);
+void FFT_radix2_twiddle_butterfly(mp_limb_t *u, mp_limb_t *v, mp_limb_t *s, mp_limb_t *t,
+                                  mp_size_t NW, mp_bitcnt_t b1, mp_bitcnt_t b2);
+void FFT_radix2_twiddle_inverse_butterfly(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2,
+                                          mp_size_t NW, mp_bitcnt_t b1, mp_bitcnt_t b2);
+void FFT_twiddle(mp_limb_t *r, mp_limb_t *i1, mp_size_t i, mp_size_t n, mp_bitcnt_t w);
+
+/* mul_fft.c:272, 470, 494, 303, 394  arithmetic mod 2^(64 l)+1 on one block */
+void mpn_normmod_2expp1(mp_limb_t *t, mp_size_t l);
+void mpn_mul_2expmod_2expp1(mp_limb_t *t, mp_limb_t *i1, mp_size_t limbs, mp_bitcnt_t d);
+void mpn_div_2expmod_2expp1(mp_limb_t *t, mp_limb_t *i1, mp_size_t limbs, mp_bitcnt_t d);
+void mpn_lshB_sumdiffmod_2expp1(mp_limb_t *t, mp_limb_t *u, mp_limb_t *i1, mp_limb_t *i2,
+                                mp_size_t limbs, mp_size_t x, mp_size_t y);
+void mpn_sumdiff_rshBmod_2expp1(mp_limb_t *t, mp_limb_t *u, mp_limb_t *i1, mp_limb_t *i2,
+                                mp_size_t limbs, mp_size_t x, mp_size_t y);
+
+/* mul_fft.c:115, 87, 207, 180  integer <-> polynomial */
+mp_size_t FFT_split_bits(mp_limb_t **poly, mp_limb_t *limbs, mp_size_t total_limbs, mp_size_t bits,
+                         mp_size_t output_limbs);
+mp_size_t FFT_split(mp_limb_t **poly, mp_limb_t *limbs, mp_size_t total_limbs,
+                    mp_size_t coeff_limbs, mp_size_t output_limbs);
+void FFT_combine_bits(mp_limb_t *res, mp_limb_t **poly, mp_size_t length, mp_size_t bits,
+                      mp_size_t output_limbs, mp_size_t total_limbs);
+void FFT_combine(mp_limb_t *res, mp_limb_t **poly, mp_size_t length, mp_size_t coeff_limbs,
+                 mp_size_t output_limbs, mp_size_t total_limbs);
+
+/* mul_fft.c:63  bit reversal (pure host arithmetic) */
+mp_limb_t mpir_revbin(mp_limb_t in, mp_bitcnt_t bits);
+
+/* ============================ Part 2: device-resident API ============================== */
+
+#define MPIRFFT_OK          0
+#define MPIRFFT_ENODEV     (-1)   /* no usable CUDA device / CUDA error (see mpirfft_last_error) */
+#define MPIRFFT_EINVAL     (-2)   /* illegal parameters (A.5 of SURVEY.md) */
+#define MPIRFFT_ENOMEM     (-3)
+
+/* Select the device for this process (default 0) and create the context.  Idempotent. */
+int  mpirfft_init(int device);
+int  mpirfft_device_count(void);
+const char *mpirfft_last_error(void);
+const char *mpirfft_version(void);
+
+/* Parameter legality of new_mpn_mul (mul_fft.c:3193-3203); fills the derived sizes. */
+typedef struct {
+   uint64_t n, bits1, sqrt, j1, j2, trunc, limbs, n2, trunc_rows;
+} mpirfft_mul_params;
+int  mpirfft_mul_params_get(mpirfft_mul_params *out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
+                            mp_bitcnt_t w);
+/* A small chooser for benchmarks (the reference has none, mul_fft.c:3177-3178): smallest legal
+ * (depth, w) with w in {1,2} for an n1 x n2 limb product. */
+int  mpirfft_choose_params(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w);
+
+/* A multiplication plan owns the schedules and the HBM slabs for one (n1, n2, depth, w). */
+typedef struct mpirfft_mul_plan mpirfft_mul_plan;
+int  mpirfft_mul_plan_create(mpirfft_mul_plan **plan, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
+                             mp_bitcnt_t w);
+void mpirfft_mul_plan_destroy(mpirfft_mul_plan *plan);
+/* d_r[0..n1+n2) = d_i1 * d_i2, all three device pointers; asynchronous on `stream`
+ * (a cudaStream_t, NULL = default stream). */
+int  mpirfft_mul_exec_device(mpirfft_mul_plan *plan, mp_limb_t *d_r, const mp_limb_t *d_i1,
+                             const mp_limb_t *d_i2, void *stream);
+/* same with host operands: H2D copies, the product, D2H copy, synchronised on return */
+int  mpirfft_mul_exec_host(mpirfft_mul_plan *plan, mp_limb_t *r, const mp_limb_t *i1,
+                           const mp_limb_t *i2);
+/* run only one stage group of the pipeline on the plan's internal buffers (bench / profiling):
+ * 0 split+fft(i1), 1 split+fft(i2), 2 pointwise, 3 ifft, 4 combine */
+int  mpirfft_mul_exec_phase(mpirfft_mul_plan *plan, int phase, mp_limb_t *d_r,
+                            const mp_limb_t *d_i1, const mp_limb_t *d_i2, void *stream);
+size_t mpirfft_mul_plan_device_bytes(const mpirfft_mul_plan *plan);
+/* number of kernel launches one product issues */
+uint64_t mpirfft_mul_plan_launches(const mpirfft_mul_plan *plan);
+
+/* Batched pointwise products on device: for k < count,
+ *   d_a[k*pitch .. +l] = d_a[k] * d_b[k] mod 2^(64 l)+1   (blocks canonical: top 0, or top 1 & body 0) */
+int  mpirfft_mulmod_batch_device(mp_limb_t *d_a, const mp_limb_t *d_b, size_t count, size_t l,
+                                 size_t pitch, void *stream);
+
+/* device memory helpers (so that a host language needs nothing but this ABI) */
+void *mpirfft_malloc_device(size_t bytes);
+void  mpirfft_free_device(void *p);
+void *mpirfft_malloc_pinned(size_t bytes);
+void  mpirfft_free_pinned(void *p);
+int   mpirfft_memcpy_h2d(void *d, const void *h, size_t bytes, void *stream);
+int   mpirfft_memcpy_d2h(void *h, const void *d, size_t bytes, void *stream);
+int   mpirfft_stream_sync(void *stream);
+
+/* launches issued through the library since the last reset (bench.py's gpu_launches) */
+uint64_t mpirfft_launch_count(void);
+void     mpirfft_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,730 @@
+/* mfft_kernels.cu -- sm_100a kernels and the thin launch ABI declared in mfft_internal.h.
+ *
+ * Kernels (one warp owns one coefficient block unless noted):
+ *   k_run_stage   one stage of a transform: every (op, batch entry) pair is a warp computing up to
+ *                 two outputs  sA*A*2^eA + sB*B*2^eB  (butterflies / twiddles of mul_fft.c:517-957)
+ *   k_finalize    gather + optional 2^shift scaling + mpn_normmod_2expp1 (mul_fft.c:272-294,
+ *                 2397-2407, 3256-3260)
+ *   k_pointwise   a*b mod 2^NW+1 as a 32-block negacyclic schoolbook product inside a warp
+ *                 (new_mpn_mulmod_2expp1, mul_fft.c:3119-3123, 3244-3253)
+ *   k_split       FFT_split_bits (mul_fft.c:115-170) + zero fill (3235-3236)
+ *   k_combine_*   FFT_combine_bits (mul_fft.c:207-267) as a gather + global carry lookahead
+ *
+ * There is no CPU fallback anywhere in this file: without a usable device every entry point
+ * returns an error and the C host side aborts with a diagnostic.
+ */
+#ifdef MFFT_EMU
+#include "cuda_emu.h"      /* tests/emu: CPU emulation of the SIMT model, test builds only */
+#else
+#include <cuda_runtime.h>
+#define MFFT_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MFFT_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+#include <stdio.h>
+#include <string.h>
+#include "../mfft_internal.h"
+#include "mfft_arith.h"
+
+#define FULL 0xffffffffu
+
+static char g_err[512] = "";
+static uint64_t g_launches = 0;
+static int g_device = -1;
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) {                       \
+      snprintf(g_err, sizeof g_err, "%s:%d: %s: %s", __FILE__, __LINE__, #call,                 \
+               cudaGetErrorString(e__)); return -1; } } while (0)
+#define CKL() do { cudaError_t e__ = cudaGetLastError(); g_launches++; if (e__ != cudaSuccess) { \
+      snprintf(g_err, sizeof g_err, "%s:%d: launch: %s", __FILE__, __LINE__,                    \
+               cudaGetErrorString(e__)); return -1; } } while (0)
+
+/* ------------------------------------------------------------------------------------------ */
+/* warp-level   out = sA*A*2^eA + sB*B*2^eB   (see mfft_arith.h for the derivation)            */
+/* ------------------------------------------------------------------------------------------ */
+template <int M>
+__device__ __forceinline__ void lincomb_out(limb_t *out, const limb_t *A, int sA, uint64_t eA,
+                                            const limb_t *B, int sB, uint64_t eB, uint32_t l,
+                                            uint32_t lane)
+{
+   int64_t top_acc = 0; int ones = 0;
+   mfft_term ta, tb;
+   mfft_term_setup(&ta, A, l, sA, eA, &top_acc, &ones);
+   mfft_term_setup(&tb, B, l, sB, eB, &top_acc, &ones);
+   uint32_t tc = ones ? 1u : 0u;
+   if (ones == 2) top_acc -= 1;
+
+   for (uint32_t k0 = 0; k0 < l; k0 += 32u * M)
+   {
+      const uint32_t kb = k0 + lane * M;
+      limb_t s[M];
+      uint32_t c = 0; bool ones_all = true;
+#pragma unroll
+      for (int i = 0; i < M; i++)
+      {
+         const uint32_t k = kb + i;
+         limb_t x = ~(limb_t)0, z = 0;            /* limbs past l just pass the carry on */
+         if (k < l)
+         {
+            x = ta.present ? mfft_term_limb(&ta, l, k) : 0;
+            z = tb.present ? mfft_term_limb(&tb, l, k) : 0;
+         }
+         mfft_u128 acc = (mfft_u128) x + z + c;
+         s[i] = (limb_t) acc; c = (uint32_t)(acc >> 64);
+         ones_all = ones_all && (s[i] == ~(limb_t)0);
+      }
+      const uint32_t G = __ballot_sync(FULL, c != 0);
+      const uint32_t P = __ballot_sync(FULL, ones_all);
+      const uint64_t la = mfft_lookahead(G, P, tc);
+      uint32_t myc = (uint32_t)(la >> lane) & 1u;
+      tc = (uint32_t)(la >> 32) & 1u;
+#pragma unroll
+      for (int i = 0; i < M; i++)
+      {
+         const uint32_t k = kb + i;
+         limb_t v = s[i] + myc;
+         myc = (myc && v == 0) ? 1u : 0u;
+         if (k < l) out[k] = v;
+      }
+   }
+   top_acc += tc;
+   __syncwarp();
+   if (lane == 0)
+   {
+      if (ta.present && tb.present && ta.y == tb.y) { ta.K += tb.K; tb.K = 0; }
+      if (ta.present) mfft_inject(out, l, &top_acc, ta.y, ta.K);
+      if (tb.present) mfft_inject(out, l, &top_acc, tb.y, tb.K);
+      out[l] = (limb_t) top_acc;
+   }
+   __syncwarp();
+}
+
+/* warp-level mpn_normmod_2expp1 (mul_fft.c:272-294): canonical form in [0, 2^NW] */
+__device__ __forceinline__ void normalise_block(limb_t *blk, uint32_t l, uint32_t lane)
+{
+   for (int it = 0; it < 4; it++)
+   {
+      __syncwarp();
+      const int64_t top = (int64_t) blk[l];
+      if (top == 0) break;
+      if (top == 1)
+      {  /* 2^NW itself is canonical: top 1, body 0 */
+         bool z = true;
+         for (uint32_t k = lane; k < l; k += 32) z = z && (blk[k] == 0);
+         if (__all_sync(FULL, z)) break;
+      }
+      __syncwarp();
+      if (lane == 0)
+      {
+         int64_t nt = 0;
+         mfft_inject(blk, l, &nt, 0, -(mfft_i128) top);
+         blk[l] = (limb_t) nt;
+      }
+   }
+   __syncwarp();
+}
+
+__device__ __forceinline__ limb_t *block_ptr(limb_t *slab, const mfft_geom &g, uint32_t slot,
+                                             const mfft_batch &b)
+{
+   const uint32_t half = (slot / g.S) ^ b.parity;
+   const uint64_t idx = (uint64_t) half * g.half_blocks + b.base + (uint64_t)(slot % g.S) * g.slot_stride;
+   return slab + idx * g.pitch;
+}
+
+template <int M>
+__global__ void __launch_bounds__(128)
+k_run_stage(limb_t *slab, mfft_geom g, const mfft_op *__restrict__ ops, uint32_t count,
+            const mfft_batch *__restrict__ batch, uint32_t nbatch)
+{
+   const uint64_t wid = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const uint32_t lane = threadIdx.x & 31;
+   if (wid >= (uint64_t) count * nbatch) return;
+   const mfft_op op = ops[wid / nbatch];
+   const mfft_batch b = batch[wid % nbatch];
+   const uint64_t M2 = 128ull * g.l;
+   const limb_t *A = block_ptr(slab, g, op.inA, b);
+   const limb_t *B = (op.inB != MFFT_NONE) ? block_ptr(slab, g, op.inB, b) : A;
+   limb_t *S = block_ptr(slab, g, op.outS, b);
+   lincomb_out<M>(S, A, op.sSA, (op.eSA + (uint64_t) b.col * op.cSA) % M2,
+                     B, op.sSB, (op.eSB + (uint64_t) b.col * op.cSB) % M2, g.l, lane);
+   if (op.outT != MFFT_NONE)
+   {
+      limb_t *Tt = block_ptr(slab, g, op.outT, b);
+      lincomb_out<M>(Tt, A, op.sTA, (op.eTA + (uint64_t) b.col * op.cTA) % M2,
+                         B, op.sTB, (op.eTB + (uint64_t) b.col * op.cTB) % M2, g.l, lane);
+   }
+}
+
+template <int M>
+__global__ void __launch_bounds__(128)
+k_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *__restrict__ dst_base,
+           limb_t *slab, mfft_geom g, const mfft_move *__restrict__ moves, uint32_t nmoves,
+           const mfft_batch *__restrict__ batch, uint32_t nbatch, uint32_t shift, int normalise)
+{
+   const uint64_t wid = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const uint32_t lane = threadIdx.x & 31;
+   if (wid >= (uint64_t) nmoves * nbatch) return;
+   const mfft_move mv = moves[wid / nbatch];
+   const uint32_t bi = (uint32_t)(wid % nbatch);
+   const mfft_batch b = batch[bi];
+   const limb_t *src = block_ptr(slab, g, mv.src_slot, b);
+   limb_t *out = dst + ((uint64_t) dst_base[bi] + (uint64_t) mv.dst_pos * dst_stride) * g.pitch;
+   lincomb_out<M>(out, src, 1, shift, src, 0, 0, g.l, lane);
+   if (normalise) normalise_block(out, g.l, lane);
+}
+
+__global__ void __launch_bounds__(128)
+k_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk)
+{
+   const uint64_t wid = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   if (wid >= nblk) return;
+   normalise_block(slab + wid * pitch, l, threadIdx.x & 31);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* pointwise product mod 2^NW + 1                                                              */
+/* ------------------------------------------------------------------------------------------ */
+/* One warp per product; l = 16*C limbs, i.e. every lane owns C 32-bit words of each operand.
+ * The operands are cut into 32 blocks of C words; lane K accumulates
+ *      sum_{I+J=K} A_I*B_J  -  sum_{I+J=K+32} A_I*B_J            (B^l == -1)
+ * by walking I = 0..31 with A_I broadcast from shared memory and the B blocks rotating
+ * through the lanes by shuffle.  Each block product is a CxC schoolbook product.           */
+template <int C>
+__global__ void __launch_bounds__(128)
+k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
+            uint32_t nblk, uint32_t l, uint32_t pitch)
+{
+   MFFT_DYN_SMEM(uint32_t, smem);
+   const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const uint64_t wid = (uint64_t) blockIdx.x * (blockDim.x >> 5) + wib;
+   if (wid >= nblk) return;
+   uint32_t *sA = smem + wib * (32 * C);
+   limb_t *A = a_slab + (uint64_t) blocks[wid] * pitch;
+   const limb_t *B = b_slab + (uint64_t) blocks[wid] * pitch;
+
+   const int64_t topA = (int64_t) A[l], topB = (int64_t) B[l];
+   __syncwarp();          /* every lane has read the tops before any lane rewrites A */
+   if (topA | topB)
+   {  /* canonical inputs: top == 1 means the operand is 2^NW == -1 (body zero) */
+      if (topA && topB)
+      {
+         for (uint32_t k = lane; k < l; k += 32) A[k] = (k == 0);
+         if (lane == 0) A[l] = 0;
+      } else if (topA)
+      {
+         lincomb_out<1>(A, B, -1, 0, B, 0, 0, l, lane);
+         normalise_block(A, l, lane);
+      } else
+      {
+         __syncwarp();
+         /* -A in place: each lane rewrites exactly the limbs it read in the same tile */
+         lincomb_out<1>(A, A, -1, 0, A, 0, 0, l, lane);
+         normalise_block(A, l, lane);
+      }
+      return;
+   }
+
+   uint32_t a[C], b[C];
+#pragma unroll
+   for (int i = 0; i < C; i += 2)
+   {
+      const limb_t va = A[(lane * C + i) >> 1], vb = B[(lane * C + i) >> 1];
+      a[i] = (uint32_t) va; a[i + 1] = (uint32_t)(va >> 32);
+      b[i] = (uint32_t) vb; b[i + 1] = (uint32_t)(vb >> 32);
+   }
+#pragma unroll
+   for (int i = 0; i < C; i++) sA[lane * C + i] = a[i];
+   __syncwarp();
+
+   uint32_t acc[2 * C + 1];
+#pragma unroll
+   for (int i = 0; i < 2 * C + 1; i++) acc[i] = 0;
+
+   for (uint32_t s = 0; s < 32; s++)
+   {
+      uint32_t ab[C];
+#pragma unroll
+      for (int i = 0; i < C; i++) ab[i] = sA[s * C + i];
+      uint32_t prod[2 * C];
+#pragma unroll
+      for (int i = 0; i < 2 * C; i++) prod[i] = 0;
+#pragma unroll
+      for (int j = 0; j < C; j++)
+      {
+         uint64_t cy = 0;
+#pragma unroll
+         for (int t = 0; t < C; t++)
+         {
+            const uint64_t v = (uint64_t) ab[t] * b[j] + prod[j + t] + cy;
+            prod[j + t] = (uint32_t) v; cy = v >> 32;
+         }
+         prod[j + C] = (uint32_t) cy;
+      }
+      /* block index of the B block this lane holds is (lane - s) mod 32: negative wrap if lane < s */
+      const uint32_t m = (lane < s) ? 0xffffffffu : 0u;
+      uint64_t cy = m & 1u;
+#pragma unroll
+      for (int i = 0; i < 2 * C; i++)
+      {
+         const uint64_t v = (uint64_t) acc[i] + (prod[i] ^ m) + cy;
+         acc[i] = (uint32_t) v; cy = v >> 32;
+      }
+      acc[2 * C] += (uint32_t) cy + m;            /* + carry, and -1 when subtracting */
+      const uint32_t src = (lane + 31) & 31;
+#pragma unroll
+      for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src);
+   }
+
+   /* lane K: r = acc[0..C) + (high part of lane K-1), lane 0 takes -(high part of lane 31) */
+   uint32_t hi[C + 1];
+   const uint32_t src = (lane + 31) & 31;
+#pragma unroll
+   for (int i = 0; i <= C; i++) hi[i] = __shfl_sync(FULL, acc[C + i], src);
+   int32_t carry;
+   {
+      const uint32_t m = (lane == 0) ? 0xffffffffu : 0u;
+      uint64_t cy = m & 1u;
+      /* sign extension word of hi (its top word acc[2C] is a small signed count) */
+      const uint32_t ext = ((int32_t) hi[C] < 0) ? 0xffffffffu : 0u;
+#pragma unroll
+      for (int i = 0; i < C; i++)
+      {
+         const uint64_t v = (uint64_t) acc[i] + (hi[i] ^ m) + cy;
+         acc[i] = (uint32_t) v; cy = v >> 32;
+      }
+      /* carry out of the C words: cy + (signed) (hi[C] ^ m) with one more extension word */
+      const int64_t top = (int64_t)(int32_t)(hi[C] ^ m) + (int64_t) cy;
+      (void) ext;
+      carry = (int32_t) top;
+   }
+   /* signed carries ripple to the next lane; lane 31's leave through the top limb (2^NW == -1) */
+   int64_t top = 0;
+   for (int it = 0; it < 40; it++)
+   {
+      if (!__any_sync(FULL, carry != 0)) break;
+      int32_t cin = __shfl_up_sync(FULL, carry, 1);
+      const int32_t c31 = __shfl_sync(FULL, carry, 31);
+      top += c31;
+      if (lane == 0) cin = 0;
+      /* add the signed cin to the C words */
+      int64_t cc = cin;
+#pragma unroll
+      for (int i = 0; i < C; i++)
+      {
+         const int64_t v = (int64_t)(uint64_t) acc[i] + cc;
+         acc[i] = (uint32_t) v; cc = v >> 32;       /* arithmetic shift keeps the sign */
+      }
+      carry = (int32_t) cc;
+   }
+#pragma unroll
+   for (int i = 0; i < C; i += 2)
+      A[(lane * C + i) >> 1] = (limb_t) acc[i] | ((limb_t) acc[i + 1] << 32);
+   if (lane == 0) A[l] = (limb_t) top;
+   normalise_block(A, l, lane);
+}
+
+/* generic fallback: any l.  One CTA per product, thread per 64-bit output column. */
+__global__ void __launch_bounds__(256)
+k_pointwise_generic(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
+                    uint32_t nblk, uint32_t l, uint32_t pitch, limb_t *scratch)
+{
+   MFFT_DYN_SMEM(uint32_t, smem);
+   limb_t *sa = (limb_t *) smem, *sb = sa + l;
+   limb_t *A = a_slab + (uint64_t) blocks[blockIdx.x] * pitch;
+   const limb_t *B = b_slab + (uint64_t) blocks[blockIdx.x] * pitch;
+   limb_t *col = scratch + (uint64_t) blockIdx.x * 3 * l;     /* 3 limbs per column: lo, hi, signed ovf */
+   const int64_t topA = (int64_t) A[l], topB = (int64_t) B[l];
+   const uint32_t lane = threadIdx.x & 31;
+   __syncthreads();       /* every thread has read the tops before warp 0 rewrites A */
+   if (topA | topB)
+   {
+      if (threadIdx.x < 32)
+      {
+         if (topA && topB) { for (uint32_t k = lane; k < l; k += 32) A[k] = (k == 0); if (lane == 0) A[l] = 0; }
+         else if (topA) { lincomb_out<1>(A, B, -1, 0, B, 0, 0, l, lane); normalise_block(A, l, lane); }
+         else { lincomb_out<1>(A, A, -1, 0, A, 0, 0, l, lane); normalise_block(A, l, lane); }
+      }
+      return;
+   }
+   for (uint32_t k = threadIdx.x; k < l; k += blockDim.x) { sa[k] = A[k]; sb[k] = B[k]; }
+   __syncthreads();
+   for (uint32_t c = threadIdx.x; c < l; c += blockDim.x)
+   {
+      mfft_u128 pos = 0, neg = 0; uint32_t pov = 0, nov = 0;
+      for (uint32_t i = 0; i < l; i++)
+      {
+         const uint32_t j = (c >= i) ? c - i : c + l - i;
+         const mfft_u128 pr = (mfft_u128) sa[i] * sb[j];
+         if (c >= i) { const mfft_u128 o = pos; pos += pr; pov += (pos < o); }
+         else        { const mfft_u128 o = neg; neg += pr; nov += (neg < o); }
+      }
+      /* column value = pos - neg as a signed 192-bit number */
+      const mfft_u128 d = pos - neg;
+      const int64_t ov = (int64_t) pov - (int64_t) nov - (pos < neg ? 1 : 0);
+      col[3 * c] = (limb_t) d; col[3 * c + 1] = (limb_t)(d >> 64); col[3 * c + 2] = (limb_t) ov;
+   }
+   __syncthreads();
+   if (threadIdx.x == 0)
+   {  /* serial carry pass (fallback path only).  Column c holds lo at limb c, hi at c+1 and a
+         signed overflow count at c+2; limbs l, l+1, l+2 of the sum wrap around negated. */
+      mfft_i128 cy = 0; limb_t hi3[3]; int64_t top = 0;
+      for (uint32_t k = 0; k < l + 2; k++)
+      {
+         mfft_i128 v = cy;
+         if (k < l) v += (mfft_i128)(mfft_u128) col[3 * k];
+         if (k >= 1 && k - 1 < l) v += (mfft_i128)(mfft_u128) col[3 * (k - 1) + 1];
+         if (k >= 2 && k - 2 < l) v += (mfft_i128)(int64_t) col[3 * (k - 2) + 2];
+         if (k < l) A[k] = (limb_t) v; else hi3[k - l] = (limb_t) v;
+         cy = v >> 64;
+      }
+      hi3[2] = (limb_t) cy;                      /* signed */
+      A[l] = 0;
+      for (uint32_t t = 0; t < 3; t++)
+      {  /* add hi3[t] * B^(l+t):  B^l == -1, so position (l+t) mod l with the sign flipped once
+            per wrap */
+         mfft_i128 val = (t == 2) ? (mfft_i128)(int64_t) hi3[t] : (mfft_i128)(mfft_u128) hi3[t];
+         uint32_t pos = l + t;
+         while (pos >= l) { pos -= l; val = -val; }
+         mfft_inject(A, l, &top, pos, val);
+      }
+      A[l] = (limb_t) top;
+   }
+   __syncthreads();
+   if (threadIdx.x < 32) normalise_block(A, l, lane);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* split / combine                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+/* bits [off, off+64) of {src, n} (zero beyond the end) */
+__device__ __forceinline__ limb_t bits_at(const limb_t *src, uint64_t n, uint64_t off)
+{
+   const uint64_t q = off >> 6; const uint32_t r = (uint32_t)(off & 63);
+   if (q >= n) return 0;
+   limb_t v = src[q] >> r;
+   if (r && q + 1 < n) v |= src[q + 1] << (64 - r);
+   return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *__restrict__ src, uint64_t nlimbs,
+        uint64_t bits, uint64_t ncoef, uint64_t nzero)
+{
+   const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+   const uint64_t per = (uint64_t) l + 1;
+   if (t >= nzero * per) return;
+   const uint64_t i = t / per; const uint32_t k = (uint32_t)(t % per);
+   limb_t v = 0;
+   if (i < ncoef && k < l && (uint64_t) k * 64 < bits)
+   {
+      v = bits_at(src, nlimbs, i * bits + (uint64_t) k * 64);
+      const uint64_t rem = bits - (uint64_t) k * 64;
+      if (rem < 64) v &= (((limb_t) 1 << rem) - 1);
+   }
+   slab[i * pitch + k] = v;
+}
+
+/* res[k] = low 64 bits of the sum of all coefficient windows covering limb k; cvec[k+1] = the
+ * high part of that sum (a small count) */
+__global__ void __launch_bounds__(256)
+k_combine_sum(limb_t *res, uint32_t *cvec, uint64_t total, const limb_t *__restrict__ slab,
+              uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef)
+{
+   const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+   if (k > total) return;
+   if (k == 0) cvec[0] = 0;
+   if (k == total) return;
+   const uint64_t lo_bit = k * 64, NWb = (uint64_t) l * 64;
+   /* coefficients i with i*bits <= lo_bit+63 and i*bits + NW > lo_bit */
+   uint64_t imax = (lo_bit + 63) / bits;
+   if (imax >= ncoef) imax = ncoef - 1;
+   uint64_t imin = (lo_bit >= NWb) ? (lo_bit - NWb) / bits + 1 : 0;
+   mfft_u128 acc = 0;
+   for (uint64_t i = imin; i <= imax && i < ncoef; i++)
+   {
+      const limb_t *c = slab + i * pitch;
+      const uint64_t start = i * bits;            /* bit offset of coefficient i in the result */
+      limb_t v;
+      if (start <= lo_bit) v = bits_at(c, l, lo_bit - start);
+      else v = c[0] << (start - lo_bit);          /* coefficient begins inside this limb */
+      acc += v;
+   }
+   res[k] = (limb_t) acc;
+   cvec[k + 1] = (uint32_t)(acc >> 64);
+}
+
+#define CMB_M 8       /* limbs per lane in the carry passes: one warp tile = 256 limbs */
+
+/* pass 2: res += cvec (tile-local, carry-in 0); per tile: generate bit and propagate bit */
+__global__ void __launch_bounds__(128)
+k_combine_add(limb_t *res, const uint32_t *__restrict__ cvec, uint64_t total, uint32_t *tileG,
+              uint32_t *tileP, uint64_t ntiles)
+{
+   const uint64_t tile = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const uint32_t lane = threadIdx.x & 31;
+   if (tile >= ntiles) return;
+   const uint64_t kb = tile * (32 * CMB_M) + (uint64_t) lane * CMB_M;
+   limb_t s[CMB_M]; uint32_t c = 0; bool ones_all = true;
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++)
+   {
+      const uint64_t k = kb + i;
+      limb_t x = ~(limb_t) 0, z = 0;
+      if (k < total) { x = res[k]; z = cvec[k]; }
+      const mfft_u128 acc = (mfft_u128) x + z + c;
+      s[i] = (limb_t) acc; c = (uint32_t)(acc >> 64);
+      ones_all = ones_all && (s[i] == ~(limb_t) 0);
+   }
+   const uint32_t G = __ballot_sync(FULL, c != 0), P = __ballot_sync(FULL, ones_all);
+   const uint64_t la = mfft_lookahead(G, P, 0);
+   uint32_t myc = (uint32_t)(la >> lane) & 1u;
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++)
+   {
+      const uint64_t k = kb + i;
+      const limb_t v = s[i] + myc;
+      myc = (myc && v == 0) ? 1u : 0u;
+      if (k < total) res[k] = v;
+      s[i] = v;
+   }
+   /* tile generates iff carry out with cin 0; propagates iff every limb is now all ones */
+   bool all1 = true;
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++) all1 = all1 && (kb + i >= total || s[i] == ~(limb_t) 0);
+   const bool tp = __all_sync(FULL, all1);
+   if (lane == 0) { tileG[tile] = (uint32_t)(la >> 32) & 1u; tileP[tile] = tp ? 1u : 0u; }
+}
+
+/* pass 3: one warp scans the tile generate/propagate bits, 32 tiles per step */
+__global__ void __launch_bounds__(32)
+k_combine_scan(const uint32_t *__restrict__ tileG, const uint32_t *__restrict__ tileP,
+               uint32_t *tileC, uint64_t ntiles)
+{
+   const uint32_t lane = threadIdx.x;
+   uint32_t cin = 0;
+   for (uint64_t t0 = 0; t0 < ntiles; t0 += 32)
+   {
+      const uint64_t t = t0 + lane;
+      const uint32_t g = (t < ntiles) ? tileG[t] : 0u, p = (t < ntiles) ? tileP[t] : 1u;
+      const uint32_t G = __ballot_sync(FULL, g != 0), P = __ballot_sync(FULL, p != 0);
+      const uint64_t la = mfft_lookahead(G, P, cin);
+      if (t < ntiles) tileC[t] = (uint32_t)(la >> lane) & 1u;
+      cin = (uint32_t)(la >> 32) & 1u;
+   }
+}
+
+/* pass 4: tiles with carry-in 1 add it (it ripples through the all-ones prefix of the tile) */
+__global__ void __launch_bounds__(128)
+k_combine_fix(limb_t *res, uint64_t total, const uint32_t *__restrict__ tileC, uint64_t ntiles)
+{
+   const uint64_t tile = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const uint32_t lane = threadIdx.x & 31;
+   if (tile >= ntiles) return;
+   if (!tileC[tile]) return;
+   const uint64_t kb = tile * (32 * CMB_M) + (uint64_t) lane * CMB_M;
+   limb_t s[CMB_M]; bool ones_all = true;
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++)
+   {
+      const uint64_t k = kb + i;
+      s[i] = (k < total) ? res[k] : ~(limb_t) 0;
+      ones_all = ones_all && (s[i] == ~(limb_t) 0);
+   }
+   const uint32_t P = __ballot_sync(FULL, ones_all);
+   const uint64_t la = mfft_lookahead(0, P, 1);
+   uint32_t myc = (uint32_t)(la >> lane) & 1u;
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++)
+   {
+      const uint64_t k = kb + i;
+      const limb_t v = s[i] + myc;
+      myc = (myc && v == 0) ? 1u : 0u;
+      if (k < total) res[k] = v;
+   }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* launch ABI                                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+extern "C" {
+
+const char *mfft_dev_last_error(void) { return g_err; }
+uint64_t mfft_dev_launch_count(void) { return g_launches; }
+void mfft_dev_launch_count_reset(void) { g_launches = 0; }
+
+int mfft_dev_count(void)
+{
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+   return n;
+}
+
+int mfft_dev_init(int device)
+{
+   int n = mfft_dev_count();
+   if (n <= 0) { snprintf(g_err, sizeof g_err, "no CUDA device visible (this library has no CPU path)"); return -1; }
+   if (device < 0 || device >= n) { snprintf(g_err, sizeof g_err, "device %d out of range (%d visible)", device, n); return -1; }
+   CK(cudaSetDevice(device));
+   CK(cudaFree(0));
+   g_device = device;
+   return 0;
+}
+
+void *mfft_dev_alloc(size_t bytes)
+{
+   void *p = NULL;
+   if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess)
+   {
+      snprintf(g_err, sizeof g_err, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+      return NULL;
+   }
+   return p;
+}
+void mfft_dev_free(void *p) { if (p) cudaFree(p); }
+void *mfft_host_alloc_pinned(size_t bytes)
+{
+   void *p = NULL;
+   if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return NULL; }
+   return p;
+}
+void mfft_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+int mfft_dev_h2d(void *d, const void *h, size_t bytes, void *stream)
+{ CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t) stream)); return 0; }
+int mfft_dev_d2h(void *h, const void *d, size_t bytes, void *stream)
+{ CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t) stream)); return 0; }
+int mfft_dev_h2d_2d(void *d, size_t dpitch, const void *h, size_t hpitch, size_t width, size_t rows, void *stream)
+{ CK(cudaMemcpy2DAsync(d, dpitch, h, hpitch, width, rows, cudaMemcpyHostToDevice, (cudaStream_t) stream)); return 0; }
+int mfft_dev_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, void *stream)
+{ CK(cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, rows, cudaMemcpyDeviceToHost, (cudaStream_t) stream)); return 0; }
+int mfft_dev_memset0(void *d, size_t bytes, void *stream)
+{ CK(cudaMemsetAsync(d, 0, bytes, (cudaStream_t) stream)); return 0; }
+int mfft_dev_sync(void *stream)
+{ CK(cudaStreamSynchronize((cudaStream_t) stream)); return 0; }
+
+static int pick_m(uint32_t l)
+{
+   if (l % 256 == 0) return 8;
+   if (l % 128 == 0) return 4;
+   if (l % 64 == 0) return 2;
+   return 1;
+}
+
+int mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
+                       const mfft_batch *d_batch, uint32_t nbatch, void *stream)
+{
+   if (!count || !nbatch) return 0;
+   const uint64_t warps = (uint64_t) count * nbatch;
+   const unsigned grid = (unsigned)((warps + 3) / 4);
+   cudaStream_t st = (cudaStream_t) stream;
+   switch (pick_m(g->l))
+   {
+   case 8: MFFT_LAUNCH(k_run_stage<8>, grid, 128, 0, st, slab, *g, d_ops, count, d_batch, nbatch); break;
+   case 4: MFFT_LAUNCH(k_run_stage<4>, grid, 128, 0, st, slab, *g, d_ops, count, d_batch, nbatch); break;
+   case 2: MFFT_LAUNCH(k_run_stage<2>, grid, 128, 0, st, slab, *g, d_ops, count, d_batch, nbatch); break;
+   default: MFFT_LAUNCH(k_run_stage<1>, grid, 128, 0, st, slab, *g, d_ops, count, d_batch, nbatch); break;
+   }
+   CKL();
+   return 0;
+}
+
+int mfft_dev_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst_base,
+                      const limb_t *slab, const mfft_geom *g, const mfft_move *d_moves, uint32_t nmoves,
+                      const mfft_batch *d_batch, uint32_t nbatch, uint32_t shift, int normalise,
+                      void *stream)
+{
+   if (!nmoves || !nbatch) return 0;
+   const uint64_t warps = (uint64_t) nmoves * nbatch;
+   const unsigned grid = (unsigned)((warps + 3) / 4);
+   cudaStream_t st = (cudaStream_t) stream;
+   limb_t *s = (limb_t *) slab;
+   switch (pick_m(g->l))
+   {
+   case 8: MFFT_LAUNCH(k_finalize<8>, grid, 128, 0, st, dst, dst_stride, d_dst_base, s, *g, d_moves, nmoves, d_batch, nbatch, shift, normalise); break;
+   case 4: MFFT_LAUNCH(k_finalize<4>, grid, 128, 0, st, dst, dst_stride, d_dst_base, s, *g, d_moves, nmoves, d_batch, nbatch, shift, normalise); break;
+   case 2: MFFT_LAUNCH(k_finalize<2>, grid, 128, 0, st, dst, dst_stride, d_dst_base, s, *g, d_moves, nmoves, d_batch, nbatch, shift, normalise); break;
+   default: MFFT_LAUNCH(k_finalize<1>, grid, 128, 0, st, dst, dst_stride, d_dst_base, s, *g, d_moves, nmoves, d_batch, nbatch, shift, normalise); break;
+   }
+   CKL();
+   return 0;
+}
+
+int mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, void *stream)
+{
+   if (!nblk) return 0;
+   MFFT_LAUNCH(k_normalise, (unsigned)((nblk + 3) / 4), 128, 0, (cudaStream_t) stream, slab, l, pitch, nblk);
+   CKL();
+   return 0;
+}
+
+static limb_t *g_pw_scratch = NULL; static size_t g_pw_scratch_bytes = 0;
+
+int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uint32_t nblk,
+                       uint32_t l, uint32_t pitch, void *stream)
+{
+   if (!nblk) return 0;
+   cudaStream_t st = (cudaStream_t) stream;
+   const unsigned grid = (nblk + 3) / 4;
+   if (l == 64)       MFFT_LAUNCH(k_pointwise<4>, grid, 128, 4 * 32 * 4 * 4, st, a, b, d_blocks, nblk, l, pitch);
+   else if (l == 128) MFFT_LAUNCH(k_pointwise<8>, grid, 128, 4 * 32 * 8 * 4, st, a, b, d_blocks, nblk, l, pitch);
+   else if (l == 256) MFFT_LAUNCH(k_pointwise<16>, grid, 128, 4 * 32 * 16 * 4, st, a, b, d_blocks, nblk, l, pitch);
+   else if (l == 512) MFFT_LAUNCH(k_pointwise<32>, grid, 128, 4 * 32 * 32 * 4, st, a, b, d_blocks, nblk, l, pitch);
+   else
+   {
+      const size_t need = (size_t) nblk * 3 * l * sizeof(limb_t);
+      const size_t sm = 2 * (size_t) l * sizeof(limb_t);
+      if (sm > 200 * 1024) { snprintf(g_err, sizeof g_err, "pointwise: l=%u too large for the direct kernel", l); return -2; }
+      if (need > g_pw_scratch_bytes)
+      {
+         CK(cudaStreamSynchronize(st));
+         if (g_pw_scratch) cudaFree(g_pw_scratch);
+         g_pw_scratch = NULL; g_pw_scratch_bytes = 0;
+         CK(cudaMalloc(&g_pw_scratch, need)); g_pw_scratch_bytes = need;
+      }
+      CK(cudaFuncSetAttribute(k_pointwise_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+      MFFT_LAUNCH(k_pointwise_generic, nblk, 256, sm, st, a, b, d_blocks, nblk, l, pitch, g_pw_scratch);
+   }
+   CKL();
+   return 0;
+}
+
+int mfft_dev_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, uint64_t nlimbs,
+                   uint64_t bits, uint64_t ncoef, uint64_t nzero, void *stream)
+{
+   if (nzero < ncoef) nzero = ncoef;
+   const uint64_t threads = nzero * ((uint64_t) l + 1);
+   if (!threads) return 0;
+   MFFT_LAUNCH(k_split, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t) stream, slab, l, pitch, src, nlimbs, bits, ncoef, nzero);
+   CKL();
+   return 0;
+}
+
+size_t mfft_dev_combine_work(uint64_t total)
+{
+   const uint64_t ntiles = (total + 32 * CMB_M - 1) / (32 * CMB_M);
+   return (size_t)((total + 1) * 4 + 3 * (ntiles + 32) * 4 + 256);
+}
+
+int mfft_dev_combine(limb_t *res, uint64_t total, const limb_t *slab, uint32_t l, uint32_t pitch,
+                     uint64_t bits, uint64_t ncoef, void *work, void *stream)
+{
+   cudaStream_t st = (cudaStream_t) stream;
+   if (!total) return 0;
+   if (!ncoef) { CK(cudaMemsetAsync(res, 0, total * 8, st)); return 0; }
+   const uint64_t ntiles = (total + 32 * CMB_M - 1) / (32 * CMB_M);
+   uint32_t *cvec = (uint32_t *) work;
+   uint32_t *tileG = cvec + ((total + 1 + 63) / 64) * 64;
+   uint32_t *tileP = tileG + ntiles + 32 - (ntiles % 32);
+   uint32_t *tileC = tileP + ntiles + 32 - (ntiles % 32);
+   MFFT_LAUNCH(k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef);
+   CKL();
+   MFFT_LAUNCH(k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);
+   CKL();
+   MFFT_LAUNCH(k_combine_scan, 1, 32, 0, st, tileG, tileP, tileC, ntiles);
+   CKL();
+   MFFT_LAUNCH(k_combine_fix, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, total, tileC, ntiles);
+   CKL();
+   return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,432 @@
+/* api.c -- the remaining reference entry points (host pointer tables in, host blocks out).
+ *
+ * The reference's transforms take `mp_limb_t **ii`: a table of host pointers into a slab of
+ * (l+1)-limb blocks which they permute (README:56).  Here each call gathers the blocks into one
+ * pinned-size staging buffer, copies it to an HBM slab, runs the device schedule, and writes result
+ * k back into the block ii[k] points to (the identity permutation, which the reference's contract
+ * allows: after return {ii[*], *t1, *t2} is still a permutation of the caller's block set).
+ * t1/t2/temp are accepted and never touched.  These per-call entry points exist for drop-in and
+ * parity testing; the fast path is the device-resident plan API (mul.c).
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "runtime.h"
+#include "../../../include/mpirfft_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+mp_limb_t mpir_revbin(mp_limb_t in, mp_bitcnt_t bits) { return (mp_limb_t) mfft_revbin(in, (uint32_t) bits); }
+
+/* Run a schedule over S host blocks.  in[k] == NULL: position k starts as zero.  out[k] == NULL:
+ * position k is not written back.  Takes ownership of s. */
+static void run_on_host_blocks(const char *fn, mfft_sched *s, uint32_t l, mp_limb_t **in, mp_limb_t **out,
+                               uint32_t col, int normalise)
+{
+   uint32_t S = s->S, k, pitch = l + 1, zero = 0;
+   size_t half = (size_t) S * pitch * sizeof(limb_t);
+   limb_t *stage = (limb_t *) calloc((size_t) S * pitch, sizeof(limb_t));
+   limb_t *d_slab = NULL, *d_dst = NULL; mfft_batch b, *d_b = NULL; mfft_move *mv = NULL, *d_mv = NULL;
+   uint32_t *d_base = NULL; mfft_dsched ds; mfft_geom g;
+   if (!stage) mfft_die(fn, "out of host memory");
+   mfft_lock();
+   mfft_require_device(fn);
+   for (k = 0; k < S; k++) if (in[k]) memcpy(stage + (size_t) k*pitch, in[k], pitch*sizeof(limb_t));
+   d_slab = (limb_t *) mfft_dev_alloc(2*half); d_dst = (limb_t *) mfft_dev_alloc(half);
+   b.base = 0; b.parity = 0; b.col = col; b.pad = 0;
+   d_b = (mfft_batch *) mfft_upload(&b, sizeof b);
+   d_base = (uint32_t *) mfft_upload(&zero, sizeof zero);
+   if (!d_slab || !d_dst || !d_b || !d_base) mfft_die(fn, "device allocation failed: %s", mfft_dev_last_error());
+   if (mfft_dsched_upload(&ds, s) != 0) mfft_die(fn, "schedule upload failed: %s", mfft_dev_last_error());
+   mv = (mfft_move *) malloc(sizeof(mfft_move) * S);
+   if (!mv) mfft_die(fn, "out of host memory");
+   for (k = 0; k < S; k++) { mv[k].src_slot = s->slot[k]; mv[k].dst_pos = k; }
+   d_mv = (mfft_move *) mfft_upload(mv, sizeof(mfft_move) * S);
+   if (!d_mv) mfft_die(fn, "device allocation failed: %s", mfft_dev_last_error());
+   g.S = S; g.slot_stride = 1; g.half_blocks = S; g.l = l; g.pitch = pitch;
+   if (mfft_dev_h2d(d_slab, stage, half, NULL) ||
+       mfft_dsched_run(&ds, d_slab, &g, d_b, 1, NULL) ||
+       mfft_dev_finalize(d_dst, 1, d_base, d_slab, &g, d_mv, S, d_b, 1, 0, normalise, NULL) ||
+       mfft_dev_d2h(stage, d_dst, half, NULL) || mfft_dev_sync(NULL))
+      mfft_die(fn, "device execution failed: %s", mfft_dev_last_error());
+   for (k = 0; k < S; k++) if (out[k]) memcpy(out[k], stage + (size_t) k*pitch, pitch*sizeof(limb_t));
+   mfft_dsched_free(&ds);
+   mfft_dev_free(d_slab); mfft_dev_free(d_dst); mfft_dev_free(d_b); mfft_dev_free(d_base); mfft_dev_free(d_mv);
+   mfft_unlock();
+   free(mv); free(stage);
+}
+
+static void check_ring(const char *fn, mp_size_t n, mp_bitcnt_t w)
+{
+   if (n <= 0 || (n & (n - 1)) || w == 0 || ((uint64_t) n*w) % 64)
+      mfft_die(fn, "illegal ring: n=%ld w=%lu (need n a power of two and 64 | n*w)", (long) n, (unsigned long) w);
+}
+
+/* all 1-D transforms share this: positions k < 2n are ii[k*is] */
+static void transform_1d(const char *fn, mfft_transform_kind kind, mp_limb_t **ii, mp_size_t is, mp_size_t n,
+                         mp_bitcnt_t w, mp_size_t ws, mp_size_t r, mp_size_t c, mp_size_t rs, mp_size_t trunc)
+{
+   uint32_t S, k; mfft_sched *s; mp_limb_t **tab;
+   check_ring(fn, n, w);
+   if (is <= 0) mfft_die(fn, "illegal stride %ld", (long) is);
+   S = (uint32_t)(2*n);
+   s = mfft_sched_new(S, (uint64_t) n*w);
+   tab = (mp_limb_t **) malloc(sizeof(mp_limb_t *) * S);
+   if (!s || !tab) mfft_die(fn, "out of host memory");
+   if (mfft_sched_emit(s, kind, 0, 1, (uint64_t) n, w, (uint64_t) ws, (uint64_t) r, (uint64_t) rs, (uint64_t) trunc) != 0)
+      mfft_die(fn, "illegal transform parameters (n=%ld w=%lu trunc=%ld; trunc must be even, 2 <= trunc <= 2n)",
+               (long) n, (unsigned long) w, (long) trunc);
+   for (k = 0; k < S; k++) tab[k] = ii[(size_t) k*is];
+   run_on_host_blocks(fn, s, (uint32_t)((uint64_t) n*w/64), tab, tab, (uint32_t) c, 0);
+   free(tab);
+}
+
+void FFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
+  transform_1d("FFT_radix2", MFFT_T_FFT, ii, 1, n, w, 0, 0, 0, 0, 0); }
+
+void IFFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                 mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
+  transform_1d("IFFT_radix2", MFFT_T_IFFT, ii, 1, n, w, 0, 0, 0, 0, 0); }
+
+void FFT_radix2_truncate(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                         mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
+  transform_1d("FFT_radix2_truncate", MFFT_T_FFT_TRUNC, ii, 1, n, w, 0, 0, 0, 0, trunc); }
+
+void FFT_radix2_truncate1(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                          mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
+  transform_1d("FFT_radix2_truncate1", MFFT_T_FFT_TRUNC1, ii, 1, n, w, 0, 0, 0, 0, trunc); }
+
+void IFFT_radix2_truncate(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                          mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
+  transform_1d("IFFT_radix2_truncate", MFFT_T_IFFT_TRUNC, ii, 1, n, w, 0, 0, 0, 0, trunc); }
+
+void IFFT_radix2_truncate1(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                           mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
+  transform_1d("IFFT_radix2_truncate1", MFFT_T_IFFT_TRUNC1, ii, 1, n, w, 0, 0, 0, 0, trunc); }
+
+void FFT_radix2_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                        mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c, mp_size_t rs)
+{ (void) t1; (void) t2; (void) temp;
+  transform_1d("FFT_radix2_twiddle", MFFT_T_FFT, ii, is, n, w, ws, r, c, rs, 0); }
+
+void IFFT_radix2_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                         mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c, mp_size_t rs)
+{ (void) t1; (void) t2; (void) temp;
+  transform_1d("IFFT_radix2_twiddle", MFFT_T_IFFT, ii, is, n, w, ws, r, c, rs, 0); }
+
+void FFT_radix2_truncate_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                                 mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c,
+                                 mp_size_t rs, mp_size_t trunc)
+{ (void) t1; (void) t2; (void) temp;
+  transform_1d("FFT_radix2_truncate_twiddle", MFFT_T_FFT_TRUNC, ii, is, n, w, ws, r, c, rs, trunc); }
+
+void FFT_radix2_truncate1_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                                  mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c,
+                                  mp_size_t rs, mp_size_t trunc)
+{ (void) t1; (void) t2; (void) temp;
+  transform_1d("FFT_radix2_truncate1_twiddle", MFFT_T_FFT_TRUNC1, ii, is, n, w, ws, r, c, rs, trunc); }
+
+void IFFT_radix2_truncate_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                                  mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c,
+                                  mp_size_t rs, mp_size_t trunc)
+{ (void) t1; (void) t2; (void) temp;
+  transform_1d("IFFT_radix2_truncate_twiddle", MFFT_T_IFFT_TRUNC, ii, is, n, w, ws, r, c, rs, trunc); }
+
+void IFFT_radix2_truncate1_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                                   mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c,
+                                   mp_size_t rs, mp_size_t trunc)
+{ (void) t1; (void) t2; (void) temp;
+  transform_1d("IFFT_radix2_truncate1_twiddle", MFFT_T_IFFT_TRUNC1, ii, is, n, w, ws, r, c, rs, trunc); }
+
+void FFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                           mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
+  if (w & 1) mfft_die("FFT_radix2_negacyclic", "odd w needs the sqrt2 path, which is out of scope");
+  transform_1d("FFT_radix2_negacyclic", MFFT_T_FFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); }
+
+void IFFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                            mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
+  if (w & 1) mfft_die("IFFT_radix2_negacyclic", "odd w needs the sqrt2 path, which is out of scope");
+  transform_1d("IFFT_radix2_negacyclic", MFFT_T_IFFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); }
+
+/* ------------------------------- MFA on host pointer tables -------------------------------- */
+static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_size_t n1,
+                     mp_size_t trunc, int truncated)
+{
+   mfft_mfa m; int rc; uint64_t N, k, i, j; size_t half; limb_t *stage, *d_slab, *d_dst; uint32_t pitch;
+   check_ring(fn, n, w);
+   mfft_lock();
+   mfft_require_device(fn);
+   rc = mfft_mfa_build(&m, inverse, (uint64_t) n, w, (uint64_t) n1, truncated ? (uint64_t) trunc : 0);
+   if (rc != 0) mfft_die(fn, "illegal MFA parameters n=%ld w=%lu n1=%ld trunc=%ld (code %d; trunc must be a multiple "
+                         "of 2*n1, mul_fft.c:2209-2211)", (long) n, (unsigned long) w, (long) n1, (long) trunc, rc);
+   N = m.N; pitch = m.pitch; half = (size_t) N*pitch*sizeof(limb_t);
+   stage = (limb_t *) calloc((size_t) N*pitch, sizeof(limb_t));
+   d_slab = (limb_t *) mfft_dev_alloc(2*half); d_dst = (limb_t *) mfft_dev_alloc(half);
+   if (!stage || !d_slab || !d_dst) mfft_die(fn, "allocation failed: %s", mfft_dev_last_error());
+   for (k = 0; k < N; k++) memcpy(stage + k*pitch, ii[k], pitch*sizeof(limb_t));
+   if (mfft_dev_h2d(d_slab, stage, half, NULL) ||
+       mfft_dev_h2d(d_dst, stage, half, NULL) ||          /* rows the transform does not produce keep their input */
+       mfft_mfa_exec(&m, d_slab, d_dst, 0, truncated, NULL) ||
+       mfft_dev_d2h(stage, d_dst, half, NULL) || mfft_dev_sync(NULL))
+      mfft_die(fn, "device execution failed: %s", mfft_dev_last_error());
+   if (!inverse)
+   {  /* valid outputs: rows revbin(s), s < trunc_rows, all columns (2392-2408) */
+      for (i = 0; i < m.nrows; i++)
+         for (j = 0; j < m.n1; j++)
+         {  k = (uint64_t) m.rows[i]*m.n1 + j; memcpy(ii[k], stage + k*pitch, pitch*sizeof(limb_t)); }
+   } else
+   {  /* valid outputs: positions j < trunc (2974-2976) */
+      for (k = 0; k < m.trunc_rows*m.n1; k++) memcpy(ii[k], stage + k*pitch, pitch*sizeof(limb_t));
+   }
+   mfft_dev_free(d_slab); mfft_dev_free(d_dst); free(stage);
+   mfft_mfa_free(&m);
+   mfft_unlock();
+}
+
+void FFT_radix2_mfa(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                    mp_limb_t **temp, mp_size_t n1)
+{ (void) t1; (void) t2; (void) temp; mfa_host("FFT_radix2_mfa", 0, ii, n, w, n1, 0, 0); }
+
+void IFFT_radix2_mfa(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                     mp_limb_t **temp, mp_size_t n1)
+{ (void) t1; (void) t2; (void) temp; mfa_host("IFFT_radix2_mfa", 1, ii, n, w, n1, 0, 0); }
+
+void FFT_radix2_mfa_truncate(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                             mp_limb_t **temp, mp_size_t n1, mp_size_t trunc)
+{ (void) t1; (void) t2; (void) temp; mfa_host("FFT_radix2_mfa_truncate", 0, ii, n, w, n1, trunc, 1); }
+
+void IFFT_radix2_mfa_truncate(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                              mp_limb_t **temp, mp_size_t n1, mp_size_t trunc)
+{ (void) t1; (void) t2; (void) temp; mfa_host("IFFT_radix2_mfa_truncate", 1, ii, n, w, n1, trunc, 1); }
+
+/* ----------------------------- single-block primitives ------------------------------------- */
+/* positions 0,1 = inputs A,B; outputs S -> position 0, T -> position 1 */
+static void two_block_op(const char *fn, uint32_t l, mp_limb_t *outS, mp_limb_t *outT, mp_limb_t *A, mp_limb_t *B,
+                         int sSA, uint64_t eSA, int sSB, uint64_t eSB, int sTA, uint64_t eTA, int sTB, uint64_t eTB,
+                         int normalise)
+{
+   mfft_sched *s = mfft_sched_new(2, 64ull*l);
+   mp_limb_t *in[2], *out[2];
+   if (!s) mfft_die(fn, "out of host memory");
+   if (l == 0) mfft_die(fn, "zero-limb ring");
+   in[0] = A; in[1] = B; out[0] = outS; out[1] = outT;
+   mfft_sched_emit_op(s, 0, B ? 1 : MFFT_NONE, 0, sSA, eSA, sSB, eSB, outT ? 1 : MFFT_NONE, sTA, eTA, sTB, eTB);
+   run_on_host_blocks(fn, s, l, in, out, 0, normalise);
+}
+
+#define M2OF(l) (128ull*(uint64_t)(l))
+#define NEGE(e, l) ((M2OF(l) - ((uint64_t)(e) % M2OF(l))) % M2OF(l))
+
+void mpn_normmod_2expp1(mp_limb_t *t, mp_size_t l)
+{ two_block_op("mpn_normmod_2expp1", (uint32_t) l, t, NULL, t, NULL, 1, 0, 0, 0, 0, 0, 0, 0, 1); }
+
+void mpn_mul_2expmod_2expp1(mp_limb_t *t, mp_limb_t *i1, mp_size_t limbs, mp_bitcnt_t d)
+{
+   if (d >= 64) mfft_die("mpn_mul_2expmod_2expp1", "d=%lu out of range", (unsigned long) d);
+   two_block_op("mpn_mul_2expmod_2expp1", (uint32_t) limbs, t, NULL, i1, NULL, 1, d, 0, 0, 0, 0, 0, 0, 0);
+}
+
+void mpn_div_2expmod_2expp1(mp_limb_t *t, mp_limb_t *i1, mp_size_t limbs, mp_bitcnt_t d)
+{
+   if (d >= 64) mfft_die("mpn_div_2expmod_2expp1", "d=%lu out of range", (unsigned long) d);
+   two_block_op("mpn_div_2expmod_2expp1", (uint32_t) limbs, t, NULL, i1, NULL, 1, NEGE(d, limbs), 0, 0, 0, 0, 0, 0, 0);
+}
+
+void mpn_lshB_sumdiffmod_2expp1(mp_limb_t *t, mp_limb_t *u, mp_limb_t *i1, mp_limb_t *i2, mp_size_t limbs,
+                                mp_size_t x, mp_size_t y)
+{
+   if (x < 0 || y < 0 || x > limbs || y > limbs) mfft_die("mpn_lshB_sumdiffmod_2expp1", "shift out of range");
+   two_block_op("mpn_lshB_sumdiffmod_2expp1", (uint32_t) limbs, t, u, i1, i2,
+                1, 64ull*x, 1, 64ull*x, 1, 64ull*y, -1, 64ull*y, 0);
+}
+
+void mpn_sumdiff_rshBmod_2expp1(mp_limb_t *t, mp_limb_t *u, mp_limb_t *i1, mp_limb_t *i2, mp_size_t limbs,
+                                mp_size_t x, mp_size_t y)
+{
+   if (x < 0 || y < 0 || x > limbs || y > limbs) mfft_die("mpn_sumdiff_rshBmod_2expp1", "shift out of range");
+   two_block_op("mpn_sumdiff_rshBmod_2expp1", (uint32_t) limbs, t, u, i1, i2,
+                1, NEGE(64ull*x, limbs), 1, NEGE(64ull*y, limbs), 1, NEGE(64ull*x, limbs), -1, NEGE(64ull*y, limbs), 0);
+}
+
+void FFT_radix2_butterfly(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2, mp_size_t i, mp_size_t n, mp_bitcnt_t w)
+{
+   uint64_t l, e;
+   check_ring("FFT_radix2_butterfly", n, w);
+   l = (uint64_t) n*w/64; e = ((uint64_t) i % (2*(uint64_t) n)) * w;
+   two_block_op("FFT_radix2_butterfly", (uint32_t) l, s, t, i1, i2, 1, 0, 1, 0, 1, e, -1, e, 0);
+}
+
+void FFT_radix2_inverse_butterfly(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2, mp_size_t i, mp_size_t n, mp_bitcnt_t w)
+{
+   uint64_t l, e;
+   check_ring("FFT_radix2_inverse_butterfly", n, w);
+   l = (uint64_t) n*w/64; e = NEGE(((uint64_t) i % (2*(uint64_t) n)) * w, l);
+   two_block_op("FFT_radix2_inverse_butterfly", (uint32_t) l, s, t, i1, i2, 1, 0, 1, e, 1, 0, -1, e, 0);
+}
+
+void FFT_radix2_twiddle_butterfly(mp_limb_t *u, mp_limb_t *v, mp_limb_t *s, mp_limb_t *t, mp_size_t NW, mp_bitcnt_t b1, mp_bitcnt_t b2)
+{
+   uint64_t l = (uint64_t) NW/64;
+   if (NW <= 0 || NW % 64) mfft_die("FFT_radix2_twiddle_butterfly", "NW=%ld must be a positive multiple of 64", (long) NW);
+   b1 %= 2*(uint64_t) NW; b2 %= 2*(uint64_t) NW;
+   two_block_op("FFT_radix2_twiddle_butterfly", (uint32_t) l, u, v, s, t, 1, b1, 1, b1, 1, b2, -1, b2, 0);
+}
+
+void FFT_radix2_twiddle_inverse_butterfly(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2, mp_size_t NW, mp_bitcnt_t b1, mp_bitcnt_t b2)
+{
+   uint64_t l = (uint64_t) NW/64;
+   if (NW <= 0 || NW % 64) mfft_die("FFT_radix2_twiddle_inverse_butterfly", "NW=%ld must be a positive multiple of 64", (long) NW);
+   two_block_op("FFT_radix2_twiddle_inverse_butterfly", (uint32_t) l, s, t, i1, i2,
+                1, NEGE(b1, l), 1, NEGE(b2, l), 1, NEGE(b1, l), -1, NEGE(b2, l), 0);
+}
+
+void FFT_twiddle(mp_limb_t *r, mp_limb_t *i1, mp_size_t i, mp_size_t n, mp_bitcnt_t w)
+{
+   uint64_t l, e;
+   check_ring("FFT_twiddle", n, w);
+   l = (uint64_t) n*w/64; e = ((uint64_t) i % (2*(uint64_t) n)) * w;
+   two_block_op("FFT_twiddle", (uint32_t) l, r, NULL, i1, NULL, 1, e, 0, 0, 0, 0, 0, 0, 0);
+}
+
+/* ---------------------------------- split / combine ---------------------------------------- */
+mp_size_t FFT_split_bits(mp_limb_t **poly, mp_limb_t *limbs, mp_size_t total_limbs, mp_size_t bits, mp_size_t output_limbs)
+{
+   uint64_t length, k; uint32_t l = (uint32_t) output_limbs, pitch = l + 1;
+   limb_t *d_src, *d_slab, *stage;
+   if (total_limbs <= 0 || bits <= 0 || output_limbs <= 0 || (uint64_t) bits > 64ull*(uint64_t) output_limbs)
+      mfft_die("FFT_split_bits", "illegal sizes total=%ld bits=%ld output_limbs=%ld", (long) total_limbs, (long) bits, (long) output_limbs);
+   length = (64ull*(uint64_t) total_limbs - 1)/(uint64_t) bits + 1;             /* mul_fft.c:118 */
+   mfft_lock();
+   mfft_require_device("FFT_split_bits");
+   d_src = (limb_t *) mfft_dev_alloc((size_t) total_limbs*8);
+   d_slab = (limb_t *) mfft_dev_alloc((size_t) length*pitch*8);
+   stage = (limb_t *) malloc((size_t) length*pitch*8);
+   if (!d_src || !d_slab || !stage) mfft_die("FFT_split_bits", "allocation failed: %s", mfft_dev_last_error());
+   if (mfft_dev_h2d(d_src, limbs, (size_t) total_limbs*8, NULL) ||
+       mfft_dev_split(d_slab, l, pitch, d_src, (uint64_t) total_limbs, (uint64_t) bits, length, length, NULL) ||
+       mfft_dev_d2h(stage, d_slab, (size_t) length*pitch*8, NULL) || mfft_dev_sync(NULL))
+      mfft_die("FFT_split_bits", "device execution failed: %s", mfft_dev_last_error());
+   for (k = 0; k < length; k++) memcpy(poly[k], stage + k*pitch, pitch*8);
+   mfft_dev_free(d_src); mfft_dev_free(d_slab); free(stage);
+   mfft_unlock();
+   return (mp_size_t) length;
+}
+
+mp_size_t FFT_split(mp_limb_t **poly, mp_limb_t *limbs, mp_size_t total_limbs, mp_size_t coeff_limbs, mp_size_t output_limbs)
+{ return FFT_split_bits(poly, limbs, total_limbs, 64*coeff_limbs, output_limbs); }
+
+/* Blocks are read as output_limbs+1 limbs (the reference adds the carry limb too when the
+ * coefficient is bit-shifted, mul_fft.c:231-232); res is overwritten (the reference requires it
+ * zeroed on entry, 203-204). */
+void FFT_combine_bits(mp_limb_t *res, mp_limb_t **poly, mp_size_t length, mp_size_t bits, mp_size_t output_limbs, mp_size_t total_limbs)
+{
+   uint32_t l = (uint32_t) output_limbs + 1, pitch = l; uint64_t k;
+   limb_t *d_res, *d_slab, *stage; void *work;
+   if (length < 0 || bits <= 0 || output_limbs <= 0 || total_limbs <= 0)
+      mfft_die("FFT_combine_bits", "illegal sizes length=%ld bits=%ld output_limbs=%ld total=%ld", (long) length, (long) bits, (long) output_limbs, (long) total_limbs);
+   mfft_lock();
+   mfft_require_device("FFT_combine_bits");
+   d_res = (limb_t *) mfft_dev_alloc((size_t) total_limbs*8);
+   d_slab = (limb_t *) mfft_dev_alloc((size_t)(length ? length : 1)*pitch*8);
+   work = mfft_dev_alloc(mfft_dev_combine_work((uint64_t) total_limbs));
+   stage = (limb_t *) malloc((size_t)(length ? length : 1)*pitch*8);
+   if (!d_res || !d_slab || !work || !stage) mfft_die("FFT_combine_bits", "allocation failed: %s", mfft_dev_last_error());
+   for (k = 0; k < (uint64_t) length; k++) memcpy(stage + k*pitch, poly[k], pitch*8);
+   if (mfft_dev_h2d(d_slab, stage, (size_t) length*pitch*8, NULL) ||
+       mfft_dev_combine(d_res, (uint64_t) total_limbs, d_slab, l, pitch, (uint64_t) bits, (uint64_t) length, work, NULL) ||
+       mfft_dev_d2h(res, d_res, (size_t) total_limbs*8, NULL) || mfft_dev_sync(NULL))
+      mfft_die("FFT_combine_bits", "device execution failed: %s", mfft_dev_last_error());
+   mfft_dev_free(d_res); mfft_dev_free(d_slab); mfft_dev_free(work); free(stage);
+   mfft_unlock();
+}
+
+void FFT_combine(mp_limb_t *res, mp_limb_t **poly, mp_size_t length, mp_size_t coeff_limbs, mp_size_t output_limbs, mp_size_t total_limbs)
+{
+   /* the limb-aligned variant adds exactly output_limbs limbs per coefficient (mul_fft.c:188);
+      clear the carry limbs of a private copy so that both variants share one kernel */
+   mp_size_t k; mp_limb_t **tab, *copy; size_t sz = (size_t) output_limbs + 1;
+   if (length <= 0) { memset(res, 0, (size_t) total_limbs*8); return; }
+   tab = (mp_limb_t **) malloc(sizeof(mp_limb_t *) * (size_t) length);
+   copy = (mp_limb_t *) malloc(sz*8*(size_t) length);
+   if (!tab || !copy) mfft_die("FFT_combine", "out of host memory");
+   for (k = 0; k < length; k++)
+   {
+      tab[k] = copy + (size_t) k*sz; memcpy(tab[k], poly[k], (sz - 1)*8); tab[k][sz - 1] = 0;
+   }
+   FFT_combine_bits(res, tab, length, 64*coeff_limbs, output_limbs, total_limbs);
+   free(tab); free(copy);
+}
+
+/* ---------------------------------- mulmod 2^bits + 1 -------------------------------------- */
+int mpirfft_mulmod_batch_device(mp_limb_t *d_a, const mp_limb_t *d_b, size_t count, size_t l, size_t pitch, void *stream)
+{
+   uint32_t *idx, *d_idx; size_t k; int rc;
+   if (!count) return 0;
+   if (l == 0 || pitch < l + 1 || count > 0xffffffffu) return MPIRFFT_EINVAL;
+   mfft_lock();
+   if ((rc = mfft_try_device()) != 0) { mfft_unlock(); return rc; }
+   idx = (uint32_t *) malloc(sizeof(uint32_t)*count);
+   if (!idx) { mfft_unlock(); return MPIRFFT_ENOMEM; }
+   for (k = 0; k < count; k++) idx[k] = (uint32_t) k;
+   d_idx = (uint32_t *) mfft_upload(idx, sizeof(uint32_t)*count);
+   free(idx);
+   if (!d_idx) { mfft_unlock(); return MPIRFFT_ENODEV; }
+   rc = mfft_dev_pointwise((limb_t *) d_a, (const limb_t *) d_b, d_idx, (uint32_t) count, (uint32_t) l, (uint32_t) pitch, stream);
+   if (rc == 0) rc = mfft_dev_sync(stream);
+   mfft_dev_free(d_idx);
+   mfft_unlock();
+   return rc ? MPIRFFT_ENODEV : 0;
+}
+
+/* one product on host blocks: a = {i1, top ta}, b = {i2, top tb}; returns the top bit */
+static mp_limb_t mulmod_host(const char *fn, mp_limb_t *r, const mp_limb_t *i1, mp_limb_t ta, const mp_limb_t *i2,
+                             mp_limb_t tb, uint32_t l)
+{
+   size_t bytes = ((size_t) l + 1)*8; limb_t *ha, *hb, *da, *db; mp_limb_t top; int rc;
+   ha = (limb_t *) malloc(bytes); hb = (limb_t *) malloc(bytes);
+   if (!ha || !hb) mfft_die(fn, "out of host memory");
+   memcpy(ha, i1, (size_t) l*8); ha[l] = ta; memcpy(hb, i2, (size_t) l*8); hb[l] = tb;
+   mfft_lock(); mfft_require_device(fn);
+   da = (limb_t *) mfft_upload(ha, bytes); db = (limb_t *) mfft_upload(hb, bytes);
+   mfft_unlock();
+   if (!da || !db) mfft_die(fn, "device allocation failed: %s", mfft_dev_last_error());
+   rc = mpirfft_mulmod_batch_device((mp_limb_t *) da, (const mp_limb_t *) db, 1, l, (size_t) l + 1, NULL);
+   if (rc != 0 || mfft_dev_d2h(ha, da, bytes, NULL) || mfft_dev_sync(NULL))
+      mfft_die(fn, "device execution failed: %s", mfft_dev_last_error());
+   memcpy(r, ha, (size_t) l*8); top = ha[l];
+   mfft_dev_free(da); mfft_dev_free(db); free(ha); free(hb);
+   return top;
+}
+
+mp_limb_t new_mpn_mulmod_2expp1(mp_limb_t *r, mp_limb_t *i1, mp_limb_t *i2, mp_limb_t c, mp_limb_t bits, mp_limb_t *tt)
+{
+   (void) tt;
+   if (bits == 0 || bits % 64) mfft_die("new_mpn_mulmod_2expp1", "bits=%lu must be a positive multiple of 64", (unsigned long) bits);
+   return mulmod_host("new_mpn_mulmod_2expp1", r, i1, c & 1, i2, (c >> 1) & 1, (uint32_t)(bits/64));
+}
+
+mp_limb_t fft_mulmod_2expp1(mp_limb_t *r, mp_limb_t *i1, mp_limb_t *i2, mp_size_t n, mp_size_t w, mp_limb_t *tt)
+{
+   uint64_t bits = (uint64_t) n*(uint64_t) w; uint32_t l; mp_limb_t top;
+   (void) tt;
+   if (n <= 0 || w <= 0 || bits % 64) mfft_die("fft_mulmod_2expp1", "n*w=%lu must be a positive multiple of 64", (unsigned long) bits);
+   l = (uint32_t)(bits/64);
+   top = mulmod_host("fft_mulmod_2expp1", r, i1, i1[l], i2, i2[l], l);
+   if (l >= 250) r[l] = top;       /* the reference's large path writes limbs+1 limbs (3164, 3083) */
+   return top;
+}
+
+void FFT_mulmod_2expp1(mp_limb_t *r1, mp_limb_t *i1, mp_limb_t *i2, mp_size_t r_limbs, mp_bitcnt_t depth, mp_bitcnt_t w)
+{
+   (void) depth; (void) w;
+   if (r_limbs <= 0) mfft_die("FFT_mulmod_2expp1", "r_limbs=%ld", (long) r_limbs);
+   r1[r_limbs] = mulmod_host("FFT_mulmod_2expp1", r1, i1, 0, i2, 0, (uint32_t) r_limbs);
+}

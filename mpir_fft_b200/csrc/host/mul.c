@@ -1,0 +1,221 @@
+/* mul.c -- the integer multiplication driver: new_mpn_mul (mul_fft.c:3190-3265) on device slabs.
+ *
+ * Pipeline (every step a kernel or a stage list; the slabs never leave HBM):
+ *   split i1 -> X.half0      FFT_split_bits + zero fill            3234-3236
+ *   fwd MFA  X -> Z.half0    FFT_radix2_mfa_truncate               3237
+ *   split i2 -> X.half0 ; fwd MFA X -> Y                           3239-3242
+ *   pointwise Z.half0 *= Y on the valid rows                        3244-3253 (row set corrected)
+ *   inv MFA  Z -> X.half0, scaled by 2^-(depth+1), normalised       3255-3260
+ *   combine  X.half0 -> r                                           3261-3262
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "runtime.h"
+#include "../../../include/mpirfft_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct mpirfft_mul_plan {
+   mp_size_t n1, n2; mp_bitcnt_t depth, w;
+   mpirfft_mul_params p;
+   uint32_t l, pitch;
+   mfft_mfa fwd, inv;
+   limb_t *X, *Z, *Y;          /* 2N, 2N, N blocks */
+   uint32_t *d_pw_blocks; uint32_t npw;
+   void *combine_work;
+   limb_t *d_i1, *d_i2, *d_r;  /* staging for the host-pointer entry */
+   size_t dev_bytes;
+};
+
+int mpirfft_mul_params_get(mpirfft_mul_params *o, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth, mp_bitcnt_t w)
+{
+   uint64_t n, nw;
+   memset(o, 0, sizeof(*o));
+   if (n1 <= 0 || n2 <= 0 || depth < 2 || depth > 26 || w == 0 || w > 4096) return MPIRFFT_EINVAL;
+   n = (uint64_t)1 << depth; nw = n*w;
+   if (nw % 64) return MPIRFFT_EINVAL;                       /* mul_fft.c:48 */
+   if (nw <= depth + 1) return MPIRFFT_EINVAL;
+   o->n = n;
+   o->bits1 = (nw - depth)/2;                                /* 3194 */
+   o->sqrt = (uint64_t)1 << (depth/2);                       /* 3195 */
+   o->j1 = ((uint64_t) n1*64 - 1)/o->bits1 + 1;              /* 3198 */
+   o->j2 = ((uint64_t) n2*64 - 1)/o->bits1 + 1;              /* 3199 */
+   o->trunc = ((o->j1 + o->j2 - 2 + 2*o->sqrt)/(2*o->sqrt))*2*o->sqrt;   /* 3200 */
+   o->limbs = nw/64;                                         /* 3202 */
+   o->n2 = 2*n/o->sqrt;
+   o->trunc_rows = o->trunc/o->sqrt;
+   if (o->j1 + o->j2 - 1 > 2*n || o->trunc > 2*n) return MPIRFFT_EINVAL;   /* would segfault, 3186 */
+   if (o->n2 < 4 || o->sqrt < 2) return MPIRFFT_EINVAL;
+   return 0;
+}
+
+int mpirfft_choose_params(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w)
+{
+   mp_bitcnt_t d, ww;
+   mpirfft_mul_params p;
+   /* smallest coefficient size first: n*w ascending, preferring w = 1 */
+   for (d = 6; d <= 26; d++)
+      for (ww = 1; ww <= 2; ww++)
+         if (mpirfft_mul_params_get(&p, n1, n2, d, ww) == 0)
+         {
+            /* a deeper transform with w=1 has the same ring as this depth with w=2; take the first hit */
+            *depth = d; *w = ww; return 0;
+         }
+   return MPIRFFT_EINVAL;
+}
+
+void mpirfft_mul_plan_destroy(mpirfft_mul_plan *pl)
+{
+   if (!pl) return;
+   mfft_lock();
+   mfft_mfa_free(&pl->fwd); mfft_mfa_free(&pl->inv);
+   mfft_dev_free(pl->X); mfft_dev_free(pl->Z); mfft_dev_free(pl->Y);
+   mfft_dev_free(pl->d_pw_blocks); mfft_dev_free(pl->combine_work);
+   mfft_dev_free(pl->d_i1); mfft_dev_free(pl->d_i2); mfft_dev_free(pl->d_r);
+   mfft_unlock();
+   free(pl);
+}
+
+int mpirfft_mul_plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth, mp_bitcnt_t w)
+{
+   mpirfft_mul_plan *pl; int rc; uint64_t N, i, j; size_t half; uint32_t *blocks = NULL;
+   *out = NULL;
+   pl = (mpirfft_mul_plan *) calloc(1, sizeof(*pl));
+   if (!pl) return MPIRFFT_ENOMEM;
+   pl->n1 = n1; pl->n2 = n2; pl->depth = depth; pl->w = w;
+   if ((rc = mpirfft_mul_params_get(&pl->p, n1, n2, depth, w)) != 0) { free(pl); return rc; }
+   mfft_lock();
+   if ((rc = mfft_try_device()) != 0) goto fail;
+   pl->l = (uint32_t) pl->p.limbs; pl->pitch = pl->l + 1;
+   N = 2*pl->p.n;
+   if ((rc = mfft_mfa_build(&pl->fwd, 0, pl->p.n, w, pl->p.sqrt, pl->p.trunc)) != 0) goto fail;
+   if ((rc = mfft_mfa_build(&pl->inv, 1, pl->p.n, w, pl->p.sqrt, pl->p.trunc)) != 0) goto fail;
+   half = (size_t) N * pl->pitch * sizeof(limb_t);
+   rc = MPIRFFT_ENOMEM;
+   pl->X = (limb_t *) mfft_dev_alloc(2*half);
+   pl->Z = (limb_t *) mfft_dev_alloc(2*half);
+   pl->Y = (limb_t *) mfft_dev_alloc(half);
+   pl->combine_work = mfft_dev_alloc(mfft_dev_combine_work((uint64_t)(n1 + n2)));
+   if (!pl->X || !pl->Z || !pl->Y || !pl->combine_work) goto fail;
+   pl->dev_bytes = 5*half + mfft_dev_combine_work((uint64_t)(n1 + n2));
+   /* the rows whose coefficients get multiplied: revbin(s, depth+1-depth/2), s < trunc/sqrt
+      (mul_fft.c:3244-3253 with the bit width of 3246 corrected, cf. 3629, 3642) */
+   pl->npw = (uint32_t)(pl->p.trunc_rows * pl->p.sqrt);
+   blocks = (uint32_t *) malloc(sizeof(uint32_t) * pl->npw);
+   if (!blocks) goto fail;
+   for (i = 0; i < pl->p.trunc_rows; i++)
+      for (j = 0; j < pl->p.sqrt; j++)
+         blocks[i*pl->p.sqrt + j] = (uint32_t)(pl->fwd.rows[i]*pl->p.sqrt + j);
+   pl->d_pw_blocks = (uint32_t *) mfft_upload(blocks, sizeof(uint32_t) * pl->npw);
+   free(blocks);
+   if (!pl->d_pw_blocks) { rc = MPIRFFT_ENODEV; goto fail; }
+   mfft_unlock();
+   *out = pl;
+   return 0;
+fail:
+   mfft_unlock();
+   mpirfft_mul_plan_destroy(pl);
+   return rc;
+}
+
+size_t mpirfft_mul_plan_device_bytes(const mpirfft_mul_plan *pl) { return pl->dev_bytes; }
+
+uint64_t mpirfft_mul_plan_launches(const mpirfft_mul_plan *pl)
+{
+   /* 2 x (split + fwd) + pointwise + inv + combine (4 kernels) */
+   return 2*(1 + mfft_mfa_launches(&pl->fwd)) + 1 + mfft_mfa_launches(&pl->inv) + 4;
+}
+
+int mpirfft_mul_exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, const mp_limb_t *d_i1,
+                           const mp_limb_t *d_i2, void *stream)
+{
+   const mpirfft_mul_params *p = &pl->p;
+   int rc = 0;
+   switch (phase)
+   {
+   case 0:
+      if (mfft_dev_split(pl->X, pl->l, pl->pitch, (const limb_t *) d_i1, (uint64_t) pl->n1, p->bits1, p->j1, p->trunc, stream)) return MPIRFFT_ENODEV;
+      rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Z, 0, 1, stream);
+      break;
+   case 1:
+      if (mfft_dev_split(pl->X, pl->l, pl->pitch, (const limb_t *) d_i2, (uint64_t) pl->n2, p->bits1, p->j2, p->trunc, stream)) return MPIRFFT_ENODEV;
+      rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Y, 0, 1, stream);
+      break;
+   case 2:
+      if (mfft_dev_pointwise(pl->Z, pl->Y, pl->d_pw_blocks, pl->npw, pl->l, pl->pitch, stream)) return MPIRFFT_ENODEV;
+      break;
+   case 3:
+   {  /* unscaled inverse, then / 2^(depth+1) and normalise fused into the finalize (3256-3260) */
+      uint64_t M2 = 128ull * pl->l;
+      rc = mfft_mfa_exec(&pl->inv, pl->Z, pl->X, (uint32_t)(M2 - (pl->depth + 1)), 1, stream);
+      break;
+   }
+   case 4:
+      if (mfft_dev_combine((limb_t *) d_r, (uint64_t)(pl->n1 + pl->n2), pl->X, pl->l, pl->pitch, p->bits1,
+                           p->j1 + p->j2 - 1, pl->combine_work, stream)) return MPIRFFT_ENODEV;
+      break;
+   default: return MPIRFFT_EINVAL;
+   }
+   return rc;
+}
+
+int mpirfft_mul_exec_device(mpirfft_mul_plan *pl, mp_limb_t *d_r, const mp_limb_t *d_i1,
+                            const mp_limb_t *d_i2, void *stream)
+{
+   int ph, rc;
+   for (ph = 0; ph < 5; ph++)
+      if ((rc = mpirfft_mul_exec_phase(pl, ph, d_r, d_i1, d_i2, stream)) != 0) return rc;
+   return 0;
+}
+
+int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i1, const mp_limb_t *i2)
+{
+   int rc;
+   size_t b1 = (size_t) pl->n1*8, b2 = (size_t) pl->n2*8;
+   mfft_lock();
+   if (!pl->d_i1)
+   {
+      pl->d_i1 = (limb_t *) mfft_dev_alloc(b1); pl->d_i2 = (limb_t *) mfft_dev_alloc(b2);
+      pl->d_r = (limb_t *) mfft_dev_alloc(b1 + b2);
+      if (!pl->d_i1 || !pl->d_i2 || !pl->d_r) { mfft_unlock(); return MPIRFFT_ENOMEM; }
+   }
+   rc = MPIRFFT_ENODEV;
+   if (mfft_dev_h2d(pl->d_i1, i1, b1, NULL) || mfft_dev_h2d(pl->d_i2, i2, b2, NULL)) goto done;
+   if ((rc = mpirfft_mul_exec_device(pl, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, NULL)) != 0) goto done;
+   rc = MPIRFFT_ENODEV;
+   if (mfft_dev_d2h(r, pl->d_r, b1 + b2, NULL) || mfft_dev_sync(NULL)) goto done;
+   rc = 0;
+done:
+   mfft_unlock();
+   return rc;
+}
+
+/* a tiny plan cache so that the drop-in symbol does not rebuild schedules on every call */
+#define PLAN_CACHE 4
+static mpirfft_mul_plan *g_cache[PLAN_CACHE];
+static unsigned g_cache_next = 0;
+
+void new_mpn_mul(mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2,
+                 mp_bitcnt_t depth, mp_bitcnt_t w)
+{
+   mpirfft_mul_plan *pl = NULL; int k, rc;
+   mpirfft_mul_params p;
+   if (!r1 || !i1 || !i2) mfft_die("new_mpn_mul", "null operand");
+   if (mpirfft_mul_params_get(&p, n1, n2, depth, w) != 0)
+      mfft_die("new_mpn_mul", "illegal parameters n1=%ld n2=%ld depth=%lu w=%lu: need 64 | 2^depth*w and "
+               "j1+j2-1 <= 2^(depth+1) (mul_fft.c:3186-3187)", (long) n1, (long) n2, (unsigned long) depth, (unsigned long) w);
+   mfft_lock(); mfft_require_device("new_mpn_mul"); mfft_unlock();
+   for (k = 0; k < PLAN_CACHE; k++)
+      if (g_cache[k] && g_cache[k]->n1 == n1 && g_cache[k]->n2 == n2 && g_cache[k]->depth == depth && g_cache[k]->w == w)
+         pl = g_cache[k];
+   if (!pl)
+   {
+      if ((rc = mpirfft_mul_plan_create(&pl, n1, n2, depth, w)) != 0)
+         mfft_die("new_mpn_mul", "cannot build the plan (code %d): %s", rc, mfft_dev_last_error());
+      k = (int)(g_cache_next++ % PLAN_CACHE);
+      if (g_cache[k]) mpirfft_mul_plan_destroy(g_cache[k]);
+      g_cache[k] = pl;
+   }
+   if ((rc = mpirfft_mul_exec_host(pl, r1, i1, i2)) != 0)
+      mfft_die("new_mpn_mul", "device execution failed (code %d): %s", rc, mfft_dev_last_error());
+}

@@ -1,0 +1,265 @@
+/* runtime.c -- device binding, schedule upload/run, and the MFA transform driver (plain C99). */
+#define _POSIX_C_SOURCE 200809L
+#include "runtime.h"
+#include "../../../include/mpirfft_b200.h"
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_ready = 0;
+
+void mfft_lock(void) { pthread_mutex_lock(&g_mu); }
+void mfft_unlock(void) { pthread_mutex_unlock(&g_mu); }
+
+void mfft_die(const char *fn, const char *fmt, ...)
+{
+   va_list ap;
+   fprintf(stderr, "libmpirfft_b200: %s: ", fn);
+   va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
+   fprintf(stderr, "\n");
+   fflush(stderr);
+   abort();
+}
+
+int mfft_try_device(void)
+{
+   if (!g_ready)
+   {
+      const char *e = getenv("MPIRFFT_DEVICE");
+      int dev = e ? atoi(e) : 0;
+      if (mfft_dev_init(dev) != 0) return MPIRFFT_ENODEV;
+      g_ready = 1;
+   }
+   return 0;
+}
+
+void mfft_require_device(const char *fn)
+{
+   if (mfft_try_device() != 0)
+      mfft_die(fn, "no usable CUDA device (%s); this library has no CPU fallback", mfft_dev_last_error());
+}
+
+int mpirfft_init(int device)
+{
+   int rc;
+   mfft_lock();
+   rc = mfft_dev_init(device);
+   if (rc == 0) g_ready = 1;
+   mfft_unlock();
+   return rc == 0 ? MPIRFFT_OK : MPIRFFT_ENODEV;
+}
+
+int mpirfft_device_count(void) { return mfft_dev_count(); }
+const char *mpirfft_last_error(void) { return mfft_dev_last_error(); }
+const char *mpirfft_version(void) { return "mpirfft_b200 0.1 (sm_100a)"; }
+uint64_t mpirfft_launch_count(void) { return mfft_dev_launch_count(); }
+void mpirfft_launch_count_reset(void) { mfft_dev_launch_count_reset(); }
+
+void *mpirfft_malloc_device(size_t bytes) { return mfft_try_device() ? NULL : mfft_dev_alloc(bytes); }
+void  mpirfft_free_device(void *p) { mfft_dev_free(p); }
+void *mpirfft_malloc_pinned(size_t bytes) { return mfft_try_device() ? NULL : mfft_host_alloc_pinned(bytes); }
+void  mpirfft_free_pinned(void *p) { mfft_host_free_pinned(p); }
+int   mpirfft_memcpy_h2d(void *d, const void *h, size_t bytes, void *stream) { return mfft_dev_h2d(d, h, bytes, stream) ? MPIRFFT_ENODEV : 0; }
+int   mpirfft_memcpy_d2h(void *h, const void *d, size_t bytes, void *stream) { return mfft_dev_d2h(h, d, bytes, stream) ? MPIRFFT_ENODEV : 0; }
+int   mpirfft_stream_sync(void *stream) { return mfft_dev_sync(stream) ? MPIRFFT_ENODEV : 0; }
+
+void *mfft_upload(const void *h, size_t bytes)
+{
+   void *d = mfft_dev_alloc(bytes);
+   if (!d) return NULL;
+   if (bytes && (mfft_dev_h2d(d, h, bytes, NULL) != 0 || mfft_dev_sync(NULL) != 0)) { mfft_dev_free(d); return NULL; }
+   return d;
+}
+
+int mfft_dsched_upload(mfft_dsched *ds, mfft_sched *s)
+{
+   ds->s = s; ds->d_ops = NULL;
+   if (mfft_sched_finish(s) != 0) return MPIRFFT_ENOMEM;
+   ds->d_ops = (mfft_op *) mfft_upload(s->ops, sizeof(mfft_op) * (s->nops ? s->nops : 1));
+   return ds->d_ops ? 0 : MPIRFFT_ENODEV;
+}
+
+void mfft_dsched_free(mfft_dsched *ds)
+{
+   if (ds->d_ops) mfft_dev_free(ds->d_ops);
+   if (ds->s) mfft_sched_free(ds->s);
+   ds->d_ops = NULL; ds->s = NULL;
+}
+
+int mfft_dsched_run(const mfft_dsched *ds, limb_t *slab, const mfft_geom *g,
+                    const mfft_batch *d_batch, uint32_t nbatch, void *stream)
+{
+   uint32_t st;
+   for (st = 1; st <= ds->s->nstages; st++)
+   {
+      uint32_t lo = ds->s->stage_off[st - 1], hi = ds->s->stage_off[st];
+      if (hi > lo && mfft_dev_run_stage(slab, g, ds->d_ops + lo, hi - lo, d_batch, nbatch, stream) != 0)
+         return MPIRFFT_ENODEV;
+   }
+   return 0;
+}
+
+static uint32_t ilog2(uint64_t x) { uint32_t b = 0; while (((uint64_t)1 << b) < x) b++; return b; }
+
+void mfft_mfa_free(mfft_mfa *m)
+{
+   if (m->col.s) m->h_col = NULL;     /* ownership moved to the uploaded schedule */
+   if (m->row.s) m->h_row = NULL;
+   mfft_dsched_free(&m->col); mfft_dsched_free(&m->row);
+   if (m->h_col) mfft_sched_free(m->h_col);
+   if (m->h_row) mfft_sched_free(m->h_row);
+   mfft_dev_free(m->d_colb); mfft_dev_free(m->d_rowb); mfft_dev_free(m->d_moves); mfft_dev_free(m->d_dst_base);
+   free(m->rows); free(m->h_colb); free(m->h_rowb); free(m->h_moves); free(m->h_dst_base);
+   memset(m, 0, sizeof(*m));
+}
+
+int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc)
+{
+   uint64_t NW = n*w, n2, i, j;
+   mfft_sched *cs, *rs; mfft_batch *colb, *rowb; mfft_move *mv; uint32_t *dstb;
+   int rc = MPIRFFT_EINVAL;
+
+   memset(m, 0, sizeof(*m));
+   if (n == 0 || (n & (n - 1)) || w == 0 || (NW % 64) || n1 < 2 || (n1 & (n1 - 1)) || n1 > n) return MPIRFFT_EINVAL;
+   n2 = 2*n/n1;
+   if (n2 < 2) return MPIRFFT_EINVAL;
+   m->inverse = inverse; m->truncated = (trunc != 0);
+   m->n = n; m->w = w; m->n1 = n1; m->n2 = n2; m->N = 2*n;
+   m->l = (uint32_t)(NW/64); m->pitch = m->l + 1;
+   m->depth1 = ilog2(n2); m->depth2 = ilog2(n1);
+   if (trunc)
+   {  /* trunc must be a multiple of 2*n1 (mul_fft.c:2209-2211, 3200) */
+      if (trunc % (2*n1) || trunc > 2*n) return MPIRFFT_EINVAL;
+      m->trunc_rows = trunc/n1;
+   } else m->trunc_rows = n2;
+
+   /* the valid rows: revbin(s), s < trunc_rows (2392-2394, 2942-2944) */
+   m->nrows = (uint32_t) m->trunc_rows;
+   m->rows = (uint32_t *) malloc(sizeof(uint32_t) * m->nrows);
+   m->h_col = cs = mfft_sched_new((uint32_t) n2, NW);
+   m->h_row = rs = mfft_sched_new((uint32_t) n1, NW);
+   m->h_colb = colb = (mfft_batch *) calloc(n1, sizeof(mfft_batch));
+   m->h_rowb = rowb = (mfft_batch *) calloc(m->nrows, sizeof(mfft_batch));
+   if (!m->rows || !cs || !rs || !colb || !rowb) { rc = MPIRFFT_ENOMEM; goto fail; }
+   for (i = 0; i < m->nrows; i++) m->rows[i] = (uint32_t) mfft_revbin(i, m->depth1);
+
+   m->gcol.S = (uint32_t) n2; m->gcol.slot_stride = (uint32_t) n1; m->gcol.half_blocks = m->N;
+   m->gcol.l = m->l; m->gcol.pitch = m->pitch;
+   m->grow.S = (uint32_t) n1; m->grow.slot_stride = 1; m->grow.half_blocks = m->N;
+   m->grow.l = m->l; m->grow.pitch = m->pitch;
+   m->ncolb = (uint32_t) n1; m->nrowb = m->nrows;
+
+   if (!inverse)
+   {
+      /* column FFTs with the fused twist (2374-2379), then the row relabel (2380-2389) */
+      if (mfft_sched_emit(cs, trunc ? MFFT_T_FFT_TRUNC : MFFT_T_FFT, 0, 1, n2/2, w*n1, w, 0, 1, m->trunc_rows) != 0) goto fail;
+      mfft_sched_revbin(cs, 0, 1, m->depth1);
+      for (j = 0; j < n1; j++) { colb[j].base = (uint32_t) j; colb[j].parity = 0; colb[j].col = (uint32_t) j; }
+      /* row FFTs on the valid rows (2392-2395), then the in-row relabel (2397-2405) */
+      if (mfft_sched_emit(rs, MFFT_T_FFT, 0, 1, n1/2, w*n2, 0, 0, 0, 0) != 0) goto fail;
+      mfft_sched_revbin(rs, 0, 1, m->depth2);
+      for (i = 0; i < m->nrows; i++)
+      {
+         uint32_t slot = cs->slot[m->rows[i]];
+         rowb[i].base = (uint32_t)((slot % n2) * n1); rowb[i].parity = (uint32_t)(slot / n2); rowb[i].col = 0;
+      }
+      /* finalize: logical (row i, col j) -> dst block i*n1 + j */
+      m->nmoves = (uint32_t) n1; m->ndst = m->nrows;
+      m->h_moves = mv = (mfft_move *) calloc(m->nmoves, sizeof(mfft_move));
+      m->h_dst_base = dstb = (uint32_t *) calloc(m->ndst, sizeof(uint32_t));
+      if (!mv || !dstb) { rc = MPIRFFT_ENOMEM; goto fail; }
+      for (j = 0; j < n1; j++) { mv[j].src_slot = rs->slot[j]; mv[j].dst_pos = (uint32_t) j; }
+      for (i = 0; i < m->nrows; i++) dstb[i] = (uint32_t)(m->rows[i] * n1);
+      m->dst_stride = 1;
+   } else
+   {
+      /* in-row relabel then row IFFTs on the valid rows (2942-2956) */
+      mfft_sched_revbin(rs, 0, 1, m->depth2);
+      if (mfft_sched_emit(rs, MFFT_T_IFFT, 0, 1, n1/2, w*n2, 0, 0, 0, 0) != 0) goto fail;
+      for (i = 0; i < m->nrows; i++) { rowb[i].base = (uint32_t)(m->rows[i] * n1); rowb[i].parity = 0; rowb[i].col = 0; }
+      /* row relabel then column IFFTs with the twist removed (2959-2974) */
+      mfft_sched_revbin(cs, 0, 1, m->depth1);
+      if (mfft_sched_emit(cs, trunc ? MFFT_T_IFFT_TRUNC : MFFT_T_IFFT, 0, 1, n2/2, w*n1, w, 0, 1, m->trunc_rows) != 0) goto fail;
+      for (j = 0; j < n1; j++)
+      {
+         uint32_t slot = rs->slot[j];
+         colb[j].base = (uint32_t)(slot % n1); colb[j].parity = (uint32_t)(slot / n1); colb[j].col = (uint32_t) j;
+      }
+      /* finalize: logical (row r < trunc_rows, col j) -> dst block r*n1 + j */
+      m->nmoves = (uint32_t) m->trunc_rows; m->ndst = (uint32_t) n1;
+      m->h_moves = mv = (mfft_move *) calloc(m->nmoves, sizeof(mfft_move));
+      m->h_dst_base = dstb = (uint32_t *) calloc(m->ndst, sizeof(uint32_t));
+      if (!mv || !dstb) { rc = MPIRFFT_ENOMEM; goto fail; }
+      for (i = 0; i < m->nmoves; i++) { mv[i].src_slot = cs->slot[i]; mv[i].dst_pos = (uint32_t) i; }
+      for (j = 0; j < n1; j++) dstb[j] = (uint32_t) j;
+      m->dst_stride = (uint32_t) n1;
+   }
+   if (mfft_sched_finish(cs) != 0 || mfft_sched_finish(rs) != 0) { rc = MPIRFFT_ENOMEM; goto fail; }
+   return 0;
+fail:
+   mfft_mfa_free(m);
+   return rc;
+}
+
+int mfft_mfa_upload(mfft_mfa *m)
+{
+   if (mfft_dsched_upload(&m->col, m->h_col) != 0) return MPIRFFT_ENODEV;
+   if (mfft_dsched_upload(&m->row, m->h_row) != 0) return MPIRFFT_ENODEV;
+   m->d_colb = (mfft_batch *) mfft_upload(m->h_colb, sizeof(mfft_batch) * m->ncolb);
+   m->d_rowb = (mfft_batch *) mfft_upload(m->h_rowb, sizeof(mfft_batch) * m->nrowb);
+   m->d_moves = (mfft_move *) mfft_upload(m->h_moves, sizeof(mfft_move) * m->nmoves);
+   m->d_dst_base = (uint32_t *) mfft_upload(m->h_dst_base, sizeof(uint32_t) * m->ndst);
+   if (!m->d_colb || !m->d_rowb || !m->d_moves || !m->d_dst_base) return MPIRFFT_ENODEV;
+   return 0;
+}
+
+int mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc)
+{
+   int rc = mfft_mfa_plan(m, inverse, n, w, n1, trunc);
+   if (rc != 0) return rc;
+   if ((rc = mfft_mfa_upload(m)) != 0) { mfft_mfa_free(m); return rc; }
+   return 0;
+}
+
+/* accessors for the CPU-side schedule tests (tests/schedsim.py) */
+mfft_mfa *mfft_mfa_debug_new(int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc)
+{
+   mfft_mfa *m = (mfft_mfa *) calloc(1, sizeof(*m));
+   if (m && mfft_mfa_plan(m, inverse, n, w, n1, trunc) != 0) { free(m); return NULL; }
+   return m;
+}
+void mfft_mfa_debug_free(mfft_mfa *m) { if (m) { mfft_mfa_free(m); free(m); } }
+mfft_sched *mfft_mfa_debug_sched(mfft_mfa *m, int which) { return which ? m->h_row : m->h_col; }
+mfft_batch *mfft_mfa_debug_batch(mfft_mfa *m, int which, uint32_t *count)
+{ *count = which ? m->nrowb : m->ncolb; return which ? m->h_rowb : m->h_colb; }
+mfft_move *mfft_mfa_debug_moves(mfft_mfa *m, uint32_t *count, uint32_t *dst_stride)
+{ *count = m->nmoves; *dst_stride = m->dst_stride; return m->h_moves; }
+uint32_t *mfft_mfa_debug_dst_base(mfft_mfa *m, uint32_t *count) { *count = m->ndst; return m->h_dst_base; }
+uint32_t *mfft_mfa_debug_rows(mfft_mfa *m, uint32_t *count) { *count = m->nrows; return m->rows; }
+
+int mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, uint32_t shift, int normalise, void *stream)
+{
+   int rc;
+   if (!m->inverse)
+   {
+      if ((rc = mfft_dsched_run(&m->col, slab, &m->gcol, m->d_colb, m->ncolb, stream)) != 0) return rc;
+      if ((rc = mfft_dsched_run(&m->row, slab, &m->grow, m->d_rowb, m->nrowb, stream)) != 0) return rc;
+      if (mfft_dev_finalize(dst, m->dst_stride, m->d_dst_base, slab, &m->grow, m->d_moves, m->nmoves,
+                            m->d_rowb, m->nrowb, shift, normalise, stream) != 0) return MPIRFFT_ENODEV;
+   } else
+   {
+      if ((rc = mfft_dsched_run(&m->row, slab, &m->grow, m->d_rowb, m->nrowb, stream)) != 0) return rc;
+      if ((rc = mfft_dsched_run(&m->col, slab, &m->gcol, m->d_colb, m->ncolb, stream)) != 0) return rc;
+      if (mfft_dev_finalize(dst, m->dst_stride, m->d_dst_base, slab, &m->gcol, m->d_moves, m->nmoves,
+                            m->d_colb, m->ncolb, shift, normalise, stream) != 0) return MPIRFFT_ENODEV;
+   }
+   return 0;
+}
+
+uint64_t mfft_mfa_launches(const mfft_mfa *m)
+{
+   return (uint64_t) m->col.s->nstages + m->row.s->nstages + 1;
+}

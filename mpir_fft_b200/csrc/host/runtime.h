@@ -1,0 +1,69 @@
+/* runtime.h -- host-side plumbing shared by the C files of the library (plain C99). */
+#ifndef MFFT_RUNTIME_H
+#define MFFT_RUNTIME_H
+
+#include "../mfft_internal.h"
+#include "sched.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* abort with a diagnostic: the reference's entry points have no error channel */
+void mfft_die(const char *fn, const char *fmt, ...);
+/* lazily bind the process to a device (MPIRFFT_DEVICE, default 0); dies if there is none */
+void mfft_require_device(const char *fn);
+int  mfft_try_device(void);            /* same, returning <0 instead of dying */
+void mfft_lock(void);
+void mfft_unlock(void);
+
+/* A schedule uploaded to the device */
+typedef struct {
+   mfft_sched *s;          /* host copy (owned) */
+   mfft_op    *d_ops;      /* device copy of s->ops */
+} mfft_dsched;
+
+int  mfft_dsched_upload(mfft_dsched *ds, mfft_sched *s);   /* takes ownership of s */
+void mfft_dsched_free(mfft_dsched *ds);
+/* run every stage of the schedule */
+int  mfft_dsched_run(const mfft_dsched *ds, limb_t *slab, const mfft_geom *g,
+                     const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+
+void *mfft_upload(const void *h, size_t bytes);            /* cudaMalloc + sync H2D; NULL on error */
+
+/* One MFA transform (forward or inverse, truncated or not) as two passes + a finalize step.
+ * Forward: mul_fft.c:2021-2068 / 2357-2409.  Inverse: 2411-2459 / 2925-2979. */
+typedef struct {
+   int inverse, truncated;
+   uint64_t n, w, n1, n2, trunc_rows, N;      /* N = 2n blocks per slab half */
+   uint32_t l, pitch, depth1, depth2;          /* depth1 = log2 n2, depth2 = log2 n1 */
+   mfft_dsched col, row;
+   mfft_batch *d_colb, *d_rowb; uint32_t ncolb, nrowb;
+   mfft_move  *d_moves; uint32_t nmoves;
+   uint32_t   *d_dst_base; uint32_t dst_stride;
+   mfft_geom   gcol, grow;
+   uint32_t   *rows;                           /* [nrows] logical valid rows, host */
+   uint32_t    nrows;
+   /* host copies of the tables (kept for the CPU-side schedule tests) */
+   mfft_sched *h_col, *h_row;                  /* owned by col/row once uploaded */
+   mfft_batch *h_colb, *h_rowb; mfft_move *h_moves; uint32_t *h_dst_base; uint32_t ndst;
+} mfft_mfa;
+
+/* trunc = 0: untruncated.  Returns 0 or a negative MPIRFFT_* code.
+ * mfft_mfa_plan builds the schedules and tables on the host only (no device needed);
+ * mfft_mfa_upload copies them to the device; mfft_mfa_build does both. */
+int  mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc);
+int  mfft_mfa_upload(mfft_mfa *m);
+int  mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc);
+void mfft_mfa_free(mfft_mfa *m);
+/* slab: 2N blocks, input in half 0 in reference order (ii[k] = block k); dst: N blocks.
+ * shift: extra factor 2^shift (bit exponent mod 2NW) applied in the finalize step;
+ * normalise: reduce outputs to canonical form. */
+int  mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, uint32_t shift, int normalise,
+                   void *stream);
+uint64_t mfft_mfa_launches(const mfft_mfa *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,319 @@
+/* sched.c -- data-independent schedules for the radix-2 transforms over Z/(2^NW+1).
+ *
+ * The reference executes its transforms recursively, one butterfly at a time, writing into two
+ * scratch blocks and swapping host pointers (mul_fft.c:810-826, README:56).  On a GPU we want
+ * every independent butterfly of a layer in ONE launch, so this file walks the same recursions
+ * symbolically and emits ops (mfft_internal.h) instead of doing arithmetic:
+ *
+ *   - every logical position keeps two candidate slots (slab half 0 / half 1); an op always
+ *     writes the half its target position is NOT currently in, so no op ever overwrites data
+ *     another op of the same stage reads, and the pointer swaps of the reference become the
+ *     index permutation `slot[]`;
+ *   - the stage of an op is 1 + the latest stage that produced one of its inputs or touched
+ *     one of its output slots (plain list scheduling); ops of one stage are independent.
+ *
+ * Everything here is plain C99 host code.  Each emitter cites the reference routine it walks.
+ */
+#include "sched.h"
+#include <stdlib.h>
+#include <string.h>
+
+uint64_t mfft_revbin(uint64_t in, uint32_t bits)
+{
+   uint64_t out = 0; uint32_t i;
+   for (i = 0; i < bits; i++) { out = (out << 1) | (in & 1); in >>= 1; }
+   return out;
+}
+
+mfft_sched *mfft_sched_new(uint32_t S, uint64_t NW)
+{
+   mfft_sched *s = (mfft_sched *) calloc(1, sizeof(*s));
+   uint32_t i;
+   if (!s) return NULL;
+   s->S = S; s->NW = NW; s->M2 = 2*NW;
+   s->slot = (uint32_t *) malloc(sizeof(uint32_t) * S);
+   s->wr_stage = (uint32_t *) calloc(2*(size_t)S, sizeof(uint32_t));
+   s->rd_stage = (uint32_t *) calloc(2*(size_t)S, sizeof(uint32_t));
+   s->cap = 1024; s->ops = (mfft_op *) malloc(sizeof(mfft_op) * s->cap);
+   if (!s->slot || !s->wr_stage || !s->rd_stage || !s->ops) { mfft_sched_free(s); return NULL; }
+   for (i = 0; i < S; i++) s->slot[i] = i;
+   return s;
+}
+
+void mfft_sched_free(mfft_sched *s)
+{
+   if (!s) return;
+   free(s->slot); free(s->wr_stage); free(s->rd_stage); free(s->ops); free(s->stage_off); free(s);
+}
+
+void mfft_sched_swap(mfft_sched *s, uint32_t a, uint32_t b)
+{
+   uint32_t t = s->slot[a]; s->slot[a] = s->slot[b]; s->slot[b] = t;
+}
+
+void mfft_sched_revbin(mfft_sched *s, uint32_t p0, uint32_t is, uint32_t bits)
+{
+   uint64_t j, cnt = (uint64_t)1 << bits;
+   for (j = 0; j < cnt; j++)
+   {
+      uint64_t t = mfft_revbin(j, bits);
+      if (j < t) mfft_sched_swap(s, (uint32_t)(p0 + is*j), (uint32_t)(p0 + is*t));
+   }
+}
+
+/* a term of an output: sign * input * 2^(e + col*c) */
+typedef struct { int sign; uint64_t e, c; } term;
+
+static term T(int sign, uint64_t e, uint64_t c) { term t; t.sign = sign; t.e = e; t.c = c; return t; }
+static const term T0 = {0, 0, 0};
+
+static uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+/* outS -> position pS (from A=posA, B=posB), outT -> position pT; pT/posB may be MFFT_NONE */
+static void emit(mfft_sched *s, uint32_t posA, uint32_t posB, uint32_t pS, term sa, term sb,
+                 uint32_t pT, term ta, term tb)
+{
+   mfft_op *op; uint32_t st = 0, S = s->S;
+   if (s->nops == s->cap)
+   {
+      s->cap *= 2; s->ops = (mfft_op *) realloc(s->ops, sizeof(mfft_op) * s->cap);
+      if (!s->ops) abort();
+   }
+   op = &s->ops[s->nops++];
+   memset(op, 0, sizeof(*op));
+   op->inA = s->slot[posA];
+   op->inB = (posB == MFFT_NONE) ? MFFT_NONE : s->slot[posB];
+   op->outS = (s->slot[pS] < S) ? s->slot[pS] + S : s->slot[pS] - S;
+   op->outT = MFFT_NONE;
+   if (pT != MFFT_NONE) op->outT = (s->slot[pT] < S) ? s->slot[pT] + S : s->slot[pT] - S;
+   op->sSA = (int8_t) sa.sign; op->eSA = (uint32_t)(sa.e % s->M2); op->cSA = (uint32_t)(sa.c % s->M2);
+   op->sSB = (int8_t) sb.sign; op->eSB = (uint32_t)(sb.e % s->M2); op->cSB = (uint32_t)(sb.c % s->M2);
+   op->sTA = (int8_t) ta.sign; op->eTA = (uint32_t)(ta.e % s->M2); op->cTA = (uint32_t)(ta.c % s->M2);
+   op->sTB = (int8_t) tb.sign; op->eTB = (uint32_t)(tb.e % s->M2); op->cTB = (uint32_t)(tb.c % s->M2);
+   if (op->inB == MFFT_NONE) { op->sSB = 0; op->sTB = 0; }
+
+   st = s->wr_stage[op->inA];
+   if (op->inB != MFFT_NONE) st = umax(st, s->wr_stage[op->inB]);
+   st = umax(st, umax(s->rd_stage[op->outS], s->wr_stage[op->outS]));
+   if (op->outT != MFFT_NONE) st = umax(st, umax(s->rd_stage[op->outT], s->wr_stage[op->outT]));
+   st += 1;
+   op->stage = st;
+   s->rd_stage[op->inA] = umax(s->rd_stage[op->inA], st);
+   if (op->inB != MFFT_NONE) s->rd_stage[op->inB] = umax(s->rd_stage[op->inB], st);
+   s->wr_stage[op->outS] = st; s->slot[pS] = op->outS;
+   if (op->outT != MFFT_NONE) { s->wr_stage[op->outT] = st; s->slot[pT] = op->outT; }
+}
+
+void mfft_sched_emit_op(mfft_sched *s, uint32_t posA, uint32_t posB,
+                        uint32_t pS, int sSA, uint64_t eSA, int sSB, uint64_t eSB,
+                        uint32_t pT, int sTA, uint64_t eTA, int sTB, uint64_t eTB)
+{
+   emit(s, posA, posB, pS, T(sSA, eSA, 0), T(sSB, eSB, 0), pT, T(sTA, eTA, 0), T(sTB, eTB, 0));
+}
+
+/* the walker's context: positions p0 + is*k, ring exponents mod M2, twist unit ws */
+typedef struct { mfft_sched *s; uint32_t is; uint64_t ws; } ctx;
+
+#define POS(k) ((uint32_t)(p0 + (uint64_t)c->is*(k)))
+#define NEG(e) ((c->s->M2 - ((e) % c->s->M2)) % c->s->M2)
+
+/* forward butterfly [a,b] -> [a+b, 2^{iw}(a-b)]   (FFT_radix2_butterfly, mul_fft.c:553-576) */
+static void fwd_bfly(ctx *c, uint32_t pa, uint32_t pb, uint64_t e)
+{
+   emit(c->s, pa, pb, pa, T(1, 0, 0), T(1, 0, 0), pb, T(1, e, 0), T(-1, e, 0));
+}
+
+/* inverse butterfly [a,b] -> [a + 2^{-iw}b, a - 2^{-iw}b]   (mul_fft.c:639-652) */
+static void inv_bfly(ctx *c, uint32_t pa, uint32_t pb, uint64_t e)
+{
+   emit(c->s, pa, pb, pa, T(1, 0, 0), T(1, NEG(e), 0), pb, T(1, 0, 0), T(-1, NEG(e), 0));
+}
+
+/* FFT_radix2 (786-827) / FFT_radix2_twiddle (1397-1442) */
+static void fft_full(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, uint64_t rs)
+{
+   uint64_t i;
+   if (n == 1)
+   {  /* leaf: FFT_radix2_twiddle_butterfly (517-548) with b1 = r*c*ws, b2 = (r+rs)*c*ws */
+      uint64_t c1 = (r % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
+      uint64_t c2 = ((r + rs) % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
+      emit(c->s, POS(0), POS(1), POS(0), T(1, 0, c1), T(1, 0, c1), POS(1), T(1, 0, c2), T(-1, 0, c2));
+      return;
+   }
+   for (i = 0; i < n; i++) fwd_bfly(c, POS(i), POS(n + i), i*w);
+   fft_full(c, p0, n/2, 2*w, r, 2*rs);
+   fft_full(c, POS(n), n/2, 2*w, r + rs, 2*rs);
+}
+
+/* FFT_radix2_truncate1 (1028-1074) / FFT_radix2_truncate1_twiddle (1076-1122) */
+static void fft_trunc1(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, uint64_t rs, uint64_t trunc)
+{
+   uint64_t i;
+   if (trunc == 2*n) { fft_full(c, p0, n, w, r, rs); return; }
+   if (trunc <= n)
+   {
+      for (i = 0; i < n; i++)      /* mpn_add_n(ii[i], ii[i], ii[i+n]), 1093-1094 */
+         emit(c->s, POS(i), POS(i + n), POS(i), T(1, 0, 0), T(1, 0, 0), MFFT_NONE, T0, T0);
+      fft_trunc1(c, p0, n/2, 2*w, r, 2*rs, trunc);
+   } else
+   {
+      for (i = 0; i < n; i++) fwd_bfly(c, POS(i), POS(n + i), i*w);
+      fft_full(c, p0, n/2, 2*w, r, 2*rs);
+      fft_trunc1(c, POS(n), n/2, 2*w, r + rs, 2*rs, trunc - n);
+   }
+}
+
+/* FFT_radix2_truncate (1128-1177) / FFT_radix2_truncate_twiddle (1179-1228): zeros past trunc */
+static void fft_trunc(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, uint64_t rs, uint64_t trunc)
+{
+   uint64_t i;
+   if (trunc == 2*n) { fft_full(c, p0, n, w, r, rs); return; }
+   if (trunc <= n) { fft_trunc(c, p0, n/2, 2*w, r, 2*rs, trunc); return; }
+   for (i = 0; i < trunc - n; i++) fwd_bfly(c, POS(i), POS(n + i), i*w);
+   for (i = trunc; i < 2*n; i++)   /* FFT_twiddle(ii[i], ii[i-n], i-n, n, w), 1217-1220 */
+      emit(c->s, POS(i - n), MFFT_NONE, POS(i), T(1, (i - n)*w, 0), T0, MFFT_NONE, T0, T0);
+   fft_full(c, p0, n/2, 2*w, r, 2*rs);
+   fft_trunc1(c, POS(n), n/2, 2*w, r + rs, 2*rs, trunc - n);
+}
+
+/* IFFT_radix2 (1444-1486) / IFFT_radix2_twiddle (1964-2010) */
+static void ifft_full(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, uint64_t rs)
+{
+   uint64_t i;
+   if (n == 1)
+   {  /* FFT_radix2_twiddle_inverse_butterfly (721-752): 2^{-b1} a +- 2^{-b2} b */
+      uint64_t c1 = (r % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
+      uint64_t c2 = ((r + rs) % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
+      emit(c->s, POS(0), POS(1), POS(0), T(1, 0, NEG(c1)), T(1, 0, NEG(c2)),
+                                 POS(1), T(1, 0, NEG(c1)), T(-1, 0, NEG(c2)));
+      return;
+   }
+   ifft_full(c, p0, n/2, 2*w, r, 2*rs);
+   ifft_full(c, POS(n), n/2, 2*w, r + rs, 2*rs);
+   for (i = 0; i < n; i++) inv_bfly(c, POS(i), POS(n + i), i*w);
+}
+
+/* IFFT_radix2_truncate1 (1538-1602) / IFFT_radix2_truncate1_twiddle (1604-1668) */
+static void ifft_trunc1(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, uint64_t rs, uint64_t trunc)
+{
+   uint64_t i, M2 = c->s->M2;
+   if (trunc == 2*n) { ifft_full(c, p0, n, w, r, rs); return; }
+   if (trunc <= n)
+   {
+      for (i = trunc; i < n; i++)   /* (ii[i] + ii[i+n])/2, 1622-1626 */
+         emit(c->s, POS(i), POS(i + n), POS(i), T(1, M2 - 1, 0), T(1, M2 - 1, 0), MFFT_NONE, T0, T0);
+      ifft_trunc1(c, p0, n/2, 2*w, r, 2*rs, trunc);
+      for (i = 0; i < trunc; i++)   /* mpn_addsub_n: 2*ii[i] - ii[n+i], 1630-1631 */
+         emit(c->s, POS(i), POS(n + i), POS(i), T(1, 1, 0), T(-1, 0, 0), MFFT_NONE, T0, T0);
+      return;
+   }
+   ifft_full(c, p0, n/2, 2*w, r, 2*rs);
+   for (i = trunc - n; i < n; i++)  /* 1639-1647: ii[i+n] = z^i (a - b); ii[i] = 2a - b */
+      emit(c->s, POS(i), POS(i + n), POS(i), T(1, 1, 0), T(-1, 0, 0),
+                                     POS(i + n), T(1, i*w, 0), T(-1, i*w, 0));
+   ifft_trunc1(c, POS(n), n/2, 2*w, r + rs, 2*rs, trunc - n);
+   for (i = 0; i < trunc - n; i++) inv_bfly(c, POS(i), POS(n + i), i*w);
+}
+
+/* IFFT_radix2_truncate (1674-1731) / IFFT_radix2_truncate_twiddle (1733-1790) */
+static void ifft_trunc(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, uint64_t rs, uint64_t trunc)
+{
+   uint64_t i;
+   if (trunc == 2*n) { ifft_full(c, p0, n, w, r, rs); return; }
+   if (trunc <= n)
+   {
+      ifft_trunc(c, p0, n/2, 2*w, r, 2*rs, trunc);
+      for (i = 0; i < trunc; i++)   /* doubling, 1753-1754 */
+         emit(c->s, POS(i), MFFT_NONE, POS(i), T(1, 1, 0), T0, MFFT_NONE, T0, T0);
+      return;
+   }
+   ifft_full(c, p0, n/2, 2*w, r, 2*rs);
+   for (i = trunc; i < 2*n; i++)    /* FFT_twiddle(ii[i], ii[i-n], i-n, n, w), 1763-1766 */
+      emit(c->s, POS(i - n), MFFT_NONE, POS(i), T(1, (i - n)*w, 0), T0, MFFT_NONE, T0, T0);
+   ifft_trunc1(c, POS(n), n/2, 2*w, r + rs, 2*rs, trunc - n);
+   for (i = 0; i < trunc - n; i++) inv_bfly(c, POS(i), POS(n + i), i*w);
+   for (i = trunc - n; i < n; i++)  /* doubling, 1788-1789 */
+      emit(c->s, POS(i), MFFT_NONE, POS(i), T(1, 1, 0), T0, MFFT_NONE, T0, T0);
+}
+
+/* FFT_radix2_negacyclic, even w (1346-1373): twist by 2^{i*w/2}, then one butterfly layer */
+static void fft_negacyclic(ctx *c, uint32_t p0, uint64_t n, uint64_t w)
+{
+   uint64_t i, h = w/2;
+   for (i = 0; i < n; i++)
+   {
+      uint64_t ea = i*h, eb = (n + i)*h, e = i*w;
+      emit(c->s, POS(i), POS(n + i), POS(i), T(1, ea, 0), T(1, eb, 0),
+                                     POS(n + i), T(1, ea + e, 0), T(-1, eb + e, 0));
+   }
+   fft_full(c, p0, n/2, 2*w, 0, 0);
+   fft_full(c, POS(n), n/2, 2*w, 0, 0);
+}
+
+/* IFFT_radix2_negacyclic, even w (1882-1886, 1940-1960) */
+static void ifft_negacyclic(ctx *c, uint32_t p0, uint64_t n, uint64_t w)
+{
+   uint64_t i, h = w/2;
+   ifft_full(c, p0, n/2, 2*w, 0, 0);
+   ifft_full(c, POS(n), n/2, 2*w, 0, 0);
+   for (i = 0; i < n; i++)
+   {  /* s = a + 2^{-iw} b, t = a - 2^{-iw} b, then s *= 2^{-i w/2}, t *= 2^{-(n+i) w/2} */
+      uint64_t ua = NEG(i*h), ub = NEG((n + i)*h), e = NEG(i*w);
+      emit(c->s, POS(i), POS(n + i), POS(i), T(1, ua, 0), T(1, ua + e, 0),
+                                     POS(n + i), T(1, ub, 0), T(-1, ub + e, 0));
+   }
+}
+
+int mfft_sched_emit(mfft_sched *s, mfft_transform_kind kind, uint32_t p0, uint32_t is,
+                    uint64_t n, uint64_t w, uint64_t ws, uint64_t r, uint64_t rs, uint64_t trunc)
+{
+   ctx c; c.s = s; c.is = is; c.ws = ws;
+   if (n == 0 || (n & (n - 1)) || n*w != s->NW) return -1;
+   if ((uint64_t) p0 + (uint64_t) is*(2*n - 1) >= s->S) return -1;
+   switch (kind)
+   {
+   case MFFT_T_FFT:  fft_full(&c, p0, n, w, r, rs); break;
+   case MFFT_T_IFFT: ifft_full(&c, p0, n, w, r, rs); break;
+   case MFFT_T_FFT_TRUNC: case MFFT_T_FFT_TRUNC1: case MFFT_T_IFFT_TRUNC: case MFFT_T_IFFT_TRUNC1:
+      /* odd trunc recurses forever in the reference (1438); reject it */
+      if (trunc < 2 || trunc > 2*n || (trunc & 1)) return -1;
+      if (kind == MFFT_T_FFT_TRUNC)   fft_trunc(&c, p0, n, w, r, rs, trunc);
+      if (kind == MFFT_T_FFT_TRUNC1)  fft_trunc1(&c, p0, n, w, r, rs, trunc);
+      if (kind == MFFT_T_IFFT_TRUNC)  ifft_trunc(&c, p0, n, w, r, rs, trunc);
+      if (kind == MFFT_T_IFFT_TRUNC1) ifft_trunc1(&c, p0, n, w, r, rs, trunc);
+      break;
+   case MFFT_T_FFT_NEGACYCLIC:
+      if ((w & 1) || n < 2) return -1;
+      fft_negacyclic(&c, p0, n, w); break;
+   case MFFT_T_IFFT_NEGACYCLIC:
+      if ((w & 1) || n < 2) return -1;
+      ifft_negacyclic(&c, p0, n, w); break;
+   default: return -1;
+   }
+   return 0;
+}
+
+int mfft_sched_finish(mfft_sched *s)
+{
+   size_t i; uint32_t st, maxst = 0; mfft_op *sorted; uint32_t *cnt;
+   for (i = 0; i < s->nops; i++) if (s->ops[i].stage > maxst) maxst = s->ops[i].stage;
+   s->nstages = maxst;
+   free(s->stage_off);
+   s->stage_off = (uint32_t *) calloc((size_t) maxst + 2, sizeof(uint32_t));
+   cnt = (uint32_t *) calloc((size_t) maxst + 2, sizeof(uint32_t));
+   sorted = (mfft_op *) malloc(sizeof(mfft_op) * (s->nops ? s->nops : 1));
+   if (!s->stage_off || !cnt || !sorted) { free(cnt); free(sorted); return -1; }
+   for (i = 0; i < s->nops; i++) cnt[s->ops[i].stage]++;
+   /* stage k (1-based) occupies [stage_off[k-1], stage_off[k]) */
+   s->stage_off[0] = 0;
+   for (st = 1; st <= maxst; st++) s->stage_off[st] = s->stage_off[st - 1] + cnt[st];
+   memset(cnt, 0, sizeof(uint32_t) * ((size_t) maxst + 2));
+   for (i = 0; i < s->nops; i++)
+   {
+      st = s->ops[i].stage;
+      sorted[s->stage_off[st - 1] + cnt[st]++] = s->ops[i];
+   }
+   free(s->ops); s->ops = sorted; s->cap = s->nops ? s->nops : 1;
+   free(cnt);
+   return 0;
+}

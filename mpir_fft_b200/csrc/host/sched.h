@@ -1,0 +1,67 @@
+/* sched.h -- host-side (plain C) schedule generator: turns the reference's recursive radix-2
+ * transforms into data-independent op lists (see mfft_internal.h for the op format). */
+#ifndef MFFT_SCHED_H
+#define MFFT_SCHED_H
+
+#include "../mfft_internal.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+   uint32_t  S;          /* logical positions */
+   uint64_t  NW;         /* ring is 2^NW + 1 */
+   uint64_t  M2;         /* 2*NW: exponents live mod M2 */
+   uint32_t *slot;       /* [S]  current slot of each logical position (in [0,2S)) */
+   uint32_t *wr_stage;   /* [2S] last stage that wrote the slot */
+   uint32_t *rd_stage;   /* [2S] last stage that read the slot */
+   mfft_op  *ops;        /* emitted ops; after mfft_sched_finish sorted by stage */
+   size_t    nops, cap;
+   uint32_t  nstages;    /* valid after finish; stages are numbered 1..nstages */
+   uint32_t *stage_off;  /* [nstages+1] offsets into ops (after finish) */
+} mfft_sched;
+
+typedef enum {
+   MFFT_T_FFT = 0,          /* FFT_radix2 / FFT_radix2_twiddle            mul_fft.c:786, 1397  */
+   MFFT_T_FFT_TRUNC,        /* FFT_radix2_truncate(_twiddle)             mul_fft.c:1128, 1179 */
+   MFFT_T_FFT_TRUNC1,       /* FFT_radix2_truncate1(_twiddle)            mul_fft.c:1028, 1076 */
+   MFFT_T_IFFT,             /* IFFT_radix2 / IFFT_radix2_twiddle          mul_fft.c:1444, 1964 */
+   MFFT_T_IFFT_TRUNC,       /* IFFT_radix2_truncate(_twiddle)            mul_fft.c:1674, 1733 */
+   MFFT_T_IFFT_TRUNC1,      /* IFFT_radix2_truncate1(_twiddle)           mul_fft.c:1538, 1604 */
+   MFFT_T_FFT_NEGACYCLIC,   /* FFT_radix2_negacyclic (even w)            mul_fft.c:1290 */
+   MFFT_T_IFFT_NEGACYCLIC   /* IFFT_radix2_negacyclic (even w)           mul_fft.c:1861 */
+} mfft_transform_kind;
+
+/* S = number of logical positions, NW = n*w of the ring */
+mfft_sched *mfft_sched_new(uint32_t S, uint64_t NW);
+void        mfft_sched_free(mfft_sched *s);
+
+/* Emit the ops of one length-2n transform over positions p0, p0+is, ..., root of unity 2^w,
+ * per-column twist 2^{ws*c*(r + rs*f)} on frequency f (ws = 0: untwisted), truncation `trunc`
+ * (ignored by the untruncated kinds).  Returns 0, or <0 on illegal parameters. */
+int  mfft_sched_emit(mfft_sched *s, mfft_transform_kind kind, uint32_t p0, uint32_t is,
+                     uint64_t n, uint64_t w, uint64_t ws, uint64_t r, uint64_t rs, uint64_t trunc);
+
+/* Emit one explicit op: position pS <- sSA*A*2^eSA + sSB*B*2^eSB and (optionally) position
+ * pT <- sTA*A*2^eTA + sTB*B*2^eTB, A/B = current contents of positions posA/posB (posB and pT
+ * may be MFFT_NONE).  Exponents are bit counts mod 2*NW. */
+void mfft_sched_emit_op(mfft_sched *s, uint32_t posA, uint32_t posB,
+                        uint32_t pS, int sSA, uint64_t eSA, int sSB, uint64_t eSB,
+                        uint32_t pT, int sTA, uint64_t eTA, int sTB, uint64_t eTB);
+
+/* swap the slots of logical positions a and b (the reference's pointer swaps, e.g. 2380-2389) */
+void mfft_sched_swap(mfft_sched *s, uint32_t a, uint32_t b);
+
+/* bit-reverse relabel of positions p0 + is*j, j < 2^bits (mul_fft.c:2041-2050 and twins) */
+void mfft_sched_revbin(mfft_sched *s, uint32_t p0, uint32_t is, uint32_t bits);
+
+/* sort ops by stage and build stage_off */
+int  mfft_sched_finish(mfft_sched *s);
+
+uint64_t mfft_revbin(uint64_t in, uint32_t bits);   /* mpir_revbin, mul_fft.c:63-79 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,122 @@
+/* mfft_internal.h -- shared between the C host side (csrc/host) and the thin CUDA launch
+ * ABI (csrc/cuda).  Not a public header; the public C ABI is include/mpirfft_b200.h.
+ *
+ * Vocabulary (follows the reference, /root/reference/mul_fft.c:44-50 and README:48-60):
+ *   p = 2^NW + 1, NW = n*w bits, l = NW/64 limbs; a *coefficient block* is l limbs of body plus
+ *   one signed carry limb ("top"), value = body + top*2^NW  (== body - top mod p).
+ *   Coefficient blocks live in one contiguous HBM *slab* with a fixed pitch (in limbs).
+ *
+ * The reference permutes host pointers (README:56); here every logical position has two
+ * candidate *slots* (slab half 0 and half 1, "ping-pong") and a transform is a data-independent
+ * list of *ops* grouped into *stages*; ops of one stage are independent and run as one launch.
+ */
+#ifndef MFFT_INTERNAL_H
+#define MFFT_INTERNAL_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t limb_t;
+
+#define MFFT_NONE 0xFFFFFFFFu
+
+/* One op: up to two outputs, each a signed sum of up to two inputs multiplied by powers of two:
+ *   outS = sSA * A * 2^(eSA + col*cSA) + sSB * B * 2^(eSB + col*cSB)      (mod p)
+ *   outT = sTA * A * 2^(eTA + col*cTA) + sTB * B * 2^(eTB + col*cTB)      (mod p)
+ * All exponents are bit counts reduced mod 2*NW (2^NW == -1).  `col` is the per-batch-entry
+ * column index (the MFA twist z^{r*c}, mul_fft.c:1409-1411); it is 0 for untwisted passes.
+ * inA/inB/outS/outT are slots in [0, 2*S).  sXY == 0 means "term absent". */
+typedef struct {
+   uint32_t inA, inB, outS, outT;
+   uint32_t eSA, eSB, eTA, eTB;
+   uint32_t cSA, cSB, cTA, cTB;
+   int8_t   sSA, sSB, sTA, sTB;
+   uint32_t stage;
+} mfft_op;
+
+/* One batch entry: which strided family of blocks an op list is applied to. */
+typedef struct {
+   uint32_t base;    /* block index of position 0 (before slot stride) inside a slab half */
+   uint32_t parity;  /* 0/1: xor'ed into the slab-half bit of every slot */
+   uint32_t col;     /* column index used for the twist exponents */
+   uint32_t pad;
+} mfft_batch;
+
+/* Geometry of one pass over a slab. block index of (slot, batch b) =
+ *   (((slot / S) ^ parity_b) * half_blocks) + base_b + (slot % S) * slot_stride            */
+typedef struct {
+   uint32_t S;            /* positions in the pass */
+   uint32_t slot_stride;  /* in blocks */
+   uint64_t half_blocks;  /* blocks per slab half */
+   uint32_t l;            /* limbs of body */
+   uint32_t pitch;        /* limbs per block in the slab (>= l+1) */
+} mfft_geom;
+
+/* gather/normalise descriptor (finalize step of a transform): for logical position k:
+ * src slot (with batch parity/base as above) -> dst block index  dst_base_b + dst[k]*dst_stride */
+typedef struct {
+   uint32_t src_slot;
+   uint32_t dst_pos;
+} mfft_move;
+
+/* ------------------------------------------------------------------------------------------
+ * CUDA launch ABI (implemented in csrc/cuda/mfft_kernels.cu).  All pointers are device
+ * pointers unless named h_*.  `stream` is a cudaStream_t passed as void*.  Every function
+ * returns 0 on success or a negative mfft error code; none of them ever falls back to the CPU.
+ * ------------------------------------------------------------------------------------------ */
+int  mfft_dev_init(int device);                       /* select device, create context; <0 if no GPU */
+int  mfft_dev_count(void);
+void *mfft_dev_alloc(size_t bytes);                   /* NULL on failure */
+void mfft_dev_free(void *p);
+void *mfft_host_alloc_pinned(size_t bytes);
+void mfft_host_free_pinned(void *p);
+int  mfft_dev_h2d(void *d, const void *h, size_t bytes, void *stream);
+int  mfft_dev_d2h(void *h, const void *d, size_t bytes, void *stream);
+int  mfft_dev_h2d_2d(void *d, size_t dpitch, const void *h, size_t hpitch, size_t width, size_t rows, void *stream);
+int  mfft_dev_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, void *stream);
+int  mfft_dev_memset0(void *d, size_t bytes, void *stream);
+int  mfft_dev_sync(void *stream);
+const char *mfft_dev_last_error(void);
+
+/* run ops[first .. first+count) (one stage) over nbatch batch entries */
+int  mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
+                        const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+
+/* dst[dst_base_b + mv.dst_pos*dst_stride] = normalise( src(slot mv.src_slot, batch b) * 2^shift )
+ * shift is a bit exponent mod 2*NW (0 = none); if !normalise the block is copied unreduced. */
+int  mfft_dev_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst_base,
+                       const limb_t *slab, const mfft_geom *g, const mfft_move *d_moves, uint32_t nmoves,
+                       const mfft_batch *d_batch, uint32_t nbatch, uint32_t shift, int normalise,
+                       void *stream);
+
+/* pointwise a[i] = a[i]*b[i] mod p over nblk canonical blocks listed in d_blocks (block indices) */
+int  mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uint32_t nblk,
+                        uint32_t l, uint32_t pitch, void *stream);
+
+/* split: coefficient i (i < ncoef) = bits [i*bits, (i+1)*bits) of {src, nlimbs}, zero-extended to a
+ * block (FFT_split_bits, mul_fft.c:115-170); blocks ncoef..nzero-1 are zeroed (mul_fft.c:3235). */
+int  mfft_dev_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, uint64_t nlimbs,
+                    uint64_t bits, uint64_t ncoef, uint64_t nzero, void *stream);
+
+/* combine: res[0..total) = sum_{i<ncoef} block_i * 2^(i*bits) truncated to total limbs
+ * (FFT_combine_bits, mul_fft.c:207-267, including the MPN_ZERO of mul_fft.c:3261).
+ * blocks must be normalised with zero top limb.  work: >= mfft_dev_combine_work(total) bytes. */
+size_t mfft_dev_combine_work(uint64_t total);
+int  mfft_dev_combine(limb_t *res, uint64_t total, const limb_t *slab, uint32_t l, uint32_t pitch,
+                      uint64_t bits, uint64_t ncoef, void *work, void *stream);
+
+/* normalise nblk blocks in place (mpn_normmod_2expp1, mul_fft.c:272-294) */
+int  mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, void *stream);
+
+/* counters for bench.py: number of kernel launches issued through this ABI since reset */
+uint64_t mfft_dev_launch_count(void);
+void     mfft_dev_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
