@@ -194,6 +194,13 @@ int   mpirfft_memcpy_h2d(void *d, const void *h, size_t bytes, void *stream);
 int   mpirfft_memcpy_d2h(void *h, const void *d, size_t bytes, void *stream);
 int   mpirfft_stream_sync(void *stream);
 
+/* Optional per-kernel-class timing with CUDA events on the launching stream (used by bench.py
+ * for the roofline figures; off by default).  Classes: 0 transform stage, 1 finalize/normalise
+ * gather, 2 pointwise, 3 split, 4 combine, 5 normalise.  read() drains and sums the records:
+ * total ms, launches and algorithmic bytes (stage class only) per class. */
+void mpirfft_profile_enable(int on);
+int  mpirfft_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass);
+
 /* launches issued through the library since the last reset (bench.py's gpu_launches) */
 uint64_t mpirfft_launch_count(void);
 void     mpirfft_launch_count_reset(void);

@@ -66,6 +66,8 @@ def bind(L):
         "mpirfft_memcpy_h2d": (i32, [vp, vp, sz, vp]),
         "mpirfft_memcpy_d2h": (i32, [vp, vp, sz, vp]),
         "mpirfft_stream_sync": (i32, [vp]),
+        "mpirfft_profile_enable": (None, [i32]),
+        "mpirfft_profile_read": (i32, [C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(C.c_double), i32]),
         "mpirfft_launch_count": (u64, []),
         "mpirfft_launch_count_reset": (None, []),
         "new_mpn_mul": (None, [vp, vp, i64, vp, i64, u64, u64]),

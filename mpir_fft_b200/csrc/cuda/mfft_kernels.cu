@@ -31,6 +31,30 @@ static char g_err[512] = "";
 static uint64_t g_launches = 0;
 static int g_device = -1;
 
+/* optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
+ * leg).  Off by default; never part of the timed end-to-end path. */
+enum { PC_STAGE = 0, PC_FINALIZE, PC_POINTWISE, PC_SPLIT, PC_COMBINE, PC_NORMALISE, PC_COUNT };
+static int g_prof_on = 0;
+static double g_prof_bytes_next = 0.0;
+#ifndef MFFT_EMU
+#include <vector>
+struct prof_rec { cudaEvent_t a, b; int cls; double bytes; };
+static std::vector<prof_rec> g_prof;
+struct prof_scope {
+   int on; prof_rec r; cudaStream_t st;
+   prof_scope(int cls, cudaStream_t s) : on(g_prof_on), st(s)
+   {
+      if (!on) return;
+      r.cls = cls; r.bytes = g_prof_bytes_next; g_prof_bytes_next = 0.0;
+      cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st);
+   }
+   ~prof_scope() { if (on) { cudaEventRecord(r.b, st); g_prof.push_back(r); } }
+};
+#define PROF(cls, st) prof_scope prof__(cls, (cudaStream_t)(st))
+#else
+#define PROF(cls, st) do { } while (0)
+#endif
+
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) {                       \
       snprintf(g_err, sizeof g_err, "%s:%d: %s: %s", __FILE__, __LINE__, #call,                 \
                cudaGetErrorString(e__)); return -1; } } while (0)
@@ -549,6 +573,25 @@ k_combine_fix(limb_t *res, uint64_t total, const uint32_t *__restrict__ tileC, u
 extern "C" {
 
 const char *mfft_dev_last_error(void) { return g_err; }
+
+void mfft_dev_profile_enable(int on) { g_prof_on = on; }
+void mfft_dev_profile_bytes(double bytes) { if (g_prof_on) g_prof_bytes_next = bytes; }
+/* drain the recorded launches: per class total ms, launch count, algorithmic bytes */
+int mfft_dev_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass)
+{
+   for (int i = 0; i < nclass; i++) { ms[i] = 0; launches[i] = 0; bytes[i] = 0; }
+#ifndef MFFT_EMU
+   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+   for (size_t i = 0; i < g_prof.size(); i++)
+   {
+      float t = 0; cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b);
+      if (g_prof[i].cls < nclass) { ms[g_prof[i].cls] += t; launches[g_prof[i].cls]++; bytes[g_prof[i].cls] += g_prof[i].bytes; }
+      cudaEventDestroy(g_prof[i].a); cudaEventDestroy(g_prof[i].b);
+   }
+   g_prof.clear();
+#endif
+   return 0;
+}
 uint64_t mfft_dev_launch_count(void) { return g_launches; }
 void mfft_dev_launch_count_reset(void) { g_launches = 0; }
 
@@ -617,6 +660,7 @@ int mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, u
    const uint64_t warps = (uint64_t) count * nbatch;
    const unsigned grid = (unsigned)((warps + 3) / 4);
    cudaStream_t st = (cudaStream_t) stream;
+   PROF(PC_STAGE, st);
    switch (pick_m(g->l))
    {
    case 8: MFFT_LAUNCH(k_run_stage<8>, grid, 128, 0, st, slab, *g, d_ops, count, d_batch, nbatch); break;
@@ -638,6 +682,7 @@ int mfft_dev_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst_ba
    const unsigned grid = (unsigned)((warps + 3) / 4);
    cudaStream_t st = (cudaStream_t) stream;
    limb_t *s = (limb_t *) slab;
+   PROF(PC_FINALIZE, st);
    switch (pick_m(g->l))
    {
    case 8: MFFT_LAUNCH(k_finalize<8>, grid, 128, 0, st, dst, dst_stride, d_dst_base, s, *g, d_moves, nmoves, d_batch, nbatch, shift, normalise); break;
@@ -652,6 +697,7 @@ int mfft_dev_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst_ba
 int mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, void *stream)
 {
    if (!nblk) return 0;
+   PROF(PC_NORMALISE, stream);
    MFFT_LAUNCH(k_normalise, (unsigned)((nblk + 3) / 4), 128, 0, (cudaStream_t) stream, slab, l, pitch, nblk);
    CKL();
    return 0;
@@ -665,6 +711,7 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
    if (!nblk) return 0;
    cudaStream_t st = (cudaStream_t) stream;
    const unsigned grid = (nblk + 3) / 4;
+   PROF(PC_POINTWISE, st);
    if (l == 64)       MFFT_LAUNCH(k_pointwise<4>, grid, 128, 4 * 32 * 4 * 4, st, a, b, d_blocks, nblk, l, pitch);
    else if (l == 128) MFFT_LAUNCH(k_pointwise<8>, grid, 128, 4 * 32 * 8 * 4, st, a, b, d_blocks, nblk, l, pitch);
    else if (l == 256) MFFT_LAUNCH(k_pointwise<16>, grid, 128, 4 * 32 * 16 * 4, st, a, b, d_blocks, nblk, l, pitch);
@@ -694,6 +741,7 @@ int mfft_dev_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, 
    if (nzero < ncoef) nzero = ncoef;
    const uint64_t threads = nzero * ((uint64_t) l + 1);
    if (!threads) return 0;
+   PROF(PC_SPLIT, stream);
    MFFT_LAUNCH(k_split, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t) stream, slab, l, pitch, src, nlimbs, bits, ncoef, nzero);
    CKL();
    return 0;
@@ -716,6 +764,7 @@ int mfft_dev_combine(limb_t *res, uint64_t total, const limb_t *slab, uint32_t l
    uint32_t *tileG = cvec + ((total + 1 + 63) / 64) * 64;
    uint32_t *tileP = tileG + ntiles + 32 - (ntiles % 32);
    uint32_t *tileC = tileP + ntiles + 32 - (ntiles % 32);
+   PROF(PC_COMBINE, st);
    MFFT_LAUNCH(k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef);
    CKL();
    MFFT_LAUNCH(k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);

@@ -55,6 +55,10 @@ int mpirfft_init(int device)
 int mpirfft_device_count(void) { return mfft_dev_count(); }
 const char *mpirfft_last_error(void) { return mfft_dev_last_error(); }
 const char *mpirfft_version(void) { return "mpirfft_b200 0.1 (sm_100a)"; }
+void mpirfft_profile_enable(int on) { mfft_dev_profile_enable(on); }
+int  mpirfft_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass)
+{ return mfft_dev_profile_read(ms, launches, bytes, nclass) ? MPIRFFT_ENODEV : 0; }
+
 uint64_t mpirfft_launch_count(void) { return mfft_dev_launch_count(); }
 void mpirfft_launch_count_reset(void) { mfft_dev_launch_count_reset(); }
 
@@ -95,7 +99,11 @@ int mfft_dsched_run(const mfft_dsched *ds, limb_t *slab, const mfft_geom *g,
    uint32_t st;
    for (st = 1; st <= ds->s->nstages; st++)
    {
-      uint32_t lo = ds->s->stage_off[st - 1], hi = ds->s->stage_off[st];
+      uint32_t lo = ds->s->stage_off[st - 1], hi = ds->s->stage_off[st], k;
+      double blocks = 0;     /* blocks read + written by this stage: the algorithmic traffic */
+      for (k = lo; k < hi; k++)
+         blocks += 2 + (ds->s->ops[k].inB != MFFT_NONE) + (ds->s->ops[k].outT != MFFT_NONE);
+      mfft_dev_profile_bytes(blocks * nbatch * 8.0 * (g->l + 1));
       if (hi > lo && mfft_dev_run_stage(slab, g, ds->d_ops + lo, hi - lo, d_batch, nbatch, stream) != 0)
          return MPIRFFT_ENODEV;
    }

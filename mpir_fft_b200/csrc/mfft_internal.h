@@ -112,6 +112,12 @@ int  mfft_dev_combine(limb_t *res, uint64_t total, const limb_t *slab, uint32_t 
 /* normalise nblk blocks in place (mpn_normmod_2expp1, mul_fft.c:272-294) */
 int  mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, void *stream);
 
+/* optional per-kernel-class CUDA-event timing (bench.py's roofline leg); classes in order:
+ * 0 stage, 1 finalize, 2 pointwise, 3 split, 4 combine, 5 normalise */
+void mfft_dev_profile_enable(int on);
+void mfft_dev_profile_bytes(double bytes);     /* algorithmic bytes of the next launch */
+int  mfft_dev_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass);
+
 /* counters for bench.py: number of kernel launches issued through this ABI since reset */
 uint64_t mfft_dev_launch_count(void);
 void     mfft_dev_launch_count_reset(void);

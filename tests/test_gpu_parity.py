@@ -1,0 +1,320 @@
+"""GPU parity tests: every call goes through the C ABI of libmpirfft_b200.so and is compared,
+bit for bit, with the CPU checkers (GMP mpn_mul for products -- the product is unique -- and the
+compiled reference oracle/_ref for the transform entry points, after mpn_normmod_2expp1 exactly as
+the reference's own tests compare, mul_fft.c:4547-4557).  Integer work: the bar is bit-exact.
+"""
+import ctypes as C
+import numpy as np
+import pytest
+
+import mpir_fft_b200 as M
+from oracle import loader as oracle
+from common import (operand, rand_blocks, residues, first_diff, ptr, cl, cul, block_to_int,
+                    int_to_block, splitmix64)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = M.lib()
+    assert L.mpirfft_device_count() > 0, "no CUDA device visible"
+    M.init(0)
+    return L
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = oracle.load_ref(True)
+    if r is None:
+        pytest.skip("oracle/_ref not built")
+    return r
+
+
+def check_mul(n1, n2, depth, w, kind1="uniform", kind2="uniform"):
+    a, b = operand(kind1, n1, 0x5EED0001), operand(kind2, n2, 0x5EED0002)
+    got = M.new_mpn_mul(a, b, depth, w)
+    want = oracle.gmp_mul(a, b)
+    assert first_diff(got, want) is None, "new_mpn_mul %dx%d depth %d w %d (%s,%s): (first,last,count)=%s" % (
+        n1, n2, depth, w, kind1, kind2, first_diff(got, want))
+
+
+# ---- BASELINE.json configs 1-3 ----
+def test_cfg1_2p16(lib):
+    check_mul(1 << 16, 1 << 16, 12, 1)
+
+
+def test_cfg1_matches_patched_reference(lib, ref):
+    n = 1 << 16
+    a, b = operand("uniform", n, 1), operand("uniform", n, 2)
+    want = np.zeros(2 * n, dtype=np.uint64)
+    ref.new_mpn_mul(ptr(want), ptr(a), cl(n), ptr(b), cl(n), cul(12), cul(1))
+    assert first_diff(M.new_mpn_mul(a, b, 12, 1), want) is None
+
+
+def test_cfg2_2p20(lib):
+    check_mul(1 << 20, 1 << 20, 14, 1)
+
+
+def test_cfg3_truncated_depth14_w2(lib):
+    check_mul(3000000, 1700000, 14, 2)
+
+
+def test_cfg3_truncated_depth15_w1(lib):
+    check_mul(3000000, 1700000, 15, 1)
+
+
+@pytest.mark.parametrize("kinds", [("ones", "ones"), ("runs", "runs"), ("pow2", "uniform"), ("ones", "uniform")])
+def test_adversarial_operands_2p16(lib, kinds):
+    check_mul(1 << 16, 1 << 16, 12, 1, *kinds)
+
+
+def test_cfg2_all_ones(lib):
+    check_mul(1 << 20, 1 << 20, 14, 1, "ones", "ones")
+
+
+@pytest.mark.parametrize("case", [
+    (1, 1, 6, 1), (20, 13, 6, 1), (40, 40, 6, 2), (200000, 3, 14, 1), (123457, 65521, 13, 1),
+    (100000, 100000, 12, 3), (1 << 17, 1 << 17, 11, 8), (1 << 18, 1 << 18, 13, 1),
+    (700, 900, 7, 12), (3000, 3000, 7, 96), (12000, 9000, 6, 512), (3 << 16, 3 << 16, 13, 2),
+])
+def test_odd_sizes(lib, case):
+    check_mul(*case)
+
+
+def test_size_independent_properties_cfg2(lib):
+    """at full size: commutativity, and (a*b) mod small primes from the inputs alone"""
+    n = 1 << 20
+    a, b = operand("uniform", n, 11), operand("runs", n, 12)
+    r1 = M.new_mpn_mul(a, b, 14, 1)
+    r2 = M.new_mpn_mul(b, a, 14, 1)
+    assert first_diff(r1, r2) is None
+    for p in (2305843009213693951, 18446744073709551557, 4294967291):
+        # fold limbs mod p with python ints in chunks
+        def modp(x):
+            v = int.from_bytes(x.tobytes(), "little")
+            return v % p
+        assert modp(r1) == (modp(a) * modp(b)) % p
+
+
+def test_illegal_parameters_rejected():
+    with pytest.raises(ValueError):
+        M.new_mpn_mul(np.ones(1 << 17, np.uint64), np.ones(1 << 17, np.uint64), 11, 4)   # needs 4103 > 4096 coeffs
+    with pytest.raises(ValueError):
+        M.new_mpn_mul(np.ones(8, np.uint64), np.ones(8, np.uint64), 5, 1)               # 64 does not divide n*w
+
+
+# ---- mulmod 2^(64 l)+1 ----
+@pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
+def test_mulmod_vs_bigint(lib, l):
+    import random
+    random.seed(l)
+    NW = 64 * l
+    p = (1 << NW) + 1
+    A = [random.getrandbits(NW) for _ in range(20)] + [p - 2, p - 2, p - 1, p - 1, 0, 1, p - 2,
+                                                       (1 << (NW // 2)) - 1, (1 << NW) - (1 << (NW // 2))]
+    B = [random.getrandbits(NW) for _ in range(20)] + [p - 2, 2, p - 1, 12345, 77, p - 2, 1 << (NW - 1),
+                                                       (1 << (NW // 2)) - 1, (1 << NW) - (1 << (NW // 2))]
+    a = np.stack([int_to_block(v, l) for v in A])
+    b = np.stack([int_to_block(v, l) for v in B])
+    out = M.mulmod_batch(a, b)
+    for k in range(len(A)):
+        want = int_to_block(A[k] * B[k] % p, l)
+        assert np.array_equal(out[k], want), "mulmod l=%d case %d" % (l, k)
+
+
+def test_new_mpn_mulmod_2expp1_symbol(lib):
+    l = 64
+    a, b = splitmix64(5, l), splitmix64(6, l)
+    r = np.zeros(l, dtype=np.uint64)
+    tt = np.zeros(2 * l + 2, dtype=np.uint64)
+    top = lib.new_mpn_mulmod_2expp1(ptr(r), ptr(a), ptr(b), 0, 64 * l, ptr(tt))
+    p = (1 << (64 * l)) + 1
+    want = int.from_bytes(a.tobytes(), "little") * int.from_bytes(b.tobytes(), "little") % p
+    got = int.from_bytes(r.tobytes(), "little") + (int(top) << (64 * l))
+    assert got == want
+    # c = 1: i1 is 2^bits (limbs zero)
+    z = np.zeros(l, dtype=np.uint64)
+    top = lib.new_mpn_mulmod_2expp1(ptr(r), ptr(z), ptr(b), 1, 64 * l, ptr(tt))
+    got = int.from_bytes(r.tobytes(), "little") + (int(top) << (64 * l))
+    assert got == (p - 1) * int.from_bytes(b.tobytes(), "little") % p
+
+
+# ---- transform entry points against the compiled reference (normalised, as its tests do) ----
+def _run_pair(lib_fn, ref_fn, N, l, data, args_after_ii):
+    s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+    ref_fn(*([s1.ii] + [x(s1) if callable(x) else x for x in args_after_ii]))
+    lib_fn(*([s2.ii] + [x(s2) if callable(x) else x for x in args_after_ii]))
+    return residues(s1.all(), l), residues(s2.all(), l)
+
+
+T1 = lambda s: s.pt1   # noqa: E731
+T2 = lambda s: s.pt2   # noqa: E731
+TT = lambda s: s.ptmp  # noqa: E731
+II = lambda s: s.ii    # noqa: E731
+
+
+@pytest.mark.parametrize("n,w", [(16, 4), (64, 3), (32, 64), (8, 256)])
+def test_fft_ifft_radix2(lib, ref, n, w):
+    rng = np.random.default_rng(n * w)
+    l, N = n * w // 64, 2 * n
+    data = rand_blocks(rng, N, l)
+    for name in ("FFT_radix2", "IFFT_radix2"):
+        L_, R_ = getattr(lib, name), getattr(ref, name)
+        s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+        R_(s1.ii, cl(1), s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp)
+        L_(s2.ii, cl(1), s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp)
+        assert residues(s1.all(), l) == residues(s2.all(), l), name
+
+
+@pytest.mark.parametrize("trunc", [2, 6, 16, 18, 24, 30, 32])
+def test_truncated_1d(lib, ref, trunc):
+    n, w = 16, 8
+    rng = np.random.default_rng(trunc)
+    l, N = n * w // 64, 2 * n
+    for name, zero in (("FFT_radix2_truncate", True), ("FFT_radix2_truncate1", False),
+                       ("IFFT_radix2_truncate", False), ("IFFT_radix2_truncate1", False)):
+        data = rand_blocks(rng, N, l)
+        if zero:
+            data[trunc:] = 0
+        s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+        getattr(ref, name)(s1.ii, cl(1), s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, cl(trunc))
+        getattr(lib, name)(s2.ii, cl(1), s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, cl(trunc))
+        assert residues(s1.all()[:trunc], l) == residues(s2.all()[:trunc], l), name
+    for name, zero in (("FFT_radix2_truncate_twiddle", True), ("FFT_radix2_truncate1_twiddle", False),
+                       ("IFFT_radix2_truncate_twiddle", False), ("IFFT_radix2_truncate1_twiddle", False)):
+        data = rand_blocks(rng, N, l)
+        if zero:
+            data[trunc:] = 0
+        s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+        a = (cl(1), cl(n), cul(w))
+        getattr(ref, name)(s1.ii, *a, s1.pt1, s1.pt2, s1.ptmp, cl(1), cl(2), cl(3), cl(1), cl(trunc))
+        getattr(lib, name)(s2.ii, *a, s2.pt1, s2.pt2, s2.ptmp, cl(1), cl(2), cl(3), cl(1), cl(trunc))
+        assert residues(s1.all()[:trunc], l) == residues(s2.all()[:trunc], l), name
+
+
+@pytest.mark.parametrize("n,w,n1,trunc", [(32, 2, 8, 0), (64, 1, 4, 0), (32, 2, 8, 48), (64, 1, 4, 72),
+                                          (64, 2, 16, 96), (2048, 1, 64, 2176), (128, 32, 16, 160)])
+def test_mfa(lib, ref, n, w, n1, trunc):
+    rng = np.random.default_rng(n + trunc)
+    l, N = n * w // 64, 2 * n
+    n2 = N // n1
+    depth = n2.bit_length() - 1
+    rows = [int(lib.mpir_revbin(s, depth)) for s in range((trunc // n1) if trunc else n2)]
+    for inverse in (0, 1):
+        data = rand_blocks(rng, N, l)
+        if trunc and not inverse:
+            data[trunc:] = 0
+        name = ("I" if inverse else "") + "FFT_radix2_mfa" + ("_truncate" if trunc else "")
+        s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+        extra = (cl(trunc),) if trunc else ()
+        getattr(ref, name)(s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, cl(n1), *extra)
+        getattr(lib, name)(s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, cl(n1), *extra)
+        r1, r2 = residues(s1.all(), l), residues(s2.all(), l)
+        if not inverse:
+            idx = [i * n1 + j for i in rows for j in range(n1)]
+        else:
+            idx = list(range(trunc if trunc else N))
+        assert [r1[k] for k in idx] == [r2[k] for k in idx], name
+
+
+def test_mfa_roundtrip_scaled(lib):
+    """IFFT(FFT(x)) == 2n * x (mul_fft.c:4938), at the cfg1 ring, truncated"""
+    n, w, n1, trunc = 4096, 1, 64, 4224
+    rng = np.random.default_rng(1)
+    l, N = n * w // 64, 2 * n
+    data = rand_blocks(rng, N, l, tops=False)
+    data[trunc:] = 0
+    s = oracle.Slab(N, l, data)
+    lib.FFT_radix2_mfa_truncate(s.ii, cl(n), cul(w), s.pt1, s.pt2, s.ptmp, cl(n1), cl(trunc))
+    lib.IFFT_radix2_mfa_truncate(s.ii, cl(n), cul(w), s.pt1, s.pt2, s.ptmp, cl(n1), cl(trunc))
+    p = (1 << (64 * l)) + 1
+    got = residues(s.all()[:trunc], l)
+    want = [(block_to_int(data[k], l) * N) % p for k in range(trunc)]
+    assert got == want
+
+
+def test_butterflies_and_primitives(lib, ref):
+    rng = np.random.default_rng(9)
+    for (n, w) in [(64, 1), (64, 3), (256, 4), (64, 64)]:
+        l = n * w // 64
+        for i in (0, 1, 5, n - 1, n, n + 3, 2 * n - 1):
+            blk = rand_blocks(rng, 2, l)
+            for name in ("FFT_radix2_butterfly", "FFT_radix2_inverse_butterfly"):
+                if name.endswith("inverse_butterfly") and i >= n:
+                    continue
+                outs = []
+                for Lb in (ref, lib):
+                    a, b = blk[0].copy(), blk[1].copy()
+                    s, t = np.zeros(l + 1, np.uint64), np.zeros(l + 1, np.uint64)
+                    getattr(Lb, name)(ptr(s), ptr(t), ptr(a), ptr(b), cl(i), cl(n), cul(w))
+                    outs.append((block_to_int(s, l), block_to_int(t, l)))
+                assert outs[0] == outs[1], (name, n, w, i)
+            outs = []
+            for Lb in (ref, lib):
+                a = blk[0].copy()
+                r = np.zeros(l + 1, np.uint64)
+                Lb.FFT_twiddle(ptr(r), ptr(a), cl(i), cl(n), cul(w))
+                outs.append(block_to_int(r, l))
+            assert outs[0] == outs[1], ("FFT_twiddle", n, w, i)
+        NW = n * w
+        for (b1, b2) in [(0, 0), (1, 63), (64, 65), (NW - 1, NW + 1), (2 * NW - 1, 3 * NW + 7)]:
+            for name in ("FFT_radix2_twiddle_butterfly", "FFT_radix2_twiddle_inverse_butterfly"):
+                outs = []
+                for Lb in (ref, lib):
+                    a, b = blk[0].copy(), blk[1].copy()
+                    s, t = np.zeros(l + 1, np.uint64), np.zeros(l + 1, np.uint64)
+                    getattr(Lb, name)(ptr(s), ptr(t), ptr(a), ptr(b), cl(NW), cul(b1), cul(b2))
+                    outs.append((block_to_int(s, l), block_to_int(t, l)))
+                assert outs[0] == outs[1], (name, NW, b1, b2)
+        for d in (0, 1, 31, 63):
+            for name in ("mpn_mul_2expmod_2expp1", "mpn_div_2expmod_2expp1"):
+                outs = []
+                for Lb in (ref, lib):
+                    a = blk[0].copy()
+                    r = np.zeros(l + 1, np.uint64)
+                    getattr(Lb, name)(ptr(r), ptr(a), cl(l), cul(d))
+                    outs.append(block_to_int(r, l))
+                assert outs[0] == outs[1], (name, l, d)
+        for (x, y) in [(0, 0), (0, 1), (1, 0), (l // 2, l // 2), (l - 1, 1), (1, l - 1)]:
+            if max(x, y) >= l:
+                continue
+            for name in ("mpn_lshB_sumdiffmod_2expp1", "mpn_sumdiff_rshBmod_2expp1"):
+                outs = []
+                for Lb in (ref, lib):
+                    a, b = blk[0].copy(), blk[1].copy()
+                    s, t = np.zeros(l + 1, np.uint64), np.zeros(l + 1, np.uint64)
+                    getattr(Lb, name)(ptr(s), ptr(t), ptr(a), ptr(b), cl(l), cl(x), cl(y))
+                    outs.append((block_to_int(s, l), block_to_int(t, l)))
+                assert outs[0] == outs[1], (name, l, x, y)
+        # normalise: limb-for-limb canonical form
+        for top in (0, 1, -1, 5, -7):
+            a = blk[0].copy()
+            a[l] = np.int64(top).view(np.uint64)
+            b = a.copy()
+            ref.mpn_normmod_2expp1(ptr(a), cl(l))
+            lib.mpn_normmod_2expp1(ptr(b), cl(l))
+            assert np.array_equal(a, b)
+
+
+def test_split_combine(lib, ref):
+    rng = np.random.default_rng(4)
+    for (total, bits, out) in [(100, 29, 1), (1000, 2045, 64), (777, 640, 12), (4096, 8185, 256), (50, 64, 3)]:
+        limbs = rng.integers(0, 2 ** 64, total, dtype=np.uint64)
+        length = (64 * total - 1) // bits + 1
+        res = []
+        for Lb in (ref, lib):
+            s = oracle.Slab(length, out)
+            Lb.FFT_split_bits.restype = C.c_long
+            got = Lb.FFT_split_bits(s.ii, ptr(limbs), cl(total), cl(bits), cl(out))
+            assert got == length
+            res.append(s.all())
+        assert np.array_equal(res[0], res[1]), ("split", total, bits, out)
+        # combine back (coefficients are < 2^bits so the sum is the original integer)
+        outs = []
+        for Lb in (ref, lib):
+            s = oracle.Slab(length, out, res[0])
+            r = np.zeros(total, dtype=np.uint64)
+            Lb.FFT_combine_bits(ptr(r), s.ii, cl(length), cl(bits), cl(out), cl(total))
+            outs.append(r)
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], limbs), ("combine", total, bits, out)
