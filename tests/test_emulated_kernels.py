@@ -1,0 +1,56 @@
+"""CPU: the *actual kernel source* (csrc/cuda/mfft_kernels.cu) compiled by g++ against the SIMT
+emulator in tests/emu and driven through the same C ABI, compared with GMP / big integers.
+This is a check of kernel arithmetic and host logic on a machine without a GPU; the emulated
+library is test infrastructure and is never loaded by the product package."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import loader as L
+from common import operand, ptr, block_to_int, int_to_block
+from mpir_fft_b200._lib import bind
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    return bind(C.CDLL(os.path.join(EMU_DIR, "libmpirfft_emu.so"), mode=C.RTLD_LOCAL))
+
+
+@pytest.mark.parametrize("case", [
+    (1, 1, 6, 1, "uniform"), (20, 13, 6, 1, "uniform"), (40, 40, 6, 2, "ones"),      # l = 1, 2: generic paths
+    (1500, 1500, 6, 64, "ones"), (3000, 2000, 6, 128, "uniform"),                   # l = 64, 128
+    (6000, 6000, 6, 256, "ones"), (6000, 10, 6, 256, "runs"),                       # l = 256 (cfg2 ring)
+    (12000, 9000, 6, 512, "uniform"), (700, 900, 7, 12, "runs"), (3000, 3000, 7, 96, "ones"),
+])
+def test_emulated_new_mpn_mul(emu, case):
+    n1, n2, depth, w, kind = case
+    a, b = operand(kind, n1, 1), operand(kind, n2, 2)
+    r = np.zeros(n1 + n2, dtype=np.uint64)
+    emu.new_mpn_mul(ptr(r), ptr(a), n1, ptr(b), n2, depth, w)
+    assert np.array_equal(r, L.gmp_mul(a, b))
+
+
+@pytest.mark.parametrize("l", [1, 3, 24, 64, 256])
+def test_emulated_mulmod_adversarial(emu, l):
+    random.seed(l)
+    NW = 64 * l
+    p = (1 << NW) + 1
+    A = [random.getrandbits(NW) for _ in range(3)] + [p - 2, p - 2, p - 1, p - 1, 0, 1, p - 2, (1 << (NW // 2)) - 1]
+    B = [random.getrandbits(NW) for _ in range(3)] + [p - 2, 2, p - 1, 12345, 77, p - 2, 1 << (NW - 1), (1 << (NW // 2)) - 1]
+    a = np.stack([int_to_block(v, l) for v in A])
+    b = np.stack([int_to_block(v, l) for v in B])
+    da, db = emu.mpirfft_malloc_device(a.nbytes), emu.mpirfft_malloc_device(b.nbytes)
+    emu.mpirfft_memcpy_h2d(da, ptr(a), a.nbytes, None)
+    emu.mpirfft_memcpy_h2d(db, ptr(b), b.nbytes, None)
+    assert emu.mpirfft_mulmod_batch_device(da, db, len(A), l, l + 1, None) == 0
+    out = np.empty_like(a)
+    emu.mpirfft_memcpy_d2h(ptr(out), da, a.nbytes, None)
+    for k in range(len(A)):
+        assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), (l, k)
