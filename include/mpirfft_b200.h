@@ -201,6 +201,10 @@ int   mpirfft_stream_sync(void *stream);
 void mpirfft_profile_enable(int on);
 int  mpirfft_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass);
 
+/* Integer multiply-accumulate issue rate of this GPU in MAD/s (the denominator of the pointwise
+ * kernel's roofline): mode 0 IMAD.WIDE.U32, 1 IMAD.WIDE.U32.X carry chains, 2 32-bit IMAD. */
+double mpirfft_measure_imad_rate(int mode);
+
 /* launches issued through the library since the last reset (bench.py's gpu_launches) */
 uint64_t mpirfft_launch_count(void);
 void     mpirfft_launch_count_reset(void);

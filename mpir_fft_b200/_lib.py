@@ -68,6 +68,7 @@ def bind(L):
         "mpirfft_stream_sync": (i32, [vp]),
         "mpirfft_profile_enable": (None, [i32]),
         "mpirfft_profile_read": (i32, [C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(C.c_double), i32]),
+        "mpirfft_measure_imad_rate": (C.c_double, [i32]),
         "mpirfft_launch_count": (u64, []),
         "mpirfft_launch_count_reset": (None, []),
         "new_mpn_mul": (None, [vp, vp, i64, vp, i64, u64, u64]),

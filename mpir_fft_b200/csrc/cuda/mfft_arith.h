@@ -49,21 +49,22 @@ typedef struct {
    uint32_t bs;         /* bit shift 0..63 */
    int      neg;        /* 1: the whole term is subtracted (after folding e >= NW) */
    int      present;
+   uint32_t ps;         /* storage index of limb q is q + (q >> ps): 31 = dense (global memory),
+                           log2(M) = one pad limb per M limbs (bank-conflict-free shared memory) */
    mfft_i128 K;         /* constant to inject at limb y (0 if none) */
 } mfft_term;
 
 /* fold exponent e (mod 2*NW) and sign into (y, bs, neg); returns the term's contributions to
  * the output top limb in *top_acc and the number of "+1 at bit 0" constants in *ones. */
-MFFT_HD void mfft_term_setup(mfft_term *t, const mfft_limb *blk, uint32_t l, int sign, uint64_t e,
-                             int64_t *top_acc, int *ones)
+MFFT_HD void mfft_term_setup2(mfft_term *t, const mfft_limb *blk, int64_t top, uint32_t ps, uint32_t l,
+                              int sign, uint64_t e, int64_t *top_acc, int *ones)
 {
    uint64_t NW = 64ull * l;
-   t->p = blk; t->present = (sign != 0); t->K = 0; t->y = 0; t->bs = 0; t->neg = 0;
+   t->p = blk; t->present = (sign != 0); t->K = 0; t->y = 0; t->bs = 0; t->neg = 0; t->ps = ps;
    if (!sign) return;
    if (e >= NW) { e -= NW; sign = -sign; }
    t->y = (uint32_t)(e >> 6); t->bs = (uint32_t)(e & 63); t->neg = (sign < 0);
    {
-      int64_t top = (int64_t) blk[l];
       if (e == 0)
       {
          if (sign > 0) *top_acc += top;
@@ -77,15 +78,22 @@ MFFT_HD void mfft_term_setup(mfft_term *t, const mfft_limb *blk, uint32_t l, int
    }
 }
 
+/* dense blocks with the top limb stored at blk[l] (global memory layout) */
+MFFT_HD void mfft_term_setup(mfft_term *t, const mfft_limb *blk, uint32_t l, int sign, uint64_t e,
+                             int64_t *top_acc, int *ones)
+{
+   mfft_term_setup2(t, blk, sign ? (int64_t) blk[l] : 0, 31, l, sign, e, top_acc, ones);
+}
+
 /* limb k of the complemented rotation of the term's body */
 MFFT_HD mfft_limb mfft_term_limb(const mfft_term *t, uint32_t l, uint32_t k)
 {
    uint32_t q = (k >= t->y) ? k - t->y : k + l - t->y;
-   mfft_limb v = t->p[q], m;
+   mfft_limb v = t->p[q + (q >> t->ps)], m;
    if (t->bs)
    {
       uint32_t q1 = (q == 0) ? l - 1 : q - 1;
-      v = (v << t->bs) | (t->p[q1] >> (64 - t->bs));
+      v = (v << t->bs) | (t->p[q1 + (q1 >> t->ps)] >> (64 - t->bs));
    }
    m = (k < t->y) ? ~(mfft_limb)0 : ((k == t->y) ? (((mfft_limb)1 << t->bs) - 1) : 0);
    if (t->neg) m = ~m;
@@ -103,21 +111,25 @@ MFFT_HD uint64_t mfft_lookahead(uint32_t G, uint32_t P, uint32_t cin)
 
 /* add the signed 128-bit constant K at limb y of the stored block `out`, rippling upwards;
  * whatever leaves limb l-1 goes into *top. */
-MFFT_HD void mfft_inject(mfft_limb *out, uint32_t l, int64_t *top, uint32_t y, mfft_i128 K)
+MFFT_HD void mfft_inject2(mfft_limb *out, uint32_t ps, uint32_t l, int64_t *top, uint32_t y, mfft_i128 K)
 {
    uint32_t pos = y;
    mfft_limb v, nv; int64_t carry;
    if (K == 0) return;
-   v = out[pos]; nv = v + (mfft_limb) K;
+   v = out[pos + (pos >> ps)]; nv = v + (mfft_limb) K;
    carry = (int64_t)(K >> 64) + (nv < v ? 1 : 0);
-   out[pos] = nv; pos++;
+   out[pos + (pos >> ps)] = nv; pos++;
    while (carry != 0)
    {
       if (pos == l) { *top += carry; return; }
-      v = out[pos]; nv = v + (mfft_limb) carry;
+      v = out[pos + (pos >> ps)]; nv = v + (mfft_limb) carry;
       carry = (carry > 0) ? (nv < v ? 1 : 0) : (nv > v ? -1 : 0);
-      out[pos] = nv; pos++;
+      out[pos + (pos >> ps)] = nv; pos++;
    }
+}
+MFFT_HD void mfft_inject(mfft_limb *out, uint32_t l, int64_t *top, uint32_t y, mfft_i128 K)
+{
+   mfft_inject2(out, 31, l, top, y, K);
 }
 
 #endif

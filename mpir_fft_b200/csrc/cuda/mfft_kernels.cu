@@ -197,6 +197,188 @@ k_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *__restrict__ dst_ba
    if (normalise) normalise_block(out, g.l, lane);
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* fused tile executor: several stages of a transform inside shared memory                     */
+/* ------------------------------------------------------------------------------------------ */
+/* A coefficient of l = 32*M*NT limbs lives in shared memory with one pad limb after every M
+ * limbs (storage index q + q/M): lane j of a warp owns limbs [j*M, j*M+M) of each 32*M-limb
+ * tile, and with the pad the 16 lanes of an LDS.64 phase hit 16 different 8-byte banks.
+ * One warp executes one op: it builds both outputs in registers from the (rotated,
+ * complemented) shared-memory operands, and only then overwrites the operands.             */
+template <int M, int NT>
+__device__ __forceinline__ void lincomb_regs(limb_t *r, int64_t *top_out, mfft_term *ta, mfft_term *tb,
+                                             const limb_t *A, int64_t topA, int sA, uint64_t eA,
+                                             const limb_t *B, int64_t topB, int sB, uint64_t eB,
+                                             uint32_t ps, uint32_t l, uint32_t lane)
+{
+   int64_t top_acc = 0; int ones = 0;
+   mfft_term_setup2(ta, A, topA, ps, l, sA, eA, &top_acc, &ones);
+   mfft_term_setup2(tb, B, topB, ps, l, sB, eB, &top_acc, &ones);
+   uint32_t tc = ones ? 1u : 0u;
+   if (ones == 2) top_acc -= 1;
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t kb = ti * 32u * M + lane * M;
+      uint32_t c = 0; bool ones_all = true;
+#pragma unroll
+      for (int i = 0; i < M; i++)
+      {
+         const uint32_t k = kb + i;
+         const limb_t x = ta->present ? mfft_term_limb(ta, l, k) : 0;
+         const limb_t z = tb->present ? mfft_term_limb(tb, l, k) : 0;
+         const mfft_u128 acc = (mfft_u128) x + z + c;
+         r[ti * M + i] = (limb_t) acc; c = (uint32_t)(acc >> 64);
+         ones_all = ones_all && (r[ti * M + i] == ~(limb_t) 0);
+      }
+      const uint32_t G = __ballot_sync(FULL, c != 0);
+      const uint32_t P = __ballot_sync(FULL, ones_all);
+      const uint64_t la = mfft_lookahead(G, P, tc);
+      uint32_t myc = (uint32_t)(la >> lane) & 1u;
+      tc = (uint32_t)(la >> 32) & 1u;
+#pragma unroll
+      for (int i = 0; i < M; i++)
+      {
+         const limb_t v = r[ti * M + i] + myc;
+         myc = (myc && v == 0) ? 1u : 0u;
+         r[ti * M + i] = v;
+      }
+   }
+   *top_out = top_acc + tc;
+   if (ta->present && tb->present && ta->y == tb->y) { ta->K += tb->K; tb->K = 0; }
+}
+
+template <int M, int NT>
+__device__ __forceinline__ void store_regs(limb_t *out, const limb_t *r, uint32_t ps, uint32_t lane)
+{
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+      for (int i = 0; i < M; i++)
+      {
+         const uint32_t k = ti * 32u * M + lane * M + i;
+         out[k + (k >> ps)] = r[ti * M + i];
+      }
+}
+
+/* warp-level mpn_normmod_2expp1 on a padded shared-memory coefficient with a separate top */
+__device__ __forceinline__ void normalise_sm(limb_t *blk, uint32_t ps, uint32_t l, int64_t *topp, uint32_t lane)
+{
+   for (int it = 0; it < 4; it++)
+   {
+      __syncwarp();
+      const int64_t top = *topp;
+      if (top == 0) break;
+      if (top == 1)
+      {
+         bool z = true;
+         for (uint32_t k = lane; k < l; k += 32) z = z && (blk[k + (k >> ps)] == 0);
+         if (__all_sync(FULL, z)) break;
+      }
+      __syncwarp();
+      if (lane == 0)
+      {
+         int64_t nt = 0;
+         mfft_inject2(blk, ps, l, &nt, 0, -(mfft_i128) top);
+         *topp = nt;
+      }
+   }
+   __syncwarp();
+}
+
+template <int M, int NT>
+__global__ void __launch_bounds__(256)
+k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
+            const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
+            limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
+            uint32_t dst_stride, int normalise)
+{
+   MFFT_DYN_SMEM(limb_t, sm);
+   constexpr uint32_t L = 32u * M * NT;
+   constexpr uint32_t PS = (M == 1) ? 31u : (M == 2 ? 1u : (M == 4 ? 2u : 3u));
+   constexpr uint32_t SP = (M == 1) ? L : L + L / M;          /* shared-memory pitch of a coefficient */
+   const uint32_t bi = blockIdx.x % nbatch;
+   const mfft_tile T = tiles[blockIdx.x / nbatch];
+   const mfft_batch b = batch[bi];
+   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+   int64_t *tops = (int64_t *)(sm + (size_t) T.npos * SP);
+   const uint64_t M2 = 128ull * L;
+
+   /* load the positions that are read before being written */
+   for (uint32_t p = warp; p < T.npos; p += nwarps)
+   {
+      const uint32_t pp = pos[T.pos_off + p];
+      if (!(pp & MFFT_TILE_LOAD)) continue;
+      const limb_t *src = block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
+      limb_t *d = sm + (size_t) p * SP;
+      for (uint32_t k = lane; k < L; k += 32) d[k + (k >> PS)] = src[k];
+      if (lane == 0) tops[p] = (int64_t) src[L];
+   }
+   __syncthreads();
+
+   uint32_t o0 = 0;
+   for (uint32_t st = 0; st < T.nstages; st++)
+   {
+      uint32_t o1 = o0;
+      while (o1 < T.nops && ops[T.op_off + o1].lstage == st) o1++;
+      for (uint32_t oi = o0 + warp; oi < o1; oi += nwarps)
+      {
+         const mfft_tileop op = ops[T.op_off + oi];
+         const limb_t *A = sm + (size_t) op.a * SP;
+         const limb_t *B = (op.b != 0xFFFF) ? sm + (size_t) op.b * SP : A;
+         const int64_t topA = tops[op.a], topB = (op.b != 0xFFFF) ? tops[op.b] : 0;
+         limb_t rs[M * NT], rt[M * NT];
+         int64_t topS = 0, topT = 0;
+         mfft_term sa, sb, ta, tb;
+         lincomb_regs<M, NT>(rs, &topS, &sa, &sb, A, topA, op.sSA, (op.eSA + (uint64_t) b.col * op.cSA) % M2,
+                             B, topB, op.sSB, (op.eSB + (uint64_t) b.col * op.cSB) % M2, PS, L, lane);
+         const bool hasT = (op.t != 0xFFFF);
+         if (hasT)
+            lincomb_regs<M, NT>(rt, &topT, &ta, &tb, A, topA, op.sTA, (op.eTA + (uint64_t) b.col * op.cTA) % M2,
+                                B, topB, op.sTB, (op.eTB + (uint64_t) b.col * op.cTB) % M2, PS, L, lane);
+         __syncwarp();                      /* every lane has read the operands */
+         limb_t *S = sm + (size_t) op.s * SP;
+         store_regs<M, NT>(S, rs, PS, lane);
+         limb_t *Tt = hasT ? sm + (size_t) op.t * SP : S;
+         if (hasT) store_regs<M, NT>(Tt, rt, PS, lane);
+         __syncwarp();
+         if (lane == 0)
+         {
+            if (sa.present) mfft_inject2(S, PS, L, &topS, sa.y, sa.K);
+            if (sb.present) mfft_inject2(S, PS, L, &topS, sb.y, sb.K);
+            tops[op.s] = topS;
+            if (hasT)
+            {
+               if (ta.present) mfft_inject2(Tt, PS, L, &topT, ta.y, ta.K);
+               if (tb.present) mfft_inject2(Tt, PS, L, &topT, tb.y, tb.K);
+               tops[op.t] = topT;
+            }
+         }
+      }
+      o0 = o1;
+      __syncthreads();
+   }
+
+   /* store what was written: in place, or gathered (and normalised) into dst */
+   for (uint32_t p = warp; p < T.npos; p += nwarps)
+   {
+      const uint32_t pp = pos[T.pos_off + p];
+      if (!(pp & MFFT_TILE_STORE)) continue;
+      limb_t *out;
+      if (dst)
+      {
+         const uint32_t dp = dstpos[pp & MFFT_TILE_POSMASK];
+         if (dp == MFFT_NONE) continue;
+         out = dst + ((uint64_t) dst_base[bi] + (uint64_t) dp * dst_stride) * g.pitch;
+      } else out = block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
+      limb_t *sblk = sm + (size_t) p * SP;
+      if (normalise) normalise_sm(sblk, PS, L, &tops[p], lane);
+      for (uint32_t k = lane; k < L; k += 32) out[k] = sblk[k + (k >> PS)];
+      if (lane == 0) out[L] = (limb_t) tops[p];
+   }
+}
+
 __global__ void __launch_bounds__(128)
 k_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk)
 {
@@ -572,6 +754,10 @@ k_combine_fix(limb_t *res, uint64_t total, const uint32_t *__restrict__ tileC, u
 /* ------------------------------------------------------------------------------------------ */
 extern "C" {
 
+#ifdef MFFT_EMU
+double mfft_dev_imad_rate(int) { return -1.0; }     /* the microbenchmark lives in imad_peak.cu */
+#endif
+
 const char *mfft_dev_last_error(void) { return g_err; }
 
 void mfft_dev_profile_enable(int on) { g_prof_on = on; }
@@ -668,6 +854,68 @@ int mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, u
    case 2: MFFT_LAUNCH(k_run_stage<2>, grid, 128, 0, st, slab, *g, d_ops, count, d_batch, nbatch); break;
    default: MFFT_LAUNCH(k_run_stage<1>, grid, 128, 0, st, slab, *g, d_ops, count, d_batch, nbatch); break;
    }
+   CKL();
+   return 0;
+}
+
+
+static int tiles_cfg(uint32_t l, int *M, int *NT)
+{
+   switch (l)
+   {
+   case 64:  *M = 2; *NT = 1; return 1;
+   case 128: *M = 4; *NT = 1; return 1;
+   case 192: *M = 2; *NT = 3; return 1;
+   case 256: *M = 8; *NT = 1; return 1;
+   case 384: *M = 4; *NT = 3; return 1;
+   case 512: *M = 8; *NT = 2; return 1;
+   default: return 0;
+   }
+}
+
+int mfft_dev_tiles_supported(uint32_t l) { int m, nt; return tiles_cfg(l, &m, &nt); }
+
+static size_t tiles_coeff_bytes(uint32_t l)
+{
+   int m = 1, nt = 1; tiles_cfg(l, &m, &nt);
+   return ((size_t) l + l / m) * 8 + 8;
+}
+
+uint32_t mfft_dev_tiles_max_npos(uint32_t l)
+{
+   if (!mfft_dev_tiles_supported(l)) return 0;
+   size_t n = (96 * 1024) / tiles_coeff_bytes(l);
+   uint32_t p = 4;
+   while (p * 2 <= n && p * 2 <= 128) p *= 2;
+   return p;
+}
+
+int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tiles, uint32_t ntiles,
+                       const uint32_t *d_pos, const mfft_tileop *d_ops, uint32_t max_npos,
+                       const mfft_batch *d_batch, uint32_t nbatch,
+                       limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
+                       uint32_t dst_stride, int normalise, void *stream)
+{
+   int M = 0, NT = 0;
+   if (!ntiles || !nbatch) return 0;
+   if (!tiles_cfg(g->l, &M, &NT)) { snprintf(g_err, sizeof g_err, "run_tiles: l=%u unsupported", g->l); return -2; }
+   const size_t smem = (size_t) max_npos * tiles_coeff_bytes(g->l);
+   const unsigned grid = ntiles * nbatch;
+   cudaStream_t st = (cudaStream_t) stream;
+   PROF(PC_STAGE, st);
+#define RUN_TILES(MM, NN)                                                                          \
+   do {                                                                                            \
+      CK(cudaFuncSetAttribute(k_run_tiles<MM, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+      MFFT_LAUNCH((k_run_tiles<MM, NN>), grid, 256, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
+                  dst, d_dstpos, d_dst_base, dst_stride, normalise);                                \
+   } while (0)
+   if (M == 2 && NT == 1) RUN_TILES(2, 1);
+   else if (M == 4 && NT == 1) RUN_TILES(4, 1);
+   else if (M == 2 && NT == 3) RUN_TILES(2, 3);
+   else if (M == 8 && NT == 1) RUN_TILES(8, 1);
+   else if (M == 4 && NT == 3) RUN_TILES(4, 3);
+   else RUN_TILES(8, 2);
+#undef RUN_TILES
    CKL();
    return 0;
 }

@@ -164,7 +164,7 @@ static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, m
    check_ring(fn, n, w);
    mfft_lock();
    mfft_require_device(fn);
-   rc = mfft_mfa_build(&m, inverse, (uint64_t) n, w, (uint64_t) n1, truncated ? (uint64_t) trunc : 0);
+   rc = mfft_mfa_build(&m, inverse, (uint64_t) n, w, (uint64_t) n1, truncated ? (uint64_t) trunc : 0, 0, truncated);
    if (rc != 0) mfft_die(fn, "illegal MFA parameters n=%ld w=%lu n1=%ld trunc=%ld (code %d; trunc must be a multiple "
                          "of 2*n1, mul_fft.c:2209-2211)", (long) n, (unsigned long) w, (long) n1, (long) trunc, rc);
    N = m.N; pitch = m.pitch; half = (size_t) N*pitch*sizeof(limb_t);
@@ -174,7 +174,7 @@ static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, m
    for (k = 0; k < N; k++) memcpy(stage + k*pitch, ii[k], pitch*sizeof(limb_t));
    if (mfft_dev_h2d(d_slab, stage, half, NULL) ||
        mfft_dev_h2d(d_dst, stage, half, NULL) ||          /* rows the transform does not produce keep their input */
-       mfft_mfa_exec(&m, d_slab, d_dst, 0, truncated, NULL) ||
+       mfft_mfa_exec(&m, d_slab, d_dst, NULL) ||
        mfft_dev_d2h(stage, d_dst, half, NULL) || mfft_dev_sync(NULL))
       mfft_die(fn, "device execution failed: %s", mfft_dev_last_error());
    if (!inverse)

@@ -88,8 +88,10 @@ int mpirfft_mul_plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, 
    if ((rc = mfft_try_device()) != 0) goto fail;
    pl->l = (uint32_t) pl->p.limbs; pl->pitch = pl->l + 1;
    N = 2*pl->p.n;
-   if ((rc = mfft_mfa_build(&pl->fwd, 0, pl->p.n, w, pl->p.sqrt, pl->p.trunc)) != 0) goto fail;
-   if ((rc = mfft_mfa_build(&pl->inv, 1, pl->p.n, w, pl->p.sqrt, pl->p.trunc)) != 0) goto fail;
+   if ((rc = mfft_mfa_build(&pl->fwd, 0, pl->p.n, w, pl->p.sqrt, pl->p.trunc, 0, 1)) != 0) goto fail;
+   /* the inverse is unscaled: fold / 2^(depth+1) and the normalisation into its last pass (3256-3260) */
+   if ((rc = mfft_mfa_build(&pl->inv, 1, pl->p.n, w, pl->p.sqrt, pl->p.trunc,
+                            (uint32_t)(128ull*pl->l - (depth + 1)), 1)) != 0) goto fail;
    half = (size_t) N * pl->pitch * sizeof(limb_t);
    rc = MPIRFFT_ENOMEM;
    pl->X = (limb_t *) mfft_dev_alloc(2*half);
@@ -135,21 +137,18 @@ int mpirfft_mul_exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, cons
    {
    case 0:
       if (mfft_dev_split(pl->X, pl->l, pl->pitch, (const limb_t *) d_i1, (uint64_t) pl->n1, p->bits1, p->j1, p->trunc, stream)) return MPIRFFT_ENODEV;
-      rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Z, 0, 1, stream);
+      rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Z, stream);
       break;
    case 1:
       if (mfft_dev_split(pl->X, pl->l, pl->pitch, (const limb_t *) d_i2, (uint64_t) pl->n2, p->bits1, p->j2, p->trunc, stream)) return MPIRFFT_ENODEV;
-      rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Y, 0, 1, stream);
+      rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Y, stream);
       break;
    case 2:
       if (mfft_dev_pointwise(pl->Z, pl->Y, pl->d_pw_blocks, pl->npw, pl->l, pl->pitch, stream)) return MPIRFFT_ENODEV;
       break;
    case 3:
-   {  /* unscaled inverse, then / 2^(depth+1) and normalise fused into the finalize (3256-3260) */
-      uint64_t M2 = 128ull * pl->l;
-      rc = mfft_mfa_exec(&pl->inv, pl->Z, pl->X, (uint32_t)(M2 - (pl->depth + 1)), 1, stream);
+      rc = mfft_mfa_exec(&pl->inv, pl->Z, pl->X, stream);
       break;
-   }
    case 4:
       if (mfft_dev_combine((limb_t *) d_r, (uint64_t)(pl->n1 + pl->n2), pl->X, pl->l, pl->pitch, p->bits1,
                            p->j1 + p->j2 - 1, pl->combine_work, stream)) return MPIRFFT_ENODEV;

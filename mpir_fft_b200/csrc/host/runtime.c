@@ -55,6 +55,9 @@ int mpirfft_init(int device)
 int mpirfft_device_count(void) { return mfft_dev_count(); }
 const char *mpirfft_last_error(void) { return mfft_dev_last_error(); }
 const char *mpirfft_version(void) { return "mpirfft_b200 0.1 (sm_100a)"; }
+double mfft_dev_imad_rate(int mode);
+double mpirfft_measure_imad_rate(int mode) { return mfft_try_device() ? -1.0 : mfft_dev_imad_rate(mode); }
+
 void mpirfft_profile_enable(int on) { mfft_dev_profile_enable(on); }
 int  mpirfft_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass)
 { return mfft_dev_profile_read(ms, launches, bytes, nclass) ? MPIRFFT_ENODEV : 0; }
@@ -112,6 +115,14 @@ int mfft_dsched_run(const mfft_dsched *ds, limb_t *slab, const mfft_geom *g,
 
 static uint32_t ilog2(uint64_t x) { uint32_t b = 0; while (((uint64_t)1 << b) < x) b++; return b; }
 
+static void dpass_free(struct mfft_dpass *d, uint32_t n)
+{
+   uint32_t i;
+   if (!d) return;
+   for (i = 0; i < n; i++) { mfft_dev_free(d[i].d_tiles); mfft_dev_free(d[i].d_pos); mfft_dev_free(d[i].d_ops); }
+   free(d);
+}
+
 void mfft_mfa_free(mfft_mfa *m)
 {
    if (m->col.s) m->h_col = NULL;     /* ownership moved to the uploaded schedule */
@@ -119,16 +130,22 @@ void mfft_mfa_free(mfft_mfa *m)
    mfft_dsched_free(&m->col); mfft_dsched_free(&m->row);
    if (m->h_col) mfft_sched_free(m->h_col);
    if (m->h_row) mfft_sched_free(m->h_row);
+   dpass_free(m->dcol, m->pcol.npasses); dpass_free(m->drow, m->prow.npasses);
+   mfft_passes_free(&m->pcol); mfft_passes_free(&m->prow);
    mfft_dev_free(m->d_colb); mfft_dev_free(m->d_rowb); mfft_dev_free(m->d_moves); mfft_dev_free(m->d_dst_base);
+   mfft_dev_free(m->d_dstpos);
    free(m->rows); free(m->h_colb); free(m->h_rowb); free(m->h_moves); free(m->h_dst_base);
+   free(m->h_must_store); free(m->h_dstpos);
    memset(m, 0, sizeof(*m));
 }
 
-int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc)
+int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
+                  uint32_t final_shift, int normalise, int mode)
 {
    uint64_t NW = n*w, n2, i, j;
-   mfft_sched *cs, *rs; mfft_batch *colb, *rowb; mfft_move *mv; uint32_t *dstb;
+   mfft_sched *cs, *rs, *last; mfft_batch *colb, *rowb; mfft_move *mv; uint32_t *dstb;
    int rc = MPIRFFT_EINVAL;
+   const char *env = getenv("MPIRFFT_UNFUSED");
 
    memset(m, 0, sizeof(*m));
    if (n == 0 || (n & (n - 1)) || w == 0 || (NW % 64) || n1 < 2 || (n1 & (n1 - 1)) || n1 > n) return MPIRFFT_EINVAL;
@@ -138,6 +155,8 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
    m->n = n; m->w = w; m->n1 = n1; m->n2 = n2; m->N = 2*n;
    m->l = (uint32_t)(NW/64); m->pitch = m->l + 1;
    m->depth1 = ilog2(n2); m->depth2 = ilog2(n1);
+   m->final_shift = (uint32_t)(final_shift % (2*NW)); m->normalise = normalise;
+   m->fused = (mode == 0) && mfft_dev_tiles_supported(m->l) && !(env && env[0] == '1');
    if (trunc)
    {  /* trunc must be a multiple of 2*n1 (mul_fft.c:2209-2211, 3200) */
       if (trunc % (2*n1) || trunc > 2*n) return MPIRFFT_EINVAL;
@@ -170,8 +189,8 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
       if (mfft_sched_emit(rs, MFFT_T_FFT, 0, 1, n1/2, w*n2, 0, 0, 0, 0) != 0) goto fail;
       mfft_sched_revbin(rs, 0, 1, m->depth2);
       for (i = 0; i < m->nrows; i++)
-      {
-         uint32_t slot = cs->slot[m->rows[i]];
+      {  /* where the column pass left logical row rows[i]: slot (ping-pong) or physical row (fused) */
+         uint32_t slot = m->fused ? cs->phys[m->rows[i]] : cs->slot[m->rows[i]];
          rowb[i].base = (uint32_t)((slot % n2) * n1); rowb[i].parity = (uint32_t)(slot / n2); rowb[i].col = 0;
       }
       /* finalize: logical (row i, col j) -> dst block i*n1 + j */
@@ -182,6 +201,7 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
       for (j = 0; j < n1; j++) { mv[j].src_slot = rs->slot[j]; mv[j].dst_pos = (uint32_t) j; }
       for (i = 0; i < m->nrows; i++) dstb[i] = (uint32_t)(m->rows[i] * n1);
       m->dst_stride = 1;
+      last = rs;
    } else
    {
       /* in-row relabel then row IFFTs on the valid rows (2942-2956) */
@@ -193,7 +213,7 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
       if (mfft_sched_emit(cs, trunc ? MFFT_T_IFFT_TRUNC : MFFT_T_IFFT, 0, 1, n2/2, w*n1, w, 0, 1, m->trunc_rows) != 0) goto fail;
       for (j = 0; j < n1; j++)
       {
-         uint32_t slot = rs->slot[j];
+         uint32_t slot = m->fused ? rs->phys[j] : rs->slot[j];
          colb[j].base = (uint32_t)(slot % n1); colb[j].parity = (uint32_t)(slot / n1); colb[j].col = (uint32_t) j;
       }
       /* finalize: logical (row r < trunc_rows, col j) -> dst block r*n1 + j */
@@ -204,12 +224,45 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
       for (i = 0; i < m->nmoves; i++) { mv[i].src_slot = cs->slot[i]; mv[i].dst_pos = (uint32_t) i; }
       for (j = 0; j < n1; j++) dstb[j] = (uint32_t) j;
       m->dst_stride = (uint32_t) n1;
+      last = cs;
+   }
+   if (m->fused)
+   {  /* the last schedule's final pass gathers the logical outputs into dst; a final scaling is
+         one more in-place op per output */
+      uint32_t nout = m->nmoves, S = last->S, k;
+      uint32_t pmax = mfft_dev_tiles_max_npos(m->l);
+      m->h_must_store = (uint8_t *) calloc(S, 1);
+      m->h_dstpos = (uint32_t *) malloc(sizeof(uint32_t) * S);
+      if (!m->h_must_store || !m->h_dstpos) { rc = MPIRFFT_ENOMEM; goto fail; }
+      for (k = 0; k < S; k++) m->h_dstpos[k] = MFFT_NONE;
+      if (m->final_shift)
+         for (k = 0; k < nout; k++)
+            mfft_sched_emit_op(last, k, MFFT_NONE, k, 1, m->final_shift, 0, 0, MFFT_NONE, 0, 0, 0, 0);
+      for (k = 0; k < nout; k++) { m->h_must_store[last->phys[k]] = 1; m->h_dstpos[last->phys[k]] = k; }
+      if (mfft_passes_build(&m->pcol, cs, pmax, last == cs ? m->h_must_store : NULL) != 0 ||
+          mfft_passes_build(&m->prow, rs, pmax, last == rs ? m->h_must_store : NULL) != 0) { rc = MPIRFFT_ENOMEM; goto fail; }
    }
    if (mfft_sched_finish(cs) != 0 || mfft_sched_finish(rs) != 0) { rc = MPIRFFT_ENOMEM; goto fail; }
    return 0;
 fail:
    mfft_mfa_free(m);
    return rc;
+}
+
+static struct mfft_dpass *dpass_upload(const mfft_passes *P)
+{
+   uint32_t i;
+   struct mfft_dpass *d = (struct mfft_dpass *) calloc(P->npasses ? P->npasses : 1, sizeof(*d));
+   if (!d) return NULL;
+   for (i = 0; i < P->npasses; i++)
+   {
+      const mfft_pass *p = &P->pass[i];
+      d[i].d_tiles = (mfft_tile *) mfft_upload(p->tiles, sizeof(mfft_tile) * (p->ntiles ? p->ntiles : 1));
+      d[i].d_pos = (uint32_t *) mfft_upload(p->pos, sizeof(uint32_t) * (p->npos_total ? p->npos_total : 1));
+      d[i].d_ops = (mfft_tileop *) mfft_upload(p->ops, sizeof(mfft_tileop) * (p->nops_total ? p->nops_total : 1));
+      if (!d[i].d_tiles || !d[i].d_pos || !d[i].d_ops) { dpass_free(d, P->npasses); return NULL; }
+   }
+   return d;
 }
 
 int mfft_mfa_upload(mfft_mfa *m)
@@ -221,12 +274,20 @@ int mfft_mfa_upload(mfft_mfa *m)
    m->d_moves = (mfft_move *) mfft_upload(m->h_moves, sizeof(mfft_move) * m->nmoves);
    m->d_dst_base = (uint32_t *) mfft_upload(m->h_dst_base, sizeof(uint32_t) * m->ndst);
    if (!m->d_colb || !m->d_rowb || !m->d_moves || !m->d_dst_base) return MPIRFFT_ENODEV;
+   if (m->fused)
+   {
+      uint32_t S = m->inverse ? m->gcol.S : m->grow.S;
+      m->dcol = dpass_upload(&m->pcol); m->drow = dpass_upload(&m->prow);
+      m->d_dstpos = (uint32_t *) mfft_upload(m->h_dstpos, sizeof(uint32_t) * S);
+      if (!m->dcol || !m->drow || !m->d_dstpos) return MPIRFFT_ENODEV;
+   }
    return 0;
 }
 
-int mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc)
+int mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
+                   uint32_t final_shift, int normalise)
 {
-   int rc = mfft_mfa_plan(m, inverse, n, w, n1, trunc);
+   int rc = mfft_mfa_plan(m, inverse, n, w, n1, trunc, final_shift, normalise, 0);
    if (rc != 0) return rc;
    if ((rc = mfft_mfa_upload(m)) != 0) { mfft_mfa_free(m); return rc; }
    return 0;
@@ -236,7 +297,7 @@ int mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1
 mfft_mfa *mfft_mfa_debug_new(int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc)
 {
    mfft_mfa *m = (mfft_mfa *) calloc(1, sizeof(*m));
-   if (m && mfft_mfa_plan(m, inverse, n, w, n1, trunc) != 0) { free(m); return NULL; }
+   if (m && mfft_mfa_plan(m, inverse, n, w, n1, trunc, 0, 0, 1) != 0) { free(m); return NULL; }
    return m;
 }
 void mfft_mfa_debug_free(mfft_mfa *m) { if (m) { mfft_mfa_free(m); free(m); } }
@@ -248,26 +309,62 @@ mfft_move *mfft_mfa_debug_moves(mfft_mfa *m, uint32_t *count, uint32_t *dst_stri
 uint32_t *mfft_mfa_debug_dst_base(mfft_mfa *m, uint32_t *count) { *count = m->ndst; return m->h_dst_base; }
 uint32_t *mfft_mfa_debug_rows(mfft_mfa *m, uint32_t *count) { *count = m->nrows; return m->rows; }
 
-int mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, uint32_t shift, int normalise, void *stream)
+/* algorithmic traffic of a fused pass: every position of every tile is read and/or written once */
+static double pass_bytes(const mfft_pass *p, uint32_t nbatch, uint32_t l)
+{
+   double blocks = 0; uint32_t i;
+   for (i = 0; i < p->npos_total; i++)
+      blocks += ((p->pos[i] & MFFT_TILE_LOAD) ? 1 : 0) + ((p->pos[i] & MFFT_TILE_STORE) ? 1 : 0);
+   return blocks * nbatch * 8.0 * (l + 1);
+}
+
+static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft_dpass *d, limb_t *slab,
+                      const mfft_geom *g, const mfft_batch *d_batch, uint32_t nbatch, limb_t *dst, void *stream)
+{
+   uint32_t i;
+   for (i = 0; i < P->npasses; i++)
+   {
+      const mfft_pass *p = &P->pass[i];
+      const int lastp = (i + 1 == P->npasses) && dst != NULL;
+      mfft_dev_profile_bytes(pass_bytes(p, nbatch, g->l));
+      if (mfft_dev_run_tiles(slab, g, d[i].d_tiles, p->ntiles, d[i].d_pos, d[i].d_ops, p->max_npos, d_batch, nbatch,
+                             lastp ? dst : NULL, m->d_dstpos, m->d_dst_base, m->dst_stride,
+                             lastp ? m->normalise : 0, stream) != 0) return MPIRFFT_ENODEV;
+   }
+   return 0;
+}
+
+int mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, void *stream)
 {
    int rc;
+   if (m->fused)
+   {
+      if (!m->inverse)
+      {
+         if ((rc = run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->ncolb, NULL, stream)) != 0) return rc;
+         return run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->nrowb, dst, stream);
+      }
+      if ((rc = run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->nrowb, NULL, stream)) != 0) return rc;
+      return run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->ncolb, dst, stream);
+   }
    if (!m->inverse)
    {
       if ((rc = mfft_dsched_run(&m->col, slab, &m->gcol, m->d_colb, m->ncolb, stream)) != 0) return rc;
       if ((rc = mfft_dsched_run(&m->row, slab, &m->grow, m->d_rowb, m->nrowb, stream)) != 0) return rc;
       if (mfft_dev_finalize(dst, m->dst_stride, m->d_dst_base, slab, &m->grow, m->d_moves, m->nmoves,
-                            m->d_rowb, m->nrowb, shift, normalise, stream) != 0) return MPIRFFT_ENODEV;
+                            m->d_rowb, m->nrowb, m->final_shift, m->normalise, stream) != 0) return MPIRFFT_ENODEV;
    } else
    {
       if ((rc = mfft_dsched_run(&m->row, slab, &m->grow, m->d_rowb, m->nrowb, stream)) != 0) return rc;
       if ((rc = mfft_dsched_run(&m->col, slab, &m->gcol, m->d_colb, m->ncolb, stream)) != 0) return rc;
       if (mfft_dev_finalize(dst, m->dst_stride, m->d_dst_base, slab, &m->gcol, m->d_moves, m->nmoves,
-                            m->d_colb, m->ncolb, shift, normalise, stream) != 0) return MPIRFFT_ENODEV;
+                            m->d_colb, m->ncolb, m->final_shift, m->normalise, stream) != 0) return MPIRFFT_ENODEV;
    }
    return 0;
 }
 
 uint64_t mfft_mfa_launches(const mfft_mfa *m)
 {
+   if (m->fused) return (uint64_t) m->pcol.npasses + m->prow.npasses;
    return (uint64_t) m->col.s->nstages + m->row.s->nstages + 1;
 }

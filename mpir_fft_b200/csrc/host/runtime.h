@@ -4,6 +4,7 @@
 
 #include "../mfft_internal.h"
 #include "sched.h"
+#include "tile.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -44,6 +45,11 @@ typedef struct {
    mfft_geom   gcol, grow;
    uint32_t   *rows;                           /* [nrows] logical valid rows, host */
    uint32_t    nrows;
+   /* fused mode: the passes of each schedule, uploaded (tile.c / k_run_tiles) */
+   int fused; uint32_t final_shift; int normalise;
+   mfft_passes pcol, prow;
+   struct mfft_dpass { mfft_tile *d_tiles; uint32_t *d_pos; mfft_tileop *d_ops; } *dcol, *drow;
+   uint32_t *d_dstpos; uint8_t *h_must_store; uint32_t *h_dstpos;
    /* host copies of the tables (kept for the CPU-side schedule tests) */
    mfft_sched *h_col, *h_row;                  /* owned by col/row once uploaded */
    mfft_batch *h_colb, *h_rowb; mfft_move *h_moves; uint32_t *h_dst_base; uint32_t ndst;
@@ -52,15 +58,17 @@ typedef struct {
 /* trunc = 0: untruncated.  Returns 0 or a negative MPIRFFT_* code.
  * mfft_mfa_plan builds the schedules and tables on the host only (no device needed);
  * mfft_mfa_upload copies them to the device; mfft_mfa_build does both. */
-int  mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc);
+/* final_shift: extra factor 2^final_shift (bit exponent mod 2NW) on every output; normalise:
+ * outputs in canonical form.  mode: 0 = fused shared-memory passes when the coefficient size
+ * allows (MPIRFFT_UNFUSED=1 in the environment overrides), 1 = one launch per radix-2 stage. */
+int  mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
+                   uint32_t final_shift, int normalise, int mode);
 int  mfft_mfa_upload(mfft_mfa *m);
-int  mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc);
+int  mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
+                    uint32_t final_shift, int normalise);
 void mfft_mfa_free(mfft_mfa *m);
-/* slab: 2N blocks, input in half 0 in reference order (ii[k] = block k); dst: N blocks.
- * shift: extra factor 2^shift (bit exponent mod 2NW) applied in the finalize step;
- * normalise: reduce outputs to canonical form. */
-int  mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, uint32_t shift, int normalise,
-                   void *stream);
+/* slab: 2N blocks, input in half 0 in reference order (ii[k] = block k); dst: N blocks */
+int  mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, void *stream);
 uint64_t mfft_mfa_launches(const mfft_mfa *m);
 
 #ifdef __cplusplus

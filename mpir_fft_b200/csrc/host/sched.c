@@ -35,20 +35,26 @@ mfft_sched *mfft_sched_new(uint32_t S, uint64_t NW)
    s->wr_stage = (uint32_t *) calloc(2*(size_t)S, sizeof(uint32_t));
    s->rd_stage = (uint32_t *) calloc(2*(size_t)S, sizeof(uint32_t));
    s->cap = 1024; s->ops = (mfft_op *) malloc(sizeof(mfft_op) * s->cap);
-   if (!s->slot || !s->wr_stage || !s->rd_stage || !s->ops) { mfft_sched_free(s); return NULL; }
-   for (i = 0; i < S; i++) s->slot[i] = i;
+   s->phys = (uint32_t *) malloc(sizeof(uint32_t) * S);
+   s->pwr_stage = (uint32_t *) calloc((size_t) S, sizeof(uint32_t));
+   s->prd_stage = (uint32_t *) calloc((size_t) S, sizeof(uint32_t));
+   if (!s->slot || !s->wr_stage || !s->rd_stage || !s->ops || !s->phys || !s->pwr_stage || !s->prd_stage)
+   { mfft_sched_free(s); return NULL; }
+   for (i = 0; i < S; i++) { s->slot[i] = i; s->phys[i] = i; }
    return s;
 }
 
 void mfft_sched_free(mfft_sched *s)
 {
    if (!s) return;
-   free(s->slot); free(s->wr_stage); free(s->rd_stage); free(s->ops); free(s->stage_off); free(s);
+   free(s->slot); free(s->wr_stage); free(s->rd_stage); free(s->ops); free(s->stage_off);
+   free(s->phys); free(s->pwr_stage); free(s->prd_stage); free(s);
 }
 
 void mfft_sched_swap(mfft_sched *s, uint32_t a, uint32_t b)
 {
    uint32_t t = s->slot[a]; s->slot[a] = s->slot[b]; s->slot[b] = t;
+   t = s->phys[a]; s->phys[a] = s->phys[b]; s->phys[b] = t;
 }
 
 void mfft_sched_revbin(mfft_sched *s, uint32_t p0, uint32_t is, uint32_t bits)
@@ -102,6 +108,25 @@ static void emit(mfft_sched *s, uint32_t posA, uint32_t posB, uint32_t pS, term 
    if (op->inB != MFFT_NONE) s->rd_stage[op->inB] = umax(s->rd_stage[op->inB], st);
    s->wr_stage[op->outS] = st; s->slot[pS] = op->outS;
    if (op->outT != MFFT_NONE) { s->wr_stage[op->outT] = st; s->slot[pT] = op->outT; }
+
+   /* in-place view: an op reads physical pA/pB completely, then overwrites pS/pT */
+   op->pA = s->phys[posA]; op->pB = (posB == MFFT_NONE) ? MFFT_NONE : s->phys[posB];
+   op->pS = s->phys[pS];   op->pT = (pT == MFFT_NONE) ? MFFT_NONE : s->phys[pT];
+   st = s->pwr_stage[op->pA];
+   if (op->pB != MFFT_NONE) st = umax(st, s->pwr_stage[op->pB]);
+   st = umax(st, umax(s->pwr_stage[op->pS], (op->pS == op->pA || op->pS == op->pB) ? 0 : s->prd_stage[op->pS]));
+   if (op->pS == op->pA || op->pS == op->pB)
+   {  /* overwriting an own input: other readers of that position must be done */
+      st = umax(st, s->prd_stage[op->pS]);
+   }
+   if (op->pT != MFFT_NONE) st = umax(st, umax(s->pwr_stage[op->pT], s->prd_stage[op->pT]));
+   st += 1;
+   op->pstage = st;
+   s->prd_stage[op->pA] = umax(s->prd_stage[op->pA], st);
+   if (op->pB != MFFT_NONE) s->prd_stage[op->pB] = umax(s->prd_stage[op->pB], st);
+   s->pwr_stage[op->pS] = st;
+   if (op->pT != MFFT_NONE) s->pwr_stage[op->pT] = st;
+   if (st > s->npstages) s->npstages = st;
 }
 
 void mfft_sched_emit_op(mfft_sched *s, uint32_t posA, uint32_t posB,

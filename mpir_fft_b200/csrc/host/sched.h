@@ -20,6 +20,11 @@ typedef struct {
    size_t    nops, cap;
    uint32_t  nstages;    /* valid after finish; stages are numbered 1..nstages */
    uint32_t *stage_off;  /* [nstages+1] offsets into ops (after finish) */
+   /* position-based view (fused executor): phys[k] = physical position holding logical k */
+   uint32_t *phys;       /* [S] */
+   uint32_t *pwr_stage;  /* [S] last pstage that wrote the physical position */
+   uint32_t *prd_stage;  /* [S] last pstage that read it */
+   uint32_t  npstages;
 } mfft_sched;
 
 typedef enum {

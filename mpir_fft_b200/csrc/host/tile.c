@@ -1,0 +1,203 @@
+/* tile.c -- partition a schedule into fused passes for the shared-memory tile executor.
+ *
+ * The reference's MFA exists for cache locality (README:74-91): sub-transforms of ~sqrt(2n)
+ * coefficients fit the cache.  On B200 the same idea one level down: a window of consecutive
+ * stages is cut into connected components of positions (the radix-2^k sub-transforms, or the
+ * irregular pieces of the truncated variants); components are packed into tiles of at most
+ * `max_npos` coefficients, and one CTA runs ALL the stages of a tile inside shared memory, so a
+ * pass costs one read and one write of the live slab instead of one per radix-2 layer.
+ *
+ * The input is the position-based view of the schedule (mfft_op.pA/pB/pS/pT/pstage): ops work in
+ * place on physical blocks of slab half 0, so passes need no ping-pong.
+ */
+#include "tile.h"
+#include <stdlib.h>
+#include <string.h>
+
+static uint32_t uf_find(uint32_t *par, uint32_t x)
+{
+   while (par[x] != x) { par[x] = par[par[x]]; x = par[x]; }
+   return x;
+}
+
+/* union; returns the size of the merged component */
+static uint32_t uf_union(uint32_t *par, uint32_t *sz, uint32_t a, uint32_t b)
+{
+   a = uf_find(par, a); b = uf_find(par, b);
+   if (a == b) return sz[a];
+   if (sz[a] < sz[b]) { uint32_t t = a; a = b; b = t; }
+   par[b] = a; sz[a] += sz[b];
+   return sz[a];
+}
+
+static int cmp_pstage(const void *x, const void *y)
+{
+   const mfft_op *a = (const mfft_op *) x, *b = (const mfft_op *) y;
+   if (a->pstage != b->pstage) return a->pstage < b->pstage ? -1 : 1;
+   return 0;
+}
+
+void mfft_passes_free(mfft_passes *P)
+{
+   uint32_t i;
+   if (!P) return;
+   for (i = 0; i < P->npasses; i++)
+   {
+      free(P->pass[i].tiles); free(P->pass[i].pos); free(P->pass[i].ops);
+   }
+   free(P->pass);
+   memset(P, 0, sizeof(*P));
+}
+
+/* build one pass from ops[lo..hi) (sorted by pstage; window = stages s0..s1) */
+static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, uint32_t S,
+                      uint32_t s0, uint32_t max_npos, const uint32_t *par_in, uint32_t *scratch,
+                      const uint8_t *must_store)
+{
+   /* scratch: 6*S uint32: root->tile map, first-access kind, written flag, local index, order */
+   uint32_t *root_tile = scratch, *first = scratch + S, *written = scratch + 2*S, *local = scratch + 3*S;
+   uint32_t *tile_fill = scratch + 4*S, *par = scratch + 5*S;
+   uint32_t ntiles = 0, p; size_t k;
+   uint32_t *tile_npos, *tile_nops, *pos_cursor, *op_cursor;
+
+   memcpy(par, par_in, sizeof(uint32_t) * S);
+   for (p = 0; p < S; p++) { root_tile[p] = MFFT_NONE; first[p] = 0; written[p] = 0; local[p] = MFFT_NONE; }
+
+   /* first access kind per position: 1 = read first (needs load), 2 = written first */
+   for (k = lo; k < hi; k++)
+   {
+      const mfft_op *o = &ops[k];
+      if (!first[o->pA]) first[o->pA] = 1;
+      if (o->pB != MFFT_NONE && !first[o->pB]) first[o->pB] = 1;
+      if (!first[o->pS]) first[o->pS] = 2;
+      written[o->pS] = 1;
+      if (o->pT != MFFT_NONE) { if (!first[o->pT]) first[o->pT] = 2; written[o->pT] = 1; }
+   }
+   if (must_store)
+      for (p = 0; p < S; p++)
+         if (must_store[p]) { if (!first[p]) first[p] = 1; written[p] = 1; }
+   /* component sizes */
+   memset(tile_fill, 0, sizeof(uint32_t) * S);
+   for (p = 0; p < S; p++) if (first[p]) tile_fill[uf_find(par, p)]++;      /* size per root */
+   /* pack components into tiles, first fit in order of appearance */
+   {
+      uint32_t cur_fill = 0, cur = MFFT_NONE;
+      for (p = 0; p < S; p++)
+      {
+         uint32_t r;
+         if (!first[p]) continue;
+         r = uf_find(par, p);
+         if (root_tile[r] != MFFT_NONE) continue;
+         if (tile_fill[r] > max_npos) return -1;
+         if (cur == MFFT_NONE || cur_fill + tile_fill[r] > max_npos) { cur = ntiles++; cur_fill = 0; }
+         root_tile[r] = cur; cur_fill += tile_fill[r];
+      }
+   }
+   out->ntiles = ntiles; out->max_npos = 0; out->nstages = 0;
+   out->tiles = (mfft_tile *) calloc(ntiles ? ntiles : 1, sizeof(mfft_tile));
+   tile_npos = (uint32_t *) calloc(4 * (size_t)(ntiles ? ntiles : 1), sizeof(uint32_t));
+   if (!out->tiles || !tile_npos) { free(tile_npos); return -1; }
+   tile_nops = tile_npos + ntiles; pos_cursor = tile_nops + ntiles; op_cursor = pos_cursor + ntiles;
+   for (p = 0; p < S; p++) if (first[p]) tile_npos[root_tile[uf_find(par, p)]]++;
+   for (k = lo; k < hi; k++) tile_nops[root_tile[uf_find(par, ops[k].pA)]]++;
+   {
+      uint32_t po = 0, oo = 0, t;
+      for (t = 0; t < ntiles; t++)
+      {
+         out->tiles[t].pos_off = po; out->tiles[t].npos = tile_npos[t];
+         out->tiles[t].op_off = oo; out->tiles[t].nops = tile_nops[t];
+         pos_cursor[t] = po; op_cursor[t] = oo;
+         po += tile_npos[t]; oo += tile_nops[t];
+         if (tile_npos[t] > out->max_npos) out->max_npos = tile_npos[t];
+      }
+      out->npos_total = po; out->nops_total = oo;
+   }
+   out->pos = (uint32_t *) malloc(sizeof(uint32_t) * (out->npos_total ? out->npos_total : 1));
+   out->ops = (mfft_tileop *) calloc(out->nops_total ? out->nops_total : 1, sizeof(mfft_tileop));
+   if (!out->pos || !out->ops) { free(tile_npos); return -1; }
+   for (p = 0; p < S; p++)
+   {
+      uint32_t t;
+      if (!first[p]) continue;
+      t = root_tile[uf_find(par, p)];
+      local[p] = pos_cursor[t] - out->tiles[t].pos_off;
+      out->pos[pos_cursor[t]++] = p | (first[p] == 1 ? MFFT_TILE_LOAD : 0) | (written[p] ? MFFT_TILE_STORE : 0);
+   }
+   for (k = lo; k < hi; k++)      /* ops are in pstage order, so each tile's list is too */
+   {
+      const mfft_op *o = &ops[k];
+      uint32_t t = root_tile[uf_find(par, o->pA)];
+      mfft_tileop *d = &out->ops[op_cursor[t]++];
+      d->a = (uint16_t) local[o->pA];
+      d->b = (o->pB == MFFT_NONE) ? 0xFFFF : (uint16_t) local[o->pB];
+      d->s = (uint16_t) local[o->pS];
+      d->t = (o->pT == MFFT_NONE) ? 0xFFFF : (uint16_t) local[o->pT];
+      d->eSA = o->eSA; d->eSB = o->eSB; d->eTA = o->eTA; d->eTB = o->eTB;
+      d->cSA = o->cSA; d->cSB = o->cSB; d->cTA = o->cTA; d->cTB = o->cTB;
+      d->sSA = o->sSA; d->sSB = o->sSB; d->sTA = o->sTA; d->sTB = o->sTB;
+      d->lstage = o->pstage - s0;
+      if (d->lstage + 1 > out->tiles[t].nstages) out->tiles[t].nstages = d->lstage + 1;
+      if (d->lstage + 1 > out->nstages) out->nstages = d->lstage + 1;
+   }
+   free(tile_npos);
+   return 0;
+}
+
+int mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, const uint8_t *must_store)
+{
+   uint32_t S = s->S, maxst = s->npstages, s0, p;
+   mfft_op *ops; uint32_t *par, *sz, *par2, *sz2, *scratch; size_t *st_off; size_t k;
+   int rc = -1;
+   memset(P, 0, sizeof(*P));
+   if (max_npos < 4) return -1;
+   ops = (mfft_op *) malloc(sizeof(mfft_op) * (s->nops ? s->nops : 1));
+   par = (uint32_t *) malloc(sizeof(uint32_t) * 4 * (size_t) S);
+   scratch = (uint32_t *) malloc(sizeof(uint32_t) * 6 * (size_t) S);
+   st_off = (size_t *) calloc((size_t) maxst + 2, sizeof(size_t));
+   P->pass = (mfft_pass *) calloc((size_t) maxst + 1, sizeof(mfft_pass));
+   if (!ops || !par || !scratch || !st_off || !P->pass) goto done;
+   sz = par + S; par2 = sz + S; sz2 = par2 + S;
+   memcpy(ops, s->ops, sizeof(mfft_op) * s->nops);
+   qsort(ops, s->nops, sizeof(mfft_op), cmp_pstage);       /* stable enough: same-stage ops are independent */
+   for (k = 0; k < s->nops; k++) st_off[ops[k].pstage]++;
+   {  /* st_off[t] = first op of stage t (1-based stages) */
+      size_t acc = 0; uint32_t t;
+      for (t = 0; t <= maxst + 1; t++) { size_t c = st_off[t]; st_off[t] = acc; acc += c; }
+   }
+   s0 = 1;
+   while (s0 <= maxst)
+   {
+      uint32_t s1 = s0, worst = 0;
+      for (p = 0; p < S; p++) { par[p] = p; sz[p] = 1; }
+      for (;;)
+      {  /* try to take stage s1 into the window */
+         memcpy(par2, par, sizeof(uint32_t) * S); memcpy(sz2, sz, sizeof(uint32_t) * S);
+         worst = 0;
+         for (k = st_off[s1]; k < st_off[s1 + 1]; k++)
+         {
+            const mfft_op *o = &ops[k]; uint32_t m = 1;
+            if (o->pB != MFFT_NONE) m = uf_union(par2, sz2, o->pA, o->pB);
+            m = uf_union(par2, sz2, o->pA, o->pS);
+            if (o->pT != MFFT_NONE) m = uf_union(par2, sz2, o->pA, o->pT);
+            if (m > worst) worst = m;
+         }
+         if (worst > max_npos)
+         {
+            if (s1 == s0) goto done;          /* a single stage must always fit (<= 4 positions) */
+            s1--; break;
+         }
+         memcpy(par, par2, sizeof(uint32_t) * S); memcpy(sz, sz2, sizeof(uint32_t) * S);
+         if (s1 == maxst) break;
+         s1++;
+      }
+      if (build_pass(&P->pass[P->npasses], ops, st_off[s0], st_off[s1 + 1], S, s0, max_npos, par, scratch,
+                     (s1 == maxst) ? must_store : NULL) != 0) goto done;
+      P->npasses++;
+      s0 = s1 + 1;
+   }
+   rc = 0;
+done:
+   free(ops); free(par); free(scratch); free(st_off);
+   if (rc != 0) mfft_passes_free(P);
+   return rc;
+}

@@ -1,0 +1,27 @@
+/* tile.h -- fused passes for the shared-memory tile executor (see tile.c) */
+#ifndef MFFT_TILE_H
+#define MFFT_TILE_H
+#include "sched.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+   uint32_t     ntiles, max_npos, nstages, npos_total, nops_total;
+   mfft_tile   *tiles;     /* [ntiles] */
+   uint32_t    *pos;       /* [npos_total] physical position | MFFT_TILE_LOAD | MFFT_TILE_STORE */
+   mfft_tileop *ops;       /* [nops_total] */
+} mfft_pass;
+
+typedef struct { uint32_t npasses; mfft_pass *pass; } mfft_passes;
+
+/* cut schedule s (position-based view) into passes whose tiles hold <= max_npos coefficients.
+ * must_store (may be NULL): [S] flags of physical positions the LAST pass has to store even if no
+ * op of its window writes them (the outputs of a transform whose last pass gathers into dst). */
+int  mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, const uint8_t *must_store);
+void mfft_passes_free(mfft_passes *P);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -36,6 +36,11 @@ typedef struct {
    uint32_t cSA, cSB, cTA, cTB;
    int8_t   sSA, sSB, sTA, sTB;
    uint32_t stage;
+   /* the same op in terms of PHYSICAL positions (blocks of slab half 0 that never move; the
+    * relabelling of the reference's pointer swaps is folded in) and its stage under in-place
+    * hazards -- used by the fused shared-memory tile executor (tile.c, k_run_tiles) */
+   uint32_t pA, pB, pS, pT;
+   uint32_t pstage;
 } mfft_op;
 
 /* One batch entry: which strided family of blocks an op list is applied to. */
@@ -55,6 +60,20 @@ typedef struct {
    uint32_t l;            /* limbs of body */
    uint32_t pitch;        /* limbs per block in the slab (>= l+1) */
 } mfft_geom;
+
+/* ---- fused tile passes: several stages executed inside shared memory ---------------------- */
+#define MFFT_TILE_LOAD  0x80000000u      /* flags in the position list */
+#define MFFT_TILE_STORE 0x40000000u
+#define MFFT_TILE_POSMASK 0x3FFFFFFFu
+
+typedef struct {            /* one op of a tile; a,b,s,t index the tile's position list */
+   uint16_t a, b, s, t;     /* 0xFFFF = none */
+   uint32_t eSA, eSB, eTA, eTB, cSA, cSB, cTA, cTB;
+   int8_t   sSA, sSB, sTA, sTB;
+   uint32_t lstage;         /* stage inside the pass, 0-based, ops sorted by it */
+} mfft_tileop;
+
+typedef struct { uint32_t pos_off, npos, op_off, nops, nstages, pad; } mfft_tile;
 
 /* gather/normalise descriptor (finalize step of a transform): for logical position k:
  * src slot (with batch parity/base as above) -> dst block index  dst_base_b + dst[k]*dst_stride */
@@ -85,6 +104,19 @@ const char *mfft_dev_last_error(void);
 /* run ops[first .. first+count) (one stage) over nbatch batch entries */
 int  mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
                         const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+
+/* One fused pass: CTA (tile, batch entry) loads the tile's positions into shared memory, runs
+ * all its stages there and stores the written positions back in place -- or, if dst != NULL,
+ * to dst[(dst_base[b] + dstpos[i]*dst_stride)*pitch] (dstpos parallel to the position list,
+ * MFFT_NONE = do not store), normalised when `normalise` is set.  max_npos bounds the tile size. */
+int  mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tiles, uint32_t ntiles,
+                        const uint32_t *d_pos, const mfft_tileop *d_ops, uint32_t max_npos,
+                        const mfft_batch *d_batch, uint32_t nbatch,
+                        limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
+                        uint32_t dst_stride, int normalise, void *stream);
+/* 1 if the fused executor supports coefficient size l (else use mfft_dev_run_stage) */
+int  mfft_dev_tiles_supported(uint32_t l);
+uint32_t mfft_dev_tiles_max_npos(uint32_t l);
 
 /* dst[dst_base_b + mv.dst_pos*dst_stride] = normalise( src(slot mv.src_slot, batch b) * 2^shift )
  * shift is a bit exponent mod 2*NW (0 = none); if !normalise the block is copied unreduced. */

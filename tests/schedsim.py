@@ -15,7 +15,8 @@ KINDS = dict(FFT=0, FFT_TRUNC=1, FFT_TRUNC1=2, IFFT=3, IFFT_TRUNC=4, IFFT_TRUNC1
 class Op(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("inA", "inB", "outS", "outT", "eSA", "eSB", "eTA", "eTB",
                                            "cSA", "cSB", "cTA", "cTB")] + \
-               [(k, C.c_int8) for k in ("sSA", "sSB", "sTA", "sTB")] + [("stage", C.c_uint32)]
+               [(k, C.c_int8) for k in ("sSA", "sSB", "sTA", "sTB")] + [("stage", C.c_uint32)] + \
+               [(k, C.c_uint32) for k in ("pA", "pB", "pS", "pT", "pstage")]
 
 
 class Sched(C.Structure):
@@ -23,7 +24,9 @@ class Sched(C.Structure):
                 ("slot", C.POINTER(C.c_uint32)), ("wr_stage", C.POINTER(C.c_uint32)),
                 ("rd_stage", C.POINTER(C.c_uint32)), ("ops", C.POINTER(Op)),
                 ("nops", C.c_size_t), ("cap", C.c_size_t), ("nstages", C.c_uint32),
-                ("stage_off", C.POINTER(C.c_uint32))]
+                ("stage_off", C.POINTER(C.c_uint32)), ("phys", C.POINTER(C.c_uint32)),
+                ("pwr_stage", C.POINTER(C.c_uint32)), ("prd_stage", C.POINTER(C.c_uint32)),
+                ("npstages", C.c_uint32)]
 
 
 def _setup():
