@@ -119,7 +119,7 @@ static void dpass_free(struct mfft_dpass *d, uint32_t n)
 {
    uint32_t i;
    if (!d) return;
-   for (i = 0; i < n; i++) { mfft_dev_free(d[i].d_tiles); mfft_dev_free(d[i].d_pos); mfft_dev_free(d[i].d_ops); }
+   for (i = 0; i < n; i++) { mfft_dev_free(d[i].d_tiles); mfft_dev_free(d[i].d_pos); mfft_dev_free(d[i].d_ops); mfft_dev_free(d[i].d_stoff); }
    free(d);
 }
 
@@ -260,7 +260,8 @@ static struct mfft_dpass *dpass_upload(const mfft_passes *P)
       d[i].d_tiles = (mfft_tile *) mfft_upload(p->tiles, sizeof(mfft_tile) * (p->ntiles ? p->ntiles : 1));
       d[i].d_pos = (uint32_t *) mfft_upload(p->pos, sizeof(uint32_t) * (p->npos_total ? p->npos_total : 1));
       d[i].d_ops = (mfft_tileop *) mfft_upload(p->ops, sizeof(mfft_tileop) * (p->nops_total ? p->nops_total : 1));
-      if (!d[i].d_tiles || !d[i].d_pos || !d[i].d_ops) { dpass_free(d, P->npasses); return NULL; }
+      d[i].d_stoff = (uint32_t *) mfft_upload(p->stoff, sizeof(uint32_t) * (p->nstoff ? p->nstoff : 1));
+      if (!d[i].d_tiles || !d[i].d_pos || !d[i].d_ops || !d[i].d_stoff) { dpass_free(d, P->npasses); return NULL; }
    }
    return d;
 }
@@ -327,9 +328,9 @@ static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft
       const mfft_pass *p = &P->pass[i];
       const int lastp = (i + 1 == P->npasses) && dst != NULL;
       mfft_dev_profile_bytes(pass_bytes(p, nbatch, g->l));
-      if (mfft_dev_run_tiles(slab, g, d[i].d_tiles, p->ntiles, d[i].d_pos, d[i].d_ops, p->max_npos, d_batch, nbatch,
+      if (mfft_dev_run_tiles(slab, g, d[i].d_tiles, p->ntiles, d[i].d_pos, d[i].d_ops, p->max_npos, p->max_nops, d_batch, nbatch,
                              lastp ? dst : NULL, m->d_dstpos, m->d_dst_base, m->dst_stride,
-                             lastp ? m->normalise : 0, stream) != 0) return MPIRFFT_ENODEV;
+                             lastp ? m->normalise : 0, d[i].d_stoff, stream) != 0) return MPIRFFT_ENODEV;
    }
    return 0;
 }

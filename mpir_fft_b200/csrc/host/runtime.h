@@ -48,7 +48,7 @@ typedef struct {
    /* fused mode: the passes of each schedule, uploaded (tile.c / k_run_tiles) */
    int fused; uint32_t final_shift; int normalise;
    mfft_passes pcol, prow;
-   struct mfft_dpass { mfft_tile *d_tiles; uint32_t *d_pos; mfft_tileop *d_ops; } *dcol, *drow;
+   struct mfft_dpass { mfft_tile *d_tiles; uint32_t *d_pos; mfft_tileop *d_ops; uint32_t *d_stoff; } *dcol, *drow;
    uint32_t *d_dstpos; uint8_t *h_must_store; uint32_t *h_dstpos;
    /* host copies of the tables (kept for the CPU-side schedule tests) */
    mfft_sched *h_col, *h_row;                  /* owned by col/row once uploaded */

@@ -43,7 +43,7 @@ void mfft_passes_free(mfft_passes *P)
    if (!P) return;
    for (i = 0; i < P->npasses; i++)
    {
-      free(P->pass[i].tiles); free(P->pass[i].pos); free(P->pass[i].ops);
+      free(P->pass[i].tiles); free(P->pass[i].pos); free(P->pass[i].ops); free(P->pass[i].stoff);
    }
    free(P->pass);
    memset(P, 0, sizeof(*P));
@@ -93,7 +93,7 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
          root_tile[r] = cur; cur_fill += tile_fill[r];
       }
    }
-   out->ntiles = ntiles; out->max_npos = 0; out->nstages = 0;
+   out->ntiles = ntiles; out->max_npos = 0; out->max_nops = 0; out->nstages = 0;
    out->tiles = (mfft_tile *) calloc(ntiles ? ntiles : 1, sizeof(mfft_tile));
    tile_npos = (uint32_t *) calloc(4 * (size_t)(ntiles ? ntiles : 1), sizeof(uint32_t));
    if (!out->tiles || !tile_npos) { free(tile_npos); return -1; }
@@ -109,6 +109,7 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
          pos_cursor[t] = po; op_cursor[t] = oo;
          po += tile_npos[t]; oo += tile_nops[t];
          if (tile_npos[t] > out->max_npos) out->max_npos = tile_npos[t];
+         if (tile_nops[t] > out->max_nops) out->max_nops = tile_nops[t];
       }
       out->npos_total = po; out->nops_total = oo;
    }
@@ -140,6 +141,24 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
       if (d->lstage + 1 > out->nstages) out->nstages = d->lstage + 1;
    }
    free(tile_npos);
+   {  /* stage offsets per tile */
+      uint32_t t, total = 0, cur = 0;
+      for (t = 0; t < ntiles; t++) total += out->tiles[t].nstages + 1;
+      out->stoff = (uint32_t *) malloc(sizeof(uint32_t) * (total ? total : 1));
+      if (!out->stoff) return -1;
+      out->nstoff = total;
+      for (t = 0; t < ntiles; t++)
+      {
+         mfft_tile *tl = &out->tiles[t]; uint32_t st, o = 0;
+         if (tl->nstages > 62) return -1;
+         tl->pad = cur;
+         for (st = 0; st <= tl->nstages; st++)
+         {
+            while (o < tl->nops && out->ops[tl->op_off + o].lstage < st) o++;
+            out->stoff[cur++] = o;
+         }
+      }
+   }
    return 0;
 }
 

@@ -7,10 +7,12 @@ extern "C" {
 #endif
 
 typedef struct {
-   uint32_t     ntiles, max_npos, nstages, npos_total, nops_total;
+   uint32_t     ntiles, max_npos, max_nops, nstages, npos_total, nops_total;
    mfft_tile   *tiles;     /* [ntiles] */
    uint32_t    *pos;       /* [npos_total] physical position | MFFT_TILE_LOAD | MFFT_TILE_STORE */
    mfft_tileop *ops;       /* [nops_total] */
+   uint32_t    *stoff;     /* per tile nstages+1 offsets (local op index of each stage's first op) */
+   uint32_t     nstoff;
 } mfft_pass;
 
 typedef struct { uint32_t npasses; mfft_pass *pass; } mfft_passes;

@@ -73,6 +73,7 @@ typedef struct {            /* one op of a tile; a,b,s,t index the tile's positi
    uint32_t lstage;         /* stage inside the pass, 0-based, ops sorted by it */
 } mfft_tileop;
 
+/* pad = offset of the tile's (nstages+1) stage offsets in the pass's stoff array (<= 63 stages) */
 typedef struct { uint32_t pos_off, npos, op_off, nops, nstages, pad; } mfft_tile;
 
 /* gather/normalise descriptor (finalize step of a transform): for logical position k:
@@ -110,10 +111,10 @@ int  mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, 
  * to dst[(dst_base[b] + dstpos[i]*dst_stride)*pitch] (dstpos parallel to the position list,
  * MFFT_NONE = do not store), normalised when `normalise` is set.  max_npos bounds the tile size. */
 int  mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tiles, uint32_t ntiles,
-                        const uint32_t *d_pos, const mfft_tileop *d_ops, uint32_t max_npos,
+                        const uint32_t *d_pos, const mfft_tileop *d_ops, uint32_t max_npos, uint32_t max_nops,
                         const mfft_batch *d_batch, uint32_t nbatch,
                         limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
-                        uint32_t dst_stride, int normalise, void *stream);
+                        uint32_t dst_stride, int normalise, const uint32_t *d_stoff, void *stream);
 /* 1 if the fused executor supports coefficient size l (else use mfft_dev_run_stage) */
 int  mfft_dev_tiles_supported(uint32_t l);
 uint32_t mfft_dev_tiles_max_npos(uint32_t l);

@@ -28,6 +28,7 @@ def emu():
     (1500, 1500, 6, 64, "ones"), (3000, 2000, 6, 128, "uniform"),                   # l = 64, 128
     (6000, 6000, 6, 256, "ones"), (6000, 10, 6, 256, "runs"),                       # l = 256 (cfg2 ring)
     (12000, 9000, 6, 512, "uniform"), (700, 900, 7, 12, "runs"), (3000, 3000, 7, 96, "ones"),
+    (8000, 8000, 8, 16, "uniform"), (3000, 5000, 9, 8, "ones"),                     # fused path, bit-shifted twiddles
 ])
 def test_emulated_new_mpn_mul(emu, case):
     n1, n2, depth, w, kind = case
