@@ -185,6 +185,10 @@ uint64_t mpirfft_mul_plan_launches(const mpirfft_mul_plan *plan);
 int  mpirfft_mulmod_batch_device(mp_limb_t *d_a, const mp_limb_t *d_b, size_t count, size_t l,
                                  size_t pitch, void *stream);
 
+/* Pointwise algorithm: 0 = schoolbook IMAD.WIDE kernel (default), 1 = nested Schoenhage-Strassen
+ * step inside a warp (the fft_mulmod_2expp1 idea, mul_fft.c:3125-3167) for l in {64,128,256,512}. */
+void mpirfft_set_pointwise_mode(int mode);
+
 /* device memory helpers (so that a host language needs nothing but this ABI) */
 void *mpirfft_malloc_device(size_t bytes);
 void  mpirfft_free_device(void *p);

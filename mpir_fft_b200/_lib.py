@@ -66,6 +66,7 @@ def bind(L):
         "mpirfft_memcpy_h2d": (i32, [vp, vp, sz, vp]),
         "mpirfft_memcpy_d2h": (i32, [vp, vp, sz, vp]),
         "mpirfft_stream_sync": (i32, [vp]),
+        "mpirfft_set_pointwise_mode": (None, [i32]),
         "mpirfft_profile_enable": (None, [i32]),
         "mpirfft_profile_read": (i32, [C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(C.c_double), i32]),
         "mpirfft_measure_imad_rate": (C.c_double, [i32]),

@@ -21,6 +21,7 @@
 #define MFFT_DYN_SMEM(type, name) extern __shared__ type name[]
 #endif
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../mfft_internal.h"
 #include "mfft_arith.h"
@@ -523,11 +524,40 @@ k_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk)
 /* ------------------------------------------------------------------------------------------ */
 /* pointwise product mod 2^NW + 1                                                              */
 /* ------------------------------------------------------------------------------------------ */
+/* 32-bit multiply-accumulate carry chains.  ptxas fuses every mad.lo.cc / madc.hi.cc pair into one
+ * IMAD.WIDE.U32(.X) with the carry in a predicate; the accumulator pair must be an aligned
+ * register pair, which is why even- and odd-offset products go to separate arrays below.
+ * (Emulation build: the same semantics in plain C with an explicit carry flag.) */
+#ifdef MFFT_EMU
+static uint32_t emu_cc;
+static inline void mad_lo_cc(uint32_t &d, uint32_t a, uint32_t b)
+{ uint64_t v = (uint64_t)(uint32_t)((uint64_t) a * b) + d; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
+static inline void madc_lo_cc(uint32_t &d, uint32_t a, uint32_t b)
+{ uint64_t v = (uint64_t)(uint32_t)((uint64_t) a * b) + d + emu_cc; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
+static inline void madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b)
+{ uint64_t v = (((uint64_t) a * b) >> 32) + d + emu_cc; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
+static inline void addc(uint32_t &d) { d += emu_cc; }
+#else
+__device__ __forceinline__ void mad_lo_cc(uint32_t &d, uint32_t a, uint32_t b)
+{ asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(a), "r"(b)); }
+__device__ __forceinline__ void madc_lo_cc(uint32_t &d, uint32_t a, uint32_t b)
+{ asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(a), "r"(b)); }
+__device__ __forceinline__ void madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b)
+{ asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(a), "r"(b)); }
+__device__ __forceinline__ void addc(uint32_t &d)
+{ asm volatile("addc.u32 %0, %0, 0;" : "+r"(d)); }
+#endif
+
 /* One warp per product; l = 16*C limbs, i.e. every lane owns C 32-bit words of each operand.
- * The operands are cut into 32 blocks of C words; lane K accumulates
- *      sum_{I+J=K} A_I*B_J  -  sum_{I+J=K+32} A_I*B_J            (B^l == -1)
- * by walking I = 0..31 with A_I broadcast from shared memory and the B blocks rotating
- * through the lanes by shuffle.  Each block product is a CxC schoolbook product.           */
+ * The operands are cut into 32 blocks of C words; lane K needs
+ *      sum_{I+J=K} A_I*B_J  -  sum_{I+J=K+32} A_I*B_J            (B^l == -1).
+ * Step s: A_s is broadcast from shared memory, the B blocks rotate up one lane per step, so
+ * lane K holds B_{(K-s) mod 32}.  A block that wraps from lane 31 to lane 0 is complemented once
+ * and stays so: a*(~b) = a*2^(32C) - a - a*b, hence every term is a non-negative product and
+ * the signs reduce to one correction  -S_K*2^(32C) + S_K,  S_K = sum_{s>K} A_s (a suffix sum).
+ * Each CxC block product is C rows of two IMAD.WIDE.U32.X chains (even / odd word offsets,
+ * accumulators e[] / o[]); a chain's final carry goes to a small counter kc[], so the chains
+ * never have to ripple into words that already hold data from earlier steps.               */
 template <int C>
 __global__ void __launch_bounds__(128)
 k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
@@ -575,43 +605,84 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
    for (int i = 0; i < C; i++) sA[lane * C + i] = a[i];
    __syncwarp();
 
-   uint32_t acc[2 * C + 1];
+   /* S_K = sum_{s > K} A_s : inclusive suffix scan over the lanes, then shift down by one */
+   uint32_t S[C + 1];
 #pragma unroll
-   for (int i = 0; i < 2 * C + 1; i++) acc[i] = 0;
+   for (int i = 0; i < C; i++) S[i] = a[i];
+   S[C] = 0;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1)
+   {
+      uint64_t cy = 0;
+      const bool take = (lane + d < 32);
+#pragma unroll
+      for (int i = 0; i <= C; i++)
+      {
+         const uint32_t other = __shfl_down_sync(FULL, S[i], d);
+         const uint64_t v = (uint64_t) S[i] + (take ? other : 0u) + cy;
+         S[i] = (uint32_t) v; cy = v >> 32;
+      }
+   }
+#pragma unroll
+   for (int i = 0; i <= C; i++)
+   {
+      const uint32_t other = __shfl_down_sync(FULL, S[i], 1);
+      S[i] = (lane == 31) ? 0u : other;
+   }
+
+   uint32_t e[2 * C + 2], o[2 * C + 2], kc[C + 2];
+#pragma unroll
+   for (int i = 0; i < 2 * C + 2; i++) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+   for (int i = 0; i < C + 2; i++) kc[i] = 0;
+   const uint32_t m0 = (lane == 0) ? 0xffffffffu : 0u;
 
    for (uint32_t s = 0; s < 32; s++)
    {
       uint32_t ab[C];
 #pragma unroll
       for (int i = 0; i < C; i++) ab[i] = sA[s * C + i];
-      uint32_t prod[2 * C];
-#pragma unroll
-      for (int i = 0; i < 2 * C; i++) prod[i] = 0;
 #pragma unroll
       for (int j = 0; j < C; j++)
       {
-         uint64_t cy = 0;
-#pragma unroll
-         for (int t = 0; t < C; t++)
+         const uint32_t bj = b[j];
+         /* even offsets t + j: t = (j & 1), +2, ... -> e[]; chain end at word C + j + (j & 1) */
          {
-            const uint64_t v = (uint64_t) ab[t] * b[j] + prod[j + t] + cy;
-            prod[j + t] = (uint32_t) v; cy = v >> 32;
-         }
-         prod[j + C] = (uint32_t) cy;
-      }
-      /* block index of the B block this lane holds is (lane - s) mod 32: negative wrap if lane < s */
-      const uint32_t m = (lane < s) ? 0xffffffffu : 0u;
-      uint64_t cy = m & 1u;
+            const int t0 = j & 1;
+            mad_lo_cc(e[t0 + j], ab[t0], bj); madc_hi_cc(e[t0 + j + 1], ab[t0], bj);
 #pragma unroll
-      for (int i = 0; i < 2 * C; i++)
-      {
-         const uint64_t v = (uint64_t) acc[i] + (prod[i] ^ m) + cy;
-         acc[i] = (uint32_t) v; cy = v >> 32;
+            for (int t = t0 + 2; t < C; t += 2) { madc_lo_cc(e[t + j], ab[t], bj); madc_hi_cc(e[t + j + 1], ab[t], bj); }
+            addc(kc[j + (j & 1)]);
+         }
+         /* odd offsets: t = 1 - (j & 1), +2, ... -> o[]; chain end at word C + j + 1 - (j & 1) */
+         {
+            const int t0 = 1 - (j & 1);          /* o[i] holds word offset i + 1, so pairs start at even i */
+            mad_lo_cc(o[t0 + j - 1], ab[t0], bj); madc_hi_cc(o[t0 + j], ab[t0], bj);
+#pragma unroll
+            for (int t = t0 + 2; t < C; t += 2) { madc_lo_cc(o[t + j - 1], ab[t], bj); madc_hi_cc(o[t + j], ab[t], bj); }
+            addc(kc[j + 1 - (j & 1)]);
+         }
       }
-      acc[2 * C] += (uint32_t) cy + m;            /* + carry, and -1 when subtracting */
+      /* rotate the B blocks up one lane; the block entering lane 0 wrapped: complement it */
       const uint32_t src = (lane + 31) & 31;
 #pragma unroll
-      for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src);
+      for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src) ^ m0;
+   }
+
+   /* R_K = P_K - S_K*2^(32C) + S_K with P_K = e + o + kc<<(32C), as 2C words + a small signed top */
+   uint32_t acc[2 * C + 1];
+   {
+      int64_t cy = 0;
+#pragma unroll
+      for (int k = 0; k < 2 * C; k++)
+      {
+         int64_t v = cy + (int64_t)(uint64_t) e[k] + (k ? (int64_t)(uint64_t) o[k - 1] : 0);
+         if (k >= C) v += (int64_t)(uint64_t) kc[k - C] - (int64_t)(uint64_t) S[k - C];
+         if (k <= C) v += (int64_t)(uint64_t) S[k];
+         acc[k] = (uint32_t) v; cy = v >> 32;
+      }
+      cy += (int64_t)(uint64_t) e[2 * C] + (int64_t)(uint64_t) o[2 * C - 1] + (int64_t)(uint64_t) kc[C] - (int64_t)(uint64_t) S[C];
+      acc[2 * C] = (uint32_t)(int32_t) cy;
    }
 
    /* lane K: r = acc[0..C) + (high part of lane K-1), lane 0 takes -(high part of lane 31) */
@@ -623,18 +694,13 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
    {
       const uint32_t m = (lane == 0) ? 0xffffffffu : 0u;
       uint64_t cy = m & 1u;
-      /* sign extension word of hi (its top word acc[2C] is a small signed count) */
-      const uint32_t ext = ((int32_t) hi[C] < 0) ? 0xffffffffu : 0u;
 #pragma unroll
       for (int i = 0; i < C; i++)
       {
          const uint64_t v = (uint64_t) acc[i] + (hi[i] ^ m) + cy;
          acc[i] = (uint32_t) v; cy = v >> 32;
       }
-      /* carry out of the C words: cy + (signed) (hi[C] ^ m) with one more extension word */
-      const int64_t top = (int64_t)(int32_t)(hi[C] ^ m) + (int64_t) cy;
-      (void) ext;
-      carry = (int32_t) top;
+      carry = (int32_t)((int64_t)(int32_t)(hi[C] ^ m) + (int64_t) cy);
    }
    /* signed carries ripple to the next lane; lane 31's leave through the top limb (2^NW == -1) */
    int64_t top = 0;
@@ -645,13 +711,12 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
       const int32_t c31 = __shfl_sync(FULL, carry, 31);
       top += c31;
       if (lane == 0) cin = 0;
-      /* add the signed cin to the C words */
       int64_t cc = cin;
 #pragma unroll
       for (int i = 0; i < C; i++)
       {
          const int64_t v = (int64_t)(uint64_t) acc[i] + cc;
-         acc[i] = (uint32_t) v; cc = v >> 32;       /* arithmetic shift keeps the sign */
+         acc[i] = (uint32_t) v; cc = v >> 32;
       }
       carry = (int32_t) cc;
    }
@@ -660,6 +725,332 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
       A[(lane * C + i) >> 1] = (limb_t) acc[i] | ((limb_t) acc[i + 1] << 32);
    if (lane == 0) A[l] = (limb_t) top;
    normalise_block(A, l, lane);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* pointwise product by a nested Schoenhage-Strassen step inside one warp                       */
+/* ------------------------------------------------------------------------------------------ */
+/* a*b mod 2^(64L)+1 as a negacyclic convolution of 2n' pieces of 64*PL bits over the small ring
+ * p' = 2^(64*LP)+1 (the scheme of fft_mulmod_2expp1 / FFT_mulmod_2expp1, mul_fft.c:3125-3167,
+ * 2998-3117, with the inner ring chosen wide enough -- 64*LP >= 2*64*PL + log2(2n') + 1 -- that the
+ * signed convolution coefficients are recovered exactly and the reference's one-limb CRT fix-up
+ * (2981-2996, 3067-3081) is not needed).  At L = 256 this replaces 65 536 limb products by
+ * 64 * 81 = 5 184.  The inner transforms are tiny (2n' coefficients of LP limbs), so one warp
+ * owns a whole product: coefficients live in shared memory (odd pitch: conflict-free), ONE LANE
+ * executes one inner butterfly with serial in-lane carries -- no ballots, no cross-lane carries.
+ * 2^w' (w' = 64*LP/n', even) is the 2n'-th root of unity, theta = 2^(w'/2) the negacyclic weight. */
+
+/* limb k of (+-)X*2^e for a coefficient in shared memory, e = 64y+bs < 64*LP, complemented in the
+ * negated bit region (same algebra as mfft_arith.h) */
+template <int LP>
+__device__ __forceinline__ limb_t ss_limb(const limb_t *X, uint32_t k, uint32_t y, uint32_t bs, uint32_t negm)
+{
+   uint32_t q = k + LP - y;
+   if (q >= (uint32_t) LP) q -= LP;
+   limb_t v = X[q];
+   if (bs)
+   {
+      const uint32_t q1 = q ? q - 1 : LP - 1;
+      v = (v << bs) | (X[q1] >> (64 - bs));
+   }
+   const uint32_t m32 = (uint32_t)((int32_t)(k - y) >> 31) ^ negm;
+   v ^= ((limb_t) m32 << 32) | m32;
+   if (k == y) v ^= (((limb_t) 1 << bs) - 1);
+   return v;
+}
+
+/* out = sa*A*2^ea + sb*B*2^eb (mod p'), serial in one lane; exponents mod 2*64*LP; sb == 0: unary */
+template <int LP>
+__device__ __forceinline__ void ss_lincomb(limb_t (&out)[LP], int64_t &top_out, const limb_t *A, int sa, uint32_t ea,
+                                           const limb_t *B, int sb, uint32_t eb)
+{
+   constexpr uint32_t NW = 64u * LP;
+   int64_t top_acc = 0; mfft_i128 carry = 0, Ka = 0, Kb = 0;
+   uint32_t ya = 0, bsa = 0, yb = 0, bsb = 0, na = 0, nb = 0;
+   {
+      if (ea >= NW) { ea -= NW; sa = -sa; }
+      ya = ea >> 6; bsa = ea & 63; na = (sa < 0) ? 0xffffffffu : 0u;
+      const int64_t top = (int64_t) A[LP];
+      if (ea == 0) { if (sa > 0) top_acc += top; else { carry += 1; top_acc -= 1 + top; } }
+      else if (sa > 0) { carry += 1; Ka = -(((mfft_i128)(1 + top)) << bsa); }
+      else { top_acc -= 1; Ka = ((mfft_i128)(1 + top)) << bsa; }
+   }
+   if (sb)
+   {
+      if (eb >= NW) { eb -= NW; sb = -sb; }
+      yb = eb >> 6; bsb = eb & 63; nb = (sb < 0) ? 0xffffffffu : 0u;
+      const int64_t top = (int64_t) B[LP];
+      if (eb == 0) { if (sb > 0) top_acc += top; else { carry += 1; top_acc -= 1 + top; } }
+      else if (sb > 0) { carry += 1; Kb = -(((mfft_i128)(1 + top)) << bsb); }
+      else { top_acc -= 1; Kb = ((mfft_i128)(1 + top)) << bsb; }
+   }
+#pragma unroll
+   for (int k = 0; k < LP; k++)
+   {
+      mfft_i128 acc = carry + (mfft_i128)(mfft_u128) ss_limb<LP>(A, k, ya, bsa, na);
+      if (sb) acc += (mfft_i128)(mfft_u128) ss_limb<LP>(B, k, yb, bsb, nb);
+      if ((uint32_t) k == ya) acc += Ka;
+      if (sb && (uint32_t) k == yb) acc += Kb;
+      out[k] = (limb_t) acc; carry = acc >> 64;
+   }
+   top_out = top_acc + (int64_t) carry;
+}
+
+/* canonical form in one lane: body in r[], top in/out */
+template <int LP>
+__device__ __forceinline__ void ss_normalise(limb_t (&r)[LP], int64_t &top)
+{
+   for (int it = 0; it < 4; it++)
+   {
+      if (top == 0) return;
+      if (top == 1)
+      {
+         limb_t any = 0;
+#pragma unroll
+         for (int k = 0; k < LP; k++) any |= r[k];
+         if (!any) return;
+      }
+      mfft_i128 c = -(mfft_i128) top; top = 0;
+#pragma unroll
+      for (int k = 0; k < LP; k++)
+      {
+         const mfft_i128 acc = c + (mfft_i128)(mfft_u128) r[k];
+         r[k] = (limb_t) acc; c = acc >> 64;
+      }
+      top = (int64_t) c;
+   }
+}
+
+template <int LP>
+__device__ __forceinline__ void ss_store(limb_t *X, const limb_t (&r)[LP], int64_t top)
+{
+#pragma unroll
+   for (int k = 0; k < LP; k++) X[k] = r[k];
+   X[LP] = (limb_t) top;
+}
+
+/* r = a*b mod p' for canonical a, b (registers), canonical result */
+template <int LP>
+__device__ __forceinline__ void ss_mulmod(limb_t (&r)[LP], int64_t &top, const limb_t (&a)[LP], int64_t ta,
+                                          const limb_t (&b)[LP], int64_t tb)
+{
+   if (ta | tb)
+   {  /* 2^NW' == -1 */
+      if (ta && tb) { for (int k = 0; k < LP; k++) r[k] = (k == 0); top = 0; return; }
+      mfft_i128 c = 1;
+#pragma unroll
+      for (int k = 0; k < LP; k++)
+      {
+         const mfft_i128 acc = c + (mfft_i128)(mfft_u128)(~(ta ? b[k] : a[k]));
+         r[k] = (limb_t) acc; c = acc >> 64;
+      }
+      top = (int64_t) c - 1;            /* -x = ~x + 1 - 2^NW' */
+      ss_normalise<LP>(r, top);
+      return;
+   }
+   limb_t lo[LP], hi[LP];
+   mfft_u128 acc = 0; uint32_t ovf = 0;
+#pragma unroll
+   for (int c = 0; c < 2 * LP - 1; c++)
+   {
+#pragma unroll
+      for (int i = 0; i < LP; i++)
+      {
+         const int j = c - i;
+         if (j < 0 || j >= LP) continue;
+         const mfft_u128 pr = (mfft_u128) a[i] * b[j];
+         const mfft_u128 old = acc; acc += pr; ovf += (acc < old);
+      }
+      if (c < LP) lo[c] = (limb_t) acc; else hi[c - LP] = (limb_t) acc;
+      acc = (acc >> 64) | ((mfft_u128) ovf << 64); ovf = 0;
+   }
+   hi[LP - 1] = (limb_t) acc;
+   /* lo - hi, borrow -> top */
+   mfft_i128 c = 0;
+#pragma unroll
+   for (int k = 0; k < LP; k++)
+   {
+      const mfft_i128 v = c + (mfft_i128)(mfft_u128) lo[k] - (mfft_i128)(mfft_u128) hi[k];
+      r[k] = (limb_t) v; c = v >> 64;
+   }
+   top = (int64_t) c;
+   ss_normalise<LP>(r, top);
+}
+
+template <int LP>
+__global__ void __launch_bounds__(128)
+k_mulmod_ss(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks, uint32_t nblk,
+            uint32_t L, uint32_t pitch, uint32_t np, uint32_t wp, uint32_t depthp)
+{
+   MFFT_DYN_SMEM(limb_t, smem64);
+   constexpr uint32_t CP = (LP + 1) | 1;                 /* odd pitch >= LP+1: body + signed top */
+   constexpr uint32_t NW = 64u * LP, M2 = 2u * NW;
+   const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const uint64_t wid = (uint64_t) blockIdx.x * (blockDim.x >> 5) + wib;
+   if (wid >= nblk) return;
+   const uint32_t ncoef = 2 * np, PL = L / ncoef;        /* limbs per piece */
+   limb_t *ca = smem64 + (size_t) wib * 2 * ncoef * CP, *cb = ca + (size_t) ncoef * CP;
+   limb_t *A = a_slab + (uint64_t) blocks[wid] * pitch;
+   const limb_t *B = b_slab + (uint64_t) blocks[wid] * pitch;
+
+   const int64_t topA = (int64_t) A[L], topB = (int64_t) B[L];
+   __syncwarp();
+   if (topA | topB)
+   {  /* an operand equal to 2^(64L) == -1 */
+      if (topA && topB) { for (uint32_t k = lane; k < L; k += 32) A[k] = (k == 0); if (lane == 0) A[L] = 0; }
+      else if (topA) { lincomb_out<1>(A, B, -1, 0, B, 0, 0, L, lane); normalise_block(A, L, lane); }
+      else { __syncwarp(); lincomb_out<1>(A, A, -1, 0, A, 0, 0, L, lane); normalise_block(A, L, lane); }
+      return;
+   }
+
+   /* split into pieces (FFT_split, mul_fft.c:87-106; pieces are limb aligned) */
+   for (uint32_t idx = lane; idx < ncoef * CP; idx += 32)
+   {
+      const uint32_t i = idx / CP, k = idx % CP;
+      ca[idx] = (k < PL) ? A[i * PL + k] : 0;
+      cb[idx] = (k < PL) ? B[i * PL + k] : 0;
+   }
+   __syncwarp();
+
+   /* forward negacyclic transforms of both operands (FFT_radix2_negacyclic, 1290-1390, even w):
+      first layer fuses the weights theta^i; then plain DIF layers */
+   const uint32_t h = wp / 2;
+   for (uint32_t t = lane; t < 2 * np; t += 32)
+   {
+      limb_t *X = (t < np) ? ca : cb;
+      const uint32_t i = (t < np) ? t : t - np;
+      limb_t *P = X + (size_t) i * CP, *Q = X + (size_t)(i + np) * CP;
+      const uint32_t ea = (i * h) % M2, eb = ((i + np) * h) % M2, e = (i * wp) % M2;
+      limb_t rs[LP], rt[LP]; int64_t ts, tt;
+      ss_lincomb<LP>(rs, ts, P, 1, ea, Q, 1, eb);
+      ss_lincomb<LP>(rt, tt, P, 1, (ea + e) % M2, Q, -1, (eb + e) % M2);
+      ss_store<LP>(P, rs, ts); ss_store<LP>(Q, rt, tt);
+   }
+   __syncwarp();
+   for (uint32_t half = np / 2, ww = 2 * wp; half >= 1; half >>= 1, ww *= 2)
+   {
+      for (uint32_t t = lane; t < 2 * np; t += 32)
+      {
+         limb_t *X = (t < np) ? ca : cb;
+         const uint32_t u = (t < np) ? t : t - np;
+         const uint32_t blk = u / half, i = u % half;
+         limb_t *P = X + (size_t)(blk * 2 * half + i) * CP, *Q = P + (size_t) half * CP;
+         const uint32_t e = (uint32_t)(((uint64_t) i * ww) % M2);
+         limb_t rs[LP], rt[LP]; int64_t ts, tt;
+         ss_lincomb<LP>(rs, ts, P, 1, 0, Q, 1, 0);
+         ss_lincomb<LP>(rt, tt, P, 1, e, Q, -1, e);
+         ss_store<LP>(P, rs, ts); ss_store<LP>(Q, rt, tt);
+      }
+      __syncwarp();
+   }
+
+   /* pointwise products in the small ring (outputs of the DIF transforms are in the same
+      bit-reversed order for both operands, so index-wise products are what is needed) */
+   for (uint32_t i = lane; i < ncoef; i += 32)
+   {
+      limb_t x[LP], y[LP], r[LP]; int64_t tx, ty, tr;
+      limb_t *P = ca + (size_t) i * CP, *Q = cb + (size_t) i * CP;
+#pragma unroll
+      for (int k = 0; k < LP; k++) { x[k] = P[k]; y[k] = Q[k]; }
+      tx = (int64_t) P[LP]; ty = (int64_t) Q[LP];
+      ss_normalise<LP>(x, tx); ss_normalise<LP>(y, ty);
+      ss_mulmod<LP>(r, tr, x, tx, y, ty);
+      ss_store<LP>(P, r, tr);
+   }
+   __syncwarp();
+
+   /* inverse transform (IFFT_radix2_negacyclic, 1861-1962): DIT layers, last layer fuses theta^-i */
+   for (uint32_t half = 1, ww = (np > 1) ? wp * np : wp; half <= np / 2; half <<= 1, ww /= 2)
+   {
+      for (uint32_t t = lane; t < np; t += 32)
+      {
+         const uint32_t blk = t / half, i = t % half;
+         limb_t *P = ca + (size_t)(blk * 2 * half + i) * CP, *Q = P + (size_t) half * CP;
+         const uint32_t e = (uint32_t)((M2 - ((uint64_t) i * ww) % M2) % M2);
+         limb_t rs[LP], rt[LP]; int64_t ts, tt;
+         ss_lincomb<LP>(rs, ts, P, 1, 0, Q, 1, e);
+         ss_lincomb<LP>(rt, tt, P, 1, 0, Q, -1, e);
+         ss_store<LP>(P, rs, ts); ss_store<LP>(Q, rt, tt);
+      }
+      __syncwarp();
+   }
+   {
+      /* last layer (pairs i, i+n') + weights theta^-i, theta^-(i+n') + 1/(2n') = 2^-(depth'+1) */
+      const uint32_t sc = M2 - (depthp + 1);
+      for (uint32_t i = lane; i < np; i += 32)
+      {
+         limb_t *P = ca + (size_t) i * CP, *Q = ca + (size_t)(i + np) * CP;
+         const uint32_t e = (M2 - (i * wp) % M2) % M2;
+         const uint32_t ua = (M2 - (i * h) % M2 + sc) % M2, ub = (M2 - ((i + np) * h) % M2 + sc) % M2;
+         limb_t rs[LP], rt[LP]; int64_t ts, tt;
+         ss_lincomb<LP>(rs, ts, P, 1, ua, Q, 1, (ua + e) % M2);
+         ss_lincomb<LP>(rt, tt, P, 1, ub, Q, -1, (ub + e) % M2);
+         ss_normalise<LP>(rs, ts); ss_normalise<LP>(rt, tt);
+         ss_store<LP>(P, rs, ts); ss_store<LP>(Q, rt, tt);
+      }
+   }
+   __syncwarp();
+
+   /* recombine: sum_i c_i * 2^(64*PL*i) with c_i the SIGNED representative (residues above p'/2
+      are negative: c = res - 2^NW' - 1); pieces at or past limb L wrap around negated.
+      Lane owns output limbs [lane*G, lane*G + G), G = L/32; signed carries then ripple lane to lane. */
+   const uint32_t G = L / 32;
+   int64_t carry_out = 0;
+   for (uint32_t g = 0; g < G; g++)
+   {
+      const uint32_t k = lane * G + g;
+      mfft_i128 acc = carry_out;
+      /* coefficients covering limb k (mod L): offsets i*PL <= pos < i*PL + LP + 1 for pos = k and pos = k + L */
+      for (uint32_t wrap = 0; wrap < 2; wrap++)
+      {
+         const uint32_t pos = k + wrap * L;
+         const int32_t ihi = (int32_t)(pos / PL);
+         int32_t ilo = (int32_t)((pos >= (uint32_t) LP) ? (pos - LP) / PL : 0);
+         for (int32_t i = ilo; i <= ihi; i++)
+         {
+            if (i < 0 || (uint32_t) i >= ncoef) continue;
+            const uint32_t off = pos - (uint32_t) i * PL;
+            if (off > (uint32_t) LP) continue;
+            const limb_t *Cc = ca + (size_t) i * CP;
+            /* sign of c_i: negative iff top == 1 or the top bit of the body is set */
+            const bool negc = (Cc[LP] != 0) || (Cc[LP - 1] >> 63);
+            mfft_i128 v = 0;
+            if (off < (uint32_t) LP) v = (mfft_i128)(mfft_u128) Cc[off];
+            else v = (mfft_i128)(int64_t) Cc[LP];                       /* top limb (0 or 1) at offset LP */
+            if (negc) { if (off == 0) v -= 1; if (off == (uint32_t) LP) v -= 1; }
+            acc += wrap ? -v : v;
+         }
+      }
+      cb[k] = (limb_t) acc;   /* reuse cb as output */
+      carry_out = (int64_t)(acc >> 64);
+   }
+   /* negative coefficients also owe their sign extension past offset LP: c_i = body - 2^NW' - 1 was
+      handled above with the two -1; nothing else.  Now ripple the signed lane carries. */
+   limb_t *outp = cb;
+   int64_t top = 0;
+   __syncwarp();
+   {
+      int64_t carry = carry_out;
+      for (int it = 0; it < 40; it++)
+      {
+         if (!__any_sync(FULL, carry != 0)) break;
+         int64_t cin = __shfl_up_sync(FULL, carry, 1);
+         const int64_t c31 = __shfl_sync(FULL, carry, 31);
+         top += c31;
+         if (lane == 0) cin = 0;
+         mfft_i128 cc = cin;
+         for (uint32_t g = 0; g < G && cc != 0; g++)
+         {
+            const mfft_i128 v = cc + (mfft_i128)(mfft_u128) outp[lane * G + g];
+            outp[lane * G + g] = (limb_t) v; cc = v >> 64;
+         }
+         carry = (int64_t) cc;
+      }
+   }
+   __syncwarp();
+   for (uint32_t k = lane; k < L; k += 32) A[k] = outp[k];
+   if (lane == 0) A[L] = (limb_t) top;
+   normalise_block(A, L, lane);
 }
 
 /* generic fallback: any l.  One CTA per product, thread per 64-bit output column. */
@@ -1087,6 +1478,8 @@ int mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, 
 }
 
 static limb_t *g_pw_scratch = NULL; static size_t g_pw_scratch_bytes = 0;
+static int g_pw_mode = -1;
+void mfft_dev_pointwise_mode(int mode) { g_pw_mode = mode; }
 
 int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uint32_t nblk,
                        uint32_t l, uint32_t pitch, void *stream)
@@ -1095,6 +1488,33 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
    cudaStream_t st = (cudaStream_t) stream;
    const unsigned grid = (nblk + 3) / 4;
    PROF(PC_POINTWISE, st);
+   {  /* mode 0 (default): schoolbook IMAD.WIDE kernel; mode 1 (MPIRFFT_POINTWISE=ss or
+         mfft_dev_pointwise_mode): the nested Schoenhage-Strassen step inside a warp (k_mulmod_ss).
+         Measured at l = 256 on B200: 0.59 ms vs 0.88 ms per 16 640 products, so direct stays default. */
+      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = (e && e[0] == 's') ? 1 : 0; }
+      uint32_t np = 0, lp = 0;
+      if (g_pw_mode == 1)
+      {
+         if (l == 64)  { np = 16; lp = 5; }       /* 32 pieces of 128 bits, ring 2^320+1,  w' = 20 */
+         if (l == 128) { np = 32; lp = 5; }       /* 64 pieces of 128 bits, ring 2^320+1,  w' = 10 */
+         if (l == 256) { np = 32; lp = 9; }       /* 64 pieces of 256 bits, ring 2^576+1,  w' = 18 */
+         if (l == 512) { np = 64; lp = 10; }      /* 128 pieces of 256 bits, ring 2^640+1, w' = 10 */
+      }
+      if (np)
+      {
+         const uint32_t wp = 64 * lp / np, cp = (lp + 1) | 1;
+         uint32_t depthp = 0; while ((1u << depthp) < np) depthp++;
+         const size_t sm = (size_t) 4 * 2 * (2 * np) * cp * 8;
+         if (lp == 5) { CK(cudaFuncSetAttribute(k_mulmod_ss<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+                        MFFT_LAUNCH(k_mulmod_ss<5>, grid, 128, sm, st, a, b, d_blocks, nblk, l, pitch, np, wp, depthp); }
+         else if (lp == 9) { CK(cudaFuncSetAttribute(k_mulmod_ss<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+                        MFFT_LAUNCH(k_mulmod_ss<9>, grid, 128, sm, st, a, b, d_blocks, nblk, l, pitch, np, wp, depthp); }
+         else { CK(cudaFuncSetAttribute(k_mulmod_ss<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+                        MFFT_LAUNCH(k_mulmod_ss<10>, grid, 128, sm, st, a, b, d_blocks, nblk, l, pitch, np, wp, depthp); }
+         CKL();
+         return 0;
+      }
+   }
    if (l == 64)       MFFT_LAUNCH(k_pointwise<4>, grid, 128, 4 * 32 * 4 * 4, st, a, b, d_blocks, nblk, l, pitch);
    else if (l == 128) MFFT_LAUNCH(k_pointwise<8>, grid, 128, 4 * 32 * 8 * 4, st, a, b, d_blocks, nblk, l, pitch);
    else if (l == 256) MFFT_LAUNCH(k_pointwise<16>, grid, 128, 4 * 32 * 16 * 4, st, a, b, d_blocks, nblk, l, pitch);

@@ -58,6 +58,8 @@ const char *mpirfft_version(void) { return "mpirfft_b200 0.1 (sm_100a)"; }
 double mfft_dev_imad_rate(int mode);
 double mpirfft_measure_imad_rate(int mode) { return mfft_try_device() ? -1.0 : mfft_dev_imad_rate(mode); }
 
+void mpirfft_set_pointwise_mode(int mode) { mfft_dev_pointwise_mode(mode); }
+
 void mpirfft_profile_enable(int on) { mfft_dev_profile_enable(on); }
 int  mpirfft_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass)
 { return mfft_dev_profile_read(ms, launches, bytes, nclass) ? MPIRFFT_ENODEV : 0; }

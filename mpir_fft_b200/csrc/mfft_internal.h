@@ -130,6 +130,9 @@ int  mfft_dev_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst_b
 int  mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uint32_t nblk,
                         uint32_t l, uint32_t pitch, void *stream);
 
+/* 0: schoolbook kernel (default), 1: nested Schoenhage-Strassen kernel where available */
+void mfft_dev_pointwise_mode(int mode);
+
 /* split: coefficient i (i < ncoef) = bits [i*bits, (i+1)*bits) of {src, nlimbs}, zero-extended to a
  * block (FFT_split_bits, mul_fft.c:115-170); blocks ncoef..nzero-1 are zeroed (mul_fft.c:3235). */
 int  mfft_dev_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, uint64_t nlimbs,

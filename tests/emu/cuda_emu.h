@@ -111,6 +111,13 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
    const unsigned lane = threadIdx.x & 31;
    T out; uint64_t r = (lane >= d) ? s[lane - d] : raw; memcpy(&out, &r, sizeof(T)); return out;
 }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d)
+{
+   uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
+   const uint64_t *s = emu_warp_exchange(raw);
+   const unsigned lane = threadIdx.x & 31;
+   T out; uint64_t r = (lane + d < 32) ? s[lane + d] : raw; memcpy(&out, &r, sizeof(T)); return out;
+}
 static inline void __syncthreads()
 {
    emu_block_sync *b = emu_cur_block();

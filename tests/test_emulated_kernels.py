@@ -38,8 +38,10 @@ def test_emulated_new_mpn_mul(emu, case):
     assert np.array_equal(r, L.gmp_mul(a, b))
 
 
-@pytest.mark.parametrize("l", [1, 3, 24, 64, 256])
-def test_emulated_mulmod_adversarial(emu, l):
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
+def test_emulated_mulmod_adversarial(emu, l, mode):
+    emu.mpirfft_set_pointwise_mode(mode)        # 0: schoolbook kernel, 1: nested SS kernel
     random.seed(l)
     NW = 64 * l
     p = (1 << NW) + 1
@@ -53,5 +55,6 @@ def test_emulated_mulmod_adversarial(emu, l):
     assert emu.mpirfft_mulmod_batch_device(da, db, len(A), l, l + 1, None) == 0
     out = np.empty_like(a)
     emu.mpirfft_memcpy_d2h(ptr(out), da, a.nbytes, None)
+    emu.mpirfft_set_pointwise_mode(0)
     for k in range(len(A)):
-        assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), (l, k)
+        assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), (l, k, mode)

@@ -105,9 +105,11 @@ def test_illegal_parameters_rejected():
 
 
 # ---- mulmod 2^(64 l)+1 ----
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
-def test_mulmod_vs_bigint(lib, l):
+def test_mulmod_vs_bigint(lib, l, mode):
     import random
+    lib.mpirfft_set_pointwise_mode(mode)       # 0: schoolbook kernel, 1: nested SS kernel
     random.seed(l)
     NW = 64 * l
     p = (1 << NW) + 1
@@ -118,9 +120,19 @@ def test_mulmod_vs_bigint(lib, l):
     a = np.stack([int_to_block(v, l) for v in A])
     b = np.stack([int_to_block(v, l) for v in B])
     out = M.mulmod_batch(a, b)
+    lib.mpirfft_set_pointwise_mode(0)
     for k in range(len(A)):
         want = int_to_block(A[k] * B[k] % p, l)
-        assert np.array_equal(out[k], want), "mulmod l=%d case %d" % (l, k)
+        assert np.array_equal(out[k], want), "mulmod l=%d case %d mode %d" % (l, k, mode)
+
+
+def test_product_with_nested_ss_pointwise(lib):
+    lib.mpirfft_set_pointwise_mode(1)
+    try:
+        check_mul(1 << 20, 1 << 20, 14, 1)
+        check_mul(1 << 16, 1 << 16, 12, 1, "ones", "ones")
+    finally:
+        lib.mpirfft_set_pointwise_mode(0)
 
 
 def test_new_mpn_mulmod_2expp1_symbol(lib):
