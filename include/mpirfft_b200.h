@@ -185,6 +185,34 @@ uint64_t mpirfft_mul_plan_launches(const mpirfft_mul_plan *plan);
 int  mpirfft_mulmod_batch_device(mp_limb_t *d_a, const mp_limb_t *d_b, size_t count, size_t l,
                                  size_t pitch, void *stream);
 
+/* ---- sharded multiplication: the MFA spread over the GPUs of one box (one process per GPU) ----
+ * Columns are block-partitioned for the column passes, the live rows for the row passes and the
+ * pointwise products.  The library runs the local phases on plan-owned HBM buffers; the host
+ * language issues the collectives on the exchange buffers named in the layout (counts in limbs):
+ *   phase 0 (which, d_in)  split + column FFTs of operand `which` -> send
+ *        A: all_to_all send -> recv;  to rank h: rows_h*ncl blocks at offset r0_h*ncl blocks
+ *   phase 1 (which)        unpack recv, row FFTs -> spectrum of operand `which`
+ *   phase 2                pointwise products
+ *   phase 3                row IFFTs -> send;  B: all_to_all send -> work; to rank g: nrl*ncl blocks at g*nrl*ncl
+ *   phase 4                column IFFTs, scaled and normalised -> send;  C: same as A
+ *   phase 5                unpack recv behind the halo slots; H: every rank > 0 copies the last
+ *                          halo_send blocks of rank-1 (mpirfft_smul_tail_blocks) into unp[0..)
+ *   phase 6                recombine my window of the result (limbs [limb_lo, limb_hi)) -> out
+ *   mpirfft_smul_carry     rank 0 .. world-1 in turn: add the carry handed over, hand on the new one */
+typedef struct mpirfft_smul_plan mpirfft_smul_plan;
+typedef struct {
+   uint32_t block_limbs, ncl, nrl, r0, trunc_rows, n1cols, halo, halo_send;
+   uint64_t limb_lo, limb_hi, send_limbs, recv_limbs, work_limbs;
+   void *send, *recv, *work, *unp, *out;
+} mpirfft_smul_layout;
+int  mpirfft_smul_plan_create(mpirfft_smul_plan **plan, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
+                              mp_bitcnt_t w, int rank, int world);
+void mpirfft_smul_plan_destroy(mpirfft_smul_plan *plan);
+int  mpirfft_smul_info(const mpirfft_smul_plan *plan, mpirfft_smul_layout *out);
+int  mpirfft_smul_phase(mpirfft_smul_plan *plan, int phase, int which, const mp_limb_t *d_in, void *stream);
+int  mpirfft_smul_carry(mpirfft_smul_plan *plan, unsigned carry_in, unsigned *carry_out, void *stream);
+mp_limb_t *mpirfft_smul_tail_blocks(mpirfft_smul_plan *plan, unsigned count);
+
 /* Pointwise algorithm: 0 = schoolbook IMAD.WIDE kernel (default), 1 = nested Schoenhage-Strassen
  * step inside a warp (the fft_mulmod_2expp1 idea, mul_fft.c:3125-3167) for l in {64,128,256,512}. */
 void mpirfft_set_pointwise_mode(int mode);

@@ -1136,14 +1136,17 @@ __device__ __forceinline__ limb_t bits_at(const limb_t *src, uint64_t n, uint64_
    return v;
 }
 
+/* Coefficient index of local block i: the blocks of a rank's column shard are rows of `ncl`
+ * consecutive coefficients taken every `n1` (ncl == n1 == 0: plain split, block i is coefficient i) */
 __global__ void __launch_bounds__(256)
 k_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *__restrict__ src, uint64_t nlimbs,
-        uint64_t bits, uint64_t ncoef, uint64_t nzero)
+        uint64_t bits, uint64_t ncoef, uint64_t nblocks, uint32_t ncl, uint32_t n1, uint32_t c0)
 {
    const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
    const uint64_t per = (uint64_t) l + 1;
-   if (t >= nzero * per) return;
-   const uint64_t i = t / per; const uint32_t k = (uint32_t)(t % per);
+   if (t >= nblocks * per) return;
+   const uint64_t blk = t / per; const uint32_t k = (uint32_t)(t % per);
+   const uint64_t i = ncl ? (blk / ncl) * n1 + c0 + (blk % ncl) : blk;
    limb_t v = 0;
    if (i < ncoef && k < l && (uint64_t) k * 64 < bits)
    {
@@ -1151,20 +1154,57 @@ k_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *__restrict__ src
       const uint64_t rem = bits - (uint64_t) k * 64;
       if (rem < 64) v &= (((limb_t) 1 << rem) - 1);
    }
-   slab[i * pitch + k] = v;
+   slab[blk * pitch + k] = v;
+}
+
+/* dst block i = src block table[i] (unpacking an all-to-all receive buffer into row order) */
+__global__ void __launch_bounds__(256)
+k_gather_blocks(limb_t *dst, const limb_t *__restrict__ src, const uint32_t *__restrict__ table,
+                uint64_t nblocks, uint32_t pitch)
+{
+   const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= nblocks * pitch) return;
+   const uint64_t blk = t / pitch; const uint32_t k = (uint32_t)(t % pitch);
+   dst[blk * pitch + k] = src[(uint64_t) table[blk] * pitch + k];
+}
+
+/* res += c at limb 0, rippling (one warp; the ripple leaves the first tile only through all-ones
+ * limbs).  *carry_out = 1 if the carry leaves limb total-1. */
+__global__ void __launch_bounds__(32)
+k_add_small(limb_t *res, uint64_t total, uint32_t c, uint32_t *carry_out)
+{
+   const uint32_t lane = threadIdx.x;
+   uint32_t cin = c;
+   for (uint64_t k0 = 0; k0 < total && cin; k0 += 32)
+   {
+      const uint64_t k = k0 + lane;
+      limb_t v = (k < total) ? res[k] : ~(limb_t) 0;
+      uint32_t g = 0;
+      if (k0 == 0 && lane == 0) { const limb_t nv = v + cin; g = (nv < v); v = nv; cin = 0; }
+      else if (k0 == 0) cin = 0;
+      cin = __shfl_sync(FULL, cin, 0);
+      const uint32_t G = __ballot_sync(FULL, g != 0), P = __ballot_sync(FULL, v == ~(limb_t) 0);
+      const uint64_t la = mfft_lookahead(G, P, (k0 == 0) ? 0u : 1u);
+      if ((la >> lane) & 1u) v += 1;
+      if (k < total) res[k] = v;
+      cin = (uint32_t)(la >> 32) & 1u;
+   }
+   if (lane == 0) *carry_out = cin;
 }
 
 /* res[k] = low 64 bits of the sum of all coefficient windows covering limb k; cvec[k+1] = the
  * high part of that sum (a small count) */
 __global__ void __launch_bounds__(256)
 k_combine_sum(limb_t *res, uint32_t *cvec, uint64_t total, const limb_t *__restrict__ slab,
-              uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef)
+              uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef, uint64_t base_bit)
 {
    const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
    if (k > total) return;
    if (k == 0) cvec[0] = 0;
    if (k == total) return;
-   const uint64_t lo_bit = k * 64, NWb = (uint64_t) l * 64;
+   /* coefficient i occupies bits [i*bits, i*bits + NW) of the full result; res[0] is the limb
+      at bit base_bit (a multiple of 64) -- the window form used by the sharded recombine */
+   const uint64_t lo_bit = base_bit + k * 64, NWb = (uint64_t) l * 64;
    /* coefficients i with i*bits <= lo_bit+63 and i*bits + NW > lo_bit */
    uint64_t imax = (lo_bit + 63) / bits;
    if (imax >= ncoef) imax = ncoef - 1;
@@ -1228,7 +1268,7 @@ k_combine_add(limb_t *res, const uint32_t *__restrict__ cvec, uint64_t total, ui
 /* pass 3: one warp scans the tile generate/propagate bits, 32 tiles per step */
 __global__ void __launch_bounds__(32)
 k_combine_scan(const uint32_t *__restrict__ tileG, const uint32_t *__restrict__ tileP,
-               uint32_t *tileC, uint64_t ntiles)
+               uint32_t *tileC, uint64_t ntiles, const uint32_t *__restrict__ cvec_last, uint32_t *carry_out)
 {
    const uint32_t lane = threadIdx.x;
    uint32_t cin = 0;
@@ -1241,6 +1281,8 @@ k_combine_scan(const uint32_t *__restrict__ tileG, const uint32_t *__restrict__ 
       if (t < ntiles) tileC[t] = (uint32_t)(la >> lane) & 1u;
       cin = (uint32_t)(la >> 32) & 1u;
    }
+   /* what leaves the window: the ripple carry plus the high part of the last limb's column sum */
+   if (lane == 0 && carry_out) *carry_out = cin + *cvec_last;
 }
 
 /* pass 4: tiles with carry-in 1 add it (it ripples through the all-ones prefix of the tile) */
@@ -1545,7 +1587,34 @@ int mfft_dev_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, 
    const uint64_t threads = nzero * ((uint64_t) l + 1);
    if (!threads) return 0;
    PROF(PC_SPLIT, stream);
-   MFFT_LAUNCH(k_split, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t) stream, slab, l, pitch, src, nlimbs, bits, ncoef, nzero);
+   MFFT_LAUNCH(k_split, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t) stream, slab, l, pitch, src, nlimbs, bits, ncoef, nzero, 0u, 0u, 0u);
+   CKL();
+   return 0;
+}
+
+int mfft_dev_split_cols(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, uint64_t nlimbs,
+                        uint64_t bits, uint64_t ncoef, uint64_t nrows, uint32_t ncl, uint32_t n1, uint32_t c0, void *stream)
+{
+   const uint64_t nblocks = nrows * ncl, threads = nblocks * ((uint64_t) l + 1);
+   if (!threads) return 0;
+   PROF(PC_SPLIT, stream);
+   MFFT_LAUNCH(k_split, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t) stream, slab, l, pitch, src, nlimbs, bits, ncoef, nblocks, ncl, n1, c0);
+   CKL();
+   return 0;
+}
+
+int mfft_dev_gather_blocks(limb_t *dst, const limb_t *src, const uint32_t *d_table, uint64_t nblocks, uint32_t pitch, void *stream)
+{
+   const uint64_t threads = nblocks * pitch;
+   if (!threads) return 0;
+   MFFT_LAUNCH(k_gather_blocks, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t) stream, dst, src, d_table, nblocks, pitch);
+   CKL();
+   return 0;
+}
+
+int mfft_dev_add_small(limb_t *res, uint64_t total, uint32_t c, uint32_t *d_carry_out, void *stream)
+{
+   MFFT_LAUNCH(k_add_small, 1, 32, 0, (cudaStream_t) stream, res, total, c, d_carry_out);
    CKL();
    return 0;
 }
@@ -1556,23 +1625,35 @@ size_t mfft_dev_combine_work(uint64_t total)
    return (size_t)((total + 1) * 4 + 3 * (ntiles + 32) * 4 + 256);
 }
 
+int mfft_dev_combine_window(limb_t *res, uint64_t total, const limb_t *slab, uint32_t l, uint32_t pitch,
+                            uint64_t bits, uint64_t ncoef, uint64_t base_bit, uint32_t *d_carry_out, void *work, void *stream);
+
 int mfft_dev_combine(limb_t *res, uint64_t total, const limb_t *slab, uint32_t l, uint32_t pitch,
                      uint64_t bits, uint64_t ncoef, void *work, void *stream)
 {
+   return mfft_dev_combine_window(res, total, slab, l, pitch, bits, ncoef, 0, NULL, work, stream);
+}
+
+/* res[k], k < total: limb k of the window that starts at bit base_bit of sum_i block_i * 2^(i*bits)
+ * (each limb sums the pieces of the coefficient windows that cover it; the carries run inside
+ * the window only).  *d_carry_out (optional): the carry that leaves limb total-1. */
+int mfft_dev_combine_window(limb_t *res, uint64_t total, const limb_t *slab, uint32_t l, uint32_t pitch,
+                            uint64_t bits, uint64_t ncoef, uint64_t base_bit, uint32_t *d_carry_out, void *work, void *stream)
+{
    cudaStream_t st = (cudaStream_t) stream;
    if (!total) return 0;
-   if (!ncoef) { CK(cudaMemsetAsync(res, 0, total * 8, st)); return 0; }
+   if (!ncoef) { CK(cudaMemsetAsync(res, 0, total * 8, st)); if (d_carry_out) CK(cudaMemsetAsync(d_carry_out, 0, 4, st)); return 0; }
    const uint64_t ntiles = (total + 32 * CMB_M - 1) / (32 * CMB_M);
    uint32_t *cvec = (uint32_t *) work;
    uint32_t *tileG = cvec + ((total + 1 + 63) / 64) * 64;
    uint32_t *tileP = tileG + ntiles + 32 - (ntiles % 32);
    uint32_t *tileC = tileP + ntiles + 32 - (ntiles % 32);
    PROF(PC_COMBINE, st);
-   MFFT_LAUNCH(k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef);
+   MFFT_LAUNCH(k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef, base_bit);
    CKL();
    MFFT_LAUNCH(k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);
    CKL();
-   MFFT_LAUNCH(k_combine_scan, 1, 32, 0, st, tileG, tileP, tileC, ntiles);
+   MFFT_LAUNCH(k_combine_scan, 1, 32, 0, st, tileG, tileP, tileC, ntiles, cvec + total, d_carry_out);
    CKL();
    MFFT_LAUNCH(k_combine_fix, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, total, tileC, ntiles);
    CKL();

@@ -1,0 +1,98 @@
+/* xform.c -- see xform.h */
+#define _POSIX_C_SOURCE 200809L
+#include "xform.h"
+#include "../../../include/mpirfft_b200.h"
+#include <stdlib.h>
+#include <string.h>
+
+int mfft_xform_halves(const mfft_xform *x) { return x->fused ? 1 : 2; }
+
+void mfft_xform_free(mfft_xform *x)
+{
+   uint32_t i;
+   if (x->dp)
+   {
+      for (i = 0; i < x->P.npasses; i++)
+      { mfft_dev_free(x->dp[i].d_tiles); mfft_dev_free(x->dp[i].d_pos); mfft_dev_free(x->dp[i].d_ops); mfft_dev_free(x->dp[i].d_stoff); }
+      free(x->dp);
+   }
+   mfft_passes_free(&x->P);
+   if (x->ds.s) { mfft_dsched_free(&x->ds); x->s = NULL; }
+   if (x->s) mfft_sched_free(x->s);
+   mfft_dev_free(x->d_batch); mfft_dev_free(x->d_dst_base); mfft_dev_free(x->d_dstpos); mfft_dev_free(x->d_moves);
+   memset(x, 0, sizeof(*x));
+}
+
+int mfft_xform_build(mfft_xform *x, mfft_sched *s, uint32_t l, uint32_t slot_stride, uint64_t half_blocks,
+                     const mfft_batch *batch, uint32_t nbatch, const uint32_t *dst_of, uint32_t nout,
+                     const uint32_t *dst_base, uint32_t dst_stride, uint32_t shift, int normalise)
+{
+   const char *env = getenv("MPIRFFT_UNFUSED");
+   uint32_t S = s->S, k; int rc = MPIRFFT_ENOMEM;
+   memset(x, 0, sizeof(*x));
+   x->s = s; x->S = S; x->nbatch = nbatch; x->nout = nout; x->dst_stride = dst_stride;
+   x->shift = (uint32_t)(shift % (128ull*l)); x->normalise = normalise;
+   x->g.S = S; x->g.slot_stride = slot_stride; x->g.half_blocks = half_blocks; x->g.l = l; x->g.pitch = l + 1;
+   x->fused = mfft_dev_tiles_supported(l) && !(env && env[0] == '1');
+   x->d_batch = (mfft_batch *) mfft_upload(batch, sizeof(mfft_batch)*nbatch);
+   x->d_dst_base = (uint32_t *) mfft_upload(dst_base, sizeof(uint32_t)*nbatch);
+   if (!x->d_batch || !x->d_dst_base) { rc = MPIRFFT_ENODEV; goto fail; }
+   if (x->fused)
+   {
+      uint8_t *must = (uint8_t *) calloc(S, 1);
+      uint32_t *dstpos = (uint32_t *) malloc(sizeof(uint32_t)*S);
+      if (!must || !dstpos) { free(must); free(dstpos); goto fail; }
+      for (k = 0; k < S; k++) dstpos[k] = MFFT_NONE;
+      if (x->shift)
+         for (k = 0; k < nout; k++) mfft_sched_emit_op(s, k, MFFT_NONE, k, 1, x->shift, 0, 0, MFFT_NONE, 0, 0, 0, 0);
+      for (k = 0; k < nout; k++) { must[s->phys[k]] = 1; dstpos[s->phys[k]] = dst_of[k]; }
+      if (mfft_passes_build(&x->P, s, mfft_dev_tiles_max_npos(l), must) != 0) { free(must); free(dstpos); goto fail; }
+      x->d_dstpos = (uint32_t *) mfft_upload(dstpos, sizeof(uint32_t)*S);
+      free(must); free(dstpos);
+      x->dp = (struct mfft_dpass *) calloc(x->P.npasses ? x->P.npasses : 1, sizeof(*x->dp));
+      if (!x->d_dstpos || !x->dp) goto fail;
+      for (k = 0; k < x->P.npasses; k++)
+      {
+         const mfft_pass *p = &x->P.pass[k];
+         x->dp[k].d_tiles = (mfft_tile *) mfft_upload(p->tiles, sizeof(mfft_tile)*(p->ntiles ? p->ntiles : 1));
+         x->dp[k].d_pos = (uint32_t *) mfft_upload(p->pos, sizeof(uint32_t)*(p->npos_total ? p->npos_total : 1));
+         x->dp[k].d_ops = (mfft_tileop *) mfft_upload(p->ops, sizeof(mfft_tileop)*(p->nops_total ? p->nops_total : 1));
+         x->dp[k].d_stoff = (uint32_t *) mfft_upload(p->stoff, sizeof(uint32_t)*(p->nstoff ? p->nstoff : 1));
+         if (!x->dp[k].d_tiles || !x->dp[k].d_pos || !x->dp[k].d_ops || !x->dp[k].d_stoff) { rc = MPIRFFT_ENODEV; goto fail; }
+      }
+   } else
+   {
+      mfft_move *mv = (mfft_move *) malloc(sizeof(mfft_move)*(nout ? nout : 1));
+      if (!mv) goto fail;
+      for (k = 0; k < nout; k++) { mv[k].src_slot = s->slot[k]; mv[k].dst_pos = dst_of[k]; }
+      x->d_moves = (mfft_move *) mfft_upload(mv, sizeof(mfft_move)*(nout ? nout : 1));
+      free(mv);
+      if (!x->d_moves) { rc = MPIRFFT_ENODEV; goto fail; }
+      if (mfft_dsched_upload(&x->ds, s) != 0) { rc = MPIRFFT_ENODEV; goto fail; }
+   }
+   return 0;
+fail:
+   mfft_xform_free(x);
+   return rc;
+}
+
+int mfft_xform_exec(const mfft_xform *x, limb_t *slab, limb_t *dst, void *stream)
+{
+   uint32_t i;
+   if (x->fused)
+   {
+      for (i = 0; i < x->P.npasses; i++)
+      {
+         const mfft_pass *p = &x->P.pass[i];
+         const int lastp = (i + 1 == x->P.npasses);
+         if (mfft_dev_run_tiles(slab, &x->g, x->dp[i].d_tiles, p->ntiles, x->dp[i].d_pos, x->dp[i].d_ops, p->max_npos,
+                                p->max_nops, x->d_batch, x->nbatch, lastp ? dst : NULL, x->d_dstpos, x->d_dst_base,
+                                x->dst_stride, lastp ? x->normalise : 0, x->dp[i].d_stoff, stream) != 0) return MPIRFFT_ENODEV;
+      }
+      return 0;
+   }
+   if (mfft_dsched_run(&x->ds, slab, &x->g, x->d_batch, x->nbatch, stream) != 0) return MPIRFFT_ENODEV;
+   if (mfft_dev_finalize(dst, x->dst_stride, x->d_dst_base, slab, &x->g, x->d_moves, x->nout, x->d_batch, x->nbatch,
+                         x->shift, x->normalise, stream) != 0) return MPIRFFT_ENODEV;
+   return 0;
+}

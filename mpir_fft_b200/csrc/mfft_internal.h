@@ -138,6 +138,18 @@ void mfft_dev_pointwise_mode(int mode);
 int  mfft_dev_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, uint64_t nlimbs,
                     uint64_t bits, uint64_t ncoef, uint64_t nzero, void *stream);
 
+/* the same for a rank's column shard: local block (r, cl) = coefficient r*n1 + c0 + cl, r < nrows */
+int  mfft_dev_split_cols(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, uint64_t nlimbs,
+                         uint64_t bits, uint64_t ncoef, uint64_t nrows, uint32_t ncl, uint32_t n1, uint32_t c0, void *stream);
+/* dst block i = src block d_table[i] */
+int  mfft_dev_gather_blocks(limb_t *dst, const limb_t *src, const uint32_t *d_table, uint64_t nblocks, uint32_t pitch, void *stream);
+/* res += c (small) with full ripple; *d_carry_out = carry leaving the array */
+int  mfft_dev_add_small(limb_t *res, uint64_t total, uint32_t c, uint32_t *d_carry_out, void *stream);
+/* windowed combine: res[k] = limb k of the window starting at bit base_bit of the full sum (carries
+ * inside the window only); *d_carry_out (optional, device) = carry leaving limb total-1 */
+int  mfft_dev_combine_window(limb_t *res, uint64_t total, const limb_t *slab, uint32_t l, uint32_t pitch,
+                             uint64_t bits, uint64_t ncoef, uint64_t base_bit, uint32_t *d_carry_out, void *work, void *stream);
+
 /* combine: res[0..total) = sum_{i<ncoef} block_i * 2^(i*bits) truncated to total limbs
  * (FFT_combine_bits, mul_fft.c:207-267, including the MPN_ZERO of mul_fft.c:3261).
  * blocks must be normalised with zero top limb.  work: >= mfft_dev_combine_work(total) bytes. */
