@@ -199,319 +199,8 @@ k_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *__restrict__ dst_ba
 }
 
 
-/* ------------------------------------------------------------------------------------------ */
-/* fused tile executor: several stages of a transform inside shared memory                     */
-/* ------------------------------------------------------------------------------------------ */
-/* A coefficient of l = 32*M*NT limbs lives in shared memory with one pad limb after every M
- * limbs (storage index q + q/M): lane j of a warp owns limbs [j*M, j*M+M) of each 32*M-limb
- * tile, and with the pad the 16 lanes of an LDS.64 phase hit 16 different 8-byte banks.
- * One warp executes one op: it builds both outputs in registers from the (rotated,
- * complemented) shared-memory operands, and only then overwrites the operands.             */
-/* Limbs [kb, kb+M) of  (+-) body * 2^(64y+bs)  as non-negative addends: the rotated limbs with the
- * negated bit region complemented (bits [0,e) for a positive term, [e,NW) for a negative one,
- * e = 64y+bs; mfft_arith.h).  y, bs, neg are warp-uniform.
- *   aligned (bs == 0 and M | y, true for all inner MFA layers since w*n1 and w*n2 are multiples
- *   of 64*M bits): the lane's M limbs are contiguous in the padded layout and the complement
- *   pattern is uniform per lane -- M loads at constant offsets and one XOR each;
- *   general: incremental wrapped index, funnel shift, branch-free per-limb mask.             */
-template <int M, uint32_t PS>
-__device__ __forceinline__ void term_chunk(limb_t (&x)[M], const limb_t *p, uint32_t l, uint32_t kb,
-                                           uint32_t y, uint32_t bs, bool neg)
-{
-   const uint32_t nm32 = neg ? 0xffffffffu : 0u;
-   uint32_t q = kb + l - y;
-   if (q >= l) q -= l;
-   if (bs == 0 && (y & (M - 1)) == 0)
-   {
-      const limb_t *src = p + q + (q >> PS);
-      const uint32_t m32 = ((kb < y) ? 0xffffffffu : 0u) ^ nm32;
-      const limb_t m = ((limb_t) m32 << 32) | m32;
-#pragma unroll
-      for (int i = 0; i < M; i++) x[i] = src[i] ^ m;
-      return;
-   }
-   if (bs == 0)
-   {
-#pragma unroll
-      for (int i = 0; i < M; i++)
-      {
-         x[i] = p[q + (q >> PS)];
-         q = (q + 1 == l) ? 0 : q + 1;
-      }
-   } else
-   {
-      const uint32_t qm = (q == 0) ? l - 1 : q - 1;
-      limb_t prev = p[qm + (qm >> PS)];
-      const uint32_t rs = 64 - bs;
-#pragma unroll
-      for (int i = 0; i < M; i++)
-      {
-         const limb_t cur = p[q + (q >> PS)];
-         x[i] = (cur << bs) | (prev >> rs);
-         prev = cur;
-         q = (q + 1 == l) ? 0 : q + 1;
-      }
-   }
-   const limb_t low = (((limb_t) 1 << bs) - 1);
-#pragma unroll
-   for (int i = 0; i < M; i++)
-   {
-      const uint32_t k = kb + i;
-      const uint32_t m32 = (uint32_t)((int32_t)(k - y) >> 31) ^ nm32;     /* all ones iff k < y */
-      x[i] ^= ((limb_t) m32 << 32) | m32;
-      if (k == y) x[i] ^= low;
-   }
-}
-
-/* r = x + z over the 32*M*NT limbs of a coefficient spread over the warp (lane owns M limbs of
- * each tile), carry-lookahead across lanes, carry-in tc into limb 0; returns the carry out. */
-template <int M, int NT>
-__device__ __forceinline__ uint32_t add_lookahead(limb_t (&r)[M * NT], const limb_t (&x)[M * NT],
-                                                  const limb_t (&z)[M * NT], uint32_t tc, uint32_t lane)
-{
-#pragma unroll
-   for (int ti = 0; ti < NT; ti++)
-   {
-      uint32_t c = 0; limb_t all1 = ~(limb_t) 0;
-#pragma unroll
-      for (int i = 0; i < M; i++)
-      {
-         const mfft_u128 acc = (mfft_u128) x[ti * M + i] + z[ti * M + i] + c;
-         r[ti * M + i] = (limb_t) acc; c = (uint32_t)(acc >> 64);
-         all1 &= (limb_t) acc;
-      }
-      const uint32_t G = __ballot_sync(FULL, c != 0);
-      const uint32_t P = __ballot_sync(FULL, all1 == ~(limb_t) 0);
-      const uint64_t la = mfft_lookahead(G, P, tc);
-      tc = (uint32_t)(la >> 32) & 1u;
-      if ((la >> lane) & 1u)
-      {  /* +1 into this lane's chunk; it cannot carry out again (that is what P encodes) */
-#pragma unroll
-         for (int i = 0; i < M; i++)
-         {
-            r[ti * M + i] += 1;
-            if (r[ti * M + i] != 0) break;
-         }
-      }
-   }
-   return tc;
-}
-
-template <int M, int NT>
-__device__ __forceinline__ void store_regs(limb_t *out, const limb_t *r, uint32_t ps, uint32_t lane)
-{
-#pragma unroll
-   for (int ti = 0; ti < NT; ti++)
-#pragma unroll
-      for (int i = 0; i < M; i++)
-      {
-         const uint32_t k = ti * 32u * M + lane * M + i;
-         out[k + (k >> ps)] = r[ti * M + i];
-      }
-}
-
-/* warp-level mpn_normmod_2expp1 on a padded shared-memory coefficient with a separate top */
-__device__ __forceinline__ void normalise_sm(limb_t *blk, uint32_t ps, uint32_t l, int64_t *topp, uint32_t lane)
-{
-   for (int it = 0; it < 4; it++)
-   {
-      __syncwarp();
-      const int64_t top = *topp;
-      if (top == 0) break;
-      if (top == 1)
-      {
-         bool z = true;
-         for (uint32_t k = lane; k < l; k += 32) z = z && (blk[k + (k >> ps)] == 0);
-         if (__all_sync(FULL, z)) break;
-      }
-      __syncwarp();
-      if (lane == 0)
-      {
-         int64_t nt = 0;
-         mfft_inject2(blk, ps, l, &nt, 0, -(mfft_i128) top);
-         *topp = nt;
-      }
-   }
-   __syncwarp();
-}
-
-/* cheap per-op scalar setup of one term (warp-uniform): exponent -> (y, bs, neg) and the term's
- * contribution to the output top limb / carry-in; the injection constant is built by lane 0 only */
-struct tterm { uint32_t y, bs; int neg, present; int64_t kfac; };   /* K = kfac << bs, kfac small */
-
-__device__ __forceinline__ void tterm_setup(tterm &t, int sign, uint32_t e, uint32_t NW, int64_t top,
-                                            int64_t &top_acc, int &ones)
-{
-   t.present = (sign != 0); t.y = 0; t.bs = 0; t.neg = 0; t.kfac = 0;
-   if (!sign) return;
-   if (e >= NW) { e -= NW; sign = -sign; }
-   t.y = e >> 6; t.bs = e & 63; t.neg = (sign < 0);
-   if (e == 0)
-   {
-      if (sign > 0) top_acc += top;
-      else { ones += 1; top_acc -= 1 + top; }
-   } else if (sign > 0) { ones += 1; t.kfac = -(1 + top); }
-   else { top_acc -= 1; t.kfac = 1 + top; }
-}
-
-__device__ __forceinline__ mfft_i128 tterm_K(const tterm &t)
-{
-   const uint64_t lo = (uint64_t) t.kfac << t.bs;
-   const int64_t hi = t.bs ? (t.kfac >> (64 - t.bs)) : (t.kfac >> 63);     /* arithmetic shifts */
-   return (mfft_i128)(((mfft_u128)(uint64_t) hi << 64) | lo);
-}
-
-template <int M, int NT>
-__global__ void __launch_bounds__(256, 2)
-k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
-            const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
-            limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
-            uint32_t dst_stride, int normalise, uint32_t desc_bytes, const uint32_t *__restrict__ stoff)
-{
-   MFFT_DYN_SMEM(limb_t, sm);
-   constexpr uint32_t L = 32u * M * NT;
-   constexpr uint32_t NW = 64u * L, M2 = 2u * NW;
-   constexpr uint32_t PS = (M == 1) ? 31u : (M == 2 ? 1u : (M == 4 ? 2u : 3u));
-   constexpr uint32_t SP = (M == 1) ? L : L + L / M;          /* shared-memory pitch of a coefficient */
-   const uint32_t bi = blockIdx.x % nbatch;
-   const mfft_tile T = tiles[blockIdx.x / nbatch];
-   const mfft_batch b = batch[bi];
-   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-   /* shared memory: [op descriptors | position list] [coefficients] [tops] */
-   mfft_tileop *sops = (mfft_tileop *) sm;
-   uint32_t *spos = (uint32_t *)(sops + T.nops);
-   uint32_t *sst = spos + T.npos;                      /* [nstages+1] first op of each stage */
-   limb_t *coef = sm + desc_bytes / 8;
-   int64_t *tops = (int64_t *)(coef + (size_t) T.npos * SP);
-
-   {  /* descriptors: one coalesced copy instead of dependent global loads inside the op loop */
-      const uint32_t *src = (const uint32_t *)(ops + T.op_off);
-      uint32_t *d = (uint32_t *) sops;
-      for (uint32_t k = tid; k < T.nops * (uint32_t)(sizeof(mfft_tileop) / 4); k += blockDim.x) d[k] = src[k];
-      for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = pos[T.pos_off + k];
-      for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = stoff[T.pad + k];
-   }
-   /* load the positions that are read before being written */
-   for (uint32_t p = warp; p < T.npos; p += nwarps)
-   {
-      const uint32_t pp = pos[T.pos_off + p];
-      if (!(pp & MFFT_TILE_LOAD)) continue;
-      const limb_t *src = block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
-      limb_t *d = coef + (size_t) p * SP;
-#pragma unroll 4
-      for (uint32_t k = lane; k < L; k += 32) d[k + (k >> PS)] = src[k];
-      if (lane == 0) tops[p] = (int64_t) src[L];
-   }
-   __syncthreads();
-
-   for (uint32_t st = 0; st < T.nstages; st++)
-   {
-      const uint32_t o0 = sst[st], o1 = sst[st + 1];
-      for (uint32_t oi = o0 + warp; oi < o1; oi += nwarps)
-      {
-         const mfft_tileop op = sops[oi];
-         const limb_t *A = coef + (size_t) op.a * SP;
-         const bool hasB = (op.b != 0xFFFF), hasT = (op.t != 0xFFFF);
-         const limb_t *B = hasB ? coef + (size_t) op.b * SP : A;
-         const int64_t topA = tops[op.a], topB = hasB ? tops[op.b] : 0;
-         uint32_t eSA = op.eSA, eSB = op.eSB, eTA = op.eTA, eTB = op.eTB;
-         if (op.cSA | op.cSB | op.cTA | op.cTB)
-         {  /* the MFA twist z^(r*c): only the twisted layer pays for the modulo */
-            eSA = (eSA + b.col * op.cSA) % M2; eSB = (eSB + b.col * op.cSB) % M2;
-            eTA = (eTA + b.col * op.cTA) % M2; eTB = (eTB + b.col * op.cTB) % M2;
-         }
-         int64_t topS = 0, topT = 0; int onesS = 0, onesT = 0;
-         tterm sa, sb, ta, tb;
-         tterm_setup(sa, op.sSA, eSA, NW, topA, topS, onesS);
-         tterm_setup(sb, hasB ? op.sSB : 0, eSB, NW, topB, topS, onesS);
-         tterm_setup(ta, hasT ? op.sTA : 0, eTA, NW, topA, topT, onesT);
-         tterm_setup(tb, (hasT && hasB) ? op.sTB : 0, eTB, NW, topB, topT, onesT);
-         if (onesS == 2) topS -= 1;
-         if (onesT == 2) topT -= 1;
-
-         limb_t xa[M * NT], xb[M * NT], rs[M * NT], rt[M * NT];
-#pragma unroll
-         for (int ti = 0; ti < NT; ti++)
-         {
-            const uint32_t kb = ti * 32u * M + lane * M;
-            limb_t (&ca)[M] = *reinterpret_cast<limb_t (*)[M]>(&xa[ti * M]);
-            limb_t (&cb)[M] = *reinterpret_cast<limb_t (*)[M]>(&xb[ti * M]);
-            if (sa.present) term_chunk<M, PS>(ca, A, L, kb, sa.y, sa.bs, sa.neg);
-            else { for (int i = 0; i < M; i++) ca[i] = 0; }
-            if (sb.present) term_chunk<M, PS>(cb, B, L, kb, sb.y, sb.bs, sb.neg);
-            else { for (int i = 0; i < M; i++) cb[i] = 0; }
-         }
-         topS += add_lookahead<M, NT>(rs, xa, xb, onesS ? 1u : 0u, lane);
-         if (hasT)
-         {
-#pragma unroll
-            for (int ti = 0; ti < NT; ti++)
-            {
-               const uint32_t kb = ti * 32u * M + lane * M;
-               limb_t (&ca)[M] = *reinterpret_cast<limb_t (*)[M]>(&xa[ti * M]);
-               limb_t (&cb)[M] = *reinterpret_cast<limb_t (*)[M]>(&xb[ti * M]);
-               if (ta.present)
-               {
-                  if (sa.present && ta.y == sa.y && ta.bs == sa.bs)
-                  {  /* same rotation as in S: only the complement pattern may differ */
-                     if (ta.neg != sa.neg) { for (int i = 0; i < M; i++) ca[i] = ~ca[i]; }
-                  } else term_chunk<M, PS>(ca, A, L, kb, ta.y, ta.bs, ta.neg);
-               } else { for (int i = 0; i < M; i++) ca[i] = 0; }
-               if (tb.present)
-               {
-                  if (sb.present && tb.y == sb.y && tb.bs == sb.bs)
-                  {
-                     if (tb.neg != sb.neg) { for (int i = 0; i < M; i++) cb[i] = ~cb[i]; }
-                  } else term_chunk<M, PS>(cb, B, L, kb, tb.y, tb.bs, tb.neg);
-               } else { for (int i = 0; i < M; i++) cb[i] = 0; }
-            }
-            topT += add_lookahead<M, NT>(rt, xa, xb, onesT ? 1u : 0u, lane);
-         }
-         __syncwarp();                      /* every lane has read the operands */
-         limb_t *S = coef + (size_t) op.s * SP;
-         store_regs<M, NT>(S, rs, PS, lane);
-         limb_t *Tt = hasT ? coef + (size_t) op.t * SP : S;
-         if (hasT) store_regs<M, NT>(Tt, rt, PS, lane);
-         __syncwarp();
-         if (lane == 0)
-         {  /* the constants at bit e of each shifted term (mfft_arith.h); same-position ones merge */
-            mfft_i128 k1 = sa.present ? tterm_K(sa) : 0, k2 = sb.present ? tterm_K(sb) : 0;
-            if (sa.present && sb.present && sa.y == sb.y) { k1 += k2; k2 = 0; }
-            mfft_inject2(S, PS, L, &topS, sa.y, k1);
-            mfft_inject2(S, PS, L, &topS, sb.y, k2);
-            tops[op.s] = topS;
-            if (hasT)
-            {
-               k1 = ta.present ? tterm_K(ta) : 0; k2 = tb.present ? tterm_K(tb) : 0;
-               if (ta.present && tb.present && ta.y == tb.y) { k1 += k2; k2 = 0; }
-               mfft_inject2(Tt, PS, L, &topT, ta.y, k1);
-               mfft_inject2(Tt, PS, L, &topT, tb.y, k2);
-               tops[op.t] = topT;
-            }
-         }
-      }
-      __syncthreads();
-   }
-
-   /* store what was written: in place, or gathered (and normalised) into dst */
-   for (uint32_t p = warp; p < T.npos; p += nwarps)
-   {
-      const uint32_t pp = spos[p];
-      if (!(pp & MFFT_TILE_STORE)) continue;
-      limb_t *out;
-      if (dst)
-      {
-         const uint32_t dp = dstpos[pp & MFFT_TILE_POSMASK];
-         if (dp == MFFT_NONE) continue;
-         out = dst + ((uint64_t) dst_base[bi] + (uint64_t) dp * dst_stride) * g.pitch;
-      } else out = block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
-      limb_t *sblk = coef + (size_t) p * SP;
-      if (normalise) normalise_sm(sblk, PS, L, &tops[p], lane);
-#pragma unroll 4
-      for (uint32_t k = lane; k < L; k += 32) out[k] = sblk[k + (k >> PS)];
-      if (lane == 0) out[L] = (limb_t) tops[p];
-   }
-}
+/* fused shared-memory tile executor (carry-save coefficients): see mfft_tiles.h */
+#include "mfft_tiles.h"
 
 __global__ void __launch_bounds__(128)
 k_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk)
@@ -1425,26 +1114,22 @@ int mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, u
 }
 
 
-static int tiles_cfg(uint32_t l, int *M, int *NT)
+/* coefficient sizes the fused executor is instantiated for: l = 64*NT limbs */
+static int tiles_cfg(uint32_t l, int *NT)
 {
    switch (l)
    {
-   case 64:  *M = 2; *NT = 1; return 1;
-   case 128: *M = 4; *NT = 1; return 1;
-   case 192: *M = 2; *NT = 3; return 1;
-   case 256: *M = 8; *NT = 1; return 1;
-   case 384: *M = 4; *NT = 3; return 1;
-   case 512: *M = 8; *NT = 2; return 1;
+   case 64: case 128: case 192: case 256: case 384: case 512: *NT = (int)(l / 64); return 1;
    default: return 0;
    }
 }
 
-int mfft_dev_tiles_supported(uint32_t l) { int m, nt; return tiles_cfg(l, &m, &nt); }
+int mfft_dev_tiles_supported(uint32_t l) { int nt; return tiles_cfg(l, &nt); }
 
 static size_t tiles_coeff_bytes(uint32_t l)
 {
-   int m = 1, nt = 1; tiles_cfg(l, &m, &nt);
-   return ((size_t) l + l / m) * 8 + 8;
+   /* l body limbs + l/2 chunks with a 32-bit carry word each (mfft_tiles.h) */
+   return (size_t) l * 8 + (size_t)(l / 2) * 4;
 }
 
 uint32_t mfft_dev_tiles_max_npos(uint32_t l)
@@ -1462,27 +1147,30 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
                        limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
                        uint32_t dst_stride, int normalise, const uint32_t *d_stoff, void *stream)
 {
-   int M = 0, NT = 0;
+   int NT = 0;
    if (!ntiles || !nbatch) return 0;
-   if (!tiles_cfg(g->l, &M, &NT)) { snprintf(g_err, sizeof g_err, "run_tiles: l=%u unsupported", g->l); return -2; }
-   /* descriptor area (ops + position list), rounded to 16 bytes, then coefficients + tops */
+   if (!tiles_cfg(g->l, &NT)) { snprintf(g_err, sizeof g_err, "run_tiles: l=%u unsupported", g->l); return -2; }
+   /* descriptor area (ops + position list), rounded to 16 bytes, then coefficients */
    const uint32_t desc = (uint32_t)(((size_t) max_nops * sizeof(mfft_tileop) + (size_t) max_npos * 4 + 4 * 64 + 15) & ~(size_t) 15);
    const size_t smem = desc + (size_t) max_npos * tiles_coeff_bytes(g->l);
    const unsigned grid = ntiles * nbatch;
    cudaStream_t st = (cudaStream_t) stream;
    PROF(PC_STAGE, st);
-#define RUN_TILES(MM, NN)                                                                          \
+#define RUN_TILES(NN)                                                                              \
    do {                                                                                            \
-      CK(cudaFuncSetAttribute(k_run_tiles<MM, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-      MFFT_LAUNCH((k_run_tiles<MM, NN>), grid, 256, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
+      CK(cudaFuncSetAttribute(k_run_tiles<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+      MFFT_LAUNCH((k_run_tiles<NN>), grid, 256, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
                   dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff);                 \
    } while (0)
-   if (M == 2 && NT == 1) RUN_TILES(2, 1);
-   else if (M == 4 && NT == 1) RUN_TILES(4, 1);
-   else if (M == 2 && NT == 3) RUN_TILES(2, 3);
-   else if (M == 8 && NT == 1) RUN_TILES(8, 1);
-   else if (M == 4 && NT == 3) RUN_TILES(4, 3);
-   else RUN_TILES(8, 2);
+   switch (NT)
+   {
+   case 1: RUN_TILES(1); break;
+   case 2: RUN_TILES(2); break;
+   case 3: RUN_TILES(3); break;
+   case 4: RUN_TILES(4); break;
+   case 6: RUN_TILES(6); break;
+   default: RUN_TILES(8); break;
+   }
 #undef RUN_TILES
    CKL();
    return 0;

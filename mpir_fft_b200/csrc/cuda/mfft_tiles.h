@@ -1,0 +1,648 @@
+/* mfft_tiles.h -- the fused shared-memory tile executor (included by mfft_kernels.cu).
+ *
+ * Several radix-2 layers of a transform (mul_fft.c:786-827, 1397-1442, 1128-1227, 1444-1536, ...)
+ * run on a tile of coefficients that stays in shared memory; HBM sees one read and one write of
+ * the tile per pass.
+ *
+ * Carry-save coefficients.  Inside a tile a coefficient of l = 64*NT limbs is NCH = 32*NT
+ * *chunks* of 2 limbs (128 bits), each with a signed 32-bit *carry word*:
+ *
+ *        value = sum_j ( x_j + c_j * B^2 ) * B^(2j)      (mod p = B^l + 1,  B = 2^64)
+ *
+ * i.e. c_j is a deferred carry into chunk j+1, and c_{NCH-1} is the reference's signed top limb
+ * (README:54).  Additions never ripple past a chunk: the carry out of the 2-limb add chain is
+ * added to the chunk's carry word.  A rotation by a whole number of chunks (every inner MFA
+ * layer: the roots are 2^(w*n1*j), 2^(w*n2*j), multiples of 128 bits from 2^20 limbs up) moves
+ * chunks together with their carry words, and the negation of a chunk that wraps around p is
+ * local too:  -(x + c*B^2) = ~x + 1 + (-1-c)*B^2.  So an aligned butterfly is purely lane-local
+ * work -- no ballots, no shuffles, no serial ripple: per lane and chunk two 16-byte loads, two
+ * 2-limb add chains, two 16-byte stores.  The carry words are resolved once per pass, when a
+ * coefficient goes back to HBM in the reference's block layout.
+ *
+ * Layout of one coefficient in shared memory: l body limbs (dense, so lane j's chunk is the 16
+ * bytes at 16 j: conflict-free LDS.128/STS.128), then the NCH carry words.
+ *
+ * Rotations that are not chunk-aligned (the z^(r*c) twist layer, halving steps of the truncated
+ * transforms, the first layers when w*n1 < 128) take the general path: rotated limb reads with a
+ * funnel shift, bit-region complement, and the source carry words re-injected at their rotated
+ * bit position as one more addend of the chunk's chain.
+ */
+#ifndef MFFT_TILES_H
+#define MFFT_TILES_H
+
+/* (r0,r1) = (a0,a1) + (b0,b1) + cin, cin in {0,1}; returns the carry out */
+__device__ __forceinline__ uint32_t add2c(limb_t &r0, limb_t &r1, limb_t a0, limb_t a1, limb_t b0, limb_t b1, uint32_t cin)
+{
+#ifdef MFFT_EMU
+   const mfft_u128 s0 = (mfft_u128) a0 + b0 + (cin ? 1u : 0u);
+   const mfft_u128 s1 = (mfft_u128) a1 + b1 + (limb_t)(s0 >> 64);
+   r0 = (limb_t) s0; r1 = (limb_t) s1;
+   return (uint32_t)(s1 >> 64);
+#else
+   uint32_t cout, tmp;
+   asm("add.cc.u32 %3, %8, 0xffffffff;\n\t"
+       "addc.cc.u64 %0, %4, %6;\n\t"
+       "addc.cc.u64 %1, %5, %7;\n\t"
+       "addc.u32 %2, 0, 0;"
+       : "=l"(r0), "=l"(r1), "=r"(cout), "=r"(tmp)
+       : "l"(a0), "l"(a1), "l"(b0), "l"(b1), "r"(cin));
+   return cout;
+#endif
+}
+
+/* (r0,r1) = (a0,a1) + (b0,b1); returns the carry out */
+__device__ __forceinline__ int32_t add2(limb_t &r0, limb_t &r1, limb_t a0, limb_t a1, limb_t b0, limb_t b1)
+{
+#ifdef MFFT_EMU
+   const mfft_u128 s0 = (mfft_u128) a0 + b0;
+   const mfft_u128 s1 = (mfft_u128) a1 + b1 + (limb_t)(s0 >> 64);
+   r0 = (limb_t) s0; r1 = (limb_t) s1;
+   return (int32_t)(s1 >> 64);
+#else
+   int32_t cout;
+   asm("add.cc.u64 %0, %3, %5;\n\t"
+       "addc.cc.u64 %1, %4, %6;\n\t"
+       "addc.u32 %2, 0, 0;"
+       : "=l"(r0), "=l"(r1), "=r"(cout) : "l"(a0), "l"(a1), "l"(b0), "l"(b1));
+   return cout;
+#endif
+}
+
+/* (r0,r1) = (a0,a1) - (b0,b1) mod B^2; returns -borrow (0 or -1) */
+__device__ __forceinline__ int32_t sub2(limb_t &r0, limb_t &r1, limb_t a0, limb_t a1, limb_t b0, limb_t b1)
+{
+#ifdef MFFT_EMU
+   const limb_t d0 = a0 - b0; const uint32_t bw0 = a0 < b0;
+   const limb_t d1 = a1 - b1 - bw0; const uint32_t bw1 = (a1 < b1) || (a1 == b1 && bw0);
+   r0 = d0; r1 = d1;
+   return -(int32_t) bw1;
+#else
+   int32_t nb;
+   asm("sub.cc.u64 %0, %3, %5;\n\t"
+       "subc.cc.u64 %1, %4, %6;\n\t"
+       "subc.u32 %2, 0, 0;"
+       : "=l"(r0), "=l"(r1), "=r"(nb) : "l"(a0), "l"(a1), "l"(b0), "l"(b1));
+   return nb;
+#endif
+}
+
+/* 16-byte chunk accesses (chunk bodies are 16-byte aligned in shared memory) */
+__device__ __forceinline__ void ld2(limb_t &x0, limb_t &x1, const limb_t *p)
+{
+#ifdef MFFT_EMU
+   x0 = p[0]; x1 = p[1];
+#else
+   const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p); x0 = v.x; x1 = v.y;
+#endif
+}
+__device__ __forceinline__ void st2(limb_t *p, limb_t x0, limb_t x1)
+{
+#ifdef MFFT_EMU
+   p[0] = x0; p[1] = x1;
+#else
+   *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(x0, x1);
+#endif
+}
+
+template <int NT> struct tile_cfg {
+   static constexpr uint32_t L = 64u * NT;           /* body limbs */
+   static constexpr uint32_t NCH = 32u * NT;         /* chunks */
+   static constexpr uint32_t SP = L + NCH / 2;       /* limbs per coefficient: body + int32 carry words */
+};
+
+/* one term of an op after folding e >= NW into the sign */
+struct tterm {
+   uint32_t present, neg;   /* neg: the term is subtracted */
+   uint32_t y, bs;          /* rotation = 64*y + bs bits */
+   uint32_t yc, yr;         /* y = 2*yc + yr */
+};
+
+__device__ __forceinline__ void tterm_setup(tterm &t, int sign, uint32_t e, uint32_t NW)
+{
+   t.present = (sign != 0); t.neg = 0; t.y = 0; t.bs = 0; t.yc = 0; t.yr = 0;
+   if (!sign) return;
+   if (e >= NW) { e -= NW; sign = -sign; }
+   t.neg = (sign < 0);
+   t.y = e >> 6; t.bs = e & 63;
+   t.yc = t.y >> 1; t.yr = t.y & 1;
+}
+
+/* ---- aligned path ------------------------------------------------------------------------- */
+/* Output chunk (ia + ta.yc) of  +-A*B^(2*ycA) +- Bt*B^(2*ycB)  from A's chunk `ia` (a0,a1,ca) and
+ * B's chunk `jb` (b0,b1,cb); stores the chunk and its carry word into `out`. */
+template <int NT>
+__device__ __forceinline__ void aligned_out(limb_t *out, const tterm &ta, const tterm &tb, uint32_t ia, uint32_t jb,
+                                            limb_t a0, limb_t a1, int32_t ca, limb_t b0, limb_t b1, int32_t cb)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH;
+   uint32_t och = ia + ta.yc, na = ta.neg;
+   if (och >= NCH) { och -= NCH; na ^= 1u; }
+   const limb_t ma = (limb_t) 0 - (limb_t) na;
+   limb_t r0, r1; int32_t k;
+   if (tb.present)
+   {
+      const uint32_t nb = tb.neg ^ ((jb + tb.yc >= NCH) ? 1u : 0u);
+      const limb_t mb = (limb_t) 0 - (limb_t) nb;
+      uint32_t c = add2c(r0, r1, a0 ^ ma, a1 ^ ma, b0 ^ mb, b1 ^ mb, na | nb);
+      k = (int32_t) c - (int32_t)(na + nb) + (na ? -ca : ca) + (nb ? -cb : cb);
+      if (na & nb)
+      {  /* -(a+b): a second +1 (both operands were complemented) */
+         c = add2c(r0, r1, r0, r1, 0, 0, 1u);
+         k += (int32_t) c;
+      }
+   } else
+   {
+      const uint32_t c = add2c(r0, r1, a0 ^ ma, a1 ^ ma, 0, 0, na);
+      k = (int32_t) c - (int32_t) na + (na ? -ca : ca);
+   }
+#ifdef MFFT_EMU
+   out[2 * och] = r0; out[2 * och + 1] = r1;
+#else
+   *reinterpret_cast<ulonglong2 *>(out + 2 * och) = make_ulonglong2(r0, r1);
+#endif
+   reinterpret_cast<int32_t *>(out + L)[och] = k;
+}
+
+/* ---- general path ------------------------------------------------------------------------- */
+/* limbs (2ch, 2ch+1) of the rotated body of X with the negated bit region complemented (bits
+ * [0,e) for a positive term, [e,NW) for a negative one), and the addend (e0,e1) + kadj*B^2 = the
+ * small signed constant that lands at local limb t.yr, bit t.bs of this chunk: the rotated carry
+ * word of source chunk ch-1-yc (negated if it wrapped), and for ch == yc the -+1 at bit e that
+ * completes the complement (-F = ~F + 2^a - 2^b; the matching +1 at bit 0 is added by the caller). */
+template <int NT>
+__device__ __forceinline__ void general_term(limb_t &x0, limb_t &x1, limb_t &e0, limb_t &e1, int32_t &kadj,
+                                             const tterm &t, const limb_t *X, uint32_t ch)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH;
+   const uint32_t k0 = 2 * ch;
+   uint32_t q0 = k0 + L - t.y;
+   if (q0 >= L) q0 -= L;
+   const uint32_t q1 = (q0 + 1 == L) ? 0 : q0 + 1;
+   const limb_t l0 = X[q0], l1 = X[q1];
+   if (t.bs)
+   {
+      const limb_t lm = X[q0 ? q0 - 1 : L - 1];
+      const uint32_t rs = 64 - t.bs;
+      x0 = (l0 << t.bs) | (lm >> rs);
+      x1 = (l1 << t.bs) | (l0 >> rs);
+   } else { x0 = l0; x1 = l1; }
+   const limb_t nm = (limb_t) 0 - (limb_t) t.neg;
+   const limb_t low = (((limb_t) 1 << t.bs) - 1);
+   const limb_t m0 = (k0 < t.y) ? ~(limb_t) 0 : ((k0 == t.y) ? low : 0);
+   const limb_t m1 = (k0 + 1 < t.y) ? ~(limb_t) 0 : ((k0 + 1 == t.y) ? low : 0);
+   x0 ^= m0 ^ nm; x1 ^= m1 ^ nm;
+   const uint32_t wrapped = (ch <= t.yc);
+   const uint32_t j = wrapped ? ch + NCH - 1 - t.yc : ch - 1 - t.yc;
+   int64_t c = (int64_t) reinterpret_cast<const int32_t *>(X + L)[j];
+   if (wrapped) c = -c;
+   if (ch == t.yc) c -= 1;
+   const int64_t V = t.neg ? -c : c;
+   const limb_t lo = (limb_t) V << t.bs;
+   const int64_t hi = t.bs ? (V >> (64 - t.bs)) : (V >> 63);
+   if (t.yr == 0) { e0 = lo; e1 = (limb_t) hi; kadj = (int32_t)(hi >> 63); }
+   else { e0 = 0; e1 = lo; kadj = (int32_t) hi; }
+}
+
+/* chunk ch of  +-A*2^eA +- B*2^eB  into (r0,r1), returns the chunk's carry word */
+template <int NT>
+__device__ __forceinline__ int32_t general_out(limb_t &r0, limb_t &r1, const tterm &ta, const limb_t *A, const tterm &tb,
+                                               const limb_t *B, uint32_t ch)
+{
+   /* the +1 at bit 0 of each term enters as carry-ins of the chains of chunk 0 */
+   const uint32_t ones = (ch == 0) ? ta.present + tb.present : 0u;
+   limb_t xa0 = 0, xa1 = 0, ea0 = 0, ea1 = 0, xb0 = 0, xb1 = 0, eb0 = 0, eb1 = 0;
+   int32_t ka = 0, kb = 0, k;
+   if (ta.present) general_term<NT>(xa0, xa1, ea0, ea1, ka, ta, A, ch);
+   if (tb.present) general_term<NT>(xb0, xb1, eb0, eb1, kb, tb, B, ch);
+   k = ka + kb;
+   k += (int32_t) add2c(r0, r1, xa0, xa1, xb0, xb1, ones >= 1u);
+   if (ta.present) k += (int32_t) add2c(r0, r1, r0, r1, ea0, ea1, ones >= 2u);
+   if (tb.present) k += (int32_t) add2c(r0, r1, r0, r1, eb0, eb1, 0u);
+   return k;
+}
+
+/* ---- leaving the tile: resolve the carry words --------------------------------------------- */
+/* The warp turns the carry-save coefficient at sblk into plain limbs (written back to the body)
+ * and returns the signed top limb.  Lane j owns chunks [j*NT, j*NT+NT). */
+template <int NT>
+__device__ __forceinline__ int64_t resolve_carries(limb_t *sblk, uint32_t lane)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH;
+   const int32_t *cw = reinterpret_cast<const int32_t *>(sblk + L);
+   limb_t r[2 * NT];
+   int64_t cy = 0;
+#pragma unroll
+   for (int t = 0; t < NT; t++)
+   {
+      const uint32_t ch = lane * NT + t;
+      if (ch) cy += (int64_t) cw[ch - 1];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+      {
+         const mfft_i128 acc = (mfft_i128) cy + (mfft_i128)(mfft_u128) sblk[2 * ch + i];
+         r[2 * t + i] = (limb_t) acc; cy = (int64_t)(acc >> 64);
+      }
+   }
+   int64_t d = cy;                                     /* carry into the next lane's first chunk */
+   int64_t top = (int64_t) cw[NCH - 1];
+   for (;;)
+   {
+      int64_t din = __shfl_up_sync(FULL, d, 1);
+      if (lane == 0) din = 0;
+      top += __shfl_sync(FULL, d, 31);
+      d = 0;
+      if (!__any_sync(FULL, din != 0)) break;
+      if (din != 0)
+      {
+         int64_t c = din;
+#pragma unroll
+         for (int i = 0; i < 2 * NT; i++)
+         {
+            const mfft_i128 acc = (mfft_i128) c + (mfft_i128)(mfft_u128) r[i];
+            r[i] = (limb_t) acc; c = (int64_t)(acc >> 64);
+         }
+         d = c;
+      }
+   }
+   __syncwarp();
+#pragma unroll
+   for (int i = 0; i < 2 * NT; i++) sblk[lane * 2 * NT + i] = r[i];
+   __syncwarp();
+   return top;
+}
+
+/* The same without touching shared memory again: lane j ends up with the resolved limbs of chunks
+ * ti*32 + j in (r0[ti], r1[ti]) -- 16 consecutive bytes per lane, i.e. one coalesced 512-byte
+ * store per ti.  Absorbing the previous chunk's carry word leaves a carry in {-1,0,1}, which
+ * moves on only through all-zero / all-one chunks, so the ripple loop almost never iterates. */
+template <int NT>
+__device__ __forceinline__ int64_t resolve_regs(limb_t (&r0)[NT], limb_t (&r1)[NT], const limb_t *sblk, uint32_t lane)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH;
+   const int32_t *cw = reinterpret_cast<const int32_t *>(sblk + L);
+   int32_t d[NT];
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t i = ti * 32u + lane;
+      limb_t x0, x1;
+      ld2(x0, x1, sblk + 2 * i);
+      const int32_t c = i ? cw[i - 1] : 0;
+      const int32_t k = add2(r0[ti], r1[ti], x0, x1, (limb_t)(int64_t) c, (limb_t)((int64_t) c >> 63));
+      d[ti] = k + (c >> 31);
+   }
+   int64_t top = (int64_t) cw[NCH - 1];
+   for (;;)
+   {
+      int32_t din[NT]; bool any = false;
+#pragma unroll
+      for (int ti = 0; ti < NT; ti++)
+      {
+         const int32_t up = __shfl_up_sync(FULL, d[ti], 1);
+         const int32_t prev = (ti > 0) ? __shfl_sync(FULL, d[ti > 0 ? ti - 1 : 0], 31) : 0;
+         din[ti] = lane ? up : prev;
+         any = any || (din[ti] != 0);
+      }
+      top += (int64_t) __shfl_sync(FULL, d[NT - 1], 31);
+      if (!__any_sync(FULL, any)) break;
+#pragma unroll
+      for (int ti = 0; ti < NT; ti++)
+      {
+         d[ti] = 0;
+         if (din[ti] != 0)
+         {
+            const int32_t c = din[ti];
+            const int32_t k = add2(r0[ti], r1[ti], r0[ti], r1[ti], (limb_t)(int64_t) c, (limb_t)((int64_t) c >> 63));
+            d[ti] = k + (c >> 31);
+         }
+      }
+   }
+   return top;
+}
+
+/* block of physical position pos (< S, slab half 0) of batch entry b */
+__device__ __forceinline__ limb_t *tile_block_ptr(limb_t *slab, const mfft_geom &g, uint32_t pos, const mfft_batch &b)
+{
+   const uint64_t idx = (uint64_t) b.parity * g.half_blocks + b.base + (uint64_t) pos * g.slot_stride;
+   return slab + idx * g.pitch;
+}
+
+/* 16-byte asynchronous copy global -> shared (LDGSTS), L2 only: the tile is read exactly once */
+__device__ __forceinline__ void cp_async16(limb_t *sdst, const limb_t *gsrc)
+{
+#ifdef MFFT_EMU
+   sdst[0] = gsrc[0]; sdst[1] = gsrc[1];
+#else
+   const uint32_t sa = (uint32_t) __cvta_generic_to_shared(sdst);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+#ifndef MFFT_EMU
+   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+/* warp-level mpn_normmod_2expp1 (mul_fft.c:272-294) on resolved limbs */
+__device__ __forceinline__ int64_t normalise_tile(limb_t *sblk, uint32_t l, int64_t top, uint32_t lane)
+{
+   for (int it = 0; it < 4; it++)
+   {
+      if (top == 0) break;
+      if (top == 1)
+      {
+         bool z = true;
+         for (uint32_t k = lane; k < l; k += 32) z = z && (sblk[k] == 0);
+         if (__all_sync(FULL, z)) break;
+      }
+      int64_t nt = 0;
+      if (lane == 0)
+      {  /* body -= top, what leaves limb l-1 is the new top */
+         int64_t c = -top;
+         for (uint32_t pos = 0; c != 0; pos++)
+         {
+            if (pos == l) { nt = c; break; }
+            const mfft_i128 acc = (mfft_i128) c + (mfft_i128)(mfft_u128) sblk[pos];
+            sblk[pos] = (limb_t) acc; c = (int64_t)(acc >> 64);
+         }
+      }
+      __syncwarp();
+      top = __shfl_sync(FULL, nt, 0);
+   }
+   return top;
+}
+
+/* ---- the kernel ----------------------------------------------------------------------------- */
+template <int NT>
+__global__ void __launch_bounds__(256, 2)
+k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
+            const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
+            limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
+            uint32_t dst_stride, int normalise, uint32_t desc_bytes, const uint32_t *__restrict__ stoff)
+{
+   MFFT_DYN_SMEM(limb_t, sm);
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP;
+   constexpr uint32_t NW = 64u * L, M2 = 2u * NW;
+   constexpr uint32_t AMASK = 127u;                           /* exponent bits that break chunk alignment */
+   const uint32_t bi = blockIdx.x % nbatch;
+   const mfft_tile T = tiles[blockIdx.x / nbatch];
+   const mfft_batch b = batch[bi];
+   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+   /* shared memory: [op descriptors | position list | stage offsets] [coefficients] */
+   mfft_tileop *sops = (mfft_tileop *) sm;
+   uint32_t *spos = (uint32_t *)(sops + T.nops);
+   uint32_t *sst = spos + T.npos;                      /* [nstages+1] first op of each stage */
+   limb_t *coef = sm + desc_bytes / 8;
+
+   {  /* descriptors: one coalesced copy instead of dependent global loads inside the op loop */
+      const uint32_t *src = (const uint32_t *)(ops + T.op_off);
+      uint32_t *d = (uint32_t *) sops;
+      for (uint32_t k = tid; k < T.nops * (uint32_t)(sizeof(mfft_tileop) / 4); k += blockDim.x) d[k] = src[k];
+      for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = pos[T.pos_off + k];
+      for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = stoff[T.pad + k];
+   }
+   /* load the positions that are read before being written: the body as it is, carry words 0
+      except the last one, which is the block's signed top limb */
+   const bool al16 = ((g.pitch & 1u) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15u) == 0) &&
+                     (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+   if (al16)
+   {  /* 16-byte aligned blocks: every thread fires its share of asynchronous 16-byte copies, one wait */
+      for (uint32_t t = tid; t < T.npos * NCH; t += blockDim.x)
+      {
+         const uint32_t p = t / NCH, c = t % NCH;
+         const uint32_t pp = pos[T.pos_off + p];
+         if (!(pp & MFFT_TILE_LOAD)) continue;
+         const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
+         limb_t *d = coef + (size_t) p * SP;
+         cp_async16(d + 2 * c, src + 2 * c);
+         reinterpret_cast<int32_t *>(d + L)[c] = (c == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
+      }
+      cp_async_wait_all();
+   } else
+   for (uint32_t p = warp; p < T.npos; p += nwarps)
+   {
+      const uint32_t pp = pos[T.pos_off + p];
+      if (!(pp & MFFT_TILE_LOAD)) continue;
+      const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
+      limb_t *d = coef + (size_t) p * SP;
+#pragma unroll 4
+      for (uint32_t k = lane; k < L; k += 32) d[k] = src[k];
+      int32_t *cw = reinterpret_cast<int32_t *>(d + L);
+#pragma unroll
+      for (uint32_t ch = lane; ch < NCH; ch += 32) cw[ch] = (ch == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
+   }
+   __syncthreads();
+
+   for (uint32_t st = 0; st < T.nstages; st++)
+   {
+      const uint32_t o0 = sst[st], o1 = sst[st + 1];
+      for (uint32_t oi = o0 + warp; oi < o1; oi += nwarps)
+      {
+         const mfft_tileop op = sops[oi];
+         const limb_t *A = coef + (size_t) op.a * SP;
+         const bool hasB = (op.b != 0xFFFF), hasT = (op.t != 0xFFFF);
+         const limb_t *B = hasB ? coef + (size_t) op.b * SP : A;
+         limb_t *S = coef + (size_t) op.s * SP;
+         limb_t *Tt = hasT ? coef + (size_t) op.t * SP : S;
+         if (op.kind != MFFT_K_ANY)
+         {  /* host-classified aligned shapes: lane-local chunk arithmetic, nothing to decode */
+            const uint32_t yc = op.kparam & 0x7fffffffu, neg = op.kparam >> 31;
+            const int32_t *cwA = reinterpret_cast<const int32_t *>(A + L);
+            const int32_t *cwB = reinterpret_cast<const int32_t *>(B + L);
+            int32_t *cwS = reinterpret_cast<int32_t *>(S + L), *cwT = reinterpret_cast<int32_t *>(Tt + L);
+            limb_t a0[NT], a1[NT], b0[NT], b1[NT]; int32_t ca[NT], cb[NT];
+            if (op.kind == MFFT_K_FWD)
+            {
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
+                  ld2(b0[ti], b1[ti], B + 2 * i); cb[ti] = cwB[i];
+               }
+               __syncwarp();
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  limb_t r0, r1; int32_t k;
+                  k = add2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]);
+                  st2(S + 2 * i, r0, r1); cwS[i] = k + ca[ti] + cb[ti];
+                  uint32_t o = i + yc, n = neg;
+                  if (o >= NCH) { o -= NCH; n ^= 1u; }
+                  if (n) k = sub2(r0, r1, b0[ti], b1[ti], a0[ti], a1[ti]) + cb[ti] - ca[ti];
+                  else   k = sub2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]) + ca[ti] - cb[ti];
+                  st2(Tt + 2 * o, r0, r1); cwT[o] = k;
+               }
+            } else if (op.kind == MFFT_K_INV)
+            {
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  const uint32_t j = (i >= yc) ? i - yc : i + NCH - yc;
+                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
+                  ld2(b0[ti], b1[ti], B + 2 * j); cb[ti] = cwB[j];
+               }
+               __syncwarp();
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  const bool n = ((i < yc) ? 1u : 0u) != neg;      /* B's chunk enters negated */
+                  limb_t *ds = n ? Tt : S, *dt = n ? S : Tt;
+                  limb_t r0, r1; int32_t k;
+                  k = add2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]);
+                  st2(ds + 2 * i, r0, r1); reinterpret_cast<int32_t *>(ds + L)[i] = k + ca[ti] + cb[ti];
+                  k = sub2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]);
+                  st2(dt + 2 * i, r0, r1); reinterpret_cast<int32_t *>(dt + L)[i] = k + ca[ti] - cb[ti];
+               }
+            } else if (op.kind == MFFT_K_ROT)
+            {
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
+               }
+               __syncwarp();
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  uint32_t o = i + yc, n = neg;
+                  if (o >= NCH) { o -= NCH; n ^= 1u; }
+                  limb_t r0 = a0[ti], r1 = a1[ti]; int32_t k = ca[ti];
+                  if (n) k = sub2(r0, r1, 0, 0, a0[ti], a1[ti]) - ca[ti];
+                  st2(S + 2 * o, r0, r1); cwS[o] = k;
+               }
+            } else
+            {  /* MFFT_K_ADD */
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  limb_t x0, x1, y0, y1, r0, r1;
+                  ld2(x0, x1, A + 2 * i); ld2(y0, y1, B + 2 * i);
+                  const int32_t k = add2(r0, r1, x0, x1, y0, y1) + cwA[i] + cwB[i];
+                  st2(S + 2 * i, r0, r1); cwS[i] = k;
+               }
+            }
+            continue;
+         }
+         uint32_t eSA = op.eSA, eSB = op.eSB, eTA = op.eTA, eTB = op.eTB;
+         if (op.cSA | op.cSB | op.cTA | op.cTB)
+         {  /* the MFA twist z^(r*c): only the twisted layer pays for the modulo */
+            eSA = (eSA + b.col * op.cSA) % M2; eSB = (eSB + b.col * op.cSB) % M2;
+            eTA = (eTA + b.col * op.cTA) % M2; eTB = (eTB + b.col * op.cTB) % M2;
+         }
+         tterm sa, sb, ta, tb;
+         tterm_setup(sa, op.sSA, eSA, NW);
+         tterm_setup(sb, hasB ? op.sSB : 0, eSB, NW);
+         tterm_setup(ta, hasT ? op.sTA : 0, eTA, NW);
+         tterm_setup(tb, (hasT && hasB) ? op.sTB : 0, eTB, NW);
+         /* chunk-aligned rotations everywhere, A in every output, and the same A-to-B chunk offset
+            in both outputs: each lane works on source chunk pairs */
+         uint32_t misal = 0;
+         if (sa.present) misal |= eSA;
+         if (sb.present) misal |= eSB;
+         if (ta.present) misal |= eTA;
+         if (tb.present) misal |= eTB;
+         bool fast = !(misal & AMASK) && sa.present && (!hasT || ta.present);
+         if (fast && sb.present && tb.present && ((sa.yc + tb.yc + 2 * NCH - sb.yc - ta.yc) % NCH) != 0) fast = false;
+
+         if (fast)
+         {
+            const tterm &ref = sb.present ? sa : ta, &refb = sb.present ? sb : tb;
+            const uint32_t dB = (ref.yc + NCH - refb.yc) % NCH;       /* B's chunk = A's chunk + dB */
+            const bool useB = sb.present || tb.present;
+            const int32_t *cwA = reinterpret_cast<const int32_t *>(A + L);
+            const int32_t *cwB = reinterpret_cast<const int32_t *>(B + L);
+            limb_t xa[NT][2], xb[NT][2]; int32_t ca[NT], cb[NT];
+#pragma unroll
+            for (int ti = 0; ti < NT; ti++)
+            {
+               const uint32_t ia = ti * 32u + lane;
+#ifdef MFFT_EMU
+               xa[ti][0] = A[2 * ia]; xa[ti][1] = A[2 * ia + 1];
+#else
+               { const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(A + 2 * ia); xa[ti][0] = v.x; xa[ti][1] = v.y; }
+#endif
+               ca[ti] = cwA[ia];
+               xb[ti][0] = 0; xb[ti][1] = 0; cb[ti] = 0;
+               if (useB)
+               {
+                  uint32_t jb = ia + dB; if (jb >= NCH) jb -= NCH;
+#ifdef MFFT_EMU
+                  xb[ti][0] = B[2 * jb]; xb[ti][1] = B[2 * jb + 1];
+#else
+                  { const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(B + 2 * jb); xb[ti][0] = v.x; xb[ti][1] = v.y; }
+#endif
+                  cb[ti] = cwB[jb];
+               }
+            }
+            __syncwarp();                   /* every lane has read its operands: in-place stores are safe */
+#pragma unroll
+            for (int ti = 0; ti < NT; ti++)
+            {
+               const uint32_t ia = ti * 32u + lane;
+               uint32_t jb = ia + dB; if (jb >= NCH) jb -= NCH;
+               aligned_out<NT>(S, sa, sb, ia, jb, xa[ti][0], xa[ti][1], ca[ti], xb[ti][0], xb[ti][1], cb[ti]);
+               if (hasT) aligned_out<NT>(Tt, ta, tb, ia, jb, xa[ti][0], xa[ti][1], ca[ti], xb[ti][0], xb[ti][1], cb[ti]);
+            }
+         } else
+         {
+            limb_t rs[NT][2], rt[NT][2]; int32_t ks[NT], kt[NT];
+#pragma unroll
+            for (int ti = 0; ti < NT; ti++)
+            {
+               const uint32_t ch = ti * 32u + lane;
+               ks[ti] = general_out<NT>(rs[ti][0], rs[ti][1], sa, A, sb, B, ch);
+               if (hasT) kt[ti] = general_out<NT>(rt[ti][0], rt[ti][1], ta, A, tb, B, ch);
+            }
+            __syncwarp();
+            int32_t *cwS = reinterpret_cast<int32_t *>(S + L), *cwT = reinterpret_cast<int32_t *>(Tt + L);
+#pragma unroll
+            for (int ti = 0; ti < NT; ti++)
+            {
+               const uint32_t ch = ti * 32u + lane;
+               S[2 * ch] = rs[ti][0]; S[2 * ch + 1] = rs[ti][1]; cwS[ch] = ks[ti];
+               if (hasT) { Tt[2 * ch] = rt[ti][0]; Tt[2 * ch + 1] = rt[ti][1]; cwT[ch] = kt[ti]; }
+            }
+         }
+      }
+      __syncthreads();
+   }
+
+   /* store what was written: in place, or gathered (and normalised) into dst */
+   for (uint32_t p = warp; p < T.npos; p += nwarps)
+   {
+      const uint32_t pp = spos[p];
+      if (!(pp & MFFT_TILE_STORE)) continue;
+      limb_t *out;
+      if (dst)
+      {
+         const uint32_t dp = dstpos[pp & MFFT_TILE_POSMASK];
+         if (dp == MFFT_NONE) continue;
+         out = dst + ((uint64_t) dst_base[bi] + (uint64_t) dp * dst_stride) * g.pitch;
+      } else out = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
+      limb_t *sblk = coef + (size_t) p * SP;
+      if (al16 && !normalise)
+      {  /* resolved limbs go straight from registers to HBM, 512 contiguous bytes per warp store */
+         limb_t r0[NT], r1[NT];
+         const int64_t tp = resolve_regs<NT>(r0, r1, sblk, lane);
+#pragma unroll
+         for (int ti = 0; ti < NT; ti++) st2(out + 2 * (ti * 32u + lane), r0[ti], r1[ti]);
+         if (lane == 0) out[L] = (limb_t) tp;
+         continue;
+      }
+      int64_t top = resolve_carries<NT>(sblk, lane);
+      if (normalise) top = normalise_tile(sblk, L, top, lane);
+#pragma unroll 4
+      for (uint32_t k = lane; k < L; k += 32) out[k] = sblk[k];
+      if (lane == 0) out[L] = (limb_t) top;
+   }
+}
+
+#endif

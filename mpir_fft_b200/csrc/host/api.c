@@ -171,7 +171,7 @@ static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, m
    stage = (limb_t *) calloc((size_t) N*pitch, sizeof(limb_t));
    d_slab = (limb_t *) mfft_dev_alloc(2*half); d_dst = (limb_t *) mfft_dev_alloc(half);
    if (!stage || !d_slab || !d_dst) mfft_die(fn, "allocation failed: %s", mfft_dev_last_error());
-   for (k = 0; k < N; k++) memcpy(stage + k*pitch, ii[k], pitch*sizeof(limb_t));
+   for (k = 0; k < N; k++) memcpy(stage + k*pitch, ii[k], (m.l + 1)*sizeof(limb_t));
    if (mfft_dev_h2d(d_slab, stage, half, NULL) ||
        mfft_dev_h2d(d_dst, stage, half, NULL) ||          /* rows the transform does not produce keep their input */
        mfft_mfa_exec(&m, d_slab, d_dst, NULL) ||
@@ -181,10 +181,10 @@ static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, m
    {  /* valid outputs: rows revbin(s), s < trunc_rows, all columns (2392-2408) */
       for (i = 0; i < m.nrows; i++)
          for (j = 0; j < m.n1; j++)
-         {  k = (uint64_t) m.rows[i]*m.n1 + j; memcpy(ii[k], stage + k*pitch, pitch*sizeof(limb_t)); }
+         {  k = (uint64_t) m.rows[i]*m.n1 + j; memcpy(ii[k], stage + k*pitch, (m.l + 1)*sizeof(limb_t)); }
    } else
    {  /* valid outputs: positions j < trunc (2974-2976) */
-      for (k = 0; k < m.trunc_rows*m.n1; k++) memcpy(ii[k], stage + k*pitch, pitch*sizeof(limb_t));
+      for (k = 0; k < m.trunc_rows*m.n1; k++) memcpy(ii[k], stage + k*pitch, (m.l + 1)*sizeof(limb_t));
    }
    mfft_dev_free(d_slab); mfft_dev_free(d_dst); free(stage);
    mfft_mfa_free(&m);

@@ -86,7 +86,7 @@ int mpirfft_mul_plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, 
    if ((rc = mpirfft_mul_params_get(&pl->p, n1, n2, depth, w)) != 0) { free(pl); return rc; }
    mfft_lock();
    if ((rc = mfft_try_device()) != 0) goto fail;
-   pl->l = (uint32_t) pl->p.limbs; pl->pitch = pl->l + 1;
+   pl->l = (uint32_t) pl->p.limbs; pl->pitch = mfft_pitch(pl->l);
    N = 2*pl->p.n;
    if ((rc = mfft_mfa_build(&pl->fwd, 0, pl->p.n, w, pl->p.sqrt, pl->p.trunc, 0, 1)) != 0) goto fail;
    /* the inverse is unscaled: fold / 2^(depth+1) and the normalisation into its last pass (3256-3260) */

@@ -155,7 +155,7 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
    if (n2 < 2) return MPIRFFT_EINVAL;
    m->inverse = inverse; m->truncated = (trunc != 0);
    m->n = n; m->w = w; m->n1 = n1; m->n2 = n2; m->N = 2*n;
-   m->l = (uint32_t)(NW/64); m->pitch = m->l + 1;
+   m->l = (uint32_t)(NW/64); m->pitch = mfft_pitch(m->l);
    m->depth1 = ilog2(n2); m->depth2 = ilog2(n1);
    m->final_shift = (uint32_t)(final_shift % (2*NW)); m->normalise = normalise;
    m->fused = (mode == 0) && mfft_dev_tiles_supported(m->l) && !(env && env[0] == '1');
@@ -370,4 +370,40 @@ uint64_t mfft_mfa_launches(const mfft_mfa *m)
 {
    if (m->fused) return (uint64_t) m->pcol.npasses + m->prow.npasses;
    return (uint64_t) m->col.s->nstages + m->row.s->nstages + 1;
+}
+
+/* developer aid (no device needed): the pass structure of a fused MFA plan on stdout --
+ * per pass and local stage the number of ops and how many of them are chunk-aligned
+ * (all exponents multiples of `align_bits`) for batch column `col` */
+void mfft_mfa_debug_dump(int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc, uint32_t col, uint32_t align_bits)
+{
+   mfft_mfa mm; int which; uint32_t i, k, st;
+   if (mfft_mfa_plan(&mm, inverse, n, w, n1, trunc, 0, 0, 0) != 0) { printf("plan failed\n"); return; }
+   if (!mm.fused) { printf("not fused\n"); mfft_mfa_free(&mm); return; }
+   for (which = 0; which < 2; which++)
+   {
+      const mfft_passes *P = which ? &mm.prow : &mm.pcol;
+      uint64_t M2 = 2*n*w;
+      printf("%s: %u passes, batch %u\n", which ? "rows" : "cols", P->npasses, which ? mm.nrowb : mm.ncolb);
+      for (i = 0; i < P->npasses; i++)
+      {
+         const mfft_pass *p = &P->pass[i];
+         uint32_t cnt[64] = {0}, al[64] = {0}, two[64] = {0}, ld = 0, stc = 0;
+         for (k = 0; k < p->npos_total; k++) { ld += (p->pos[k] & MFFT_TILE_LOAD) ? 1 : 0; stc += (p->pos[k] & MFFT_TILE_STORE) ? 1 : 0; }
+         for (k = 0; k < p->nops_total; k++)
+         {
+            const mfft_tileop *o = &p->ops[k];
+            uint64_t e[4] = { (o->eSA + (uint64_t) col*o->cSA) % M2, (o->eSB + (uint64_t) col*o->cSB) % M2,
+                              (o->eTA + (uint64_t) col*o->cTA) % M2, (o->eTB + (uint64_t) col*o->cTB) % M2 };
+            int s[4] = { o->sSA, o->b != 0xFFFF ? o->sSB : 0, o->t != 0xFFFF ? o->sTA : 0, (o->t != 0xFFFF && o->b != 0xFFFF) ? o->sTB : 0 };
+            int a = 1, j;
+            for (j = 0; j < 4; j++) if (s[j] && (e[j] % align_bits)) a = 0;
+            st = o->lstage < 63 ? o->lstage : 63;
+            cnt[st]++; al[st] += a; two[st] += (o->t != 0xFFFF);
+         }
+         printf("  pass %u: tiles %u, max_npos %u, stages %u, ops %u, loads %u, stores %u\n", i, p->ntiles, p->max_npos, p->nstages, p->nops_total, ld, stc);
+         for (st = 0; st < p->nstages && st < 64; st++) printf("     stage %2u: ops %6u  aligned %6u  two-output %6u\n", st, cnt[st], al[st], two[st]);
+      }
+   }
+   mfft_mfa_free(&mm);
 }

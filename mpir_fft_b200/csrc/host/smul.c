@@ -75,7 +75,7 @@ int mpirfft_smul_plan_create(mpirfft_smul_plan **out, mp_size_t n1, mp_size_t n2
    if ((rc = mpirfft_mul_params_get(&pl->p, n1, n2, depth, w)) != 0) { free(pl); return rc; }
    sq = pl->p.sqrt; nrows2 = pl->p.n2; tr = pl->p.trunc_rows; NW = pl->p.n*w;
    if (sq % (uint64_t) world || tr < (uint64_t) world) { free(pl); return MPIRFFT_EINVAL; }
-   pl->l = (uint32_t) pl->p.limbs; pl->pitch = pl->l + 1;
+   pl->l = (uint32_t) pl->p.limbs; pl->pitch = mfft_pitch(pl->l);
    pl->ncl = (uint32_t)(sq/world); pl->c0 = pl->ncl*(uint32_t) rank;
    rows_of((uint32_t) tr, (uint32_t) rank, (uint32_t) world, &pl->r0, &pl->r1); pl->nrl = pl->r1 - pl->r0;
    d1 = ilog2u(nrows2); d2 = ilog2u(sq);

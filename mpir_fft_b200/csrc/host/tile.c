@@ -49,10 +49,45 @@ void mfft_passes_free(mfft_passes *P)
    memset(P, 0, sizeof(*P));
 }
 
+/* Recognise the common aligned shapes (see MFFT_K_* in mfft_internal.h).  NW = ring bits. */
+static int fold_term(int sign, uint32_t e, uint64_t NW, uint32_t *yc, uint32_t *neg)
+{
+   if (e >= NW) { e -= (uint32_t) NW; sign = -sign; }
+   if (e % 128) return -1;
+   *yc = e / 128; *neg = (sign < 0);
+   return 0;
+}
+
+static void classify_op(mfft_tileop *d, uint64_t NW)
+{
+   const int hasB = (d->b != 0xFFFF), hasT = (d->t != 0xFFFF);
+   uint32_t ySA = 0, nSA = 0, ySB = 0, nSB = 0, yTA = 0, nTA = 0, yTB = 0, nTB = 0;
+   d->kind = MFFT_K_ANY; d->kparam = 0;
+   if (d->cSA | d->cSB | d->cTA | d->cTB) return;
+   if (NW % 128 || !d->sSA) return;
+   if (fold_term(d->sSA, d->eSA, NW, &ySA, &nSA)) return;
+   if (hasB) { if (!d->sSB || fold_term(d->sSB, d->eSB, NW, &ySB, &nSB)) return; }
+   if (hasT)
+   {
+      if (!d->sTA || fold_term(d->sTA, d->eTA, NW, &yTA, &nTA)) return;
+      if (hasB) { if (!d->sTB || fold_term(d->sTB, d->eTB, NW, &yTB, &nTB)) return; }
+   }
+   if (hasB && hasT)
+   {
+      if (ySA == 0 && !nSA && ySB == 0 && !nSB && yTA == yTB && nTA != nTB)
+      { d->kind = MFFT_K_FWD; d->kparam = yTA | (nTA << 31); return; }
+      if (ySA == 0 && !nSA && yTA == 0 && !nTA && ySB == yTB && nSB != nTB)
+      { d->kind = MFFT_K_INV; d->kparam = ySB | (nSB << 31); return; }
+   } else if (!hasB && !hasT)
+   { d->kind = MFFT_K_ROT; d->kparam = ySA | (nSA << 31); return; }
+   else if (hasB && !hasT && ySA == 0 && !nSA && ySB == 0 && !nSB)
+   { d->kind = MFFT_K_ADD; return; }
+}
+
 /* build one pass from ops[lo..hi) (sorted by pstage; window = stages s0..s1) */
 static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, uint32_t S,
                       uint32_t s0, uint32_t max_npos, const uint32_t *par_in, uint32_t *scratch,
-                      const uint8_t *must_store)
+                      const uint8_t *must_store, uint64_t NW)
 {
    /* scratch: 6*S uint32: root->tile map, first-access kind, written flag, local index, order */
    uint32_t *root_tile = scratch, *first = scratch + S, *written = scratch + 2*S, *local = scratch + 3*S;
@@ -137,6 +172,7 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
       d->cSA = o->cSA; d->cSB = o->cSB; d->cTA = o->cTA; d->cTB = o->cTB;
       d->sSA = o->sSA; d->sSB = o->sSB; d->sTA = o->sTA; d->sTB = o->sTB;
       d->lstage = o->pstage - s0;
+      classify_op(d, NW);
       if (d->lstage + 1 > out->tiles[t].nstages) out->tiles[t].nstages = d->lstage + 1;
       if (d->lstage + 1 > out->nstages) out->nstages = d->lstage + 1;
    }
@@ -210,7 +246,7 @@ int mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, co
          s1++;
       }
       if (build_pass(&P->pass[P->npasses], ops, st_off[s0], st_off[s1 + 1], S, s0, max_npos, par, scratch,
-                     (s1 == maxst) ? must_store : NULL) != 0) goto done;
+                     (s1 == maxst) ? must_store : NULL, s->NW) != 0) goto done;
       P->npasses++;
       s0 = s1 + 1;
    }

@@ -32,7 +32,7 @@ int mfft_xform_build(mfft_xform *x, mfft_sched *s, uint32_t l, uint32_t slot_str
    memset(x, 0, sizeof(*x));
    x->s = s; x->S = S; x->nbatch = nbatch; x->nout = nout; x->dst_stride = dst_stride;
    x->shift = (uint32_t)(shift % (128ull*l)); x->normalise = normalise;
-   x->g.S = S; x->g.slot_stride = slot_stride; x->g.half_blocks = half_blocks; x->g.l = l; x->g.pitch = l + 1;
+   x->g.S = S; x->g.slot_stride = slot_stride; x->g.half_blocks = half_blocks; x->g.l = l; x->g.pitch = mfft_pitch(l);
    x->fused = mfft_dev_tiles_supported(l) && !(env && env[0] == '1');
    x->d_batch = (mfft_batch *) mfft_upload(batch, sizeof(mfft_batch)*nbatch);
    x->d_dst_base = (uint32_t *) mfft_upload(dst_base, sizeof(uint32_t)*nbatch);

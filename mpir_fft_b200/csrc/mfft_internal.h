@@ -22,6 +22,11 @@ extern "C" {
 
 typedef uint64_t limb_t;
 
+/* pitch (limbs) of the coefficient blocks in library-owned HBM slabs: l body limbs + the top limb,
+ * rounded up to an even count so that every block starts 16-byte aligned (128-bit global accesses,
+ * 16-byte asynchronous copies into shared memory) */
+static inline uint32_t mfft_pitch(uint32_t l) { return (l + 2u) & ~1u; }
+
 #define MFFT_NONE 0xFFFFFFFFu
 
 /* One op: up to two outputs, each a signed sum of up to two inputs multiplied by powers of two:
@@ -71,7 +76,18 @@ typedef struct {            /* one op of a tile; a,b,s,t index the tile's positi
    uint32_t eSA, eSB, eTA, eTB, cSA, cSB, cTA, cTB;
    int8_t   sSA, sSB, sTA, sTB;
    uint32_t lstage;         /* stage inside the pass, 0-based, ops sorted by it */
+   /* host-side classification of untwisted ops whose rotations are all multiples of 128 bits
+      (tile.c: classify_op), so that the kernel runs the common butterfly shapes without decoding
+      exponents: kparam = chunk rotation yc (e / 128 after folding e >= NW into the sign) | neg << 31 */
+   uint32_t kind;           /* MFFT_K_* */
+   uint32_t kparam;
 } mfft_tileop;
+
+#define MFFT_K_ANY   0u     /* decode at run time (twisted or unaligned ops, rare shapes) */
+#define MFFT_K_FWD   1u     /* S = A + B,             T = +-(A - B) * 2^(128 yc)      (553-576)  */
+#define MFFT_K_INV   2u     /* S = A +- B * 2^(128 yc), T = A -+ B * 2^(128 yc)       (639-660)  */
+#define MFFT_K_ROT   3u     /* S = +-A * 2^(128 yc)                                   (926-957)  */
+#define MFFT_K_ADD   4u     /* S = A + B                                              (1093)     */
 
 /* pad = offset of the tile's (nstages+1) stage offsets in the pass's stoff array (<= 63 stages) */
 typedef struct { uint32_t pos_off, npos, op_off, nops, nstages, pad; } mfft_tile;
