@@ -1114,6 +1114,11 @@ int mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, u
 }
 
 
+/* developer aid: per-CTA phase time stamps of the next k_run_tiles launches (globaltimer ns:
+ * start, loads issued, loaded, ops done, stored; smid), 8 words per CTA */
+static unsigned long long *g_tile_timing = NULL;
+extern "C" void mfft_dev_tile_timing(void *buf) { g_tile_timing = (unsigned long long *) buf; }
+
 /* coefficient sizes the fused executor is instantiated for: l = 64*NT limbs */
 static int tiles_cfg(uint32_t l, int *NT)
 {
@@ -1145,7 +1150,7 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
                        const uint32_t *d_pos, const mfft_tileop *d_ops, uint32_t max_npos, uint32_t max_nops,
                        const mfft_batch *d_batch, uint32_t nbatch,
                        limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
-                       uint32_t dst_stride, int normalise, const uint32_t *d_stoff, void *stream)
+                       uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy, void *stream)
 {
    int NT = 0;
    if (!ntiles || !nbatch) return 0;
@@ -1156,22 +1161,34 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    const unsigned grid = ntiles * nbatch;
    cudaStream_t st = (cudaStream_t) stream;
    PROF(PC_STAGE, st);
-#define RUN_TILES(NN)                                                                              \
+   /* two CTAs per SM: 16 warps x 64 registers while a lane holds <= 4 chunk pairs of an op, else
+      8 warps x 128 registers (fewer, larger coefficients per tile) */
+#define RUN_TILES(NN, TH)                                                                          \
    do {                                                                                            \
-      CK(cudaFuncSetAttribute(k_run_tiles<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-      MFFT_LAUNCH((k_run_tiles<NN>), grid, 256, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
-                  dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff);                 \
+      CK(cudaFuncSetAttribute(k_run_tiles<NN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+      MFFT_LAUNCH((k_run_tiles<NN, TH>), grid, TH, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
+                  dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff, g_tile_timing);  \
    } while (0)
+   if (heavy && NT <= 4)
+      switch (NT)
+      {
+      case 1: RUN_TILES(1, 256); break;
+      case 2: RUN_TILES(2, 256); break;
+      case 3: RUN_TILES(3, 256); break;
+      default: RUN_TILES(4, 256); break;
+      }
+   else
    switch (NT)
    {
-   case 1: RUN_TILES(1); break;
-   case 2: RUN_TILES(2); break;
-   case 3: RUN_TILES(3); break;
-   case 4: RUN_TILES(4); break;
-   case 6: RUN_TILES(6); break;
-   default: RUN_TILES(8); break;
+   case 1: RUN_TILES(1, 512); break;
+   case 2: RUN_TILES(2, 512); break;
+   case 3: RUN_TILES(3, 512); break;
+   case 4: RUN_TILES(4, 512); break;
+   case 6: RUN_TILES(6, 256); break;
+   default: RUN_TILES(8, 256); break;
    }
 #undef RUN_TILES
+   if (g_tile_timing) g_tile_timing += (size_t) grid * 8;       /* next launch stamps behind this one */
    CKL();
    return 0;
 }

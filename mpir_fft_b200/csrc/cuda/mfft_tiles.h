@@ -374,13 +374,21 @@ __device__ __forceinline__ int64_t normalise_tile(limb_t *sblk, uint32_t l, int6
 }
 
 /* ---- the kernel ----------------------------------------------------------------------------- */
-template <int NT>
-__global__ void __launch_bounds__(256, 2)
+template <int NT, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, 2)
 k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
             const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
             limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
-            uint32_t dst_stride, int normalise, uint32_t desc_bytes, const uint32_t *__restrict__ stoff)
+            uint32_t dst_stride, int normalise, uint32_t desc_bytes, const uint32_t *__restrict__ stoff,
+            unsigned long long *timing)
 {
+#ifndef MFFT_EMU
+#define TILE_STAMP(k) do { if (timing && threadIdx.x == 0) { unsigned long long t__; \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); timing[(size_t) blockIdx.x * 8 + (k)] = t__; } } while (0)
+#else
+#define TILE_STAMP(k) do { } while (0)
+#endif
+   TILE_STAMP(0);
    MFFT_DYN_SMEM(limb_t, sm);
    constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP;
    constexpr uint32_t NW = 64u * L, M2 = 2u * NW;
@@ -395,10 +403,11 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
    uint32_t *sst = spos + T.npos;                      /* [nstages+1] first op of each stage */
    limb_t *coef = sm + desc_bytes / 8;
 
-   {  /* descriptors: one coalesced copy instead of dependent global loads inside the op loop */
-      const uint32_t *src = (const uint32_t *)(ops + T.op_off);
-      uint32_t *d = (uint32_t *) sops;
-      for (uint32_t k = tid; k < T.nops * (uint32_t)(sizeof(mfft_tileop) / 4); k += blockDim.x) d[k] = src[k];
+   {  /* descriptors: asynchronous copies that land together with the tile's coefficients */
+      static_assert(sizeof(mfft_tileop) % 16 == 0, "op descriptors are copied in 16-byte pieces");
+      const limb_t *src = (const limb_t *)(ops + T.op_off);
+      limb_t *d = (limb_t *) sops;
+      for (uint32_t k = tid; k < T.nops * (uint32_t)(sizeof(mfft_tileop) / 16); k += blockDim.x) cp_async16(d + 2 * k, src + 2 * k);
       for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = pos[T.pos_off + k];
       for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = stoff[T.pad + k];
    }
@@ -418,7 +427,6 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
          cp_async16(d + 2 * c, src + 2 * c);
          reinterpret_cast<int32_t *>(d + L)[c] = (c == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
       }
-      cp_async_wait_all();
    } else
    for (uint32_t p = warp; p < T.npos; p += nwarps)
    {
@@ -432,7 +440,10 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
 #pragma unroll
       for (uint32_t ch = lane; ch < NCH; ch += 32) cw[ch] = (ch == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
    }
+   TILE_STAMP(1);
+   cp_async_wait_all();
    __syncthreads();
+   TILE_STAMP(2);
 
    for (uint32_t st = 0; st < T.nstages; st++)
    {
@@ -615,6 +626,7 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
       __syncthreads();
    }
 
+   TILE_STAMP(3);
    /* store what was written: in place, or gathered (and normalised) into dst */
    for (uint32_t p = warp; p < T.npos; p += nwarps)
    {
@@ -643,6 +655,15 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
       for (uint32_t k = lane; k < L; k += 32) out[k] = sblk[k];
       if (lane == 0) out[L] = (limb_t) top;
    }
+#ifndef MFFT_EMU
+   if (timing)
+   {
+      __syncthreads();
+      TILE_STAMP(4);
+      if (threadIdx.x == 0) { uint32_t sm__; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm__)); timing[(size_t) blockIdx.x * 8 + 5] = sm__; }
+   }
+#endif
+#undef TILE_STAMP
 }
 
 #endif

@@ -332,7 +332,7 @@ static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft
       mfft_dev_profile_bytes(pass_bytes(p, nbatch, g->l));
       if (mfft_dev_run_tiles(slab, g, d[i].d_tiles, p->ntiles, d[i].d_pos, d[i].d_ops, p->max_npos, p->max_nops, d_batch, nbatch,
                              lastp ? dst : NULL, m->d_dstpos, m->d_dst_base, m->dst_stride,
-                             lastp ? m->normalise : 0, d[i].d_stoff, stream) != 0) return MPIRFFT_ENODEV;
+                             lastp ? m->normalise : 0, d[i].d_stoff, 5*p->nany > p->nops_total, stream) != 0) return MPIRFFT_ENODEV;
    }
    return 0;
 }

@@ -128,7 +128,7 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
          root_tile[r] = cur; cur_fill += tile_fill[r];
       }
    }
-   out->ntiles = ntiles; out->max_npos = 0; out->max_nops = 0; out->nstages = 0;
+   out->ntiles = ntiles; out->max_npos = 0; out->max_nops = 0; out->nstages = 0; out->nany = 0;
    out->tiles = (mfft_tile *) calloc(ntiles ? ntiles : 1, sizeof(mfft_tile));
    tile_npos = (uint32_t *) calloc(4 * (size_t)(ntiles ? ntiles : 1), sizeof(uint32_t));
    if (!out->tiles || !tile_npos) { free(tile_npos); return -1; }
@@ -173,6 +173,7 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
       d->sSA = o->sSA; d->sSB = o->sSB; d->sTA = o->sTA; d->sTB = o->sTB;
       d->lstage = o->pstage - s0;
       classify_op(d, NW);
+      if (d->kind == MFFT_K_ANY) out->nany++;
       if (d->lstage + 1 > out->tiles[t].nstages) out->tiles[t].nstages = d->lstage + 1;
       if (d->lstage + 1 > out->nstages) out->nstages = d->lstage + 1;
    }

@@ -81,6 +81,7 @@ typedef struct {            /* one op of a tile; a,b,s,t index the tile's positi
       exponents: kparam = chunk rotation yc (e / 128 after folding e >= NW into the sign) | neg << 31 */
    uint32_t kind;           /* MFFT_K_* */
    uint32_t kparam;
+   uint32_t pad[2];         /* 64 bytes: descriptors are fetched with 16-byte asynchronous copies */
 } mfft_tileop;
 
 #define MFFT_K_ANY   0u     /* decode at run time (twisted or unaligned ops, rare shapes) */
@@ -125,12 +126,13 @@ int  mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, 
 /* One fused pass: CTA (tile, batch entry) loads the tile's positions into shared memory, runs
  * all its stages there and stores the written positions back in place -- or, if dst != NULL,
  * to dst[(dst_base[b] + dstpos[i]*dst_stride)*pitch] (dstpos parallel to the position list,
- * MFFT_NONE = do not store), normalised when `normalise` is set.  max_npos bounds the tile size. */
+ * MFFT_NONE = do not store), normalised when `normalise` is set.  max_npos bounds the tile size.
+ * heavy: many ops of the pass need the run-time decoded general path (more registers per thread). */
 int  mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tiles, uint32_t ntiles,
                         const uint32_t *d_pos, const mfft_tileop *d_ops, uint32_t max_npos, uint32_t max_nops,
                         const mfft_batch *d_batch, uint32_t nbatch,
                         limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
-                        uint32_t dst_stride, int normalise, const uint32_t *d_stoff, void *stream);
+                        uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy, void *stream);
 /* 1 if the fused executor supports coefficient size l (else use mfft_dev_run_stage) */
 int  mfft_dev_tiles_supported(uint32_t l);
 uint32_t mfft_dev_tiles_max_npos(uint32_t l);
