@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- new_mpn_mul throughput on B200 (BASELINE.json metric), one JSON line on stdout.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload cfg2|cfg1|cfg3|cfg4|big] [--sharded]
 
 A "step" is one product of the workload (default BASELINE.json configs[1]: 2^20 x 2^20 limbs,
 depth 14, w 1) on synthetic uniform limbs (splitmix64 counter generator).
@@ -10,13 +11,18 @@ depth 14, w 1) on synthetic uniform limbs (splitmix64 counter generator, SURVEY 
              step (L2 flushed between steps), max over ranks
   e2e        the same metric through the reference-facing C symbol with HOST buffers (pinned),
              H2D/D2H inside the timed region
-  roofline   the transform-stage kernel (k_run_stage): algorithmic bytes per launch / mean launch
-             duration, from per-launch CUDA events in a separate profiling leg of the same run
+  roofline   the fused transform-pass kernel (k_run_tiles, one MFA pass per launch): algorithmic
+             bytes per launch / mean launch duration, from per-launch CUDA events in a separate
+             profiling leg of the same run; roofline_pointwise: the product kernel against the
+             IMAD issue rate measured in the same run (mpirfft_measure_imad_rate)
   cpu_baseline  the compiled reference (oracle/_ref, mul_fft.c:3246 fixed) on one host core
 
 --impl reference times only the reference's CPU implementation (all host cores, one product per
 process per step).  N > 1: one process per GPU under torchrun; each rank multiplies its own
-operands (independent products, weak scaling, no data-path collective).
+operands (independent products, weak scaling, no data-path collective).  --sharded instead spreads
+ONE product over the ranks (MFA column/row partition, NCCL all-to-all; mpir_fft_b200/sharded.py;
+strong scaling) -- meant for the large workloads (`big`: 8e6 x 8e6 limbs).
+--workload cfg4: 4096 independent 16 384-limb products mod 2^(2^20)+1 (BASELINE configs[3]).
 """
 import argparse
 import ctypes as C
@@ -39,6 +45,7 @@ WORKLOADS = {
     "cfg1": (1 << 16, 1 << 16, 12, 1),
     "cfg2": (1 << 20, 1 << 20, 14, 1),
     "cfg3": (3000000, 1700000, 14, 2),
+    "big": (8000000, 8000000, 15, 1),          # l = 512: the largest ring of the fused path
 }
 METRIC, UNIT = "new_mpn_mul Mlimb/s", "Mlimb/s"
 
@@ -135,6 +142,10 @@ def run_reference_arm(args, rank, world):
         return
     import multiprocessing as mp
     from oracle import loader as oracle
+    if args.workload not in WORKLOADS:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm times new_mpn_mul workloads only; "
+                          "--workload %s reports its own cpu_baseline" % args.workload}))
+        return
     n1, n2, depth, w = WORKLOADS[args.workload]
     kind = "reference" if oracle.load_ref(True) is not None else "port"
     cores = os.cpu_count() or 1
@@ -165,7 +176,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--sharded", action="store_true", help="one product spread over the ranks (strong scaling)")
+    ap.add_argument("--count", type=int, default=4096, help="cfg4: products per batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -190,6 +203,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if args.workload == "cfg4":
+        return run_cfg4(args, rank, local_rank, world, torch, dist, M)
+    if args.sharded:
+        return run_sharded(args, rank, local_rank, world, torch, dist, M)
     n1, n2, depth, w = WORKLOADS[args.workload]
     L = M.lib()
     plan = M.MulPlan(n1, n2, depth, w)
@@ -270,7 +287,7 @@ def main():
     e2e_value = world * e2e_steps * (n1 + n2) / e2e_dt / 1e6
 
     # ---- profiling leg: per-kernel-class CUDA events (not part of the numbers above) ----
-    roofline, phases = None, None
+    roofline, phases, roofline_pw = None, None, None
     if rank == 0:
         nclass = 6
         ms = (C.c_double * nclass)(); ln = (C.c_uint64 * nclass)(); by = (C.c_double * nclass)()
@@ -288,7 +305,7 @@ def main():
         if ln[0]:
             avg_ms = ms[0] / ln[0]
             achieved = (by[0] / ln[0]) / (avg_ms * 1e-3) / 1e9
-            roofline = {"kernel": "k_run_stage (one radix-2 layer of a transform)", "bound": "hbm",
+            roofline = {"kernel": "k_run_tiles (one fused MFA pass: several radix-2 layers in shared memory)", "bound": "hbm",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": None, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
                         "alg_bytes_per_launch": by[0] / ln[0], "avg_launch_us": avg_ms * 1e3,
@@ -298,6 +315,21 @@ def main():
         phases["B_alg_bytes"] = 18 * T * S + 16 * (n1 + n2)
         phases["B_alg_over_time_GBs"] = phases["B_alg_bytes"] / (ms_per_step * 1e-3) / 1e9
         phases["pointwise_mad32_per_product"] = 4 * prm["limbs"] ** 2 * T
+        # the product kernel against the integer-multiply issue rate measured right here
+        try:
+            L.mpirfft_measure_imad_rate.restype = C.c_double
+            imad_chain = float(L.mpirfft_measure_imad_rate(1))      # IMAD.WIDE.U32.X carry chains (what the kernel issues)
+            imad_wide = float(L.mpirfft_measure_imad_rate(0))       # IMAD.WIDE.U32 without carry
+            pw_ms = phases["pointwise"]["ms_per_product"]
+            if pw_ms > 0 and imad_chain > 0:
+                ach = phases["pointwise_mad32_per_product"] / (pw_ms * 1e-3)
+                roofline_pw = {"kernel": "k_pointwise (schoolbook 32x32->64 multiply-add chains)", "bound": "imad",
+                               "achieved": ach / 1e12, "peak": imad_chain / 1e12, "unit": "Tmad32/s",
+                               "frac": ach / imad_chain, "peak_no_carry": imad_wide / 1e12,
+                               "frac_of_no_carry_peak": ach / imad_wide if imad_wide > 0 else None,
+                               "peak_source": "measured in this run (csrc/cuda/imad_peak.cu)"}
+        except Exception:
+            roofline_pw = None
 
     # ---- CPU baseline: the compiled reference on one host core (bounded sample) ----
     cpu = None
@@ -319,7 +351,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "new_mpn_mul %d x %d limbs, depth %d, w %d (BASELINE configs[%s])" % (
-                           n1, n2, depth, w, {"cfg1": 0, "cfg2": 1, "cfg3": 2}[args.workload]),
+                           n1, n2, depth, w, {"cfg1": 0, "cfg2": 1, "cfg3": 2, "big": "-"}[args.workload]),
                        "coefficients": prm["trunc"], "limbs_per_coefficient": prm["limbs"],
                        "l2": "flushed between timed steps (256 MiB write)",
                        "multi_gpu": "independent products per rank" if world > 1 else "single GPU"},
@@ -327,13 +359,206 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (n1 + n2),
                     "d2h_bytes_per_step": 8 * (n1 + n2), "ms_per_step": e2e_dt / e2e_steps * 1e3,
                     "api": "new_mpn_mul(r, i1, n1, i2, n2, depth, w) with pinned host buffers"},
-            "roofline": roofline, "cpu_baseline": cpu, "phases": phases,
+            "roofline": roofline, "roofline_pointwise": roofline_pw, "cpu_baseline": cpu, "phases": phases,
             "bit_exact_vs_gmp": check, "wall_s_timed_region": wall,
             "step_ms_min_max": [min(step_ms), max(step_ms)],
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _timed_steps(torch, dist, world, steps, flush, fn):
+    """K steps, each bracketed by CUDA events on the current stream, L2 flushed in between"""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.zero_()
+        evs[k][0].record()
+        fn()
+        evs[k][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    total = sum(ms)
+    if world > 1:
+        t = torch.tensor([total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+    return total / steps, ms
+
+
+def run_cfg4(args, rank, local_rank, world, torch, dist, M):
+    """BASELINE configs[3]: `count` independent 16 384-limb products mod 2^(2^20)+1 per step and rank
+    (weak scaling over ranks: independent batches, no collective)"""
+    Lb = M.lib()
+    l, count = 16384, args.count
+    vp, u64 = C.c_void_p, C.c_uint64
+    Lb.mpirfft_mulmod_params.argtypes = [C.c_long, C.POINTER(u64), C.POINTER(u64)]
+    Lb.mpirfft_mulmod_plan_create.argtypes = [C.POINTER(vp), C.c_long, u64, u64, C.c_size_t]
+    Lb.mpirfft_mulmod_plan_exec.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
+    Lb.mpirfft_mulmod_plan_destroy.argtypes = [vp]
+    d, w = u64(), u64()
+    assert Lb.mpirfft_mulmod_params(l, C.byref(d), C.byref(w)) == 0
+    plan = vp()
+    rc = Lb.mpirfft_mulmod_plan_create(C.byref(plan), l, d, w, count)
+    if rc != 0:
+        raise SystemExit("mpirfft_mulmod_plan_create failed (%d): %s" % (rc, Lb.mpirfft_last_error().decode()))
+    pitch = l + 2
+    ha = splitmix64(0x5EED0004 + 1000 * rank, count * pitch).reshape(count, pitch)
+    hb = splitmix64(0x5EED0005 + 1000 * rank, count * pitch).reshape(count, pitch)
+    ha[:, l:] = 0
+    hb[:, l:] = 0
+    a = torch.from_numpy(ha.view(np.int64)).cuda()
+    b = torch.from_numpy(hb.view(np.int64)).cuda()
+    r = torch.zeros_like(a)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step():
+        rc = Lb.mpirfft_mulmod_plan_exec(plan, r.data_ptr(), a.data_ptr(), b.data_ptr(), pitch, -1, None)
+        assert rc == 0, Lb.mpirfft_last_error()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    check = None
+    if rank == 0:       # a sample of the batch against GMP (mpn_mul + fold), outside the timed region
+        from oracle import loader as oracle
+        out = r.cpu().numpy().view(np.uint64)
+        p = (1 << (64 * l)) + 1
+        check = True
+        for k in (0, count // 2, count - 1):
+            full = oracle.gmp_mul(ha[k, :l].copy(), hb[k, :l].copy())
+            want = (int.from_bytes(full[:l].tobytes(), "little") - int.from_bytes(full[l:].tobytes(), "little")) % p
+            got = int.from_bytes(out[k, :l].tobytes(), "little") + (int(out[k, l]) << (64 * l))
+            check = check and (got == want)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.2)
+    Lb.mpirfft_launch_count_reset()
+    ms_per_step, step_ms = _timed_steps(torch, dist, world, args.steps, flush, step)
+    launches = int(Lb.mpirfft_launch_count())
+    clocks = sampler.finish()
+    value = world * count * l / (ms_per_step * 1e-3) / 1e6
+    # phases
+    phase_ms = []
+    for ph in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        Lb.mpirfft_mulmod_plan_exec(plan, r.data_ptr(), a.data_ptr(), b.data_ptr(), pitch, ph, None)
+        e1.record()
+        torch.cuda.synchronize()
+        phase_ms.append(e0.elapsed_time(e1))
+    # e2e: host blocks in pinned memory, copies inside the timed region
+    pa, pb = torch.from_numpy(ha.view(np.int64)).pin_memory(), torch.from_numpy(hb.view(np.int64)).pin_memory()
+    pr = torch.zeros_like(pa).pin_memory()
+    e2e_steps = max(3, min(args.steps, 5))
+    t0 = None
+    for it in range(e2e_steps + 1):
+        if it == 1:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        a.copy_(pa, non_blocking=True)
+        b.copy_(pb, non_blocking=True)
+        step()
+        pr.copy_(r, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_dt = (time.perf_counter() - t0) / e2e_steps
+    # CPU baseline: the compiled reference's fft_mulmod_2expp1 on one core, bounded sample
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            from oracle import loader as oracle
+            ref = oracle.load_ref(True)
+            P = lambda x: C.c_void_p(x.ctypes.data)   # noqa: E731
+            rr, tt = np.zeros(l + 1, np.uint64), np.zeros(2 * l + 2, np.uint64)
+            nsample, times = 200, []
+            for k in range(nsample):
+                x, y = ha[k % count, :l + 1].copy(), hb[k % count, :l + 1].copy()
+                t = time.perf_counter()
+                ref.fft_mulmod_2expp1(P(rr), P(x), P(y), C.c_long(1 << 14), C.c_long(64), P(tt))
+                times.append(time.perf_counter() - t)
+            cpu = {"value": l / statistics.median(times) / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": "%d of the %d products, median per product %.2f ms, 1 thread" % (nsample, count, statistics.median(times) * 1e3),
+                   "cpu_model": _cpu_model(), "host_cores": os.cpu_count()}
+        except Exception as e:
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": str(e)}
+    if rank == 0:
+        mads = count * 128 * 4 * 256 ** 2
+        print(json.dumps({
+            "metric": "fft_mulmod_2expp1 batch Mlimb/s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "%d independent products of 16384 limbs mod 2^(2^20)+1 (BASELINE configs[3]); inner ring "
+                                   "2^%d+1, %d pieces" % (count, 64 * 256, 128),
+                       "l2": "flushed between timed steps (256 MiB write); batch is 1.1 GB per operand",
+                       "multi_gpu": "independent batches per rank" if world > 1 else "single GPU"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": world * count * l / e2e_dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * ha.nbytes,
+                    "d2h_bytes_per_step": ha.nbytes, "ms_per_step": e2e_dt * 1e3,
+                    "api": "mpirfft_mulmod_plan_exec on HBM blocks, pinned host blocks copied in and out every step"},
+            "roofline": {"kernel": "k_pointwise (inner products mod 2^16384+1)", "bound": "imad",
+                         "achieved": mads / (phase_ms[2] * 1e-3) / 1e12, "unit": "Tmad32/s", "peak": None, "frac": None,
+                         "traffic": None, "note": "see roofline_pointwise of the default workload for the measured IMAD rate"},
+            "cpu_baseline": cpu,
+            "phases": {"split+forward a": phase_ms[0], "split+forward b": phase_ms[1], "pointwise": phase_ms[2],
+                       "inverse": phase_ms[3], "finish": phase_ms[4], "unit": "ms per batch"},
+            "bit_exact_vs_gmp": check, "step_ms_min_max": [min(step_ms), max(step_ms)],
+        }))
+    Lb.mpirfft_mulmod_plan_destroy(plan)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sharded(args, rank, local_rank, world, torch, dist, M):
+    """one product spread over the ranks (strong scaling): MFA columns / rows partitioned, NCCL
+    all-to-all between the passes"""
+    from mpir_fft_b200.sharded import ShardedMul
+    n1, n2, depth, w = WORKLOADS[args.workload]
+    a = torch.from_numpy(splitmix64(0x5EED0001, n1).view(np.int64)).cuda()
+    b = torch.from_numpy(splitmix64(0x5EED0002, n2).view(np.int64)).cuda()
+    sm = ShardedMul(n1, n2, depth, w, cuda=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step():
+        sm.multiply(a.data_ptr(), b.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    res = sm.gather_result()
+    check = None
+    if rank == 0:
+        from oracle import loader as oracle
+        check = bool(np.array_equal(res, oracle.gmp_mul(a.cpu().numpy().view(np.uint64), b.cpu().numpy().view(np.uint64))))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.2)
+    M.lib().mpirfft_launch_count_reset()
+    ms_per_step, step_ms = _timed_steps(torch, dist, world, args.steps, flush, step)
+    launches = int(M.lib().mpirfft_launch_count())
+    clocks = sampler.finish()
+    if rank == 0:
+        lay = sm.lay
+        print(json.dumps({
+            "metric": METRIC, "value": (n1 + n2) / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "new_mpn_mul %d x %d limbs, depth %d, w %d, ONE product sharded over %d rank(s)" % (n1, n2, depth, w, world),
+                       "l2": "flushed between timed steps (256 MiB write)",
+                       "multi_gpu": "MFA columns/rows partitioned, 3 all-to-alls + halo all-gather + carry hand-off per product",
+                       "all_to_all_bytes_per_rank": int(lay.trunc_rows * lay.ncl * lay.block_limbs * 8)},
+            "clocks": clocks, "gpu_launches": launches, "e2e": None, "roofline": None, "cpu_baseline": None,
+            "bit_exact_vs_gmp": check, "step_ms_min_max": [min(step_ms), max(step_ms)],
+        }))
+    sm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
 
 
 def _cpu_model():

@@ -185,6 +185,20 @@ uint64_t mpirfft_mul_plan_launches(const mpirfft_mul_plan *plan);
 int  mpirfft_mulmod_batch_device(mp_limb_t *d_a, const mp_limb_t *d_b, size_t count, size_t l,
                                  size_t pitch, void *stream);
 
+/* ---- batched mulmod 2^(64 L)+1 through a negacyclic transform (FFT_mulmod_2expp1, mul_fft.c:2998;
+ * parameter choice after fft_mulmod_2expp1, 3125-3167).  `count` independent products per call,
+ * operands and results resident in HBM: blocks of L+1 limbs (canonical: top limb 0, or 1 with
+ * zero limbs) at `pitch` limbs; r may alias a.  Shapes: 2^depth * w = 128 * L / 2^(depth+1), w
+ * even, L / 2^(depth+1) a multiple of 32 (mpirfft_mulmod_params picks one for L). */
+typedef struct mpirfft_mulmod_plan mpirfft_mulmod_plan;
+int  mpirfft_mulmod_params(mp_size_t r_limbs, mp_bitcnt_t *depth, mp_bitcnt_t *w);
+int  mpirfft_mulmod_plan_create(mpirfft_mulmod_plan **plan, mp_size_t r_limbs, mp_bitcnt_t depth, mp_bitcnt_t w, size_t count);
+void mpirfft_mulmod_plan_destroy(mpirfft_mulmod_plan *plan);
+size_t mpirfft_mulmod_plan_device_bytes(const mpirfft_mulmod_plan *plan);
+/* phase < 0: the whole product; 0..4: split+forward(a), split+forward(b), pointwise, inverse, finish */
+int  mpirfft_mulmod_plan_exec(mpirfft_mulmod_plan *plan, mp_limb_t *d_r, const mp_limb_t *d_a, const mp_limb_t *d_b,
+                              size_t pitch, int phase, void *stream);
+
 /* ---- sharded multiplication: the MFA spread over the GPUs of one box (one process per GPU) ----
  * Columns are block-partitioned for the column passes, the live rows for the row passes and the
  * pointwise products.  The library runs the local phases on plan-owned HBM buffers; the host

@@ -1005,6 +1005,179 @@ k_combine_fix(limb_t *res, uint64_t total, const uint32_t *__restrict__ tileC, u
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* batched mulmod 2^(64 L) + 1 through a negacyclic transform (FFT_mulmod_2expp1, mul_fft.c:2998) */
+/* ------------------------------------------------------------------------------------------ */
+/* piece k of operand `prod`: limbs [k*pl, (k+1)*pl) zero-extended to a block (3038-3040, 3049-3051) */
+__global__ void __launch_bounds__(256)
+k_mm_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *__restrict__ src, uint32_t src_pitch,
+           uint32_t K, uint32_t pl, uint64_t nblocks)
+{
+   const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+   const uint64_t per = (uint64_t) l + 1;
+   if (t >= nblocks * per) return;
+   const uint64_t blk = t / per; const uint32_t k = (uint32_t)(t % per);
+   const uint64_t prod = blk / K; const uint32_t piece = (uint32_t)(blk % K);
+   slab[blk * pitch + k] = (k < pl) ? src[prod * src_pitch + (uint64_t) piece * pl + k] : 0;
+}
+
+/* Recombination of one product per CTA.  C holds the K coefficients of the negacyclic convolution
+ * reduced mod 2^(128 pl) + 1 (canonical, l = 2 pl limbs); the true coefficient is
+ *      c_k = C_k + m_k (2^(128 pl) + 1),   m_k = (c_k mod 2^64) - C_k[0]   (a small signed number),
+ * where c_k mod 2^64 comes from the negacyclic convolution of the pieces' low limbs
+ * (fft_naive_convolution_1, 2981-2996; correction 3087-3098).  The result
+ *      sum_k c_k B^(pl k)   mod B^L + 1,  L = K pl
+ * is built chunk by chunk (chunk q = limbs [q pl, (q+1) pl)): low half of C_q plus high half of
+ * C_(q-1) (minus the high half of C_(K-1) for q = 0, B^L = -1), then the small signed terms m_q,
+ * m_(q-2) + top_(q-2) and the chunk carries are injected at the chunk's first limb. */
+__global__ void __launch_bounds__(256)
+k_mm_finish(limb_t *r, uint32_t r_pitch, const limb_t *a, const limb_t *b, uint32_t ab_pitch,
+            const limb_t *__restrict__ C, uint32_t l, uint32_t c_pitch, uint32_t K, uint32_t pl)
+{
+   MFFT_DYN_SMEM(limb_t, sm);
+   limb_t *a0 = sm, *b0 = sm + K;
+   int64_t *mm = (int64_t *)(sm + 2 * K), *tm = mm + K, *F = tm + K, *F2 = F + K + 1;
+   int *flag = (int *)(F2 + K + 1);
+   const uint32_t L = K * pl, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+   const uint64_t prod = blockIdx.x;
+   const limb_t *A = a + prod * ab_pitch, *Bp = b + prod * ab_pitch;
+   limb_t *R = r + prod * r_pitch;
+   const limb_t *Cp = C + prod * K * c_pitch;
+   const limb_t topA = A[L], topB = Bp[L];
+   for (uint32_t k = tid; k < K; k += blockDim.x) { a0[k] = A[(uint64_t) k * pl]; b0[k] = Bp[(uint64_t) k * pl]; }
+   __syncthreads();
+   if (topA | topB)
+   {  /* an operand equal to 2^(64 L) == -1 (its limbs are zero): the product is the negated other
+         operand, or 1 (the reference's large path ignores the top limbs, TODO:213-221) */
+      const limb_t *X = topA ? Bp : A;
+      if (topA && topB) { for (uint32_t k = tid; k <= L; k += blockDim.x) R[k] = (k == 0); return; }
+      for (uint32_t k = tid; k < L; k += blockDim.x) R[k] = ~X[k];
+      __syncthreads();
+      if (tid == 0)
+      {  /* -x = ~x + 2 (mod B^L + 1); the ripple leaves limb 0 only through all-ones limbs */
+         limb_t c = 2; uint32_t pos = 0;
+         while (c && pos < L) { const limb_t v = R[pos], nv = v + c; R[pos] = nv; c = (nv < v); pos++; }
+         R[L] = 0;
+         if (c)
+         {  /* x was 0 or 1: ~x + 2 = B^L or B^L + 1 */
+            bool zero = true;
+            for (uint32_t k = 0; k < L && zero; k++) zero = (R[k] == 0);
+            if (zero) R[L] = 1;      /* x == 1: result B^L */
+            /* x == 0 gives B^L + 1 == 0: limbs are (1, 0, ...) with carry -> subtract 1 */
+            else { R[0] -= 1; }
+         }
+      }
+      return;
+   }
+   /* negacyclic convolution of the low limbs mod 2^64 and the correction terms */
+   for (uint32_t k = tid; k < K; k += blockDim.x)
+   {
+      limb_t acc = 0;
+      for (uint32_t i = 0; i <= k; i++) acc += a0[i] * b0[k - i];
+      for (uint32_t i = k + 1; i < K; i++) acc -= a0[i] * b0[K + k - i];
+      const limb_t *Ck = Cp + (uint64_t) k * c_pitch;
+      const int64_t m = (int64_t)(acc - Ck[0]);
+      mm[k] = m; tm[k] = m + (int64_t) Ck[l];
+   }
+   __syncthreads();
+   /* chunk sums; F[q] = what still has to be added at limb q*pl, F[K] = carry out of the top */
+   for (uint32_t q = warp; q < K; q += nwarps)
+   {
+      const limb_t *X = Cp + (uint64_t) q * c_pitch;
+      const limb_t *Y = Cp + (uint64_t)(q ? q - 1 : K - 1) * c_pitch + pl;
+      const limb_t mask = q ? 0 : ~(limb_t) 0;
+      uint32_t cin = q ? 0u : 1u;
+      for (uint32_t k0 = 0; k0 < pl; k0 += 32)
+      {
+         const limb_t x = X[k0 + lane], y = Y[k0 + lane] ^ mask;
+         limb_t sv = x + y;
+         const uint32_t G = __ballot_sync(FULL, sv < x), P = __ballot_sync(FULL, sv == ~(limb_t) 0);
+         const uint64_t la = mfft_lookahead(G, P, cin);
+         sv += (limb_t)((la >> lane) & 1u);
+         cin = (uint32_t)(la >> 32) & 1u;
+         R[(uint64_t) q * pl + k0 + lane] = sv;
+      }
+      if (lane == 0)
+      {
+         const int64_t kq = (int64_t) cin - (q ? 0 : 1);          /* chunk carry, into chunk q+1 */
+         const uint32_t q1 = q + 1;
+         int64_t e = kq;
+         if (q1 < K) e += mm[q1] + (q1 >= 2 ? tm[q1 - 2] : -tm[K - 2 + q1]);
+         F[q1] = e;
+      }
+   }
+   if (tid == 0) F[0] = mm[0] - tm[K - 2];          /* chunk 0's own small terms */
+   __syncthreads();
+   /* inject the small signed terms, rippling inside the chunk; what leaves a chunk goes round again */
+   int64_t top = 0;
+   for (int round = 0; round < 64; round++)
+   {
+      int64_t *Fa = (round & 1) ? F2 : F, *Fb = (round & 1) ? F : F2;
+      if (tid == 0) *flag = 0;
+      for (uint32_t q = tid; q <= K; q += blockDim.x) Fb[q] = 0;
+      __syncthreads();
+      for (uint32_t q = tid; q < K; q += blockDim.x)
+      {
+         int64_t c = Fa[q];
+         for (uint32_t pos = 0; c != 0 && pos < pl; pos++)
+         {
+            const mfft_i128 acc = (mfft_i128) c + (mfft_i128)(mfft_u128) R[(uint64_t) q * pl + pos];
+            R[(uint64_t) q * pl + pos] = (limb_t) acc; c = (int64_t)(acc >> 64);
+         }
+         if (c != 0) { Fb[q + 1] = c; *flag = 1; }
+      }
+      __syncthreads();
+      top += Fa[K];                       /* every thread keeps the same running top */
+      const int again = *flag;
+      __syncthreads();
+      if (!again) { top += Fb[K]; break; }
+   }
+   /* value = body + top*B^L == body - top: mpn_normmod_2expp1 (272-294) */
+   if (tid == 0)
+   {
+      for (int it = 0; it < 4 && top != 0; it++)
+      {
+         if (top == 1)
+         {
+            bool zero = true;
+            for (uint32_t k = 0; k < L && zero; k++) zero = (R[k] == 0);
+            if (zero) break;
+         }
+         int64_t c = -top; top = 0;
+         for (uint32_t pos = 0; c != 0; pos++)
+         {
+            if (pos == L) { top = c; break; }
+            const mfft_i128 acc = (mfft_i128) c + (mfft_i128)(mfft_u128) R[pos];
+            R[pos] = (limb_t) acc; c = (int64_t)(acc >> 64);
+         }
+      }
+      R[L] = (limb_t) top;
+   }
+}
+
+int mfft_dev_mm_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, uint32_t src_pitch,
+                      uint32_t K, uint32_t pl, uint64_t count, void *stream)
+{
+   const uint64_t nblocks = count * K, threads = nblocks * ((uint64_t) l + 1);
+   if (!threads) return 0;
+   PROF(PC_SPLIT, stream);
+   MFFT_LAUNCH(k_mm_split, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t) stream, slab, l, pitch, src, src_pitch, K, pl, nblocks);
+   CKL();
+   return 0;
+}
+
+int mfft_dev_mm_finish(limb_t *r, uint32_t r_pitch, const limb_t *a, const limb_t *b, uint32_t ab_pitch,
+                       const limb_t *C, uint32_t l, uint32_t c_pitch, uint32_t K, uint32_t pl, uint64_t count, void *stream)
+{
+   if (!count) return 0;
+   const size_t sm = ((size_t) 2 * K + 2 * K + 2 * (K + 1)) * 8 + 16;
+   PROF(PC_COMBINE, stream);
+   CK(cudaFuncSetAttribute(k_mm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+   MFFT_LAUNCH(k_mm_finish, (unsigned) count, 256, sm, (cudaStream_t) stream, r, r_pitch, a, b, ab_pitch, C, l, c_pitch, K, pl);
+   CKL();
+   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* launch ABI                                                                                  */
 /* ------------------------------------------------------------------------------------------ */
 extern "C" {

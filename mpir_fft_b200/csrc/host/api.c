@@ -366,11 +366,35 @@ void FFT_combine(mp_limb_t *res, mp_limb_t **poly, mp_size_t length, mp_size_t c
 }
 
 /* ---------------------------------- mulmod 2^bits + 1 -------------------------------------- */
+/* plans of the transform-based path, keyed by (limbs, count) */
+#define MM_CACHE 4
+static mpirfft_mulmod_plan *g_mm[MM_CACHE]; static size_t g_mm_l[MM_CACHE], g_mm_count[MM_CACHE]; static unsigned g_mm_next = 0;
+
 int mpirfft_mulmod_batch_device(mp_limb_t *d_a, const mp_limb_t *d_b, size_t count, size_t l, size_t pitch, void *stream)
 {
    uint32_t *idx, *d_idx; size_t k; int rc;
+   mp_bitcnt_t depth, w;
    if (!count) return 0;
    if (l == 0 || pitch < l + 1 || count > 0xffffffffu) return MPIRFFT_EINVAL;
+   if (l >= 250 && l != 256 && l != 512 && mpirfft_mulmod_params((mp_size_t) l, &depth, &w) == 0)
+   {  /* large residues: negacyclic transform over a 64..512-limb ring, like the reference's
+         fft_mulmod_2expp1 from 250 limbs up (mul_fft.c:3135-3164); 256 and 512 limbs are served
+         directly by the warp-level product kernel */
+      mpirfft_mulmod_plan *pl = NULL; int i;
+      for (i = 0; i < MM_CACHE; i++) if (g_mm[i] && g_mm_l[i] == l && g_mm_count[i] == count) pl = g_mm[i];
+      if (!pl)
+      {
+         if ((rc = mpirfft_mulmod_plan_create(&pl, (mp_size_t) l, depth, w, count)) != 0) return rc;
+         i = (int)(g_mm_next++ % MM_CACHE);
+         if (g_mm[i]) mpirfft_mulmod_plan_destroy(g_mm[i]);
+         g_mm[i] = pl; g_mm_l[i] = l; g_mm_count[i] = count;
+      }
+      mfft_lock();
+      rc = mpirfft_mulmod_plan_exec(pl, d_a, d_a, d_b, pitch, -1, stream);
+      if (rc == 0 && mfft_dev_sync(stream)) rc = MPIRFFT_ENODEV;
+      mfft_unlock();
+      return rc;
+   }
    mfft_lock();
    if ((rc = mfft_try_device()) != 0) { mfft_unlock(); return rc; }
    idx = (uint32_t *) malloc(sizeof(uint32_t)*count);

@@ -175,6 +175,16 @@ size_t mfft_dev_combine_work(uint64_t total);
 int  mfft_dev_combine(limb_t *res, uint64_t total, const limb_t *slab, uint32_t l, uint32_t pitch,
                       uint64_t bits, uint64_t ncoef, void *work, void *stream);
 
+/* batched mulmod through a negacyclic transform (FFT_mulmod_2expp1, mul_fft.c:2998-3117):
+ * split: block (prod, k), k < K, = limbs [k*pl, (k+1)*pl) of operand prod, zero-extended to l+1 limbs;
+ * finish: r[prod] = sum_k c_k B^(pl k) mod B^(K pl) + 1, canonical, from the K canonical coefficients
+ * C[prod*K + k] mod B^l + 1 (l = 2 pl) and the operands' low limbs (which fix c_k mod 2^64); operands
+ * with a set top limb (== -1) are handled exactly.  r may alias a. */
+int  mfft_dev_mm_split(limb_t *slab, uint32_t l, uint32_t pitch, const limb_t *src, uint32_t src_pitch,
+                       uint32_t K, uint32_t pl, uint64_t count, void *stream);
+int  mfft_dev_mm_finish(limb_t *r, uint32_t r_pitch, const limb_t *a, const limb_t *b, uint32_t ab_pitch,
+                        const limb_t *C, uint32_t l, uint32_t c_pitch, uint32_t K, uint32_t pl, uint64_t count, void *stream);
+
 /* normalise nblk blocks in place (mpn_normmod_2expp1, mul_fft.c:272-294) */
 int  mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, void *stream);
 

@@ -58,3 +58,24 @@ def test_emulated_mulmod_adversarial(emu, l, mode):
     emu.mpirfft_set_pointwise_mode(0)
     for k in range(len(A)):
         assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), (l, k, mode)
+
+
+@pytest.mark.parametrize("l", [1024, 2048])
+def test_emulated_mulmod_transform_path(emu, l):
+    """residues of >= 250 limbs go through the batched negacyclic-transform path (csrc/host/mm.c,
+    FFT_mulmod_2expp1 mul_fft.c:2998): random, all-ones, +-1 and 2^NW operands"""
+    random.seed(l)
+    NW = 64 * l
+    p = (1 << NW) + 1
+    A = [random.getrandbits(NW) for _ in range(2)] + [p - 1, p - 2, 0, 1, (1 << NW) - 1, p - 1, (1 << (NW // 2)) - 1, p - 2]
+    B = [random.getrandbits(NW) for _ in range(2)] + [p - 2, p - 2, 5, p - 1, (1 << NW) - 1, p - 1, (1 << (NW // 2)) - 1, 2]
+    a = np.stack([int_to_block(v, l) for v in A])
+    b = np.stack([int_to_block(v, l) for v in B])
+    da, db = emu.mpirfft_malloc_device(a.nbytes), emu.mpirfft_malloc_device(b.nbytes)
+    emu.mpirfft_memcpy_h2d(da, ptr(a), a.nbytes, None)
+    emu.mpirfft_memcpy_h2d(db, ptr(b), b.nbytes, None)
+    assert emu.mpirfft_mulmod_batch_device(da, db, len(A), l, l + 1, None) == 0
+    out = np.empty_like(a)
+    emu.mpirfft_memcpy_d2h(ptr(out), da, a.nbytes, None)
+    for k in range(len(A)):
+        assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), (l, k)

@@ -126,6 +126,64 @@ def test_mulmod_vs_bigint(lib, l, mode):
         assert np.array_equal(out[k], want), "mulmod l=%d case %d mode %d" % (l, k, mode)
 
 
+@pytest.mark.parametrize("l", [1024, 4096, 16384])
+def test_mulmod_transform_path_vs_bigint(lib, l):
+    """>= 250 limbs: batched negacyclic-transform path (mm.c; FFT_mulmod_2expp1, mul_fft.c:2998)"""
+    import random
+    random.seed(l)
+    NW = 64 * l
+    p = (1 << NW) + 1
+    A = [random.getrandbits(NW) for _ in range(6)] + [p - 1, p - 2, 0, 1, (1 << NW) - 1, p - 1, (1 << (NW // 2)) - 1, p - 2]
+    B = [random.getrandbits(NW) for _ in range(6)] + [p - 2, p - 2, 5, p - 1, (1 << NW) - 1, p - 1, (1 << (NW // 2)) - 1, 2]
+    a = np.stack([int_to_block(v, l) for v in A])
+    b = np.stack([int_to_block(v, l) for v in B])
+    out = M.mulmod_batch(a, b)
+    for k in range(len(A)):
+        assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), "mulmod l=%d case %d" % (l, k)
+
+
+def test_cfg4_batch_vs_reference_fft_mulmod(lib, ref):
+    """BASELINE configs[3] shape: independent 16 384-limb negacyclic products; a sample is compared
+    with the compiled reference's fft_mulmod_2expp1 (outer n = 2^14, w = 64: bits = 2^20) and all of
+    them with a*b mod p through GMP"""
+    l, count = 16384, 48
+    NW = 64 * l
+    a = np.zeros((count, l + 1), np.uint64)
+    b = np.zeros((count, l + 1), np.uint64)
+    for k in range(count):
+        a[k, :l] = operand("uniform" if k % 3 else "runs", l, 100 + k)
+        b[k, :l] = operand("uniform" if k % 5 else "ones", l, 200 + k)
+    out = M.mulmod_batch(a, b)
+    assert not out[:, l].any()
+    for k in range(count):
+        full = oracle.gmp_mul(a[k, :l].copy(), b[k, :l].copy())
+        lo = int.from_bytes(full[:l].tobytes(), "little")
+        hi = int.from_bytes(full[l:].tobytes(), "little")
+        want = (lo - hi) % ((1 << NW) + 1)
+        assert int.from_bytes(out[k, :l].tobytes(), "little") == want, k
+    for k in range(0, count, 16):
+        r = np.zeros(l + 1, np.uint64)
+        tt = np.zeros(2 * l + 2, np.uint64)
+        ak, bk = a[k].copy(), b[k].copy()       # keep the copies alive across the call
+        ref.fft_mulmod_2expp1(ptr(r), ptr(ak), ptr(bk), cl(1 << 14), cl(64), ptr(tt))
+        assert np.array_equal(r[:l], out[k, :l]), k
+
+
+def test_fft_mulmod_symbols_large(lib, ref):
+    """the drop-in symbols on a 1024-limb residue: both go through the transform path"""
+    l = 1024
+    a = np.zeros(l + 1, np.uint64); b = np.zeros(l + 1, np.uint64)
+    a[:l] = splitmix64(11, l); b[:l] = splitmix64(12, l)
+    r1 = np.zeros(l + 1, np.uint64); r2 = np.zeros(l + 1, np.uint64); tt = np.zeros(2 * l + 2, np.uint64)
+    lib.fft_mulmod_2expp1(ptr(r1), ptr(a), ptr(b), cl(1 << 10), cl(64), ptr(tt))
+    a2, b2 = a.copy(), b.copy()
+    ref.fft_mulmod_2expp1(ptr(r2), ptr(a2), ptr(b2), cl(1 << 10), cl(64), ptr(tt))
+    assert np.array_equal(r1[:l], r2[:l])
+    r3 = np.zeros(l + 1, np.uint64)
+    lib.FFT_mulmod_2expp1(ptr(r3), ptr(a), ptr(b), cl(l), cul(4), cul(256))
+    assert np.array_equal(r3[:l], r2[:l])
+
+
 def test_product_with_nested_ss_pointwise(lib):
     lib.mpirfft_set_pointwise_mode(1)
     try:
