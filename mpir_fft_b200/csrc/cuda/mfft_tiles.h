@@ -271,6 +271,49 @@ __device__ __forceinline__ int64_t resolve_carries(limb_t *sblk, uint32_t lane)
    return top;
 }
 
+/* d[ti] in {-1,0,1}: what still has to be added to the chunk after ti*32+lane.  Moves the carries
+ * on and returns what leaves the last chunk.  Almost always nothing moves (a carry travels on only
+ * through an all-zero / all-one chunk); otherwise the chain is solved exactly in a fixed number of
+ * steps as a prefix scan of three-state transition functions: with `in` the carry entering a chunk,
+ *      out(in) = d + [in = +1 and chunk all ones] - [in = -1 and chunk zero]      (in {-1,0,1})
+ * (sparse or cancelling coefficients -- e.g. the exact zeros beyond the end of a product -- would
+ * otherwise ripple across the whole coefficient one chunk per round). */
+__device__ __forceinline__ uint32_t tf_apply(uint32_t F, uint32_t st) { return (F >> (2u * st)) & 3u; }
+__device__ __forceinline__ uint32_t tf_compose(uint32_t G, uint32_t F)      /* G after F */
+{ return tf_apply(G, tf_apply(F, 0)) | (tf_apply(G, tf_apply(F, 1)) << 2) | (tf_apply(G, tf_apply(F, 2)) << 4); }
+
+template <int NT>
+__device__ __forceinline__ int64_t ripple_regs(limb_t (&r0)[NT], limb_t (&r1)[NT], int32_t (&d)[NT], uint32_t lane)
+{
+   {  /* fast check: nothing to hand on except out of the very last chunk */
+      bool any = false;
+#pragma unroll
+      for (int ti = 0; ti < NT; ti++) any = any || (d[ti] != 0 && !(ti == NT - 1 && lane == 31));
+      if (!__any_sync(FULL, any)) return (int64_t) __shfl_sync(FULL, d[NT - 1], 31);
+   }
+   uint32_t state = 1;                                  /* carry entering the row, biased by 1 */
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t ones = ((r0[ti] & r1[ti]) == ~(limb_t) 0), zero = ((r0[ti] | r1[ti]) == 0);
+      const int32_t dd = d[ti];
+      /* outputs for in = -1, 0, +1, biased by 1 */
+      uint32_t F = (uint32_t)(dd - (int32_t) zero + 1) | ((uint32_t)(dd + 1) << 2) | ((uint32_t)(dd + (int32_t) ones + 1) << 4);
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1)
+      {
+         const uint32_t Fp = __shfl_up_sync(FULL, F, off);
+         if (lane >= (uint32_t) off) F = tf_compose(F, Fp);
+      }
+      uint32_t Fex = __shfl_up_sync(FULL, F, 1);        /* everything before this lane's chunk */
+      const uint32_t in = lane ? tf_apply(Fex, state) : state;
+      state = tf_apply(__shfl_sync(FULL, F, 31), state);
+      const int64_t c = (int64_t) in - 1;
+      (void) add2(r0[ti], r1[ti], r0[ti], r1[ti], (limb_t) c, (limb_t)(c >> 63));
+   }
+   return (int64_t) state - 1;
+}
+
 /* The same without touching shared memory again: lane j ends up with the resolved limbs of chunks
  * ti*32 + j in (r0[ti], r1[ti]) -- 16 consecutive bytes per lane, i.e. one coalesced 512-byte
  * store per ti.  Absorbing the previous chunk's carry word leaves a carry in {-1,0,1}, which
@@ -291,31 +334,34 @@ __device__ __forceinline__ int64_t resolve_regs(limb_t (&r0)[NT], limb_t (&r1)[N
       const int32_t k = add2(r0[ti], r1[ti], x0, x1, (limb_t)(int64_t) c, (limb_t)((int64_t) c >> 63));
       d[ti] = k + (c >> 31);
    }
-   int64_t top = (int64_t) cw[NCH - 1];
-   for (;;)
+   return (int64_t) cw[NCH - 1] + ripple_regs<NT>(r0, r1, d, lane);
+}
+
+/* mpn_normmod_2expp1 (mul_fft.c:272-294) on resolved limbs held in registers (chunk ti*32+lane in
+ * (r0[ti], r1[ti])): value = body + top*B^l == body - top */
+template <int NT>
+__device__ __forceinline__ int64_t normalise_regs(limb_t (&r0)[NT], limb_t (&r1)[NT], int64_t top, uint32_t lane)
+{
+   for (int it = 0; it < 4; it++)
    {
-      int32_t din[NT]; bool any = false;
-#pragma unroll
-      for (int ti = 0; ti < NT; ti++)
+      if (top == 0) break;
+      if (top == 1)
       {
-         const int32_t up = __shfl_up_sync(FULL, d[ti], 1);
-         const int32_t prev = (ti > 0) ? __shfl_sync(FULL, d[ti > 0 ? ti - 1 : 0], 31) : 0;
-         din[ti] = lane ? up : prev;
-         any = any || (din[ti] != 0);
-      }
-      top += (int64_t) __shfl_sync(FULL, d[NT - 1], 31);
-      if (!__any_sync(FULL, any)) break;
+         bool z = true;
 #pragma unroll
-      for (int ti = 0; ti < NT; ti++)
-      {
-         d[ti] = 0;
-         if (din[ti] != 0)
-         {
-            const int32_t c = din[ti];
-            const int32_t k = add2(r0[ti], r1[ti], r0[ti], r1[ti], (limb_t)(int64_t) c, (limb_t)((int64_t) c >> 63));
-            d[ti] = k + (c >> 31);
-         }
+         for (int ti = 0; ti < NT; ti++) z = z && ((r0[ti] | r1[ti]) == 0);
+         if (__all_sync(FULL, z)) break;
       }
+      int32_t d[NT];
+#pragma unroll
+      for (int ti = 0; ti < NT; ti++) d[ti] = 0;
+      if (lane == 0)
+      {  /* body -= top at limb 0 */
+         const int64_t c = -top;
+         const int32_t k = add2(r0[0], r1[0], r0[0], r1[0], (limb_t) c, (limb_t)(c >> 63));
+         d[0] = k + (int32_t)(c >> 63);
+      }
+      top = ripple_regs<NT>(r0, r1, d, lane);
    }
    return top;
 }
@@ -373,6 +419,133 @@ __device__ __forceinline__ int64_t normalise_tile(limb_t *sblk, uint32_t l, int6
    return top;
 }
 
+/* ---- radix-4 units: two radix-2 layers per shared-memory round trip -------------------------- */
+/* signed chunk value = 2 limbs + carry word */
+struct cval { limb_t x0, x1; int32_t c; };
+__device__ __forceinline__ cval cv_add(const cval &a, const cval &b)
+{ cval r; r.c = add2(r.x0, r.x1, a.x0, a.x1, b.x0, b.x1) + a.c + b.c; return r; }
+__device__ __forceinline__ cval cv_sub(const cval &a, const cval &b)
+{ cval r; r.c = sub2(r.x0, r.x1, a.x0, a.x1, b.x0, b.x1) + a.c - b.c; return r; }
+__device__ __forceinline__ cval cv_load(const limb_t *P, uint32_t L, uint32_t ch)
+{ cval r; ld2(r.x0, r.x1, P + 2 * ch); r.c = reinterpret_cast<const int32_t *>(P + L)[ch]; return r; }
+__device__ __forceinline__ void cv_store(limb_t *P, uint32_t L, uint32_t ch, const cval &v)
+{ st2(P + 2 * ch, v.x0, v.x1); reinterpret_cast<int32_t *>(P + L)[ch] = v.c; }
+
+/* Two forward layers on positions P0..P3 in place (FFT_radix2 786-827, two levels of the recursion):
+ *    layer 1:  (P0,P2) -> P0+P2, +-(P0-P2) 2^(128 y1)      (P1,P3) -> P1+P3, +-(P1-P3) 2^(128 y1')
+ *    layer 2:  (P0,P1) -> ...,   2^(128 y2)                  (P2,P3) -> ...,   2^(128 y2')
+ * with y1' = y1 + NCH/2 (the two layer-1 twiddles differ by the quarter turn 2^(NW/2)).  A rotation by
+ * NCH/2 = 16 NT chunks maps a lane's chunk ti to its own chunk ti +- NT/2, so the whole unit is
+ * lane-local: 4 chunk loads and 4 chunk stores per lane and ti instead of 8 + 8.  q[k] = y | neg << 31. */
+template <int NT>
+__device__ __forceinline__ void fwd4_unit(limb_t *P0, limb_t *P1, limb_t *P2, limb_t *P3,
+                                          uint32_t q1, uint32_t q1p, uint32_t q2, uint32_t q2p, uint32_t lane)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH; constexpr int H = NT / 2;
+   const uint32_t y1 = q1 & 0x7fffffffu, y1p = q1p & 0x7fffffffu, y2 = q2 & 0x7fffffffu, y2p = q2p & 0x7fffffffu;
+   const uint32_t n1 = q1 >> 31, n1p = q1p >> 31, n2 = q2 >> 31, n2p = q2p >> 31;
+   cval a0[NT], a1[NT], a2[NT], a3[NT];
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t i = ti * 32u + lane;
+      a0[ti] = cv_load(P0, L, i); a1[ti] = cv_load(P1, L, i); a2[ti] = cv_load(P2, L, i); a3[ti] = cv_load(P3, L, i);
+   }
+   __syncwarp();
+   /* layer 1 in place: a0 <- a0+a2, a2 <- +-(a0-a2) (the chunk that lands at i+y1), same for a1,a3 */
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t i = ti * 32u + lane;
+      const cval s = cv_add(a0[ti], a2[ti]);
+      a2[ti] = (((i + y1 >= NCH) ? 1u : 0u) != n1) ? cv_sub(a2[ti], a0[ti]) : cv_sub(a0[ti], a2[ti]);
+      a0[ti] = s;
+      const cval sp = cv_add(a1[ti], a3[ti]);
+      a3[ti] = (((i + y1p >= NCH) ? 1u : 0u) != n1p) ? cv_sub(a3[ti], a1[ti]) : cv_sub(a1[ti], a3[ti]);
+      a1[ti] = sp;
+   }
+   /* layer 2 */
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t i = ti * 32u + lane;
+      constexpr int dummy = 0; (void) dummy;
+      const int tp = (ti + H) % NT;                         /* a3's chunk that lands where a2[ti] does */
+      cv_store(P0, L, i, cv_add(a0[ti], a1[ti]));
+      {
+         uint32_t o = i + y2, n = n2;
+         if (o >= NCH) { o -= NCH; n ^= 1u; }
+         cv_store(P1, L, o, n ? cv_sub(a1[ti], a0[ti]) : cv_sub(a0[ti], a1[ti]));
+      }
+      uint32_t j = i + y1; if (j >= NCH) j -= NCH;
+      cv_store(P2, L, j, cv_add(a2[ti], a3[tp]));
+      {
+         uint32_t o = j + y2p, n = n2p;
+         if (o >= NCH) { o -= NCH; n ^= 1u; }
+         cv_store(P3, L, o, n ? cv_sub(a3[tp], a2[ti]) : cv_sub(a2[ti], a3[tp]));
+      }
+   }
+}
+
+/* Two inverse layers on positions P0..P3 in place (IFFT_radix2 1444-1536, two levels):
+ *    layer 1:  (P0,P1) -> P0 +- P1 2^(128 y2), P0 -+ ...      (P2,P3) -> P2 +- P3 2^(128 y2'), ...
+ *    layer 2:  (P0,P2) -> P0 +- P2 2^(128 y1), ...            (P1,P3) -> P1 +- P3 2^(128 y1'), ...
+ * with y1' = y1 + NCH/2; exponents are the negated (inverse) rotations already folded mod 2NW. */
+template <int NT>
+__device__ __forceinline__ void inv4_unit(limb_t *P0, limb_t *P1, limb_t *P2, limb_t *P3,
+                                          uint32_t q2, uint32_t q2p, uint32_t q1, uint32_t q1p, uint32_t lane)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH; constexpr int H = NT / 2;
+   const uint32_t y1 = q1 & 0x7fffffffu, y1p = q1p & 0x7fffffffu, y2 = q2 & 0x7fffffffu, y2p = q2p & 0x7fffffffu;
+   const uint32_t n1 = q1 >> 31, n1p = q1p >> 31, n2 = q2 >> 31, n2p = q2p >> 31;
+   cval u0[NT], u1[NT], u2[NT], u3[NT];
+   /* u0,u1 at chunk i; u2,u3 at chunk m = i - y1 (what layer 2 adds to chunk i of P0) */
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t i = ti * 32u + lane;
+      const uint32_t jb = (i >= y2) ? i - y2 : i + NCH - y2;
+      const uint32_t m = (i >= y1) ? i - y1 : i + NCH - y1;
+      const uint32_t mb = (m >= y2p) ? m - y2p : m + NCH - y2p;
+      u0[ti] = cv_load(P0, L, i); u1[ti] = cv_load(P1, L, jb); u2[ti] = cv_load(P2, L, m); u3[ti] = cv_load(P3, L, mb);
+   }
+   __syncwarp();
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t i = ti * 32u + lane;
+      const uint32_t m = (i >= y1) ? i - y1 : i + NCH - y1;
+      {  /* (u0,u1) <- b0 +- b1', b0 -+ b1' */
+         const cval sm = cv_add(u0[ti], u1[ti]), df = cv_sub(u0[ti], u1[ti]);
+         const bool ng = ((i < y2) ? 1u : 0u) != n2;
+         u0[ti] = ng ? df : sm; u1[ti] = ng ? sm : df;
+      }
+      {
+         const cval sm = cv_add(u2[ti], u3[ti]), df = cv_sub(u2[ti], u3[ti]);
+         const bool ng = ((m < y2p) ? 1u : 0u) != n2p;
+         u2[ti] = ng ? df : sm; u3[ti] = ng ? sm : df;
+      }
+   }
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t i = ti * 32u + lane;
+      const int tp = (ti + H) % NT;                         /* u3 at chunk i - y1' = (i -+ NCH/2) - y1 */
+      {
+         const bool ng = ((i < y1) ? 1u : 0u) != n1;       /* P2's chunk enters negated */
+         limb_t *ds = ng ? P2 : P0, *dt = ng ? P0 : P2;
+         cv_store(ds, L, i, cv_add(u0[ti], u2[ti]));
+         cv_store(dt, L, i, cv_sub(u0[ti], u2[ti]));
+      }
+      {
+         const bool ng = ((i < y1p) ? 1u : 0u) != n1p;
+         limb_t *ds = ng ? P3 : P1, *dt = ng ? P1 : P3;
+         cv_store(ds, L, i, cv_add(u1[ti], u3[tp]));
+         cv_store(dt, L, i, cv_sub(u1[ti], u3[tp]));
+      }
+   }
+}
+
 /* ---- the kernel ----------------------------------------------------------------------------- */
 template <int NT, int NTHREADS>
 __global__ void __launch_bounds__(NTHREADS, 2)
@@ -425,7 +598,15 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
          const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
          limb_t *d = coef + (size_t) p * SP;
          cp_async16(d + 2 * c, src + 2 * c);
-         reinterpret_cast<int32_t *>(d + L)[c] = (c == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
+         if (c != NCH - 1) reinterpret_cast<int32_t *>(d + L)[c] = 0;
+      }
+      /* the signed top limbs: one global load per loaded coefficient, all in flight together */
+      for (uint32_t p = tid; p < T.npos; p += blockDim.x)
+      {
+         const uint32_t pp = pos[T.pos_off + p];
+         if (!(pp & MFFT_TILE_LOAD)) continue;
+         const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
+         reinterpret_cast<int32_t *>(coef + (size_t) p * SP + L)[NCH - 1] = (int32_t)(int64_t) src[L];
       }
    } else
    for (uint32_t p = warp; p < T.npos; p += nwarps)
@@ -456,6 +637,18 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
          const limb_t *B = hasB ? coef + (size_t) op.b * SP : A;
          limb_t *S = coef + (size_t) op.s * SP;
          limb_t *Tt = hasT ? coef + (size_t) op.t * SP : S;
+         if (op.kind == MFFT_K_FWD4 || op.kind == MFFT_K_INV4)
+         {  /* two layers at once on four positions (a, b, s, t hold them; the exponent fields the
+               four packed rotations); only built for even NT <= 4 */
+            if (NT <= 4 && NT % 2 == 0)
+            {
+               limb_t *P0 = coef + (size_t) op.a * SP, *P1 = coef + (size_t) op.b * SP;
+               limb_t *P2 = coef + (size_t) op.s * SP, *P3 = coef + (size_t) op.t * SP;
+               if (op.kind == MFFT_K_FWD4) fwd4_unit<(NT <= 4 && NT % 2 == 0) ? NT : 2>(P0, P1, P2, P3, op.eSA, op.eSB, op.eTA, op.eTB, lane);
+               else inv4_unit<(NT <= 4 && NT % 2 == 0) ? NT : 2>(P0, P1, P2, P3, op.eSA, op.eSB, op.eTA, op.eTB, lane);
+            }
+            continue;
+         }
          if (op.kind != MFFT_K_ANY)
          {  /* host-classified aligned shapes: lane-local chunk arithmetic, nothing to decode */
             const uint32_t yc = op.kparam & 0x7fffffffu, neg = op.kparam >> 31;
@@ -527,6 +720,43 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
                   limb_t r0 = a0[ti], r1 = a1[ti]; int32_t k = ca[ti];
                   if (n) k = sub2(r0, r1, 0, 0, a0[ti], a1[ti]) - ca[ti];
                   st2(S + 2 * o, r0, r1); cwS[o] = k;
+               }
+            } else if (op.kind == MFFT_K_DBL)
+            {  /* 2 (x + c B^2) = (2x mod B^2) + (2c + top bit of x) B^2: chunk-local */
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  limb_t x0, x1;
+                  ld2(x0, x1, A + 2 * i);
+                  const int32_t c = cwA[i];
+                  st2(S + 2 * i, x0 << 1, (x1 << 1) | (x0 >> 63));
+                  cwS[i] = 2 * c + (int32_t)(x1 >> 63);
+               }
+            } else if (op.kind == MFFT_K_HALF)
+            {  /* (A + B) / 2: halve chunk by chunk; a chunk's (and a carry word's) lowest bit is worth
+                  2^127 one chunk below, and chunk 0's lowest bit -2^(NW-1) (2^-1 == -2^(NW-1) mod p) */
+               uint32_t lowbit[NT];
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane, nx = (i + 1 == NCH) ? 0u : i + 1;
+                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
+                  ld2(b0[ti], b1[ti], B + 2 * i); cb[ti] = cwB[i];
+                  lowbit[ti] = (uint32_t)((A[2 * nx] ^ B[2 * nx]) & 1u);
+               }
+               __syncwarp();
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  limb_t t0, t1;
+                  const int32_t ct = add2(t0, t1, a0[ti], a1[ti], b0[ti], b1[ti]) + ca[ti] + cb[ti];
+                  const int32_t e = (ct & 1) + ((i + 1 == NCH) ? -(int32_t) lowbit[ti] : (int32_t) lowbit[ti]);   /* in {-1,0,1,2} */
+                  const limb_t h0 = (t0 >> 1) | (t1 << 63);
+                  const limb_t h1 = (t1 >> 1) | ((limb_t)(e & 1) << 63);
+                  st2(S + 2 * i, h0, h1);
+                  cwS[i] = (ct >> 1) + (e >> 1);
                }
             } else
             {  /* MFFT_K_ADD */
@@ -640,10 +870,11 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
          out = dst + ((uint64_t) dst_base[bi] + (uint64_t) dp * dst_stride) * g.pitch;
       } else out = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
       limb_t *sblk = coef + (size_t) p * SP;
-      if (al16 && !normalise)
+      if (al16)
       {  /* resolved limbs go straight from registers to HBM, 512 contiguous bytes per warp store */
          limb_t r0[NT], r1[NT];
-         const int64_t tp = resolve_regs<NT>(r0, r1, sblk, lane);
+         int64_t tp = resolve_regs<NT>(r0, r1, sblk, lane);
+         if (normalise) tp = normalise_regs<NT>(r0, r1, tp, lane);
 #pragma unroll
          for (int ti = 0; ti < NT; ti++) st2(out + 2 * (ti * 32u + lane), r0[ti], r1[ti]);
          if (lane == 0) out[L] = (limb_t) tp;

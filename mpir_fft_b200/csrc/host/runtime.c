@@ -332,7 +332,7 @@ static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft
       mfft_dev_profile_bytes(pass_bytes(p, nbatch, g->l));
       if (mfft_dev_run_tiles(slab, g, d[i].d_tiles, p->ntiles, d[i].d_pos, d[i].d_ops, p->max_npos, p->max_nops, d_batch, nbatch,
                              lastp ? dst : NULL, m->d_dstpos, m->d_dst_base, m->dst_stride,
-                             lastp ? m->normalise : 0, d[i].d_stoff, 5*p->nany > p->nops_total, stream) != 0) return MPIRFFT_ENODEV;
+                             lastp ? m->normalise : 0, d[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, stream) != 0) return MPIRFFT_ENODEV;
    }
    return 0;
 }
@@ -390,9 +390,12 @@ void mfft_mfa_debug_dump(int inverse, uint64_t n, uint64_t w, uint64_t n1, uint6
          const mfft_pass *p = &P->pass[i];
          uint32_t cnt[64] = {0}, al[64] = {0}, two[64] = {0}, ld = 0, stc = 0;
          for (k = 0; k < p->npos_total; k++) { ld += (p->pos[k] & MFFT_TILE_LOAD) ? 1 : 0; stc += (p->pos[k] & MFFT_TILE_STORE) ? 1 : 0; }
-         for (k = 0; k < p->nops_total; k++)
+         uint32_t tix, r4[64] = {0};
+         for (tix = 0; tix < p->ntiles; tix++)
+         for (k = p->tiles[tix].op_off; k < p->tiles[tix].op_off + p->tiles[tix].nops; k++)
          {
             const mfft_tileop *o = &p->ops[k];
+            if (o->kind == MFFT_K_FWD4 || o->kind == MFFT_K_INV4) { r4[o->lstage < 63 ? o->lstage : 63]++; continue; }
             uint64_t e[4] = { (o->eSA + (uint64_t) col*o->cSA) % M2, (o->eSB + (uint64_t) col*o->cSB) % M2,
                               (o->eTA + (uint64_t) col*o->cTA) % M2, (o->eTB + (uint64_t) col*o->cTB) % M2 };
             int s[4] = { o->sSA, o->b != 0xFFFF ? o->sSB : 0, o->t != 0xFFFF ? o->sTA : 0, (o->t != 0xFFFF && o->b != 0xFFFF) ? o->sTB : 0 };
@@ -401,8 +404,26 @@ void mfft_mfa_debug_dump(int inverse, uint64_t n, uint64_t w, uint64_t n1, uint6
             st = o->lstage < 63 ? o->lstage : 63;
             cnt[st]++; al[st] += a; two[st] += (o->t != 0xFFFF);
          }
-         printf("  pass %u: tiles %u, max_npos %u, stages %u, ops %u, loads %u, stores %u\n", i, p->ntiles, p->max_npos, p->nstages, p->nops_total, ld, stc);
-         for (st = 0; st < p->nstages && st < 64; st++) printf("     stage %2u: ops %6u  aligned %6u  two-output %6u\n", st, cnt[st], al[st], two[st]);
+         printf("  pass %u: tiles %u, max_npos %u, stages %u, ops %u (radix-4 units %u, run-time decoded %u), loads %u, stores %u\n", i, p->ntiles, p->max_npos, p->nstages, p->nops_total, p->nr4, p->nany, ld, stc);
+         for (st = 0; st < p->nstages && st < 64; st++) printf("     stage %2u: radix-2 ops %6u  aligned %6u  two-output %6u   radix-4 units %6u\n", st, cnt[st], al[st], two[st], r4[st]);
+      }
+   }
+   mfft_mfa_free(&mm);
+}
+
+/* developer aid: the ops of one tile of one pass (which: 0 cols, 1 rows) */
+void mfft_mfa_debug_tile(int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc, int which, uint32_t pass, uint32_t tile)
+{
+   mfft_mfa mm; uint32_t k;
+   if (mfft_mfa_plan(&mm, inverse, n, w, n1, trunc, 0, 0, 0) != 0 || !mm.fused) { printf("plan failed\n"); return; }
+   {
+      const mfft_passes *P = which ? &mm.prow : &mm.pcol;
+      const mfft_pass *p = &P->pass[pass]; const mfft_tile *t = &p->tiles[tile];
+      for (k = t->op_off; k < t->op_off + t->nops; k++)
+      {
+         const mfft_tileop *o = &p->ops[k];
+         printf("st %u kind %u a %u b %u s %u t %u kparam %08x | e %u %u %u %u s %d %d %d %d\n", o->lstage, o->kind, o->a, o->b, o->s, o->t,
+                o->kparam, o->eSA, o->eSB, o->eTA, o->eTB, o->sSA, o->sSB, o->sTA, o->sTB);
       }
    }
    mfft_mfa_free(&mm);

@@ -65,6 +65,9 @@ static void classify_op(mfft_tileop *d, uint64_t NW)
    d->kind = MFFT_K_ANY; d->kparam = 0;
    if (d->cSA | d->cSB | d->cTA | d->cTB) return;
    if (NW % 128 || !d->sSA) return;
+   /* the two bit-granular shapes of the truncated inverse that stay chunk-local in carry-save form */
+   if (!hasB && !hasT && d->sSA == 1 && d->eSA == 1) { d->kind = MFFT_K_DBL; return; }
+   if (hasB && !hasT && d->sSA == 1 && d->sSB == 1 && d->eSA == 2*NW - 1 && d->eSB == 2*NW - 1) { d->kind = MFFT_K_HALF; return; }
    if (fold_term(d->sSA, d->eSA, NW, &ySA, &nSA)) return;
    if (hasB) { if (!d->sSB || fold_term(d->sSB, d->eSB, NW, &ySB, &nSB)) return; }
    if (hasT)
@@ -82,6 +85,62 @@ static void classify_op(mfft_tileop *d, uint64_t NW)
    { d->kind = MFFT_K_ROT; d->kparam = ySA | (nSA << 31); return; }
    else if (hasB && !hasT && ySA == 0 && !nSA && ySB == 0 && !nSB)
    { d->kind = MFFT_K_ADD; return; }
+}
+
+/* Fuse pairs of consecutive layers into radix-4 units (MFFT_K_FWD4 / MFFT_K_INV4) where four
+ * in-place butterflies of the same kind form a 2x2 network whose quarter-turn twiddles differ by
+ * exactly NW/2 -- then the unit is lane-local in the kernel (mfft_tiles.h).  Works on one tile's op
+ * slice (sorted by lstage); absorbed ops become MFFT_K_NOP and are compacted away by the caller. */
+static void fuse_radix4(mfft_tileop *ops, uint32_t nops, uint32_t nstages, uint32_t npos, uint64_t NW, uint32_t *scratch)
+{
+   const uint32_t NCH = (uint32_t)(NW/128), NT = NCH/32;
+   uint32_t *asA0 = scratch, *asA1 = scratch + npos, s, k;      /* position -> op (as operand a) per stage */
+   const char *env = getenv("MPIRFFT_NO_RADIX4");
+   if ((env && env[0] == '1') || NW % 128 || NCH % 32 || NT > 4 || (NT & 1)) return;
+   for (s = 0; s + 1 < nstages; s += 2)
+   {
+      uint32_t lo0 = nops, hi0 = 0, lo1 = nops, hi1 = 0;
+      for (k = 0; k < nops; k++)
+      {
+         if (ops[k].lstage == s) { if (k < lo0) lo0 = k; hi0 = k + 1; }
+         if (ops[k].lstage == s + 1) { if (k < lo1) lo1 = k; hi1 = k + 1; }
+      }
+      if (lo0 >= hi0 || lo1 >= hi1) continue;
+      for (k = 0; k < npos; k++) { asA0[k] = MFFT_NONE; asA1[k] = MFFT_NONE; }
+      for (k = lo0; k < hi0; k++) if (ops[k].kind == MFFT_K_FWD || ops[k].kind == MFFT_K_INV)
+         if (ops[k].s == ops[k].a && ops[k].t == ops[k].b) asA0[ops[k].a] = k;
+      for (k = lo1; k < hi1; k++) if (ops[k].kind == MFFT_K_FWD || ops[k].kind == MFFT_K_INV)
+         if (ops[k].s == ops[k].a && ops[k].t == ops[k].b) asA1[ops[k].a] = k;
+      for (k = lo0; k < hi0; k++)
+      {  /* layer s: X = (p0,x), X' = (y,p3); layer s+1: Y = (p0,y), Z = (x,p3).  An op with zero
+            rotation (S = A+B, T = A-B) fits both the forward and the inverse shape. */
+#define FWDLIKE(o) ((o)->kind == MFFT_K_FWD || ((o)->kind == MFFT_K_INV && (o)->kparam == 0))
+#define INVLIKE(o) ((o)->kind == MFFT_K_INV || ((o)->kind == MFFT_K_FWD && (o)->kparam == 0))
+#define YC(o) ((o)->kparam & 0x7fffffffu)
+         mfft_tileop *X = &ops[k], *Xp, *Y, *Z;
+         uint32_t p0, x, y, p3; int fwd, inv;
+         if ((X->kind != MFFT_K_FWD && X->kind != MFFT_K_INV) || asA0[X->a] != k) continue;
+         p0 = X->a; x = X->b;
+         if (asA1[p0] == MFFT_NONE) continue;
+         Y = &ops[asA1[p0]]; y = Y->b;
+         if (y == x || asA0[y] == MFFT_NONE) continue;
+         Xp = &ops[asA0[y]]; p3 = Xp->b;
+         if (Xp == X || asA1[x] == MFFT_NONE) continue;
+         Z = &ops[asA1[x]];
+         if (Z->b != p3) continue;
+         fwd = FWDLIKE(X) && FWDLIKE(Xp) && FWDLIKE(Y) && FWDLIKE(Z) && ((YC(Xp) + NCH - YC(X)) % NCH) == NCH/2;
+         inv = INVLIKE(X) && INVLIKE(Xp) && INVLIKE(Y) && INVLIKE(Z) && ((YC(Z) + NCH - YC(Y)) % NCH) == NCH/2;
+         if (!fwd && !inv) continue;
+         X->eSA = X->kparam; X->eSB = Xp->kparam; X->eTA = Y->kparam; X->eTB = Z->kparam;
+         asA0[p0] = MFFT_NONE; asA0[y] = MFFT_NONE; asA1[p0] = MFFT_NONE; asA1[x] = MFFT_NONE;
+         Xp->kind = MFFT_K_NOP; Y->kind = MFFT_K_NOP; Z->kind = MFFT_K_NOP;
+         if (fwd) { X->kind = MFFT_K_FWD4; X->a = (uint16_t) p0; X->b = (uint16_t) y; X->s = (uint16_t) x; X->t = (uint16_t) p3; }
+         else     { X->kind = MFFT_K_INV4; X->a = (uint16_t) p0; X->b = (uint16_t) x; X->s = (uint16_t) y; X->t = (uint16_t) p3; }
+#undef FWDLIKE
+#undef INVLIKE
+#undef YC
+      }
+   }
 }
 
 /* build one pass from ops[lo..hi) (sorted by pstage; window = stages s0..s1) */
@@ -128,7 +187,7 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
          root_tile[r] = cur; cur_fill += tile_fill[r];
       }
    }
-   out->ntiles = ntiles; out->max_npos = 0; out->max_nops = 0; out->nstages = 0; out->nany = 0;
+   out->ntiles = ntiles; out->max_npos = 0; out->max_nops = 0; out->nstages = 0; out->nany = 0; out->nr4 = 0;
    out->tiles = (mfft_tile *) calloc(ntiles ? ntiles : 1, sizeof(mfft_tile));
    tile_npos = (uint32_t *) calloc(4 * (size_t)(ntiles ? ntiles : 1), sizeof(uint32_t));
    if (!out->tiles || !tile_npos) { free(tile_npos); return -1; }
@@ -178,6 +237,27 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
       if (d->lstage + 1 > out->nstages) out->nstages = d->lstage + 1;
    }
    free(tile_npos);
+   {  /* radix-4 fusion per tile; drop the absorbed ops and the stages that became empty */
+      uint32_t t; uint32_t *fs = (uint32_t *) malloc(sizeof(uint32_t) * 2 * (size_t)(out->max_npos ? out->max_npos : 1));
+      if (!fs) return -1;
+      out->nstages = 0; out->max_nops = 0;
+      for (t = 0; t < ntiles; t++)
+      {
+         mfft_tile *tl = &out->tiles[t]; mfft_tileop *o = out->ops + tl->op_off;
+         uint32_t k, w = 0, remap[64], used[64], ns = 0;
+         if (tl->nstages > 62) { free(fs); return -1; }
+         fuse_radix4(o, tl->nops, tl->nstages, tl->npos, NW, fs);
+         memset(used, 0, sizeof used);
+         for (k = 0; k < tl->nops; k++) if (o[k].kind != MFFT_K_NOP) used[o[k].lstage] = 1;
+         for (k = 0; k < tl->nstages; k++) { remap[k] = ns; ns += used[k]; }
+         for (k = 0; k < tl->nops; k++) if (o[k].kind != MFFT_K_NOP) { o[w] = o[k]; o[w].lstage = remap[o[k].lstage]; w++; }
+         for (k = 0; k < w; k++) if (o[k].kind == MFFT_K_FWD4 || o[k].kind == MFFT_K_INV4) out->nr4++;
+         tl->nops = w; tl->nstages = ns;
+         if (ns > out->nstages) out->nstages = ns;
+         if (w > out->max_nops) out->max_nops = w;
+      }
+      free(fs);
+   }
    {  /* stage offsets per tile */
       uint32_t t, total = 0, cur = 0;
       for (t = 0; t < ntiles; t++) total += out->tiles[t].nstages + 1;

@@ -9,6 +9,7 @@ extern "C" {
 typedef struct {
    uint32_t     ntiles, max_npos, max_nops, nstages, npos_total, nops_total;
    uint32_t     nany;      /* ops the kernel has to decode at run time (MFFT_K_ANY): register-hungry path */
+   uint32_t     nr4;       /* fused radix-4 units (hold 4 coefficients' chunks in registers) */
    mfft_tile   *tiles;     /* [ntiles] */
    uint32_t    *pos;       /* [npos_total] physical position | MFFT_TILE_LOAD | MFFT_TILE_STORE */
    mfft_tileop *ops;       /* [nops_total] */

@@ -89,6 +89,13 @@ typedef struct {            /* one op of a tile; a,b,s,t index the tile's positi
 #define MFFT_K_INV   2u     /* S = A +- B * 2^(128 yc), T = A -+ B * 2^(128 yc)       (639-660)  */
 #define MFFT_K_ROT   3u     /* S = +-A * 2^(128 yc)                                   (926-957)  */
 #define MFFT_K_ADD   4u     /* S = A + B                                              (1093)     */
+/* two consecutive layers fused on four positions (a, b, s, t = P0..P3; eSA, eSB, eTA, eTB = the four
+   packed rotations y | neg << 31; tile.c: fuse_radix4, mfft_tiles.h: fwd4_unit / inv4_unit) */
+#define MFFT_K_FWD4  5u
+#define MFFT_K_INV4  6u
+#define MFFT_K_NOP   7u     /* host only: op absorbed into a fused unit, removed before upload */
+#define MFFT_K_DBL   8u     /* S = 2 A           (the doubling steps of IFFT_radix2_truncate, 1788-1789) */
+#define MFFT_K_HALF  9u     /* S = (A + B) / 2   (the averaging steps of IFFT_radix2_truncate1, 1556-1560) */
 
 /* pad = offset of the tile's (nstages+1) stage offsets in the pass's stoff array (<= 63 stages) */
 typedef struct { uint32_t pos_off, npos, op_off, nops, nstages, pad; } mfft_tile;
