@@ -1313,9 +1313,15 @@ static size_t tiles_coeff_bytes(uint32_t l)
 uint32_t mfft_dev_tiles_max_npos(uint32_t l)
 {
    if (!mfft_dev_tiles_supported(l)) return 0;
-   size_t n = (100 * 1024) / tiles_coeff_bytes(l);
+   /* Tiles of about 45 KB, at least 16 coefficients (4 radix-2 layers per pass), at most 100 KB:
+      several small CTAs per SM overlap their load / compute / store phases better than two large
+      ones (measured at l = 256: 16 coefficients per tile, four 4-warp CTAs per SM, same pass count) */
+   const size_t cb = tiles_coeff_bytes(l), nmax = (100 * 1024) / cb, npref = (45 * 1024) / cb;
    uint32_t p = 4;
-   while (p * 2 <= n && p * 2 <= 128) p *= 2;
+   const char *env = getenv("MPIRFFT_TILE_NPOS");      /* developer aid: force the tile size */
+   while (p * 2 <= npref && p * 2 <= 128) p *= 2;
+   while (p < 16 && p * 2 <= nmax) p *= 2;
+   if (env && atoi(env) >= 4 && (size_t) atoi(env) <= nmax) p = (uint32_t) atoi(env);
    return p;
 }
 
@@ -1323,7 +1329,9 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
                        const uint32_t *d_pos, const mfft_tileop *d_ops, uint32_t max_npos, uint32_t max_nops,
                        const mfft_batch *d_batch, uint32_t nbatch,
                        limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
-                       uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy, void *stream)
+                       uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy,
+                        const mfft_tile *h_tiles, const uint32_t *h_pos, const uint32_t *h_stoff,
+                        const mfft_batch *h_batch, void *stream)
 {
    int NT = 0;
    if (!ntiles || !nbatch) return 0;
@@ -1333,6 +1341,25 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    const size_t smem = desc + (size_t) max_npos * tiles_coeff_bytes(g->l);
    const unsigned grid = ntiles * nbatch;
    cudaStream_t st = (cudaStream_t) stream;
+   /* small passes: tile descriptors, position lists and stage offsets travel as kernel parameters */
+   static tile_params tp;
+   tp.valid = 0; tp.batch_valid = 0;
+   if (h_tiles && h_pos && h_stoff && ntiles <= TP_MAXT)
+   {
+      uint32_t t, ok = 1;
+      for (t = 0; t < ntiles; t++) if (h_tiles[t].npos > TP_MAXP || h_tiles[t].nstages + 1 > TP_MAXS) ok = 0;
+      if (ok)
+      {
+         for (t = 0; t < ntiles; t++)
+         {
+            tp.tiles[t] = h_tiles[t];
+            memcpy(tp.pos + t * TP_MAXP, h_pos + h_tiles[t].pos_off, sizeof(uint32_t) * h_tiles[t].npos);
+            memcpy(tp.stoff + t * TP_MAXS, h_stoff + h_tiles[t].pad, sizeof(uint32_t) * (h_tiles[t].nstages + 1));
+         }
+         tp.valid = 1;
+      }
+   }
+   if (h_batch && nbatch <= TP_MAXB) { memcpy(tp.batch, h_batch, sizeof(mfft_batch) * nbatch); tp.batch_valid = 1; }
    PROF(PC_STAGE, st);
    /* two CTAs per SM: 16 warps x 64 registers while a lane holds <= 4 chunk pairs of an op, else
       8 warps x 128 registers (fewer, larger coefficients per tile) */
@@ -1340,9 +1367,17 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    do {                                                                                            \
       CK(cudaFuncSetAttribute(k_run_tiles<NN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
       MFFT_LAUNCH((k_run_tiles<NN, TH>), grid, TH, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
-                  dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff, g_tile_timing);  \
+                  dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff, g_tile_timing, tp); \
    } while (0)
-   if (heavy && NT <= 4)
+   if (max_npos <= 16 && NT <= 4 && smem <= 56 * 1024)
+      switch (NT)          /* small tiles: four 4-warp CTAs per SM */
+      {
+      case 1: RUN_TILES(1, 128); break;
+      case 2: RUN_TILES(2, 128); break;
+      case 3: RUN_TILES(3, 128); break;
+      default: RUN_TILES(4, 128); break;
+      }
+   else if (heavy && NT <= 4)
       switch (NT)
       {
       case 1: RUN_TILES(1, 256); break;

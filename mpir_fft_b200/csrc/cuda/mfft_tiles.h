@@ -546,14 +546,28 @@ __device__ __forceinline__ void inv4_unit(limb_t *P0, limb_t *P1, limb_t *P2, li
    }
 }
 
+/* tile descriptors of a small pass as kernel parameters (constant bank): no dependent global loads
+ * before a CTA can start fetching its coefficients */
+#define TP_MAXT 16
+#define TP_MAXP 32
+#define TP_MAXS 12
+#define TP_MAXB 256
+struct tile_params {
+   uint32_t valid, batch_valid;
+   mfft_batch batch[TP_MAXB];
+   mfft_tile tiles[TP_MAXT];
+   uint32_t pos[TP_MAXT * TP_MAXP];
+   uint32_t stoff[TP_MAXT * TP_MAXS];
+};
+
 /* ---- the kernel ----------------------------------------------------------------------------- */
 template <int NT, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, (NTHREADS == 128) ? 4 : 2)
 k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
             const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
             limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
             uint32_t dst_stride, int normalise, uint32_t desc_bytes, const uint32_t *__restrict__ stoff,
-            unsigned long long *timing)
+            unsigned long long *timing, const __grid_constant__ tile_params TP)
 {
 #ifndef MFFT_EMU
 #define TILE_STAMP(k) do { if (timing && threadIdx.x == 0) { unsigned long long t__; \
@@ -566,9 +580,9 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
    constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP;
    constexpr uint32_t NW = 64u * L, M2 = 2u * NW;
    constexpr uint32_t AMASK = 127u;                           /* exponent bits that break chunk alignment */
-   const uint32_t bi = blockIdx.x % nbatch;
-   const mfft_tile T = tiles[blockIdx.x / nbatch];
-   const mfft_batch b = batch[bi];
+   const uint32_t bi = blockIdx.x % nbatch, tix = blockIdx.x / nbatch;
+   const mfft_tile T = TP.valid ? TP.tiles[tix] : tiles[tix];
+   const mfft_batch b = TP.batch_valid ? TP.batch[bi] : batch[bi];
    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
    /* shared memory: [op descriptors | position list | stage offsets] [coefficients] */
    mfft_tileop *sops = (mfft_tileop *) sm;
@@ -581,37 +595,43 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
       const limb_t *src = (const limb_t *)(ops + T.op_off);
       limb_t *d = (limb_t *) sops;
       for (uint32_t k = tid; k < T.nops * (uint32_t)(sizeof(mfft_tileop) / 16); k += blockDim.x) cp_async16(d + 2 * k, src + 2 * k);
-      for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = pos[T.pos_off + k];
-      for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = stoff[T.pad + k];
+      if (TP.valid)
+      {
+         for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = TP.pos[tix * TP_MAXP + k];
+         for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = TP.stoff[tix * TP_MAXS + k];
+      } else
+      {
+         for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = pos[T.pos_off + k];
+         for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = stoff[T.pad + k];
+      }
    }
+   __syncthreads();                                   /* the position list is read by everybody below */
    /* load the positions that are read before being written: the body as it is, carry words 0
       except the last one, which is the block's signed top limb */
    const bool al16 = ((g.pitch & 1u) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15u) == 0) &&
                      (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
    if (al16)
-   {  /* 16-byte aligned blocks: every thread fires its share of asynchronous 16-byte copies, one wait */
+   {  /* 16-byte aligned blocks: every thread fires its share of asynchronous 16-byte copies, one wait.
+         The signed top limbs (one global load per loaded coefficient) are requested first so that
+         their latency hides behind the copy loop. */
+      limb_t topv = 0; bool have_top = false;
+      if (tid < T.npos && (spos[tid] & MFFT_TILE_LOAD))
+      { topv = tile_block_ptr(slab, g, spos[tid] & MFFT_TILE_POSMASK, b)[L]; have_top = true; }
       for (uint32_t t = tid; t < T.npos * NCH; t += blockDim.x)
       {
          const uint32_t p = t / NCH, c = t % NCH;
-         const uint32_t pp = pos[T.pos_off + p];
+         const uint32_t pp = spos[p];
          if (!(pp & MFFT_TILE_LOAD)) continue;
          const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
          limb_t *d = coef + (size_t) p * SP;
          cp_async16(d + 2 * c, src + 2 * c);
          if (c != NCH - 1) reinterpret_cast<int32_t *>(d + L)[c] = 0;
       }
-      /* the signed top limbs: one global load per loaded coefficient, all in flight together */
-      for (uint32_t p = tid; p < T.npos; p += blockDim.x)
-      {
-         const uint32_t pp = pos[T.pos_off + p];
-         if (!(pp & MFFT_TILE_LOAD)) continue;
-         const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
-         reinterpret_cast<int32_t *>(coef + (size_t) p * SP + L)[NCH - 1] = (int32_t)(int64_t) src[L];
-      }
+      if (have_top) reinterpret_cast<int32_t *>(coef + (size_t) tid * SP + L)[NCH - 1] = (int32_t)(int64_t) topv;
    } else
    for (uint32_t p = warp; p < T.npos; p += nwarps)
    {
-      const uint32_t pp = pos[T.pos_off + p];
+      const uint32_t pp = spos[p];
       if (!(pp & MFFT_TILE_LOAD)) continue;
       const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
       limb_t *d = coef + (size_t) p * SP;

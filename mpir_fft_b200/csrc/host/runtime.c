@@ -322,7 +322,7 @@ static double pass_bytes(const mfft_pass *p, uint32_t nbatch, uint32_t l)
 }
 
 static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft_dpass *d, limb_t *slab,
-                      const mfft_geom *g, const mfft_batch *d_batch, uint32_t nbatch, limb_t *dst, void *stream)
+                      const mfft_geom *g, const mfft_batch *d_batch, const mfft_batch *h_batch, uint32_t nbatch, limb_t *dst, void *stream)
 {
    uint32_t i;
    for (i = 0; i < P->npasses; i++)
@@ -332,7 +332,7 @@ static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft
       mfft_dev_profile_bytes(pass_bytes(p, nbatch, g->l));
       if (mfft_dev_run_tiles(slab, g, d[i].d_tiles, p->ntiles, d[i].d_pos, d[i].d_ops, p->max_npos, p->max_nops, d_batch, nbatch,
                              lastp ? dst : NULL, m->d_dstpos, m->d_dst_base, m->dst_stride,
-                             lastp ? m->normalise : 0, d[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, stream) != 0) return MPIRFFT_ENODEV;
+                             lastp ? m->normalise : 0, d[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, p->tiles, p->pos, p->stoff, h_batch, stream) != 0) return MPIRFFT_ENODEV;
    }
    return 0;
 }
@@ -344,11 +344,11 @@ int mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, void *stream)
    {
       if (!m->inverse)
       {
-         if ((rc = run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->ncolb, NULL, stream)) != 0) return rc;
-         return run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->nrowb, dst, stream);
+         if ((rc = run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, NULL, stream)) != 0) return rc;
+         return run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, dst, stream);
       }
-      if ((rc = run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->nrowb, NULL, stream)) != 0) return rc;
-      return run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->ncolb, dst, stream);
+      if ((rc = run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, NULL, stream)) != 0) return rc;
+      return run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, dst, stream);
    }
    if (!m->inverse)
    {

@@ -162,7 +162,16 @@ static void fft_full(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, ui
    {  /* leaf: FFT_radix2_twiddle_butterfly (517-548) with b1 = r*c*ws, b2 = (r+rs)*c*ws */
       uint64_t c1 = (r % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
       uint64_t c2 = ((r + rs) % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
-      emit(c->s, POS(0), POS(1), POS(0), T(1, 0, c1), T(1, 0, c1), POS(1), T(1, 0, c2), T(-1, 0, c2));
+      if (c1 == 0 && c2 == 0)
+         emit(c->s, POS(0), POS(1), POS(0), T(1, 0, 0), T(1, 0, 0), POS(1), T(1, 0, 0), T(-1, 0, 0));
+      else
+      {  /* the same as an untwisted butterfly followed by two rotations: (a+b) and (a-b) are
+            chunk-local in the tile executor, and each bit-granular twist then rotates one operand
+            instead of two */
+         emit(c->s, POS(0), POS(1), POS(0), T(1, 0, 0), T(1, 0, 0), POS(1), T(1, 0, 0), T(-1, 0, 0));
+         if (c1) emit(c->s, POS(0), MFFT_NONE, POS(0), T(1, 0, c1), T0, MFFT_NONE, T0, T0);
+         if (c2) emit(c->s, POS(1), MFFT_NONE, POS(1), T(1, 0, c2), T0, MFFT_NONE, T0, T0);
+      }
       return;
    }
    for (i = 0; i < n; i++) fwd_bfly(c, POS(i), POS(n + i), i*w);
@@ -209,8 +218,10 @@ static void ifft_full(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, u
    {  /* FFT_radix2_twiddle_inverse_butterfly (721-752): 2^{-b1} a +- 2^{-b2} b */
       uint64_t c1 = (r % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
       uint64_t c2 = ((r + rs) % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
-      emit(c->s, POS(0), POS(1), POS(0), T(1, 0, NEG(c1)), T(1, 0, NEG(c2)),
-                                 POS(1), T(1, 0, NEG(c1)), T(-1, 0, NEG(c2)));
+      /* the two rotations first, then an untwisted butterfly (see fft_full) */
+      if (c1) emit(c->s, POS(0), MFFT_NONE, POS(0), T(1, 0, NEG(c1)), T0, MFFT_NONE, T0, T0);
+      if (c2) emit(c->s, POS(1), MFFT_NONE, POS(1), T(1, 0, NEG(c2)), T0, MFFT_NONE, T0, T0);
+      emit(c->s, POS(0), POS(1), POS(0), T(1, 0, 0), T(1, 0, 0), POS(1), T(1, 0, 0), T(-1, 0, 0));
       return;
    }
    ifft_full(c, p0, n/2, 2*w, r, 2*rs);

@@ -19,6 +19,7 @@ void mfft_xform_free(mfft_xform *x)
    mfft_passes_free(&x->P);
    if (x->ds.s) { mfft_dsched_free(&x->ds); x->s = NULL; }
    if (x->s) mfft_sched_free(x->s);
+   free(x->h_batch);
    mfft_dev_free(x->d_batch); mfft_dev_free(x->d_dst_base); mfft_dev_free(x->d_dstpos); mfft_dev_free(x->d_moves);
    memset(x, 0, sizeof(*x));
 }
@@ -35,6 +36,8 @@ int mfft_xform_build(mfft_xform *x, mfft_sched *s, uint32_t l, uint32_t slot_str
    x->g.S = S; x->g.slot_stride = slot_stride; x->g.half_blocks = half_blocks; x->g.l = l; x->g.pitch = mfft_pitch(l);
    x->fused = mfft_dev_tiles_supported(l) && !(env && env[0] == '1');
    x->d_batch = (mfft_batch *) mfft_upload(batch, sizeof(mfft_batch)*nbatch);
+   x->h_batch = (mfft_batch *) malloc(sizeof(mfft_batch)*(nbatch ? nbatch : 1));
+   if (x->h_batch) memcpy(x->h_batch, batch, sizeof(mfft_batch)*nbatch);
    x->d_dst_base = (uint32_t *) mfft_upload(dst_base, sizeof(uint32_t)*nbatch);
    if (!x->d_batch || !x->d_dst_base) { rc = MPIRFFT_ENODEV; goto fail; }
    if (x->fused)
@@ -87,7 +90,7 @@ int mfft_xform_exec(const mfft_xform *x, limb_t *slab, limb_t *dst, void *stream
          const int lastp = (i + 1 == x->P.npasses);
          if (mfft_dev_run_tiles(slab, &x->g, x->dp[i].d_tiles, p->ntiles, x->dp[i].d_pos, x->dp[i].d_ops, p->max_npos,
                                 p->max_nops, x->d_batch, x->nbatch, lastp ? dst : NULL, x->d_dstpos, x->d_dst_base,
-                                x->dst_stride, lastp ? x->normalise : 0, x->dp[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, stream) != 0) return MPIRFFT_ENODEV;
+                                x->dst_stride, lastp ? x->normalise : 0, x->dp[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, p->tiles, p->pos, p->stoff, x->h_batch, stream) != 0) return MPIRFFT_ENODEV;
       }
       return 0;
    }

@@ -134,12 +134,16 @@ int  mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, 
  * all its stages there and stores the written positions back in place -- or, if dst != NULL,
  * to dst[(dst_base[b] + dstpos[i]*dst_stride)*pitch] (dstpos parallel to the position list,
  * MFFT_NONE = do not store), normalised when `normalise` is set.  max_npos bounds the tile size.
- * heavy: many ops of the pass need the run-time decoded general path (more registers per thread). */
+ * heavy: many ops of the pass need the run-time decoded general path (more registers per thread).
+ * h_tiles / h_pos / h_stoff (optional): host copies of the tile descriptors; small passes get them
+ * as kernel parameters, which takes two dependent global loads out of every CTA's start-up. */
 int  mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tiles, uint32_t ntiles,
                         const uint32_t *d_pos, const mfft_tileop *d_ops, uint32_t max_npos, uint32_t max_nops,
                         const mfft_batch *d_batch, uint32_t nbatch,
                         limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
-                        uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy, void *stream);
+                        uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy,
+                        const mfft_tile *h_tiles, const uint32_t *h_pos, const uint32_t *h_stoff,
+                        const mfft_batch *h_batch, void *stream);
 /* 1 if the fused executor supports coefficient size l (else use mfft_dev_run_stage) */
 int  mfft_dev_tiles_supported(uint32_t l);
 uint32_t mfft_dev_tiles_max_npos(uint32_t l);

@@ -29,6 +29,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
+#define __grid_constant__
 
 struct emu_dim3 { unsigned x, y, z; };
 extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
