@@ -954,24 +954,50 @@ k_combine_add(limb_t *res, const uint32_t *__restrict__ cvec, uint64_t total, ui
    if (lane == 0) { tileG[tile] = (uint32_t)(la >> 32) & 1u; tileP[tile] = tp ? 1u : 0u; }
 }
 
-/* pass 3: one warp scans the tile generate/propagate bits, 32 tiles per step */
-__global__ void __launch_bounds__(32)
+/* pass 3: one CTA scans the tile generate/propagate bits.  Each of the 32 warps owns a contiguous
+ * group of tiles and walks it 32 tiles per step twice: first with carry-in 0 and 1 to get the
+ * group's own generate / propagate, then -- after warp 0 has looked ahead over the 32 groups --
+ * with its true carry-in, writing the per-tile carries. */
+__global__ void __launch_bounds__(1024)
 k_combine_scan(const uint32_t *__restrict__ tileG, const uint32_t *__restrict__ tileP,
                uint32_t *tileC, uint64_t ntiles, const uint32_t *__restrict__ cvec_last, uint32_t *carry_out)
 {
-   const uint32_t lane = threadIdx.x;
-   uint32_t cin = 0;
-   for (uint64_t t0 = 0; t0 < ntiles; t0 += 32)
+   __shared__ uint32_t sG[32], sP[32], sC[33];
+   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+   const uint64_t per = (((ntiles + nwarps - 1) / nwarps + 31) / 32) * 32;     /* tiles per group, multiple of 32 */
+   const uint64_t lo = (uint64_t) warp * per, hi = (lo + per < ntiles) ? lo + per : ntiles;
+   uint32_t c0 = 0, c1 = 1;
+   for (uint64_t t0 = lo; t0 < hi; t0 += 32)
    {
       const uint64_t t = t0 + lane;
-      const uint32_t g = (t < ntiles) ? tileG[t] : 0u, p = (t < ntiles) ? tileP[t] : 1u;
+      const uint32_t g = (t < hi) ? tileG[t] : 0u, p = (t < hi) ? tileP[t] : 1u;
+      const uint32_t G = __ballot_sync(FULL, g != 0), P = __ballot_sync(FULL, p != 0);
+      c0 = (uint32_t)(mfft_lookahead(G, P, c0) >> 32) & 1u;
+      c1 = (uint32_t)(mfft_lookahead(G, P, c1) >> 32) & 1u;
+   }
+   if (lane == 0) { sG[warp] = c0; sP[warp] = (c1 && !c0) ? 1u : 0u; }
+   __syncthreads();
+   if (warp == 0)
+   {
+      const uint32_t g = (lane < nwarps) ? sG[lane] : 0u, p = (lane < nwarps) ? sP[lane] : 1u;
+      const uint32_t G = __ballot_sync(FULL, g != 0), P = __ballot_sync(FULL, p != 0);
+      const uint64_t la = mfft_lookahead(G, P, 0);
+      sC[lane] = (uint32_t)(la >> lane) & 1u;
+      if (lane == 0) sC[32] = (uint32_t)(la >> 32) & 1u;
+   }
+   __syncthreads();
+   uint32_t cin = sC[warp];
+   for (uint64_t t0 = lo; t0 < hi; t0 += 32)
+   {
+      const uint64_t t = t0 + lane;
+      const uint32_t g = (t < hi) ? tileG[t] : 0u, p = (t < hi) ? tileP[t] : 1u;
       const uint32_t G = __ballot_sync(FULL, g != 0), P = __ballot_sync(FULL, p != 0);
       const uint64_t la = mfft_lookahead(G, P, cin);
-      if (t < ntiles) tileC[t] = (uint32_t)(la >> lane) & 1u;
+      if (t < hi) tileC[t] = (uint32_t)(la >> lane) & 1u;
       cin = (uint32_t)(la >> 32) & 1u;
    }
    /* what leaves the window: the ripple carry plus the high part of the last limb's column sum */
-   if (lane == 0 && carry_out) *carry_out = cin + *cvec_last;
+   if (threadIdx.x == 0 && carry_out) *carry_out = sC[32] + *cvec_last;
 }
 
 /* pass 4: tiles with carry-in 1 add it (it ripples through the all-ones prefix of the tile) */
@@ -1258,6 +1284,16 @@ int mfft_dev_memset0(void *d, size_t bytes, void *stream)
 { CK(cudaMemsetAsync(d, 0, bytes, (cudaStream_t) stream)); return 0; }
 int mfft_dev_sync(void *stream)
 { CK(cudaStreamSynchronize((cudaStream_t) stream)); return 0; }
+
+/* streams and events for the host-pointer entry points (copies overlapped with the transforms) */
+void *mfft_dev_stream_create(void)
+{ cudaStream_t s = NULL; if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return NULL; return (void *) s; }
+void mfft_dev_stream_destroy(void *s) { if (s) cudaStreamDestroy((cudaStream_t) s); }
+void *mfft_dev_event_create(void)
+{ cudaEvent_t e = NULL; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return NULL; return (void *) e; }
+void mfft_dev_event_destroy(void *e) { if (e) cudaEventDestroy((cudaEvent_t) e); }
+int mfft_dev_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t) e, (cudaStream_t) stream)); return 0; }
+int mfft_dev_stream_wait(void *stream, void *e) { CK(cudaStreamWaitEvent((cudaStream_t) stream, (cudaEvent_t) e, 0)); return 0; }
 
 static int pick_m(uint32_t l)
 {
@@ -1566,7 +1602,7 @@ int mfft_dev_combine_window(limb_t *res, uint64_t total, const limb_t *slab, uin
    CKL();
    MFFT_LAUNCH(k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);
    CKL();
-   MFFT_LAUNCH(k_combine_scan, 1, 32, 0, st, tileG, tileP, tileC, ntiles, cvec + total, d_carry_out);
+   MFFT_LAUNCH(k_combine_scan, 1, 1024, 0, st, tileG, tileP, tileC, ntiles, cvec + total, d_carry_out);
    CKL();
    MFFT_LAUNCH(k_combine_fix, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, total, tileC, ntiles);
    CKL();

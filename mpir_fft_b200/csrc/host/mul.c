@@ -24,6 +24,7 @@ struct mpirfft_mul_plan {
    uint32_t *d_pw_blocks; uint32_t npw;
    void *combine_work;
    limb_t *d_i1, *d_i2, *d_r;  /* staging for the host-pointer entry */
+   void *s_copy, *s_comp, *ev1, *ev2;   /* copy / compute streams of the host-pointer entry */
    size_t dev_bytes;
 };
 
@@ -72,6 +73,8 @@ void mpirfft_mul_plan_destroy(mpirfft_mul_plan *pl)
    mfft_dev_free(pl->X); mfft_dev_free(pl->Z); mfft_dev_free(pl->Y);
    mfft_dev_free(pl->d_pw_blocks); mfft_dev_free(pl->combine_work);
    mfft_dev_free(pl->d_i1); mfft_dev_free(pl->d_i2); mfft_dev_free(pl->d_r);
+   mfft_dev_stream_destroy(pl->s_copy); mfft_dev_stream_destroy(pl->s_comp);
+   mfft_dev_event_destroy(pl->ev1); mfft_dev_event_destroy(pl->ev2);
    mfft_unlock();
    free(pl);
 }
@@ -177,12 +180,25 @@ int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i
       pl->d_i1 = (limb_t *) mfft_dev_alloc(b1); pl->d_i2 = (limb_t *) mfft_dev_alloc(b2);
       pl->d_r = (limb_t *) mfft_dev_alloc(b1 + b2);
       if (!pl->d_i1 || !pl->d_i2 || !pl->d_r) { mfft_unlock(); return MPIRFFT_ENOMEM; }
+      pl->s_copy = mfft_dev_stream_create(); pl->s_comp = mfft_dev_stream_create();
+      pl->ev1 = mfft_dev_event_create(); pl->ev2 = mfft_dev_event_create();
+      if (!pl->s_copy || !pl->s_comp || !pl->ev1 || !pl->ev2) { mfft_unlock(); return MPIRFFT_ENODEV; }
+   }
+   /* the second operand travels while the first one is being split and transformed */
+   rc = MPIRFFT_ENODEV;
+   if (mfft_dev_h2d(pl->d_i1, i1, b1, pl->s_copy) || mfft_dev_event_record(pl->ev1, pl->s_copy) ||
+       mfft_dev_h2d(pl->d_i2, i2, b2, pl->s_copy) || mfft_dev_event_record(pl->ev2, pl->s_copy)) goto done;
+   if (mfft_dev_stream_wait(pl->s_comp, pl->ev1)) goto done;
+   if ((rc = mpirfft_mul_exec_phase(pl, 0, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_comp)) != 0) goto done;
+   rc = MPIRFFT_ENODEV;
+   if (mfft_dev_stream_wait(pl->s_comp, pl->ev2)) goto done;
+   {
+      int ph;
+      for (ph = 1; ph < 5; ph++)
+         if ((rc = mpirfft_mul_exec_phase(pl, ph, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_comp)) != 0) goto done;
    }
    rc = MPIRFFT_ENODEV;
-   if (mfft_dev_h2d(pl->d_i1, i1, b1, NULL) || mfft_dev_h2d(pl->d_i2, i2, b2, NULL)) goto done;
-   if ((rc = mpirfft_mul_exec_device(pl, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, NULL)) != 0) goto done;
-   rc = MPIRFFT_ENODEV;
-   if (mfft_dev_d2h(r, pl->d_r, b1 + b2, NULL) || mfft_dev_sync(NULL)) goto done;
+   if (mfft_dev_d2h(r, pl->d_r, b1 + b2, pl->s_comp) || mfft_dev_sync(pl->s_comp)) goto done;
    rc = 0;
 done:
    mfft_unlock();

@@ -124,6 +124,12 @@ int  mfft_dev_h2d_2d(void *d, size_t dpitch, const void *h, size_t hpitch, size_
 int  mfft_dev_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, void *stream);
 int  mfft_dev_memset0(void *d, size_t bytes, void *stream);
 int  mfft_dev_sync(void *stream);
+void *mfft_dev_stream_create(void);                   /* non-blocking stream; NULL on failure */
+void mfft_dev_stream_destroy(void *s);
+void *mfft_dev_event_create(void);
+void mfft_dev_event_destroy(void *e);
+int  mfft_dev_event_record(void *e, void *stream);
+int  mfft_dev_stream_wait(void *stream, void *e);      /* stream waits for the event */
 const char *mfft_dev_last_error(void);
 
 /* run ops[first .. first+count) (one stage) over nbatch batch entries */
