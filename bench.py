@@ -319,14 +319,15 @@ def main():
         try:
             L.mpirfft_measure_imad_rate.restype = C.c_double
             imad_chain = float(L.mpirfft_measure_imad_rate(1))      # IMAD.WIDE.U32.X carry chains (what the kernel issues)
-            imad_wide = float(L.mpirfft_measure_imad_rate(0))       # IMAD.WIDE.U32 without carry
+            imad_wide = float(L.mpirfft_measure_imad_rate(0))       # IMAD.WIDE.U32 multiplies, accumulation split off to the ALU pipe by ptxas
             pw_ms = phases["pointwise"]["ms_per_product"]
             if pw_ms > 0 and imad_chain > 0:
                 ach = phases["pointwise_mad32_per_product"] / (pw_ms * 1e-3)
                 roofline_pw = {"kernel": "k_pointwise (schoolbook 32x32->64 multiply-add chains)", "bound": "imad",
                                "achieved": ach / 1e12, "peak": imad_chain / 1e12, "unit": "Tmad32/s",
-                               "frac": ach / imad_chain, "peak_no_carry": imad_wide / 1e12,
-                               "frac_of_no_carry_peak": ach / imad_wide if imad_wide > 0 else None,
+                               "frac": ach / imad_chain, "imad_wide_multiply_only_rate": imad_wide / 1e12,
+                               "note": "peak = fused multiply-add chains (IMAD.WIDE.U32.X), the only fused 32x32+64 form "
+                                       "ptxas emits on sm_100a; mad.wide.u32 is split into IMAD.WIDE(..,RZ) + 2 IADD3",
                                "peak_source": "measured in this run (csrc/cuda/imad_peak.cu)"}
         except Exception:
             roofline_pw = None

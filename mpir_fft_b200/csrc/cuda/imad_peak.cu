@@ -1,7 +1,10 @@
 /* imad_peak.cu -- integer-multiply issue-rate microbenchmarks (the IMAD roofline denominator of
  * the pointwise kernel; MEASURED_PEAKS.json has only HBM and bf16).  Three instruction flavours,
  * each as 8 independent dependency chains per thread so that latency is hidden:
- *   0  IMAD.WIDE.U32          64-bit accumulate, no carry      (mad.wide.u32)
+ *   0  IMAD.WIDE.U32          mad.wide.u32 -- NOTE: ptxas (sm_100a) never keeps the 64-bit addend in the
+ *                             multiply: it emits IMAD.WIDE.U32 d, a, b, RZ plus IADD3 + IADD3.X on the
+ *                             ALU pipe, so this measures multiplies with the accumulation on the other
+ *                             pipe, not a fused multiply-add rate
  *   1  IMAD.WIDE.U32.X chain  carry in/out through predicates  (mad.lo.cc + madc.hi.cc, what the
  *                             schoolbook rows of k_pointwise compile to)
  *   2  IMAD (32-bit lo)       mad.lo.u32

@@ -1481,7 +1481,11 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
    PROF(PC_POINTWISE, st);
    {  /* mode 0 (default): schoolbook IMAD.WIDE kernel; mode 1 (MPIRFFT_POINTWISE=ss or
          mfft_dev_pointwise_mode): the nested Schoenhage-Strassen step inside a warp (k_mulmod_ss).
-         Measured at l = 256 on B200: 0.59 ms vs 0.88 ms per 16 640 products, so direct stays default. */
+         Measured at l = 256 on B200: 0.59 ms vs 0.88 ms per 16 640 products, so direct stays default.
+         (A reduced-radix variant -- 27-bit digits, carry-less 64-bit column sums -- was tried and is
+         slower, 0.91 ms: ptxas never emits IMAD.WIDE with a non-zero 64-bit addend on sm_100a, it
+         splits every mad.wide.u32 into IMAD.WIDE(.., RZ) + IADD3 + IADD3.X, so the real ceiling for
+         32x32->64 multiply-ADDs is the ~31/clk/SM of the IMAD.WIDE.U32.X chains used here.) */
       if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = (e && e[0] == 's') ? 1 : 0; }
       uint32_t np = 0, lp = 0;
       if (g_pw_mode == 1)

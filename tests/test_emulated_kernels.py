@@ -41,7 +41,7 @@ def test_emulated_new_mpn_mul(emu, case):
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
 def test_emulated_mulmod_adversarial(emu, l, mode):
-    emu.mpirfft_set_pointwise_mode(mode)        # 0: schoolbook kernel, 1: nested SS kernel
+    emu.mpirfft_set_pointwise_mode(mode)        # 0: schoolbook carry-chain kernel (default), 1: nested SS kernel
     random.seed(l)
     NW = 64 * l
     p = (1 << NW) + 1

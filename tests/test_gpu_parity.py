@@ -109,7 +109,7 @@ def test_illegal_parameters_rejected():
 @pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
 def test_mulmod_vs_bigint(lib, l, mode):
     import random
-    lib.mpirfft_set_pointwise_mode(mode)       # 0: schoolbook kernel, 1: nested SS kernel
+    lib.mpirfft_set_pointwise_mode(mode)       # 0: schoolbook carry-chain kernel (default), 1: nested SS kernel
     random.seed(l)
     NW = 64 * l
     p = (1 << NW) + 1
