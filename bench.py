@@ -489,20 +489,21 @@ def run_cfg4(args, rank, local_rank, world, torch, dist, M):
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": str(e)}
     if rank == 0:
-        mads = count * 128 * 4 * 256 ** 2
+        inner_l = ((1 << d.value) * w.value) // 64
+        mads = count * (2 << d.value) * 4 * inner_l ** 2
         print(json.dumps({
             "metric": "fft_mulmod_2expp1 batch Mlimb/s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "%d independent products of 16384 limbs mod 2^(2^20)+1 (BASELINE configs[3]); inner ring "
-                                   "2^%d+1, %d pieces" % (count, 64 * 256, 128),
+                                   "2^%d+1, %d pieces" % (count, (1 << d.value) * w.value, 2 << d.value),
                        "l2": "flushed between timed steps (256 MiB write); batch is 1.1 GB per operand",
                        "multi_gpu": "independent batches per rank" if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": world * count * l / e2e_dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * ha.nbytes,
                     "d2h_bytes_per_step": ha.nbytes, "ms_per_step": e2e_dt * 1e3,
                     "api": "mpirfft_mulmod_plan_exec on HBM blocks, pinned host blocks copied in and out every step"},
-            "roofline": {"kernel": "k_pointwise (inner products mod 2^16384+1)", "bound": "imad",
+            "roofline": {"kernel": "k_pointwise (inner products mod 2^%d+1)" % (64 * inner_l), "bound": "imad",
                          "achieved": mads / (phase_ms[2] * 1e-3) / 1e12, "unit": "Tmad32/s", "peak": None, "frac": None,
                          "traffic": None, "note": "see roofline_pointwise of the default workload for the measured IMAD rate"},
             "cpu_baseline": cpu,

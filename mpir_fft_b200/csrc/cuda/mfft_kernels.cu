@@ -1135,7 +1135,7 @@ k_mm_finish(limb_t *r, uint32_t r_pitch, const limb_t *a, const limb_t *b, uint3
    __syncthreads();
    /* inject the small signed terms, rippling inside the chunk; what leaves a chunk goes round again */
    int64_t top = 0;
-   for (int round = 0; round < 64; round++)
+   for (uint32_t round = 0; round < K + 2; round++)       /* a carry can cross at most K chunks */
    {
       int64_t *Fa = (round & 1) ? F2 : F, *Fb = (round & 1) ? F : F2;
       if (tid == 0) *flag = 0;

@@ -14,8 +14,8 @@ r = torch.zeros(2 * n, dtype=torch.int64, device="cuda")
 for _ in range(3):
     plan.exec_device(r.data_ptr(), a.data_ptr(), b.data_ptr(), None)
 torch.cuda.synchronize()
-buf = torch.zeros(8 * 8192, dtype=torch.int64, device="cuda")
-for ph, name, grids in ((0, "fwd", (1024, 640, 520, 520)), (3, "inv", (520, 520, 640, 1024, 640))):
+buf = torch.zeros(8 * 16384, dtype=torch.int64, device="cuda")
+for ph, name, grids in ((0, "fwd", (2048, 1152, 1040, 1040)), (3, "inv", (1040, 1040, 1152, 2048, 1280))):
     buf.zero_()
     L.mfft_dev_tile_timing(C.c_void_p(buf.data_ptr()))
     plan.exec_phase(ph, r.data_ptr(), a.data_ptr(), b.data_ptr(), None)

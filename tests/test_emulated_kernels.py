@@ -79,3 +79,24 @@ def test_emulated_mulmod_transform_path(emu, l):
     emu.mpirfft_memcpy_d2h(ptr(out), da, a.nbytes, None)
     for k in range(len(A)):
         assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), (l, k)
+
+
+def test_emulated_mulmod_long_ripple(emu, monkeypatch):
+    """all-ones operands with many small pieces (K = 128 chunks of 32 limbs): the recombination's
+    carries cross almost the whole result, one chunk per round"""
+    monkeypatch.setenv("MPIRFFT_MM_INNER", "64")
+    l = 4096
+    NW = 64 * l
+    p = (1 << NW) + 1
+    A = [p - 2, (1 << NW) - 1, (1 << (NW // 2)) - 1, p - 2, 12345]
+    B = [p - 2, (1 << NW) - 1, (1 << (NW // 2)) - 1, 2, p - 2]
+    a = np.stack([int_to_block(v, l) for v in A])
+    b = np.stack([int_to_block(v, l) for v in B])
+    da, db = emu.mpirfft_malloc_device(a.nbytes), emu.mpirfft_malloc_device(b.nbytes)
+    emu.mpirfft_memcpy_h2d(da, ptr(a), a.nbytes, None)
+    emu.mpirfft_memcpy_h2d(db, ptr(b), b.nbytes, None)
+    assert emu.mpirfft_mulmod_batch_device(da, db, len(A), l, l + 1, None) == 0
+    out = np.empty_like(a)
+    emu.mpirfft_memcpy_d2h(ptr(out), da, a.nbytes, None)
+    for k in range(len(A)):
+        assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), k
