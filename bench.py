@@ -302,12 +302,25 @@ def main():
         phases = {names[i]: {"ms_per_product": ms[i] / reps, "launches_per_product": int(ln[i]) // reps} for i in range(nclass)}
         peaks, how = load_peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:    # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (cfg2)
+            if args.workload == "cfg2":
+                import csv
+                with open(os.path.join(ROOT, "profiles", "r01_ncu_tiles_summary.csv")) as f:
+                    rows = list(csv.reader(f))
+                ir, iw = rows[0].index("dram__bytes_read.sum"), rows[0].index("dram__bytes_write.sum")
+                vals = [(float(r[ir]) + float(r[iw])) * 1e6 for r in rows[2:] if len(r) > iw]
+                traffic = sum(vals) / len(vals) if vals else None
+        except Exception:
+            traffic = None
         if ln[0]:
             avg_ms = ms[0] / ln[0]
             achieved = (by[0] / ln[0]) / (avg_ms * 1e-3) / 1e9
             roofline = {"kernel": "k_run_tiles (one fused MFA pass: several radix-2 layers in shared memory)", "bound": "hbm",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
+                        "traffic": traffic, "traffic_source": "profiles/r01_ncu_tiles_summary.csv: mean dram read+write bytes "
+                        "per launch over 6 captured passes (ncu --set full, cold L2)" if traffic else None,
+                        "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
                         "alg_bytes_per_launch": by[0] / ln[0], "avg_launch_us": avg_ms * 1e3,
                         "share_of_step": (ms[0] / reps) / ms_per_step}
         # whole-product algorithmic traffic: 18 T S + 16 (n1+n2) bytes

@@ -778,6 +778,31 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
                   st2(S + 2 * i, h0, h1);
                   cwS[i] = (ct >> 1) + (e >> 1);
                }
+            } else if (op.kind == MFFT_K_SHR)
+            {  /* A / 2^s chunk by chunk: the s bits shifted out of a chunk (and of its carry word) are
+                  worth 2^(128-s) one chunk below; chunk 0's go to the top negated (2^-s == -2^(NW-s)) */
+               const uint32_t sh = op.kparam;
+               const limb_t fm = (((limb_t) 1 << sh) - 1);
+               limb_t lowf[NT];
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane, nx = (i + 1 == NCH) ? 0u : i + 1;
+                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
+                  lowf[ti] = A[2 * nx] & fm;
+               }
+               __syncwarp();
+#pragma unroll
+               for (int ti = 0; ti < NT; ti++)
+               {
+                  const uint32_t i = ti * 32u + lane;
+                  const int64_t r = (int64_t)((limb_t)(int64_t) ca[ti] & fm);             /* c = q 2^s + r, 0 <= r < 2^s */
+                  const int64_t e = r + ((i + 1 == NCH) ? -(int64_t) lowf[ti] : (int64_t) lowf[ti]);
+                  const limb_t h0 = (a0[ti] >> sh) | (a1[ti] << (64 - sh));
+                  const limb_t h1 = (a1[ti] >> sh) | (((limb_t) e & fm) << (64 - sh));
+                  st2(S + 2 * i, h0, h1);
+                  cwS[i] = (ca[ti] >> sh) + (int32_t)(e >> sh);
+               }
             } else
             {  /* MFFT_K_ADD */
 #pragma unroll

@@ -67,6 +67,8 @@ static void classify_op(mfft_tileop *d, uint64_t NW)
    if (NW % 128 || !d->sSA) return;
    /* the two bit-granular shapes of the truncated inverse that stay chunk-local in carry-save form */
    if (!hasB && !hasT && d->sSA == 1 && d->eSA == 1) { d->kind = MFFT_K_DBL; return; }
+   if (!hasB && !hasT && d->sSA == 1 && d->eSA > 2*NW - 32 && d->eSA < 2*NW)
+   { d->kind = MFFT_K_SHR; d->kparam = (uint32_t)(2*NW - d->eSA); return; }
    if (hasB && !hasT && d->sSA == 1 && d->sSB == 1 && d->eSA == 2*NW - 1 && d->eSB == 2*NW - 1) { d->kind = MFFT_K_HALF; return; }
    if (fold_term(d->sSA, d->eSA, NW, &ySA, &nSA)) return;
    if (hasB) { if (!d->sSB || fold_term(d->sSB, d->eSB, NW, &ySB, &nSB)) return; }

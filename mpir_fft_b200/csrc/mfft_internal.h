@@ -96,6 +96,7 @@ typedef struct {            /* one op of a tile; a,b,s,t index the tile's positi
 #define MFFT_K_NOP   7u     /* host only: op absorbed into a fused unit, removed before upload */
 #define MFFT_K_DBL   8u     /* S = 2 A           (the doubling steps of IFFT_radix2_truncate, 1788-1789) */
 #define MFFT_K_HALF  9u     /* S = (A + B) / 2   (the averaging steps of IFFT_radix2_truncate1, 1556-1560) */
+#define MFFT_K_SHR   10u    /* S = A / 2^s, 1 <= s <= 31 = kparam   (the final 2^-(depth+1) scaling, 3256-3258) */
 
 /* pad = offset of the tile's (nstages+1) stage offsets in the pass's stoff array (<= 63 stages) */
 typedef struct { uint32_t pos_off, npos, op_off, nops, nstages, pad; } mfft_tile;
