@@ -546,6 +546,68 @@ __device__ __forceinline__ void inv4_unit(limb_t *P0, limb_t *P1, limb_t *P2, li
    }
 }
 
+/* ---- one-operand rotation by any number of bits, chunk-local --------------------------------- */
+/* S = +-A * 2^t, 0 <= t < NW.  Written as a rotation by yc1 = ceil(t/128) whole chunks (chunks that
+ * wrap around p are negated) followed by a right shift by s = 128 yc1 - t < 128 bits.  The shift
+ * is chunk-local in carry-save form: the s bits leaving chunk j+1 -- and the low s bits of chunk
+ * j's own carry word -- are worth 2^(128-s) in chunk j; what leaves chunk 0 re-enters negated at
+ * the top (2^-s == -2^(NW-s)).  Used for the z^(r*c) twist rotations (1409-1411), whose exponents
+ * depend on the column. */
+__device__ __forceinline__ void shr128(limb_t &h0, limb_t &h1, limb_t x0, limb_t x1, uint32_t s)   /* 1 <= s <= 127 */
+{
+   if (s >= 64) { h0 = x1 >> (s - 64); h1 = 0; }
+   else { h0 = (x0 >> s) | (x1 << (64 - s)); h1 = x1 >> s; }
+}
+__device__ __forceinline__ void shl128(limb_t &h0, limb_t &h1, limb_t x0, limb_t x1, uint32_t u)   /* 1 <= u <= 127 */
+{
+   if (u >= 64) { h1 = x0 << (u - 64); h0 = 0; }
+   else { h1 = (x1 << u) | (x0 >> (64 - u)); h0 = x0 << u; }
+}
+
+template <int NT>
+__device__ __forceinline__ void rotg_unit(limb_t *S, const limb_t *A, uint32_t t, uint32_t neg, uint32_t lane)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH;
+   uint32_t yc1 = (t + 127u) >> 7;
+   const uint32_t s = 128u * yc1 - t;                       /* 0..127 */
+   if (yc1 == NCH) { yc1 = 0; neg ^= 1u; }                  /* a full turn is a factor -1 */
+   const int32_t *cwA = reinterpret_cast<const int32_t *>(A + L);
+   cval r[NT]; limb_t y0[NT], y1[NT];
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t j = ti * 32u + lane;
+      {  /* R_j = +-A_(j - yc1) */
+         const uint32_t wj = (j < yc1) ? 1u : 0u, sj = wj ? j + NCH - yc1 : j - yc1;
+         ld2(r[ti].x0, r[ti].x1, A + 2 * sj); r[ti].c = cwA[sj];
+         if (wj != neg) { const int32_t b = sub2(r[ti].x0, r[ti].x1, 0, 0, r[ti].x0, r[ti].x1); r[ti].c = b - r[ti].c; }
+      }
+      {  /* body of R_(j+1); for the last chunk that is R_0, which enters negated (handled below) */
+         const uint32_t j1 = (j + 1 == NCH) ? 0u : j + 1;
+         const uint32_t w1 = (j1 < yc1) ? 1u : 0u, s1 = w1 ? j1 + NCH - yc1 : j1 - yc1;
+         ld2(y0[ti], y1[ti], A + 2 * s1);
+         if (w1 != neg) (void) sub2(y0[ti], y1[ti], 0, 0, y0[ti], y1[ti]);
+      }
+   }
+   __syncwarp();
+   int32_t *cwS = reinterpret_cast<int32_t *>(S + L);
+#pragma unroll
+   for (int ti = 0; ti < NT; ti++)
+   {
+      const uint32_t j = ti * 32u + lane;
+      if (s == 0) { st2(S + 2 * j, r[ti].x0, r[ti].x1); cwS[j] = r[ti].c; continue; }
+      limb_t h0, h1, f0, f1, g0, g1, o0, o1;
+      const int64_t c64 = (int64_t) r[ti].c;
+      shr128(h0, h1, r[ti].x0, r[ti].x1, s);
+      shl128(f0, f1, (limb_t) c64, (limb_t)(c64 >> 63), 128u - s);
+      shl128(g0, g1, y0[ti], y1[ti], 128u - s);
+      h0 |= f0; h1 |= f1;                                   /* disjoint bit fields */
+      const int32_t k = (j + 1 == NCH) ? sub2(o0, o1, h0, h1, g0, g1) : add2(o0, o1, h0, h1, g0, g1);
+      st2(S + 2 * j, o0, o1);
+      cwS[j] = ((s >= 31) ? (r[ti].c >> 31) : (r[ti].c >> s)) + k;
+   }
+}
+
 /* tile descriptors of a small pass as kernel parameters (constant bank): no dependent global loads
  * before a CTA can start fetching its coefficients */
 #define TP_MAXT 16
@@ -822,6 +884,13 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
          {  /* the MFA twist z^(r*c): only the twisted layer pays for the modulo */
             eSA = (eSA + b.col * op.cSA) % M2; eSB = (eSB + b.col * op.cSB) % M2;
             eTA = (eTA + b.col * op.cTA) % M2; eTB = (eTB + b.col * op.cTB) % M2;
+         }
+         if (!hasB && !hasT && op.sSA != 0)
+         {  /* one operand, any rotation (the twist layer): chunk-local */
+            uint32_t e = eSA, ng = (op.sSA < 0) ? 1u : 0u;
+            if (e >= NW) { e -= NW; ng ^= 1u; }
+            rotg_unit<NT>(S, A, e, ng, lane);
+            continue;
          }
          tterm sa, sb, ta, tb;
          tterm_setup(sa, op.sSA, eSA, NW);
