@@ -156,9 +156,13 @@ typedef struct {
 } mpirfft_mul_params;
 int  mpirfft_mul_params_get(mpirfft_mul_params *out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
                             mp_bitcnt_t w);
-/* A small chooser for benchmarks (the reference has none, mul_fft.c:3177-3178): smallest legal
- * (depth, w) with w in {1,2} for an n1 x n2 limb product. */
+/* Parameter chooser (the reference has none, mul_fft.c:3177-3178): the smallest coefficient ring
+ * among 64..512 limbs that is legal for an n1 x n2 limb product (the fused tile executor and the
+ * warp-level product kernel), else the smallest legal (depth, w) with w in {1,2}. */
 int  mpirfft_choose_params(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w);
+/* r[0..n1+n2) = i1 * i2 with the parameters of mpirfft_choose_params: the mpn_mul-shaped entry the
+ * reference leaves as a FIXME (mul_fft.c:3177-3178).  Host pointers; aborts like new_mpn_mul. */
+void mpirfft_mpn_mul(mp_limb_t *r, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2);
 
 /* A multiplication plan owns the schedules and the HBM slabs for one (n1, n2, depth, w). */
 typedef struct mpirfft_mul_plan mpirfft_mul_plan;

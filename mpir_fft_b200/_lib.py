@@ -73,6 +73,7 @@ def bind(L):
         "mpirfft_launch_count": (u64, []),
         "mpirfft_launch_count_reset": (None, []),
         "new_mpn_mul": (None, [vp, vp, i64, vp, i64, u64, u64]),
+        "mpirfft_mpn_mul": (None, [vp, vp, i64, vp, i64]),
         "new_mpn_mulmod_2expp1": (u64, [vp, vp, vp, u64, u64, vp]),
         "fft_mulmod_2expp1": (u64, [vp, vp, vp, i64, i64, vp]),
         "FFT_mulmod_2expp1": (None, [vp, vp, vp, i64, u64, u64]),

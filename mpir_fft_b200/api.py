@@ -51,6 +51,18 @@ def new_mpn_mul(i1, i2, depth, w):
     return r
 
 
+def mpn_mul(i1, i2):
+    """r = i1 * i2 with automatically chosen (depth, w) -- mpirfft_mpn_mul"""
+    i1 = np.ascontiguousarray(i1, dtype=np.uint64)
+    i2 = np.ascontiguousarray(i2, dtype=np.uint64)
+    choose_params(len(i1), len(i2))                  # raise instead of letting the C symbol abort
+    if not have_gpu():
+        raise RuntimeError("no CUDA device: mpir_fft_b200 has no CPU path")
+    r = np.zeros(len(i1) + len(i2), dtype=np.uint64)
+    lib().mpirfft_mpn_mul(_ptr(r), _ptr(i1), len(i1), _ptr(i2), len(i2))
+    return r
+
+
 class MulPlan:
     """Device-resident multiplication plan (mpirfft_mul_plan_*)."""
 

@@ -100,3 +100,27 @@ def test_emulated_mulmod_long_ripple(emu, monkeypatch):
     emu.mpirfft_memcpy_d2h(ptr(out), da, a.nbytes, None)
     for k in range(len(A)):
         assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), k
+
+
+@pytest.mark.parametrize("n1,n2,kind", [(40000, 30000, "uniform"), (90000, 90000, "ones"), (9000, 3, "runs"), (150, 40, "uniform")])
+def test_emulated_mpn_mul_wrapper(emu, n1, n2, kind):
+    """mpirfft_mpn_mul chooses (depth, w) itself (smallest fused ring that is legal)"""
+    a, b = operand(kind, n1, 11), operand(kind, n2, 12)
+    r = np.zeros(n1 + n2, dtype=np.uint64)
+    emu.mpirfft_mpn_mul(ptr(r), ptr(a), n1, ptr(b), n2)
+    assert np.array_equal(r, L.gmp_mul(a, b))
+
+
+def test_emulated_squaring_shortcut(emu):
+    """device plan with d_i1 == d_i2: one forward transform"""
+    n, depth, w = 30000, 10, 4
+    a = operand("uniform", n, 21)
+    h = C.c_void_p()
+    assert emu.mpirfft_mul_plan_create(C.byref(h), n, n, depth, w) == 0
+    da, dr = emu.mpirfft_malloc_device(a.nbytes), emu.mpirfft_malloc_device(2 * a.nbytes)
+    emu.mpirfft_memcpy_h2d(da, ptr(a), a.nbytes, None)
+    assert emu.mpirfft_mul_exec_device(h, dr, da, da, None) == 0
+    r = np.zeros(2 * n, dtype=np.uint64)
+    emu.mpirfft_memcpy_d2h(ptr(r), dr, r.nbytes, None)
+    emu.mpirfft_mul_plan_destroy(h)
+    assert np.array_equal(r, L.gmp_mul(a, a))

@@ -104,6 +104,29 @@ def test_illegal_parameters_rejected():
         M.new_mpn_mul(np.ones(8, np.uint64), np.ones(8, np.uint64), 5, 1)               # 64 does not divide n*w
 
 
+@pytest.mark.parametrize("n1,n2,kind", [(1 << 20, 1 << 20, "uniform"), (123457, 65521, "ones"), (3000000, 1700000, "runs"),
+                                         (5000, 17, "uniform"), (1 << 16, 1 << 16, "uniform")])
+def test_mpn_mul_wrapper_chooses_parameters(lib, n1, n2, kind):
+    a, b = operand(kind, n1, 31), operand(kind, n2, 32)
+    assert np.array_equal(M.mpn_mul(a, b), oracle.gmp_mul(a, b))
+
+
+def test_squaring_uses_one_forward_transform(lib):
+    n, depth, w = 1 << 20, 14, 1
+    a = operand("uniform", n, 41)
+    plan = M.MulPlan(n, n, depth, w)
+    da, dr = lib.mpirfft_malloc_device(a.nbytes), lib.mpirfft_malloc_device(2 * a.nbytes)
+    lib.mpirfft_memcpy_h2d(da, ptr(a), a.nbytes, None)
+    lib.mpirfft_launch_count_reset()
+    plan.exec_device(dr, da, da)
+    r = np.zeros(2 * n, dtype=np.uint64)
+    lib.mpirfft_memcpy_d2h(ptr(r), dr, r.nbytes, None)
+    lib.mpirfft_stream_sync(None)
+    assert lib.mpirfft_launch_count() < plan.launches
+    lib.mpirfft_free_device(da); lib.mpirfft_free_device(dr)
+    assert np.array_equal(r, oracle.gmp_mul(a, a))
+
+
 # ---- mulmod 2^(64 l)+1 ----
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
