@@ -1328,6 +1328,13 @@ int mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, u
 static unsigned long long *g_tile_timing = NULL;
 extern "C" void mfft_dev_tile_timing(void *buf) { g_tile_timing = (unsigned long long *) buf; }
 
+/* the next mfft_dev_run_tiles launch cuts the coefficients it loads out of {src, nlimbs} itself
+ * (block k = bits [k*bits, (k+1)*bits), zero for k >= ncoef) instead of reading the slab */
+static uint32_t g_split_on = 0; static const limb_t *g_split_src = NULL;
+static uint64_t g_split_nlimbs = 0, g_split_bits = 0, g_split_ncoef = 0;
+void mfft_dev_tiles_fuse_split(const limb_t *src, uint64_t nlimbs, uint64_t bits, uint64_t ncoef)
+{ g_split_on = 1; g_split_src = src; g_split_nlimbs = nlimbs; g_split_bits = bits; g_split_ncoef = ncoef; }
+
 /* coefficient sizes the fused executor is instantiated for: l = 64*NT limbs */
 static int tiles_cfg(uint32_t l, int *NT)
 {
@@ -1380,6 +1387,9 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    /* small passes: tile descriptors, position lists and stage offsets travel as kernel parameters */
    static tile_params tp;
    tp.valid = 0; tp.batch_valid = 0;
+   tp.split = g_split_on; tp.split_src = g_split_src; tp.split_nlimbs = g_split_nlimbs;
+   tp.split_bits = g_split_bits; tp.split_ncoef = g_split_ncoef;
+   g_split_on = 0;                                      /* consumed by this launch */
    if (h_tiles && h_pos && h_stoff && ntiles <= TP_MAXT)
    {
       uint32_t t, ok = 1;

@@ -616,6 +616,9 @@ __device__ __forceinline__ void rotg_unit(limb_t *S, const limb_t *A, uint32_t t
 #define TP_MAXB 256
 struct tile_params {
    uint32_t valid, batch_valid;
+   /* split fused into the tile load (FFT_split_bits, mul_fft.c:115-170): block k of the slab is
+      coefficient k = bits [k*bits, (k+1)*bits) of {src, nlimbs}, zero beyond ncoef */
+   uint32_t split; const limb_t *split_src; uint64_t split_nlimbs, split_bits, split_ncoef;
    mfft_batch batch[TP_MAXB];
    mfft_tile tiles[TP_MAXT];
    uint32_t pos[TP_MAXT * TP_MAXP];
@@ -672,6 +675,55 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
       except the last one, which is the block's signed top limb */
    const bool al16 = ((g.pitch & 1u) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15u) == 0) &&
                      (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+   if (TP.split)
+   {  /* the tile's coefficients are cut straight out of the operand: no split kernel, no slab read */
+      /* limb k of coefficient i = bits [i*bits + 64k, +64) of the operand: two loads and a funnel
+         shift with the same shift count for the whole coefficient; consecutive threads read
+         consecutive limbs, four coefficients are in flight per thread */
+      const uint32_t blimbs = (uint32_t)((TP.split_bits + 63) >> 6);     /* limbs that receive bits */
+      const limb_t lastmask = (TP.split_bits & 63) ? (((limb_t) 1 << (TP.split_bits & 63)) - 1) : ~(limb_t) 0;
+      for (uint32_t p0 = 0; p0 < T.npos; p0 += 4)
+      {
+         uint64_t qb[4]; uint32_t rr[4]; bool ld[4], nz[4];
+#pragma unroll
+         for (int u = 0; u < 4; u++)
+         {
+            const uint32_t p = p0 + u;
+            const uint32_t pp = (p < T.npos) ? spos[p] : 0u;
+            ld[u] = (pp & MFFT_TILE_LOAD) != 0;
+            const uint64_t i = (uint64_t) b.base + (uint64_t)(pp & MFFT_TILE_POSMASK) * g.slot_stride;
+            const uint64_t off = i * TP.split_bits;
+            nz[u] = ld[u] && i < TP.split_ncoef;
+            qb[u] = off >> 6; rr[u] = (uint32_t)(off & 63);
+         }
+         for (uint32_t k = tid; k < L; k += blockDim.x)
+         {
+            limb_t lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+               lo[u] = 0; hi[u] = 0;
+               if (nz[u] && k < blimbs)
+               {
+                  const uint64_t q = qb[u] + k;
+                  if (q < TP.split_nlimbs) lo[u] = TP.split_src[q];
+                  if (q + 1 < TP.split_nlimbs) hi[u] = TP.split_src[q + 1];
+               }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+               if (!ld[u]) continue;
+               limb_t v = lo[u] >> rr[u];
+               if (rr[u]) v |= hi[u] << (64 - rr[u]);
+               if (k + 1 == blimbs) v &= lastmask;
+               coef[(size_t)(p0 + u) * SP + k] = v;
+            }
+         }
+      }
+      for (uint32_t t = tid; t < T.npos * NCH; t += blockDim.x)
+         if (spos[t / NCH] & MFFT_TILE_LOAD) reinterpret_cast<int32_t *>(coef + (size_t)(t / NCH) * SP + L)[t % NCH] = 0;
+   } else
    if (al16)
    {  /* 16-byte aligned blocks: every thread fires its share of asynchronous 16-byte copies, one wait.
          The signed top limbs (one global load per loaded coefficient) are requested first so that

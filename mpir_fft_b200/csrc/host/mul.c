@@ -143,7 +143,7 @@ size_t mpirfft_mul_plan_device_bytes(const mpirfft_mul_plan *pl) { return pl->de
 uint64_t mpirfft_mul_plan_launches(const mpirfft_mul_plan *pl)
 {
    /* 2 x (split + fwd) + pointwise + inv + combine (4 kernels) */
-   return 2*(1 + mfft_mfa_launches(&pl->fwd)) + 1 + mfft_mfa_launches(&pl->inv) + 4;
+   return 2*((mfft_mfa_can_fuse_split(&pl->fwd) ? 0 : 1) + mfft_mfa_launches(&pl->fwd)) + 1 + mfft_mfa_launches(&pl->inv) + 4;
 }
 
 int mpirfft_mul_exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, const mp_limb_t *d_i1,
@@ -154,10 +154,14 @@ int mpirfft_mul_exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, cons
    switch (phase)
    {
    case 0:
+      if (mfft_mfa_can_fuse_split(&pl->fwd))
+      { rc = mfft_mfa_exec_split(&pl->fwd, pl->X, pl->Z, (const limb_t *) d_i1, (uint64_t) pl->n1, p->bits1, p->j1, stream); break; }
       if (mfft_dev_split(pl->X, pl->l, pl->pitch, (const limb_t *) d_i1, (uint64_t) pl->n1, p->bits1, p->j1, p->trunc, stream)) return MPIRFFT_ENODEV;
       rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Z, stream);
       break;
    case 1:
+      if (mfft_mfa_can_fuse_split(&pl->fwd))
+      { rc = mfft_mfa_exec_split(&pl->fwd, pl->X, pl->Y, (const limb_t *) d_i2, (uint64_t) pl->n2, p->bits1, p->j2, stream); break; }
       if (mfft_dev_split(pl->X, pl->l, pl->pitch, (const limb_t *) d_i2, (uint64_t) pl->n2, p->bits1, p->j2, p->trunc, stream)) return MPIRFFT_ENODEV;
       rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Y, stream);
       break;

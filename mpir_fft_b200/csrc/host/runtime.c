@@ -244,6 +244,22 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
       if (mfft_passes_build(&m->pcol, cs, pmax, last == cs ? m->h_must_store : NULL) != 0 ||
           mfft_passes_build(&m->prow, rs, pmax, last == rs ? m->h_must_store : NULL) != 0) { rc = MPIRFFT_ENOMEM; goto fail; }
    }
+   if (m->fused && !inverse)
+   {  /* may the first column pass split while it loads?  Only if no later pass reads a block that
+         nothing has written before (such a block would be an input the split kernel had to provide) */
+      uint8_t *wr = (uint8_t *) calloc(cs->S, 1); uint32_t pi, k; int ok = (wr != NULL);
+      for (pi = 0; ok && pi < m->pcol.npasses; pi++)
+      {
+         const mfft_pass *p = &m->pcol.pass[pi];
+         if (pi > 0)
+            for (k = 0; k < p->npos_total; k++)
+               if ((p->pos[k] & MFFT_TILE_LOAD) && !wr[p->pos[k] & MFFT_TILE_POSMASK]) ok = 0;
+         for (k = 0; k < p->npos_total; k++)
+            if (p->pos[k] & (MFFT_TILE_STORE | MFFT_TILE_LOAD)) wr[p->pos[k] & MFFT_TILE_POSMASK] = 1;
+      }
+      free(wr);
+      m->fuse_split_ok = ok;
+   }
    if (mfft_sched_finish(cs) != 0 || mfft_sched_finish(rs) != 0) { rc = MPIRFFT_ENOMEM; goto fail; }
    return 0;
 fail:
@@ -335,6 +351,19 @@ static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft
                              lastp ? m->normalise : 0, d[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, p->tiles, p->pos, p->stoff, h_batch, stream) != 0) return MPIRFFT_ENODEV;
    }
    return 0;
+}
+
+/* forward transform straight from the operand: the first column pass splits while it loads
+ * (fused plans whose first pass reads every live input block exactly once); returns 1 if the
+ * caller still has to run the split kernel */
+int mfft_mfa_can_fuse_split(const mfft_mfa *m) { return m->fused && !m->inverse && m->pcol.npasses > 0 && m->fuse_split_ok; }
+
+int mfft_mfa_exec_split(const mfft_mfa *m, limb_t *slab, limb_t *dst, const limb_t *src, uint64_t nlimbs,
+                        uint64_t bits, uint64_t ncoef, void *stream)
+{
+   if (!mfft_mfa_can_fuse_split(m)) return MPIRFFT_EINVAL;
+   mfft_dev_tiles_fuse_split(src, nlimbs, bits, ncoef);
+   return mfft_mfa_exec(m, slab, dst, stream);
 }
 
 int mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, void *stream)

@@ -47,6 +47,7 @@ typedef struct {
    uint32_t    nrows;
    /* fused mode: the passes of each schedule, uploaded (tile.c / k_run_tiles) */
    int fused; uint32_t final_shift; int normalise;
+   int fuse_split_ok;                          /* every input block is first read by the first column pass */
    mfft_passes pcol, prow;
    struct mfft_dpass { mfft_tile *d_tiles; uint32_t *d_pos; mfft_tileop *d_ops; uint32_t *d_stoff; } *dcol, *drow;
    uint32_t *d_dstpos; uint8_t *h_must_store; uint32_t *h_dstpos;
@@ -70,6 +71,10 @@ void mfft_mfa_free(mfft_mfa *m);
 /* slab: 2N blocks, input in half 0 in reference order (ii[k] = block k); dst: N blocks */
 int  mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, void *stream);
 uint64_t mfft_mfa_launches(const mfft_mfa *m);
+/* forward transform with FFT_split_bits fused into the first column pass (fused plans only) */
+int  mfft_mfa_can_fuse_split(const mfft_mfa *m);
+int  mfft_mfa_exec_split(const mfft_mfa *m, limb_t *slab, limb_t *dst, const limb_t *src, uint64_t nlimbs,
+                         uint64_t bits, uint64_t ncoef, void *stream);
 
 #ifdef __cplusplus
 }

@@ -151,6 +151,10 @@ int  mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_til
                         uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy,
                         const mfft_tile *h_tiles, const uint32_t *h_pos, const uint32_t *h_stoff,
                         const mfft_batch *h_batch, void *stream);
+/* the NEXT mfft_dev_run_tiles launch cuts the coefficients it loads out of the operand {src, nlimbs}
+ * (block k of slab half 0 = bits [k*bits, (k+1)*bits), zero for k >= ncoef; FFT_split_bits,
+ * mul_fft.c:115-170 and the zero fill 3235-3236) instead of reading them from the slab */
+void mfft_dev_tiles_fuse_split(const limb_t *src, uint64_t nlimbs, uint64_t bits, uint64_t ncoef);
 /* 1 if the fused executor supports coefficient size l (else use mfft_dev_run_stage) */
 int  mfft_dev_tiles_supported(uint32_t l);
 uint32_t mfft_dev_tiles_max_npos(uint32_t l);
