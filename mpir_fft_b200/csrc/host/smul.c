@@ -36,6 +36,7 @@ struct mpirfft_smul_plan {
    mfft_xform fcol, frow, irow, icol;
    limb_t *work, *send, *recv, *unp, *Z, *Y, *out;
    uint32_t *d_unpack, *d_idx, *d_carry;
+   mpirfft_mulmod_plan *mm;       /* coefficient rings above 512 limbs: pointwise products through a transform */
    void *combine_work;
    size_t work_blocks, send_blocks, recv_blocks;
 };
@@ -56,6 +57,7 @@ void mpirfft_smul_plan_destroy(mpirfft_smul_plan *pl)
    mfft_dev_free(pl->Z); mfft_dev_free(pl->Y); mfft_dev_free(pl->out);
    mfft_dev_free(pl->d_unpack); mfft_dev_free(pl->d_idx); mfft_dev_free(pl->d_carry); mfft_dev_free(pl->combine_work);
    mfft_unlock();
+   if (pl->mm) mpirfft_mulmod_plan_destroy(pl->mm);
    free(pl);
 }
 
@@ -182,6 +184,15 @@ int mpirfft_smul_plan_create(mpirfft_smul_plan **out, mp_size_t n1, mp_size_t n2
    if (!pl->d_unpack || !pl->d_idx) { rc = MPIRFFT_ENODEV; goto fail; }
    free(tab); free(b); free(dst_of); free(dst_base);
    mfft_unlock();
+   if (pl->l > 512)
+   {  /* no warp-level product kernel for such coefficients: recurse like the reference does for its
+         pointwise products (fft_mulmod_2expp1, mul_fft.c:3125) -- one batched transform-based mulmod
+         over all the rank's coefficients */
+      mp_bitcnt_t d2, w2;
+      if (mpirfft_mulmod_params((mp_size_t) pl->l, &d2, &w2) != 0 ||
+          mpirfft_mulmod_plan_create(&pl->mm, (mp_size_t) pl->l, d2, w2, pl->recv_blocks) != 0)
+      { mpirfft_smul_plan_destroy(pl); return MPIRFFT_EINVAL; }
+   }
    *out = pl;
    return 0;
 fail:
@@ -218,6 +229,7 @@ int mpirfft_smul_phase(mpirfft_smul_plan *pl, int phase, int which, const mp_lim
       if (mfft_dev_gather_blocks(pl->unp, pl->recv, pl->d_unpack, pl->recv_blocks, pl->pitch, stream)) return MPIRFFT_ENODEV;
       return mfft_xform_exec(&pl->frow, pl->unp, which ? pl->Y : pl->Z, stream);
    case 2:
+      if (pl->mm) return mpirfft_mulmod_plan_exec(pl->mm, (mp_limb_t *) pl->Z, (const mp_limb_t *) pl->Z, (const mp_limb_t *) pl->Y, pl->pitch, -1, stream);
       if (mfft_dev_pointwise(pl->Z, pl->Y, pl->d_idx, (uint32_t) pl->recv_blocks, pl->l, pl->pitch, stream)) return MPIRFFT_ENODEV;
       return 0;
    case 3:   /* row IFFTs, columns gathered by owner into send */

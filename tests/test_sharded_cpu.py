@@ -56,6 +56,8 @@ CASES = [
     (700, 900, 7, 12, "runs"),           # l = 24: stagewise path
     (8000, 8000, 8, 16, "uniform"),      # bit-shifted twiddles
     (5000, 37, 7, 64, "uniform"),        # lopsided: some ranks own no result limbs
+    (30000, 28000, 6, 1024, "ones"),     # l = 1024: stage-per-launch transforms, pointwise products through the
+                                         # batched negacyclic mulmod (the route of the 2^24 .. 2^30-limb products)
 ]
 
 
