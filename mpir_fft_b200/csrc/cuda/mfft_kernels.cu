@@ -30,7 +30,6 @@
 
 static char g_err[512] = "";
 static uint64_t g_launches = 0;
-static int g_device = -1;
 
 /* optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
  * leg).  Off by default; never part of the timed end-to-end path. */
@@ -1249,7 +1248,6 @@ int mfft_dev_init(int device)
    if (device < 0 || device >= n) { snprintf(g_err, sizeof g_err, "device %d out of range (%d visible)", device, n); return -1; }
    CK(cudaSetDevice(device));
    CK(cudaFree(0));
-   g_device = device;
    return 0;
 }
 

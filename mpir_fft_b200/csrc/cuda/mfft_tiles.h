@@ -46,6 +46,7 @@ __device__ __forceinline__ uint32_t add2c(limb_t &r0, limb_t &r1, limb_t a0, lim
        "addc.u32 %2, 0, 0;"
        : "=l"(r0), "=l"(r1), "=r"(cout), "=r"(tmp)
        : "l"(a0), "l"(a1), "l"(b0), "l"(b1), "r"(cin));
+   (void) tmp;
    return cout;
 #endif
 }
