@@ -200,6 +200,8 @@ k_finalize(limb_t *dst, uint32_t dst_stride, const uint32_t *__restrict__ dst_ba
 
 /* fused shared-memory tile executor (carry-save coefficients): see mfft_tiles.h */
 #include "mfft_tiles.h"
+/* carry-save layers on HBM-resident coefficients of any size: see mfft_cs_stage.h */
+#include "mfft_cs_stage.h"
 
 __global__ void __launch_bounds__(128)
 k_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk)
@@ -1332,6 +1334,40 @@ static uint32_t g_split_on = 0; static const limb_t *g_split_src = NULL;
 static uint64_t g_split_nlimbs = 0, g_split_bits = 0, g_split_ncoef = 0;
 void mfft_dev_tiles_fuse_split(const limb_t *src, uint64_t nlimbs, uint64_t bits, uint64_t ncoef)
 { g_split_on = 1; g_split_src = src; g_split_nlimbs = nlimbs; g_split_bits = bits; g_split_ncoef = ncoef; }
+
+/* ---- carry-save stage path (mfft_cs_stage.h): any even l; cw = side array of l/2 carry words per block ---- */
+int mfft_dev_cs_init(const limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_batch *d_batch, uint32_t nbatch, void *stream)
+{
+   const uint64_t total = (uint64_t) g->S * nbatch * (g->l / 2);
+   if (!total) return 0;
+   MFFT_LAUNCH(k_cs_init, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t) stream, slab, cw, *g, d_batch, nbatch);
+   CKL();
+   return 0;
+}
+
+int mfft_dev_run_stage_cs(limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
+                          const mfft_batch *d_batch, uint32_t nbatch, void *stream)
+{
+   if (!count || !nbatch) return 0;
+   PROF(PC_STAGE, stream);
+   MFFT_LAUNCH(k_stage_cs, (unsigned)((uint64_t) count * nbatch), 256, 0, (cudaStream_t) stream, slab, cw, *g, d_ops, count, d_batch, nbatch);
+   CKL();
+   return 0;
+}
+
+int mfft_dev_finalize_cs(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst_base, limb_t *slab, int32_t *cw,
+                         const mfft_geom *g, const mfft_move *d_moves, uint32_t nmoves, const mfft_batch *d_batch,
+                         uint32_t nbatch, int normalise, void *stream)
+{
+   if (!nmoves || !nbatch) return 0;
+   const size_t sm = ((size_t) g->l + 15) & ~(size_t) 15;          /* 2 bytes per chunk */
+   PROF(PC_FINALIZE, stream);
+   CK(cudaFuncSetAttribute(k_finalize_cs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+   MFFT_LAUNCH(k_finalize_cs, (unsigned)((uint64_t) nmoves * nbatch), 256, sm, (cudaStream_t) stream, dst, dst_stride, d_dst_base,
+               slab, cw, *g, d_moves, nmoves, d_batch, nbatch, normalise);
+   CKL();
+   return 0;
+}
 
 /* coefficient sizes the fused executor is instantiated for: l = 64*NT limbs */
 static int tiles_cfg(uint32_t l, int *NT)

@@ -14,6 +14,7 @@ typedef struct {
    mfft_sched *s;                                 /* fused: host schedule (owned) */
    mfft_passes P; struct mfft_dpass *dp;          /* fused passes */
    mfft_batch *d_batch, *h_batch; uint32_t *d_dst_base, *d_dstpos; mfft_move *d_moves;
+   int cs; int32_t *d_cw;                         /* stagewise, carry-save kernel: carry words of both slab halves */
 } mfft_xform;
 
 /* s: emitted (and relabelled) schedule over S positions; ownership passes to the xform.

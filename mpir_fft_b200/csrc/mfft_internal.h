@@ -46,6 +46,8 @@ typedef struct {
     * hazards -- used by the fused shared-memory tile executor (tile.c, k_run_tiles) */
    uint32_t pA, pB, pS, pT;
    uint32_t pstage;
+   /* shape of the op for the carry-save stage kernel (xform.c: classify; MFFT_K_* below) */
+   uint32_t kind, kparam;
 } mfft_op;
 
 /* One batch entry: which strided family of blocks an op list is applied to. */
@@ -97,6 +99,7 @@ typedef struct {            /* one op of a tile; a,b,s,t index the tile's positi
 #define MFFT_K_DBL   8u     /* S = 2 A           (the doubling steps of IFFT_radix2_truncate, 1788-1789) */
 #define MFFT_K_HALF  9u     /* S = (A + B) / 2   (the averaging steps of IFFT_radix2_truncate1, 1556-1560) */
 #define MFFT_K_SHR   10u    /* S = A / 2^s, 1 <= s <= 31 = kparam   (the final 2^-(depth+1) scaling, 3256-3258) */
+#define MFFT_K_2AMB  11u    /* S = 2A - B [, T = +-(A - B) * 2^(128 yc)]   (1630-1631, 1639-1647); stage kernel only */
 
 /* pad = offset of the tile's (nstages+1) stage offsets in the pass's stoff array (<= 63 stages) */
 typedef struct { uint32_t pos_off, npos, op_off, nops, nstages, pad; } mfft_tile;
@@ -136,6 +139,18 @@ const char *mfft_dev_last_error(void);
 /* run ops[first .. first+count) (one stage) over nbatch batch entries */
 int  mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
                         const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+
+/* Carry-save stage path for coefficient rings of any even size (mfft_cs_stage.h): the same chunk
+ * arithmetic as the tile executor on HBM-resident blocks, one launch per layer; cw holds l/2 carry
+ * words per block of the slab (both halves).  init: carry words of the S positions of half 0 of
+ * every batch entry (zero, last = the block's top limb); run_stage: ops must carry a kind
+ * (MFFT_K_* or MFFT_K_ANY with a single operand); finalize: gather + resolve (+ normalise). */
+int  mfft_dev_cs_init(const limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+int  mfft_dev_run_stage_cs(limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
+                           const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+int  mfft_dev_finalize_cs(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst_base, limb_t *slab, int32_t *cw,
+                          const mfft_geom *g, const mfft_move *d_moves, uint32_t nmoves, const mfft_batch *d_batch,
+                          uint32_t nbatch, int normalise, void *stream);
 
 /* One fused pass: CTA (tile, batch entry) loads the tile's positions into shared memory, runs
  * all its stages there and stores the written positions back in place -- or, if dst != NULL,
