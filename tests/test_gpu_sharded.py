@@ -16,6 +16,8 @@ CASES = [
     (3000000, 1700000, 14, 2, "uniform"),       # cfg3, trunc > n branch, l = 512
     (1 << 18, 1 << 18, 13, 1, "ones"),          # odd depth, worst-case carries across rank windows
     (1 << 22, 1000, 15, 1, "runs"),             # lopsided
+    (1 << 22, 1 << 22, 16, 1, "ones"),          # ring of 1024 limbs: carry-save stage kernel + transform-based pointwise
+    (6000000, 2000000, 16, 1, "runs"),          # the same route, truncated and lopsided
 ]
 
 
