@@ -16,7 +16,7 @@ class Op(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("inA", "inB", "outS", "outT", "eSA", "eSB", "eTA", "eTB",
                                            "cSA", "cSB", "cTA", "cTB")] + \
                [(k, C.c_int8) for k in ("sSA", "sSB", "sTA", "sTB")] + [("stage", C.c_uint32)] + \
-               [(k, C.c_uint32) for k in ("pA", "pB", "pS", "pT", "pstage")]
+               [(k, C.c_uint32) for k in ("pA", "pB", "pS", "pT", "pstage", "kind", "kparam")]
 
 
 class Sched(C.Structure):
