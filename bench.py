@@ -75,8 +75,42 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag, self.proc = gpu, [], False, None
+        self.ready, self.marking = False, True
+
+    NVML_REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                    ("sw_power_cap", 0x4))
+
+    def _run_nvml(self):
+        """in-process NVML polling (about 1 ms per sample): the timed region of one cfg2 run is tens
+        of milliseconds, shorter than nvidia-smi's start-up"""
+        import pynvml as N
+        N.nvmlInit()
+        gpu = self.gpu
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:
+            ids = [v.strip() for v in vis.split(",")]
+            if gpu < len(ids) and ids[gpu].isdigit():
+                gpu = int(ids[gpu])
+        h = N.nvmlDeviceGetHandleByIndex(gpu)
+        mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        self.ready = True
+        while not self.stop_flag:
+            sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+            try:
+                bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                bits = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            row = [str(gpu), sm, mx, "", hex(bits)] + ["Active" if bits & m else "Not Active" for _, m in self.NVML_REASONS]
+            if self.marking:
+                self.rows.append([str(x) for x in row])
+            time.sleep(0.0005)
 
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            self.ready = True
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -88,9 +122,20 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def begin(self):
+        """wait for the first sample source to be up; samples count from here"""
+        t = time.time()
+        while not self.ready and time.time() - t < 5.0:
+            time.sleep(0.01)
+        if self.proc is None:
+            self.rows = []
+        else:
+            time.sleep(0.2)
+
     def finish(self):
         self.stop_flag = True
-        time.sleep(0.15)
+        if self.proc:
+            time.sleep(0.15)
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -239,7 +284,7 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.2)
+    sampler.begin()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -451,7 +496,7 @@ def run_cfg4(args, rank, local_rank, world, torch, dist, M):
             check = check and (got == want)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.2)
+    sampler.begin()
     Lb.mpirfft_launch_count_reset()
     ms_per_step, step_ms = _timed_steps(torch, dist, world, args.steps, flush, step)
     launches = int(Lb.mpirfft_launch_count())
@@ -552,7 +597,7 @@ def run_sharded(args, rank, local_rank, world, torch, dist, M):
         check = bool(np.array_equal(res, oracle.gmp_mul(a.cpu().numpy().view(np.uint64), b.cpu().numpy().view(np.uint64))))
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.2)
+    sampler.begin()
     M.lib().mpirfft_launch_count_reset()
     ms_per_step, step_ms = _timed_steps(torch, dist, world, args.steps, flush, step)
     launches = int(M.lib().mpirfft_launch_count())

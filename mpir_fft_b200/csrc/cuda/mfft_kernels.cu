@@ -238,6 +238,74 @@ __device__ __forceinline__ void addc(uint32_t &d)
 { asm volatile("addc.u32 %0, %0, 0;" : "+r"(d)); }
 #endif
 
+/* P += x*y for two H-word blocks (H even), P = sum e[k] 2^(32k) + sum o[k] 2^(32(k+1)) + sum kc[i] 2^(32(H+i)):
+ * H rows of two IMAD.WIDE.U32.X chains (even / odd word offsets), final carries counted in kc[] */
+template <int H>
+__device__ __forceinline__ void mac_block(uint32_t (&e)[2 * H + 2], uint32_t (&o)[2 * H + 2], uint32_t (&kc)[H + 2],
+                                          const uint32_t (&x)[H], const uint32_t (&y)[H])
+{
+#pragma unroll
+   for (int j = 0; j < H; j++)
+   {
+      const uint32_t yj = y[j];
+      {
+         const int t0 = j & 1;
+         mad_lo_cc(e[t0 + j], x[t0], yj); madc_hi_cc(e[t0 + j + 1], x[t0], yj);
+#pragma unroll
+         for (int t = t0 + 2; t < H; t += 2) { madc_lo_cc(e[t + j], x[t], yj); madc_hi_cc(e[t + j + 1], x[t], yj); }
+         addc(kc[j + (j & 1)]);
+      }
+      {
+         const int t0 = 1 - (j & 1);
+         mad_lo_cc(o[t0 + j - 1], x[t0], yj); madc_hi_cc(o[t0 + j], x[t0], yj);
+#pragma unroll
+         for (int t = t0 + 2; t < H; t += 2) { madc_lo_cc(o[t + j - 1], x[t], yj); madc_hi_cc(o[t + j], x[t], yj); }
+         addc(kc[j + 1 - (j & 1)]);
+      }
+   }
+}
+
+/* word k of the accumulator triple of mac_block, as a non-negative 64-bit value */
+template <int H>
+__device__ __forceinline__ int64_t mac_word(const uint32_t (&e)[2 * H + 2], const uint32_t (&o)[2 * H + 2],
+                                            const uint32_t (&kc)[H + 2], int k)
+{
+   int64_t v = 0;
+   if (k >= 0 && k < 2 * H + 2) v += (int64_t)(uint64_t) e[k];
+   if (k >= 1 && k - 1 < 2 * H + 2) v += (int64_t)(uint64_t) o[k - 1];
+   if (k >= H && k - H < H + 2) v += (int64_t)(uint64_t) kc[k - H];
+   return v;
+}
+
+/* S_K = sum_{s > K} A_s over the lanes' C-word blocks (C+1 words): inclusive suffix scan, then shift
+ * down by one lane.  Called after the product loop so that S is not live across it. */
+template <int C>
+__device__ __forceinline__ void suffix_block_sums(uint32_t (&S)[C + 1], const uint32_t *own, uint32_t lane)
+{
+#pragma unroll
+   for (int i = 0; i < C; i++) S[i] = own[i];
+   S[C] = 0;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1)
+   {
+      uint64_t cy = 0;
+      const bool take = (lane + d < 32);
+#pragma unroll
+      for (int i = 0; i <= C; i++)
+      {
+         const uint32_t other = __shfl_down_sync(FULL, S[i], d);
+         const uint64_t v = (uint64_t) S[i] + (take ? other : 0u) + cy;
+         S[i] = (uint32_t) v; cy = v >> 32;
+      }
+   }
+#pragma unroll
+   for (int i = 0; i <= C; i++)
+   {
+      const uint32_t other = __shfl_down_sync(FULL, S[i], 1);
+      S[i] = (lane == 31) ? 0u : other;
+   }
+}
+
 /* One warp per product; l = 16*C limbs, i.e. every lane owns C 32-bit words of each operand.
  * The operands are cut into 32 blocks of C words; lane K needs
  *      sum_{I+J=K} A_I*B_J  -  sum_{I+J=K+32} A_I*B_J            (B^l == -1).
@@ -248,16 +316,29 @@ __device__ __forceinline__ void addc(uint32_t &d)
  * Each CxC block product is C rows of two IMAD.WIDE.U32.X chains (even / odd word offsets,
  * accumulators e[] / o[]); a chain's final carry goes to a small counter kc[], so the chains
  * never have to ripple into words that already hold data from earlier steps.               */
-template <int C>
-__global__ void __launch_bounds__(128)
+/* KARA: every CxC block product is split once more inside the lane (H = C/2, W = 2^(32H)):
+ *      a*b = L + (M - L - Hh) W + Hh W^2,   L = a0 b0, Hh = a1 b1, M = (a0+a1)(b0+b1),
+ * and because the identity is linear, L, M, Hh are accumulated over the 32 steps in three separate
+ * accumulator sets and combined ONCE after the loop: 3 H^2 instead of C^2 = 4 H^2 multiply-adds per
+ * step, no subtraction inside the loop.  The carry bits of the two sums never enter a multiply:
+ * (xs + ca W)(ys + cb W) = xs ys + (ca ys + cb xs) W + ca cb W^2, a masked add per step (UV, n2).
+ * a0+a1 is formed once per block when the operand is staged in shared memory (H+1 more words per
+ * block); b0+b1 is recomputed after every rotation (the complement of a wrapped block is not the
+ * complement of its half-sum).  The additions go to the ALU pipe, next to the IMAD pipe the products
+ * keep busy. */
+template <int C, bool KARA, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB)
 k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
             uint32_t nblk, uint32_t l, uint32_t pitch)
 {
    MFFT_DYN_SMEM(uint32_t, smem);
+   constexpr int H = C / 2;
+   constexpr int WSM = KARA ? 32 * (C + H + 1) : 32 * C;       /* shared words per warp */
    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const uint64_t wid = (uint64_t) blockIdx.x * (blockDim.x >> 5) + wib;
    if (wid >= nblk) return;
-   uint32_t *sA = smem + wib * (32 * C);
+   uint32_t *sA = smem + wib * WSM;
+   uint32_t *sAs = sA + 32 * C;                                 /* KARA: a0+a1 (H words) and its carry, per block */
    limb_t *A = a_slab + (uint64_t) blocks[wid] * pitch;
    const limb_t *B = b_slab + (uint64_t) blocks[wid] * pitch;
 
@@ -293,39 +374,90 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
    }
 #pragma unroll
    for (int i = 0; i < C; i++) sA[lane * C + i] = a[i];
-   __syncwarp();
-
-   /* S_K = sum_{s > K} A_s : inclusive suffix scan over the lanes, then shift down by one */
-   uint32_t S[C + 1];
-#pragma unroll
-   for (int i = 0; i < C; i++) S[i] = a[i];
-   S[C] = 0;
-#pragma unroll
-   for (int d = 1; d < 32; d <<= 1)
+   if constexpr (KARA)
    {
       uint64_t cy = 0;
-      const bool take = (lane + d < 32);
 #pragma unroll
-      for (int i = 0; i <= C; i++)
+      for (int i = 0; i < H; i++)
       {
-         const uint32_t other = __shfl_down_sync(FULL, S[i], d);
-         const uint64_t v = (uint64_t) S[i] + (take ? other : 0u) + cy;
-         S[i] = (uint32_t) v; cy = v >> 32;
+         const uint64_t v = (uint64_t) a[i] + a[H + i] + cy;
+         sAs[lane * (H + 1) + i] = (uint32_t) v; cy = v >> 32;
       }
+      sAs[lane * (H + 1) + H] = (uint32_t) cy;
    }
-#pragma unroll
-   for (int i = 0; i <= C; i++)
-   {
-      const uint32_t other = __shfl_down_sync(FULL, S[i], 1);
-      S[i] = (lane == 31) ? 0u : other;
-   }
+   __syncwarp();
 
+   uint32_t acc[2 * C + 1];
+   const uint32_t m0 = (lane == 0) ? 0xffffffffu : 0u;
+   if constexpr (KARA)
+   {
+      uint32_t eL[2 * H + 2], oL[2 * H + 2], kL[H + 2], eM[2 * H + 2], oM[2 * H + 2], kM[H + 2],
+               eH[2 * H + 2], oH[2 * H + 2], kH[H + 2], UV[H + 1], n2 = 0;
+#pragma unroll
+      for (int i = 0; i < 2 * H + 2; i++) { eL[i] = 0; oL[i] = 0; eM[i] = 0; oM[i] = 0; eH[i] = 0; oH[i] = 0; }
+#pragma unroll
+      for (int i = 0; i < H + 2; i++) { kL[i] = 0; kM[i] = 0; kH[i] = 0; }
+#pragma unroll
+      for (int i = 0; i <= H; i++) UV[i] = 0;
+
+      for (uint32_t s = 0; s < 32; s++)
+      {
+         uint32_t x[H], y[H];
+#pragma unroll
+         for (int i = 0; i < H; i++) { x[i] = sA[s * C + i]; y[i] = b[i]; }
+         mac_block<H>(eL, oL, kL, x, y);
+#pragma unroll
+         for (int i = 0; i < H; i++) { x[i] = sA[s * C + H + i]; y[i] = b[H + i]; }
+         mac_block<H>(eH, oH, kH, x, y);
+         uint64_t cy = 0;
+#pragma unroll
+         for (int i = 0; i < H; i++)
+         {
+            const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
+            y[i] = (uint32_t) v; cy = v >> 32;
+            x[i] = sAs[s * (H + 1) + i];
+         }
+         const uint32_t cb = (uint32_t) cy, ca = sAs[s * (H + 1) + H];
+         mac_block<H>(eM, oM, kM, x, y);
+         /* carry bits of the two sums: UV += ca*ys + cb*xs, n2 += ca*cb */
+         const uint32_t ma = 0u - ca, mb = 0u - cb;
+         cy = 0;
+#pragma unroll
+         for (int i = 0; i < H; i++)
+         {
+            const uint64_t v = (uint64_t) UV[i] + (y[i] & ma) + (x[i] & mb) + cy;
+            UV[i] = (uint32_t) v; cy = v >> 32;
+         }
+         UV[H] += (uint32_t) cy;
+         n2 += ca & cb;
+         const uint32_t src = (lane + 31) & 31;
+#pragma unroll
+         for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src) ^ m0;
+      }
+
+      /* P_K = L + (M + UV W + n2 W^2 - L - Hh) W + Hh W^2;   R_K = P_K - S_K*2^(32C) + S_K */
+      uint32_t S[C + 1];
+      suffix_block_sums<C>(S, sA + lane * C, lane);
+      int64_t cy = 0;
+#pragma unroll
+      for (int k = 0; k <= 2 * C; k++)
+      {
+         int64_t v = cy + mac_word<H>(eL, oL, kL, k);
+         if (k >= H) v += mac_word<H>(eM, oM, kM, k - H) - mac_word<H>(eL, oL, kL, k - H) - mac_word<H>(eH, oH, kH, k - H);
+         if (k >= C) v += mac_word<H>(eH, oH, kH, k - C);
+         if (k >= C && k - C <= H) v += (int64_t)(uint64_t) UV[k - C];
+         if (k == 3 * H) v += (int64_t)(uint64_t) n2;
+         if (k <= C) v += (int64_t)(uint64_t) S[k];
+         if (k >= C) v -= (int64_t)(uint64_t) S[k - C];
+         acc[k] = (uint32_t) v; cy = v >> 32;
+      }
+   } else
+   {
    uint32_t e[2 * C + 2], o[2 * C + 2], kc[C + 2];
 #pragma unroll
    for (int i = 0; i < 2 * C + 2; i++) { e[i] = 0; o[i] = 0; }
 #pragma unroll
    for (int i = 0; i < C + 2; i++) kc[i] = 0;
-   const uint32_t m0 = (lane == 0) ? 0xffffffffu : 0u;
 
    for (uint32_t s = 0; s < 32; s++)
    {
@@ -360,7 +492,8 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
    }
 
    /* R_K = P_K - S_K*2^(32C) + S_K with P_K = e + o + kc<<(32C), as 2C words + a small signed top */
-   uint32_t acc[2 * C + 1];
+   uint32_t S[C + 1];
+   suffix_block_sums<C>(S, sA + lane * C, lane);
    {
       int64_t cy = 0;
 #pragma unroll
@@ -373,6 +506,7 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
       }
       cy += (int64_t)(uint64_t) e[2 * C] + (int64_t)(uint64_t) o[2 * C - 1] + (int64_t)(uint64_t) kc[C] - (int64_t)(uint64_t) S[C];
       acc[2 * C] = (uint32_t)(int32_t) cy;
+   }
    }
 
    /* lane K: r = acc[0..C) + (high part of lane K-1), lane 0 takes -(high part of lane 31) */
@@ -1515,7 +1649,8 @@ int mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, 
 }
 
 static limb_t *g_pw_scratch = NULL; static size_t g_pw_scratch_bytes = 0;
-static int g_pw_mode = -1;
+static int g_pw_mode = -1;     /* 0 auto, 1 nested SS, 2 Karatsuba blocks, 3 schoolbook blocks */
+#define PW_KARA_DEFAULT(l) (0)
 void mfft_dev_pointwise_mode(int mode) { g_pw_mode = mode; }
 
 int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uint32_t nblk,
@@ -1532,7 +1667,7 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
          slower, 0.91 ms: ptxas never emits IMAD.WIDE with a non-zero 64-bit addend on sm_100a, it
          splits every mad.wide.u32 into IMAD.WIDE(.., RZ) + IADD3 + IADD3.X, so the real ceiling for
          32x32->64 multiply-ADDs is the ~31/clk/SM of the IMAD.WIDE.U32.X chains used here.) */
-      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = (e && e[0] == 's') ? 1 : 0; }
+      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = !e ? 0 : e[0] == 's' ? 1 : e[0] == 'k' ? 2 : e[0] == 'd' ? 3 : e[0] == 'K' ? 4 : 0; }
       uint32_t np = 0, lp = 0;
       if (g_pw_mode == 1)
       {
@@ -1556,10 +1691,17 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
          return 0;
       }
    }
-   if (l == 64)       MFFT_LAUNCH(k_pointwise<4>, grid, 128, 4 * 32 * 4 * 4, st, a, b, d_blocks, nblk, l, pitch);
-   else if (l == 128) MFFT_LAUNCH(k_pointwise<8>, grid, 128, 4 * 32 * 8 * 4, st, a, b, d_blocks, nblk, l, pitch);
-   else if (l == 256) MFFT_LAUNCH(k_pointwise<16>, grid, 128, 4 * 32 * 16 * 4, st, a, b, d_blocks, nblk, l, pitch);
-   else if (l == 512) MFFT_LAUNCH(k_pointwise<32>, grid, 128, 4 * 32 * 32 * 4, st, a, b, d_blocks, nblk, l, pitch);
+#define PW_SCHOOL(CC) MFFT_LAUNCH((k_pointwise<CC, false>), grid, 128, 4 * 32 * CC * 4, st, a, b, d_blocks, nblk, l, pitch)
+#define PW_KARA(CC)   MFFT_LAUNCH((k_pointwise<CC, true>), grid, 128, 4 * 32 * (CC + CC / 2 + 1) * 4, st, a, b, d_blocks, nblk, l, pitch)
+   const bool kara = (g_pw_mode == 2) || (g_pw_mode == 0 && PW_KARA_DEFAULT(l));
+   if (l == 64)       { if (kara) PW_KARA(4); else PW_SCHOOL(4); }
+   else if (l == 128) { if (kara) PW_KARA(8); else PW_SCHOOL(8); }
+   else if (l == 256)
+   {
+      if (g_pw_mode == 4) MFFT_LAUNCH((k_pointwise<16, true, 3>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
+      else if (kara) PW_KARA(16); else PW_SCHOOL(16);
+   }
+   else if (l == 512) PW_SCHOOL(32);
    else
    {
       const size_t need = (size_t) nblk * 3 * l * sizeof(limb_t);

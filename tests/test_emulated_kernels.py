@@ -38,15 +38,34 @@ def test_emulated_new_mpn_mul(emu, case):
     assert np.array_equal(r, L.gmp_mul(a, b))
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("case", [
+    (1500, 1500, 6, 64, "ones"), (3000, 2000, 6, 128, "uniform"), (3000, 3000, 6, 128, "ones"),
+    (6000, 6000, 6, 256, "ones"), (6000, 6000, 6, 256, "uniform"), (6000, 700, 6, 256, "runs"),
+])
+def test_emulated_new_mpn_mul_product_kernels(emu, case, mode):
+    """the pointwise products of new_mpn_mul (mul_fft.c:3244-3253) through the Karatsuba-block (2) and the
+    schoolbook-block (3) kernel; all-ones operands make every half-sum a0+a1 / b0+b1 overflow"""
+    n1, n2, depth, w, kind = case
+    a, b = operand(kind, n1, 1), operand(kind, n2, 2)
+    r = np.zeros(n1 + n2, dtype=np.uint64)
+    emu.mpirfft_set_pointwise_mode(mode)
+    try:
+        emu.new_mpn_mul(ptr(r), ptr(a), n1, ptr(b), n2, depth, w)
+    finally:
+        emu.mpirfft_set_pointwise_mode(0)
+    assert np.array_equal(r, L.gmp_mul(a, b))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
 def test_emulated_mulmod_adversarial(emu, l, mode):
-    emu.mpirfft_set_pointwise_mode(mode)        # 0: schoolbook carry-chain kernel (default), 1: nested SS kernel
+    emu.mpirfft_set_pointwise_mode(mode)        # 0: default, 1: nested SS kernel, 2: Karatsuba blocks, 3: schoolbook blocks
     random.seed(l)
     NW = 64 * l
     p = (1 << NW) + 1
-    A = [random.getrandbits(NW) for _ in range(3)] + [p - 2, p - 2, p - 1, p - 1, 0, 1, p - 2, (1 << (NW // 2)) - 1]
-    B = [random.getrandbits(NW) for _ in range(3)] + [p - 2, 2, p - 1, 12345, 77, p - 2, 1 << (NW - 1), (1 << (NW // 2)) - 1]
+    A = [random.getrandbits(NW) for _ in range(3)] + [p - 2, p - 2, p - 1, p - 1, 0, 1, p - 2, (1 << (NW // 2)) - 1, p - 2, (1 << NW) - (1 << (NW // 2))]
+    B = [random.getrandbits(NW) for _ in range(3)] + [p - 2, 2, p - 1, 12345, 77, p - 2, 1 << (NW - 1), (1 << (NW // 2)) - 1, random.getrandbits(NW), (1 << NW) - (1 << (NW // 2))]
     a = np.stack([int_to_block(v, l) for v in A])
     b = np.stack([int_to_block(v, l) for v in B])
     da, db = emu.mpirfft_malloc_device(a.nbytes), emu.mpirfft_malloc_device(b.nbytes)

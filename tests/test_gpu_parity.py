@@ -128,18 +128,18 @@ def test_squaring_uses_one_forward_transform(lib):
 
 
 # ---- mulmod 2^(64 l)+1 ----
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
 def test_mulmod_vs_bigint(lib, l, mode):
     import random
-    lib.mpirfft_set_pointwise_mode(mode)       # 0: schoolbook carry-chain kernel (default), 1: nested SS kernel
+    lib.mpirfft_set_pointwise_mode(mode)       # 0: default, 1: nested SS kernel, 2: Karatsuba blocks, 3: schoolbook blocks
     random.seed(l)
     NW = 64 * l
     p = (1 << NW) + 1
     A = [random.getrandbits(NW) for _ in range(20)] + [p - 2, p - 2, p - 1, p - 1, 0, 1, p - 2,
-                                                       (1 << (NW // 2)) - 1, (1 << NW) - (1 << (NW // 2))]
+                                                       (1 << (NW // 2)) - 1, (1 << NW) - (1 << (NW // 2)), p - 2]
     B = [random.getrandbits(NW) for _ in range(20)] + [p - 2, 2, p - 1, 12345, 77, p - 2, 1 << (NW - 1),
-                                                       (1 << (NW // 2)) - 1, (1 << NW) - (1 << (NW // 2))]
+                                                       (1 << (NW // 2)) - 1, (1 << NW) - (1 << (NW // 2)), random.getrandbits(NW)]
     a = np.stack([int_to_block(v, l) for v in A])
     b = np.stack([int_to_block(v, l) for v in B])
     out = M.mulmod_batch(a, b)
