@@ -19,6 +19,21 @@
 #include <cuda_runtime.h>
 #define MFFT_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define MFFT_DYN_SMEM(type, name) extern __shared__ type name[]
+/* launch that may overlap its scheduling and prologue with the tail of the previous kernel of the
+   stream (programmatic dependent launch); the kernel must execute griddepcontrol.wait before it
+   touches anything that kernel wrote */
+#define MFFT_LAUNCH_PDL(on, kern, grid_, block_, smem_, stream_, ...)                                   \
+   do {                                                                                            \
+      if (!(on)) { kern<<<(grid_), (block_), (smem_), (stream_)>>>(__VA_ARGS__); break; }               \
+      cudaLaunchConfig_t cfg__; memset(&cfg__, 0, sizeof cfg__);                                    \
+      cfg__.gridDim = dim3(grid_); cfg__.blockDim = dim3(block_);                                     \
+      cfg__.dynamicSmemBytes = (smem_); cfg__.stream = (stream_);                                     \
+      cudaLaunchAttribute at__[1];                                                                 \
+      at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                             \
+      at__[0].val.programmaticStreamSerializationAllowed = 1;                                      \
+      cfg__.attrs = at__; cfg__.numAttrs = 1;                                                       \
+      cudaLaunchKernelEx(&cfg__, kern, __VA_ARGS__);                                                \
+   } while (0)
 #endif
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,6 +42,7 @@
 #include "mfft_arith.h"
 
 #define FULL 0xffffffffu
+#define MFFT_PDL_DEFAULT 0
 
 static char g_err[512] = "";
 static uint64_t g_launches = 0;
@@ -1020,7 +1036,7 @@ k_add_small(limb_t *res, uint64_t total, uint32_t c, uint32_t *carry_out)
  * high part of that sum (a small count) */
 __global__ void __launch_bounds__(256)
 k_combine_sum(limb_t *res, uint32_t *cvec, uint64_t total, const limb_t *__restrict__ slab,
-              uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef, uint64_t base_bit)
+              uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef, uint64_t base_bit, int small)
 {
    const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
    if (k > total) return;
@@ -1030,9 +1046,18 @@ k_combine_sum(limb_t *res, uint32_t *cvec, uint64_t total, const limb_t *__restr
       at bit base_bit (a multiple of 64) -- the window form used by the sharded recombine */
    const uint64_t lo_bit = base_bit + k * 64, NWb = (uint64_t) l * 64;
    /* coefficients i with i*bits <= lo_bit+63 and i*bits + NW > lo_bit */
-   uint64_t imax = (lo_bit + 63) / bits;
+   uint64_t imax, imin;
+   if (small)
+   {  /* every bit offset of the window fits 32 bits: two 32-bit divisions instead of two 64-bit ones */
+      const uint32_t lb = (uint32_t) lo_bit, b32 = (uint32_t) bits, nw32 = (uint32_t) NWb;
+      imax = (lb + 63u) / b32;
+      imin = (lb >= nw32) ? (lb - nw32) / b32 + 1u : 0u;
+   } else
+   {
+      imax = (lo_bit + 63) / bits;
+      imin = (lo_bit >= NWb) ? (lo_bit - NWb) / bits + 1 : 0;
+   }
    if (imax >= ncoef) imax = ncoef - 1;
-   uint64_t imin = (lo_bit >= NWb) ? (lo_bit - NWb) / bits + 1 : 0;
    mfft_u128 acc = 0;
    for (uint64_t i = imin; i <= imax && i < ncoef; i++)
    {
@@ -1576,13 +1601,15 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
       }
    }
    if (h_batch && nbatch <= TP_MAXB) { memcpy(tp.batch, h_batch, sizeof(mfft_batch) * nbatch); tp.batch_valid = 1; }
+   static int pdl = -1;
+   if (pdl < 0) { const char *e = getenv("MPIRFFT_PDL"); pdl = e ? (e[0] != '0') : MFFT_PDL_DEFAULT; }
    PROF(PC_STAGE, st);
    /* two CTAs per SM: 16 warps x 64 registers while a lane holds <= 4 chunk pairs of an op, else
       8 warps x 128 registers (fewer, larger coefficients per tile) */
 #define RUN_TILES(NN, TH)                                                                          \
    do {                                                                                            \
       CK(cudaFuncSetAttribute(k_run_tiles<NN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-      MFFT_LAUNCH((k_run_tiles<NN, TH>), grid, TH, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
+      MFFT_LAUNCH_PDL(pdl, (k_run_tiles<NN, TH>), grid, TH, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
                   dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff, g_tile_timing, tp); \
    } while (0)
    if (max_npos <= 16 && NT <= 4 && smem <= 56 * 1024)
@@ -1790,7 +1817,8 @@ int mfft_dev_combine_window(limb_t *res, uint64_t total, const limb_t *slab, uin
    uint32_t *tileP = tileG + ntiles + 32 - (ntiles % 32);
    uint32_t *tileC = tileP + ntiles + 32 - (ntiles % 32);
    PROF(PC_COMBINE, st);
-   MFFT_LAUNCH(k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef, base_bit);
+   MFFT_LAUNCH(k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef, base_bit,
+               (int)(base_bit + (total + 2) * 64 < 0xffffff00ull && bits < 0xffffffffull));
    CKL();
    MFFT_LAUNCH(k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);
    CKL();

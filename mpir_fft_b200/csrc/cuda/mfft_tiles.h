@@ -672,6 +672,13 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
       }
    }
    __syncthreads();                                   /* the position list is read by everybody below */
+#ifndef MFFT_EMU
+   /* programmatic dependent launch: when the launch carries the stream-serialisation attribute this
+      CTA may have been scheduled (and its descriptors staged) while the previous pass was still
+      draining; nothing written by that pass is read above.  Without the attribute both are no-ops. */
+   asm volatile("griddepcontrol.wait;" ::: "memory");
+   asm volatile("griddepcontrol.launch_dependents;");
+#endif
    /* load the positions that are read before being written: the body as it is, carry words 0
       except the last one, which is the block's signed top limb */
    const bool al16 = ((g.pitch & 1u) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15u) == 0) &&

@@ -14,3 +14,12 @@ PY
 done
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_a.log 2> gpurun_out/bench_a.err; echo "bench rc=$?"
 tail -c 2500 gpurun_out/bench_a.log
+MPIRFFT_PDL=1 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pdl.log 2> gpurun_out/bench_pdl.err; echo "bench pdl rc=$?"
+python - <<PY
+import json
+for f in ("bench_a", "bench_pdl"):
+    l=[x for x in open("gpurun_out/%s.log" % f) if x.startswith("{")]
+    d=json.loads(l[-1]); print(f, d["ms_per_step"], d["e2e"]["ms_per_step"], d["phases"]["stage"], d["roofline"]["frac"], d["bit_exact_vs_gmp"])
+PY
+MPIRFFT_PDL=1 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_pdl.log 2>&1; echo "pytest pdl rc=$?"
+tail -3 gpurun_out/pytest_pdl.log

@@ -138,6 +138,8 @@ static inline void __syncthreads()
 
 #define MFFT_LAUNCH(kern, grid, block, smem, stream, ...) \
    emu_launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+#define MFFT_LAUNCH_PDL(on, kern, grid, block, smem, stream, ...) \
+   do { (void)(on); MFFT_LAUNCH(kern, grid, block, smem, stream, __VA_ARGS__); } while (0)
 #define MFFT_DYN_SMEM(type, name) type *name = (type *) emu_dyn_smem()
 
 #endif
