@@ -42,7 +42,27 @@
 #include "mfft_arith.h"
 
 #define FULL 0xffffffffu
-#define MFFT_PDL_DEFAULT 0
+#define MFFT_PDL_DEFAULT 1
+#ifndef PW_UNROLL
+#define PW_UNROLL 4
+#endif
+
+/* programmatic dependent launch (see MFFT_LAUNCH_PDL): first statement of a kernel that may be
+   launched with the stream-serialisation attribute -- nothing the previous kernel wrote is read
+   before it.  No-ops without the attribute. */
+__device__ __forceinline__ void pdl_wait()
+{
+#ifndef MFFT_EMU
+   asm volatile("griddepcontrol.wait;" ::: "memory");
+   asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+static int g_pdl = -1;
+static int pdl_on(void)
+{
+   if (g_pdl < 0) { const char *e = getenv("MPIRFFT_PDL"); g_pdl = e ? (e[0] != '0') : MFFT_PDL_DEFAULT; }
+   return g_pdl;
+}
 
 static char g_err[512] = "";
 static uint64_t g_launches = 0;
@@ -243,6 +263,8 @@ static inline void madc_lo_cc(uint32_t &d, uint32_t a, uint32_t b)
 static inline void madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b)
 { uint64_t v = (((uint64_t) a * b) >> 32) + d + emu_cc; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
 static inline void addc(uint32_t &d) { d += emu_cc; }
+static inline void add_cc(uint32_t &d, uint32_t a) { uint64_t v = (uint64_t) d + a; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
+static inline void addc_cc(uint32_t &d, uint32_t a) { uint64_t v = (uint64_t) d + a + emu_cc; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
 #else
 __device__ __forceinline__ void mad_lo_cc(uint32_t &d, uint32_t a, uint32_t b)
 { asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(a), "r"(b)); }
@@ -252,11 +274,15 @@ __device__ __forceinline__ void madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b)
 { asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(a), "r"(b)); }
 __device__ __forceinline__ void addc(uint32_t &d)
 { asm volatile("addc.u32 %0, %0, 0;" : "+r"(d)); }
+__device__ __forceinline__ void add_cc(uint32_t &d, uint32_t a)
+{ asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(d) : "r"(a)); }
+__device__ __forceinline__ void addc_cc(uint32_t &d, uint32_t a)
+{ asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(d) : "r"(a)); }
 #endif
 
 /* P += x*y for two H-word blocks (H even), P = sum e[k] 2^(32k) + sum o[k] 2^(32(k+1)) + sum kc[i] 2^(32(H+i)):
  * H rows of two IMAD.WIDE.U32.X chains (even / odd word offsets), final carries counted in kc[] */
-template <int H>
+template <int H, bool SPLIT = false>
 __device__ __forceinline__ void mac_block(uint32_t (&e)[2 * H + 2], uint32_t (&o)[2 * H + 2], uint32_t (&kc)[H + 2],
                                           const uint32_t (&x)[H], const uint32_t (&y)[H])
 {
@@ -264,6 +290,28 @@ __device__ __forceinline__ void mac_block(uint32_t (&e)[2 * H + 2], uint32_t (&o
    for (int j = 0; j < H; j++)
    {
       const uint32_t yj = y[j];
+      if constexpr (SPLIT)
+      {  /* experiment: plain IMAD.WIDE.U32 products (twice the issue rate of the .X carry-chain form)
+            and the carry chains as IADD3.X on the ALU pipe */
+         uint64_t p[H];
+#pragma unroll
+         for (int t = 0; t < H; t++) p[t] = (uint64_t) x[t] * yj;
+         {
+            const int t0 = j & 1;
+            add_cc(e[t0 + j], (uint32_t) p[t0]); addc_cc(e[t0 + j + 1], (uint32_t)(p[t0] >> 32));
+#pragma unroll
+            for (int t = t0 + 2; t < H; t += 2) { addc_cc(e[t + j], (uint32_t) p[t]); addc_cc(e[t + j + 1], (uint32_t)(p[t] >> 32)); }
+            addc(kc[j + (j & 1)]);
+         }
+         {
+            const int t0 = 1 - (j & 1);
+            add_cc(o[t0 + j - 1], (uint32_t) p[t0]); addc_cc(o[t0 + j], (uint32_t)(p[t0] >> 32));
+#pragma unroll
+            for (int t = t0 + 2; t < H; t += 2) { addc_cc(o[t + j - 1], (uint32_t) p[t]); addc_cc(o[t + j], (uint32_t)(p[t] >> 32)); }
+            addc(kc[j + 1 - (j & 1)]);
+         }
+         continue;
+      }
       {
          const int t0 = j & 1;
          mad_lo_cc(e[t0 + j], x[t0], yj); madc_hi_cc(e[t0 + j + 1], x[t0], yj);
@@ -342,11 +390,12 @@ __device__ __forceinline__ void suffix_block_sums(uint32_t (&S)[C + 1], const ui
  * block); b0+b1 is recomputed after every rotation (the complement of a wrapped block is not the
  * complement of its half-sum).  The additions go to the ALU pipe, next to the IMAD pipe the products
  * keep busy. */
-template <int C, bool KARA, int MINB = 1>
+template <int C, bool KARA, int MINB = 1, bool SPLIT = false, int UNR = 4>
 __global__ void __launch_bounds__(128, MINB)
 k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
             uint32_t nblk, uint32_t l, uint32_t pitch)
 {
+   pdl_wait();
    MFFT_DYN_SMEM(uint32_t, smem);
    constexpr int H = C / 2;
    constexpr int WSM = KARA ? 32 * (C + H + 1) : 32 * C;       /* shared words per warp */
@@ -416,15 +465,16 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
 #pragma unroll
       for (int i = 0; i <= H; i++) UV[i] = 0;
 
+#pragma unroll UNR
       for (uint32_t s = 0; s < 32; s++)
       {
          uint32_t x[H], y[H];
 #pragma unroll
          for (int i = 0; i < H; i++) { x[i] = sA[s * C + i]; y[i] = b[i]; }
-         mac_block<H>(eL, oL, kL, x, y);
+         mac_block<H, SPLIT>(eL, oL, kL, x, y);
 #pragma unroll
          for (int i = 0; i < H; i++) { x[i] = sA[s * C + H + i]; y[i] = b[H + i]; }
-         mac_block<H>(eH, oH, kH, x, y);
+         mac_block<H, SPLIT>(eH, oH, kH, x, y);
          uint64_t cy = 0;
 #pragma unroll
          for (int i = 0; i < H; i++)
@@ -434,7 +484,7 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
             x[i] = sAs[s * (H + 1) + i];
          }
          const uint32_t cb = (uint32_t) cy, ca = sAs[s * (H + 1) + H];
-         mac_block<H>(eM, oM, kM, x, y);
+         mac_block<H, SPLIT>(eM, oM, kM, x, y);
          /* carry bits of the two sums: UV += ca*ys + cb*xs, n2 += ca*cb */
          const uint32_t ma = 0u - ca, mb = 0u - cb;
          cy = 0;
@@ -475,6 +525,7 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
 #pragma unroll
    for (int i = 0; i < C + 2; i++) kc[i] = 0;
 
+#pragma unroll UNR
    for (uint32_t s = 0; s < 32; s++)
    {
       uint32_t ab[C];
@@ -1038,6 +1089,7 @@ __global__ void __launch_bounds__(256)
 k_combine_sum(limb_t *res, uint32_t *cvec, uint64_t total, const limb_t *__restrict__ slab,
               uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef, uint64_t base_bit, int small)
 {
+   pdl_wait();
    const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
    if (k > total) return;
    if (k == 0) cvec[0] = 0;
@@ -1079,6 +1131,7 @@ __global__ void __launch_bounds__(128)
 k_combine_add(limb_t *res, const uint32_t *__restrict__ cvec, uint64_t total, uint32_t *tileG,
               uint32_t *tileP, uint64_t ntiles)
 {
+   pdl_wait();
    const uint64_t tile = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    const uint32_t lane = threadIdx.x & 31;
    if (tile >= ntiles) return;
@@ -1122,6 +1175,7 @@ __global__ void __launch_bounds__(1024)
 k_combine_scan(const uint32_t *__restrict__ tileG, const uint32_t *__restrict__ tileP,
                uint32_t *tileC, uint64_t ntiles, const uint32_t *__restrict__ cvec_last, uint32_t *carry_out)
 {
+   pdl_wait();
    __shared__ uint32_t sG[32], sP[32], sC[33];
    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
    const uint64_t per = (((ntiles + nwarps - 1) / nwarps + 31) / 32) * 32;     /* tiles per group, multiple of 32 */
@@ -1164,6 +1218,7 @@ k_combine_scan(const uint32_t *__restrict__ tileG, const uint32_t *__restrict__ 
 __global__ void __launch_bounds__(128)
 k_combine_fix(limb_t *res, uint64_t total, const uint32_t *__restrict__ tileC, uint64_t ntiles)
 {
+   pdl_wait();
    const uint64_t tile = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    const uint32_t lane = threadIdx.x & 31;
    if (tile >= ntiles) return;
@@ -1601,8 +1656,7 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
       }
    }
    if (h_batch && nbatch <= TP_MAXB) { memcpy(tp.batch, h_batch, sizeof(mfft_batch) * nbatch); tp.batch_valid = 1; }
-   static int pdl = -1;
-   if (pdl < 0) { const char *e = getenv("MPIRFFT_PDL"); pdl = e ? (e[0] != '0') : MFFT_PDL_DEFAULT; }
+   const int pdl = pdl_on();
    PROF(PC_STAGE, st);
    /* two CTAs per SM: 16 warps x 64 registers while a lane holds <= 4 chunk pairs of an op, else
       8 warps x 128 registers (fewer, larger coefficients per tile) */
@@ -1677,7 +1731,7 @@ int mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, 
 
 static limb_t *g_pw_scratch = NULL; static size_t g_pw_scratch_bytes = 0;
 static int g_pw_mode = -1;     /* 0 auto, 1 nested SS, 2 Karatsuba blocks, 3 schoolbook blocks */
-#define PW_KARA_DEFAULT(l) (0)
+#define PW_KARA_DEFAULT(l) ((l) == 256 || (l) == 128)
 void mfft_dev_pointwise_mode(int mode) { g_pw_mode = mode; }
 
 int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uint32_t nblk,
@@ -1694,7 +1748,7 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
          slower, 0.91 ms: ptxas never emits IMAD.WIDE with a non-zero 64-bit addend on sm_100a, it
          splits every mad.wide.u32 into IMAD.WIDE(.., RZ) + IADD3 + IADD3.X, so the real ceiling for
          32x32->64 multiply-ADDs is the ~31/clk/SM of the IMAD.WIDE.U32.X chains used here.) */
-      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = !e ? 0 : e[0] == 's' ? 1 : e[0] == 'k' ? 2 : e[0] == 'd' ? 3 : e[0] == 'K' ? 4 : 0; }
+      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = !e ? 0 : e[0] == 's' ? 1 : e[0] == 'k' ? 2 : e[0] == 'd' ? 3 : e[0] == 'K' ? 4 : e[0] == 'a' ? 5 : 0; }
       uint32_t np = 0, lp = 0;
       if (g_pw_mode == 1)
       {
@@ -1718,15 +1772,23 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
          return 0;
       }
    }
-#define PW_SCHOOL(CC) MFFT_LAUNCH((k_pointwise<CC, false>), grid, 128, 4 * 32 * CC * 4, st, a, b, d_blocks, nblk, l, pitch)
-#define PW_KARA(CC)   MFFT_LAUNCH((k_pointwise<CC, true>), grid, 128, 4 * 32 * (CC + CC / 2 + 1) * 4, st, a, b, d_blocks, nblk, l, pitch)
+   static int unr = -1;        /* step-loop unroll factor (tuning aid): MPIRFFT_PW_UNROLL = 1, 2, 4, 8; default 4 */
+   if (unr < 0) { const char *e = getenv("MPIRFFT_PW_UNROLL"); unr = e ? atoi(e) : 0; }
+   const int u = (unr == 0 && l == 512) ? 1 : unr;   /* l = 512: 252 registers already, unrolling only adds spills (measured: no gain) */
+#define PW_SCHOOL(CC) do { if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, false, 1, false, 1>), grid, 128, 4 * 32 * CC * 4, st, a, b, d_blocks, nblk, l, pitch); \
+                           else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, false, 1, false, 4>), grid, 128, 4 * 32 * CC * 4, st, a, b, d_blocks, nblk, l, pitch); } while (0)
+#define PW_KARA(CC)   MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, true>), grid, 128, 4 * 32 * (CC + CC / 2 + 1) * 4, st, a, b, d_blocks, nblk, l, pitch)
    const bool kara = (g_pw_mode == 2) || (g_pw_mode == 0 && PW_KARA_DEFAULT(l));
    if (l == 64)       { if (kara) PW_KARA(4); else PW_SCHOOL(4); }
    else if (l == 128) { if (kara) PW_KARA(8); else PW_SCHOOL(8); }
    else if (l == 256)
    {
-      if (g_pw_mode == 4) MFFT_LAUNCH((k_pointwise<16, true, 3>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
-      else if (kara) PW_KARA(16); else PW_SCHOOL(16);
+#define PW256(KA, SP, UN) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, KA, 1, SP, UN>), grid, 128, 4 * 32 * (KA ? 25 : 16) * 4, st, a, b, d_blocks, nblk, l, pitch)
+      if (g_pw_mode == 5) PW256(true, true, 4);
+      else if (g_pw_mode == 4) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 3>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
+      else if (kara) { if (u == 1) PW256(true, false, 1); else if (u == 2) PW256(true, false, 2); else if (u == 8) PW256(true, false, 8); else PW256(true, false, 4); }
+      else { if (u == 1) PW256(false, false, 1); else if (u == 2) PW256(false, false, 2); else if (u == 8) PW256(false, false, 8); else PW256(false, false, 4); }
+#undef PW256
    }
    else if (l == 512) PW_SCHOOL(32);
    else
@@ -1817,14 +1879,14 @@ int mfft_dev_combine_window(limb_t *res, uint64_t total, const limb_t *slab, uin
    uint32_t *tileP = tileG + ntiles + 32 - (ntiles % 32);
    uint32_t *tileC = tileP + ntiles + 32 - (ntiles % 32);
    PROF(PC_COMBINE, st);
-   MFFT_LAUNCH(k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef, base_bit,
+   MFFT_LAUNCH_PDL(pdl_on(), k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef, base_bit,
                (int)(base_bit + (total + 2) * 64 < 0xffffff00ull && bits < 0xffffffffull));
    CKL();
-   MFFT_LAUNCH(k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);
+   MFFT_LAUNCH_PDL(pdl_on(), k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);
    CKL();
-   MFFT_LAUNCH(k_combine_scan, 1, 1024, 0, st, tileG, tileP, tileC, ntiles, cvec + total, d_carry_out);
+   MFFT_LAUNCH_PDL(pdl_on(), k_combine_scan, 1, 1024, 0, st, tileG, tileP, tileC, ntiles, cvec + total, d_carry_out);
    CKL();
-   MFFT_LAUNCH(k_combine_fix, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, total, tileC, ntiles);
+   MFFT_LAUNCH_PDL(pdl_on(), k_combine_fix, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, total, tileC, ntiles);
    CKL();
    return 0;
 }

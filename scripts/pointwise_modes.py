@@ -18,15 +18,19 @@ from bench import splitmix64                                 # noqa: E402
 
 M.init(0); L = M.lib()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for name, (n1, n2, depth, w) in {"l64": (1 << 16, 1 << 16, 12, 1), "l128": (1 << 18, 1 << 18, 13, 1),
-                                 "l256 (cfg2)": (1 << 20, 1 << 20, 14, 1)}.items():
+CASES = {"l64": (1 << 16, 1 << 16, 12, 1), "l128": (1 << 18, 1 << 18, 13, 1), "l256 (cfg2)": (1 << 20, 1 << 20, 14, 1)}
+if len(sys.argv) > 1 and sys.argv[1] == "cfg2":
+    CASES = {"l256 (cfg2)": CASES["l256 (cfg2)"]}
+if len(sys.argv) > 1 and sys.argv[1] == "others":
+    CASES = {"l64": CASES["l64"], "l128": CASES["l128"], "l512 (cfg3)": (3000000, 1700000, 14, 2)}
+for name, (n1, n2, depth, w) in CASES.items():
     a_h, b_h = splitmix64(11, n1), splitmix64(12, n2)
     want = oracle.gmp_mul(a_h, b_h)
     a = torch.from_numpy(a_h.view(np.int64)).cuda(); b = torch.from_numpy(b_h.view(np.int64)).cuda()
     r = torch.zeros(n1 + n2, dtype=torch.int64, device="cuda")
     plan = M.MulPlan(n1, n2, depth, w)
-    for mode in (3, 2, 4):
-        if mode == 4 and plan.params["limbs"] != 256:
+    for mode in ((3, 2) if (len(sys.argv) > 1 and sys.argv[1] == "others") else (3, 2, 4, 5)):
+        if mode in (4, 5) and plan.params["limbs"] != 256:
             continue
         L.mpirfft_set_pointwise_mode(mode)
         for _ in range(3):
@@ -45,7 +49,7 @@ for name, (n1, n2, depth, w) in {"l64": (1 << 16, 1 << 16, 12, 1), "l128": (1 <<
             flush.zero_(); plan.exec_device(r.data_ptr(), a.data_ptr(), b.data_ptr(), None)
         L.mpirfft_profile_read(ms, ln, by, 6); L.mpirfft_profile_enable(0)
         print(json.dumps({"workload": name, "limbs": plan.params["limbs"], "products": plan.params["trunc"],
-                          "mode": {3: "schoolbook", 2: "karatsuba", 4: "karatsuba, 3 CTAs/SM"}[mode],
-                          "pointwise_ms": ms[2] / 5, "product_ms": tot / reps, "bit_exact_vs_gmp": ok}), flush=True)
+                          "mode": {3: "schoolbook", 2: "karatsuba", 4: "karatsuba, 3 CTAs/SM", 5: "karatsuba, IMAD.WIDE + IADD3.X chains"}[mode],
+                          "unroll": os.environ.get("MPIRFFT_PW_UNROLL", "4"), "pointwise_ms": ms[2] / 5, "product_ms": tot / reps, "bit_exact_vs_gmp": ok}), flush=True)
     L.mpirfft_set_pointwise_mode(0)
     plan.close()
