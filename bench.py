@@ -377,15 +377,22 @@ def main():
         try:
             L.mpirfft_measure_imad_rate.restype = C.c_double
             imad_chain = float(L.mpirfft_measure_imad_rate(1))      # IMAD.WIDE.U32.X carry chains (what the kernel issues)
-            imad_wide = float(L.mpirfft_measure_imad_rate(0))       # IMAD.WIDE.U32 multiplies, accumulation split off to the ALU pipe by ptxas
+            imad_wide = float(L.mpirfft_measure_imad_rate(0))       # IMAD.WIDE.U32(.., RZ) + IADD3 + IADD3.X: the split form ptxas emits for mad.wide.u32
             pw_ms = phases["pointwise"]["ms_per_product"]
             if pw_ms > 0 and imad_chain > 0:
-                ach = phases["pointwise_mad32_per_product"] / (pw_ms * 1e-3)
-                roofline_pw = {"kernel": "k_pointwise (schoolbook 32x32->64 multiply-add chains)", "bound": "imad",
-                               "achieved": ach / 1e12, "peak": imad_chain / 1e12, "unit": "Tmad32/s",
-                               "frac": ach / imad_chain, "imad_wide_multiply_only_rate": imad_wide / 1e12,
-                               "note": "peak = fused multiply-add chains (IMAD.WIDE.U32.X), the only fused 32x32+64 form "
-                                       "ptxas emits on sm_100a; mad.wide.u32 is split into IMAD.WIDE(..,RZ) + 2 IADD3",
+                school = phases["pointwise_mad32_per_product"] / (pw_ms * 1e-3)
+                # l = 128 / 256: every block product is split once (Karatsuba): 3/4 of the multiply-adds are issued
+                kara = prm["limbs"] in (128, 256) and os.environ.get("MPIRFFT_POINTWISE", "") in ("", "k")
+                issued = school * (0.75 if kara else 1.0)
+                roofline_pw = {"kernel": "k_pointwise (%s block products, 32x32->64 multiply-add carry chains)" % (
+                                   "Karatsuba-split" if kara else "schoolbook"), "bound": "imad",
+                               "achieved": issued / 1e12, "peak": imad_chain / 1e12, "unit": "Tmad32/s",
+                               "frac": issued / imad_chain,
+                               "schoolbook_equivalent": school / 1e12, "schoolbook_equivalent_frac": school / imad_chain,
+                               "imad_wide_plus_iadd3_rate": imad_wide / 1e12,
+                               "note": "achieved = multiply-adds actually issued (utilisation); schoolbook_equivalent = 4 l^2 per "
+                                       "product / time (effective).  peak = IMAD.WIDE.U32.X carry chains, the only fused "
+                                       "32x32+64 form ptxas emits on sm_100a (mad.wide.u32 becomes IMAD.WIDE(..,RZ) + IADD3 + IADD3.X)",
                                "peak_source": "measured in this run (csrc/cuda/imad_peak.cu)"}
         except Exception:
             roofline_pw = None

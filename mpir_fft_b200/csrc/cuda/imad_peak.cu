@@ -19,14 +19,19 @@ __global__ void __launch_bounds__(256) k_imad(uint32_t *out, uint32_t x, uint32_
    uint32_t a = x + threadIdx.x, b = y + blockIdx.x;
 #pragma unroll
    for (int i = 0; i < 8; i++) acc[i] = i + threadIdx.x;
+   uint32_t xs[8];
+#pragma unroll
+   for (int i = 0; i < 8; i++) xs[i] = x * (2 * i + 3) + threadIdx.x;
    for (int it = 0; it < iters; it++)
    {
       if (MODE == 0)
-      {
+      {  /* sixteen DIFFERENT products per iteration (x[i]*b, x[i]*c), factors changing every
+            iteration: nothing can be hoisted or shared between accumulators */
 #pragma unroll
-         for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+         for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(xs[i]), "r"(b));
 #pragma unroll
-         for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(b), "r"(a));
+         for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(xs[i]), "r"(a));
+         a += 0x9e3779b9u; b ^= a;
       } else if (MODE == 1)
       {
          uint32_t *w = (uint32_t *) acc;

@@ -329,6 +329,27 @@ __device__ __forceinline__ void mac_block(uint32_t (&e)[2 * H + 2], uint32_t (&o
    }
 }
 
+/* row j of mac_block (two carry chains) */
+template <int H>
+__device__ __forceinline__ void mac_row(uint32_t (&e)[2 * H + 2], uint32_t (&o)[2 * H + 2], uint32_t (&kc)[H + 2],
+                                        const uint32_t (&x)[H], const uint32_t yj, const int j)
+{
+   {
+      const int t0 = j & 1;
+      mad_lo_cc(e[t0 + j], x[t0], yj); madc_hi_cc(e[t0 + j + 1], x[t0], yj);
+#pragma unroll
+      for (int t = t0 + 2; t < H; t += 2) { madc_lo_cc(e[t + j], x[t], yj); madc_hi_cc(e[t + j + 1], x[t], yj); }
+      addc(kc[j + (j & 1)]);
+   }
+   {
+      const int t0 = 1 - (j & 1);
+      mad_lo_cc(o[t0 + j - 1], x[t0], yj); madc_hi_cc(o[t0 + j], x[t0], yj);
+#pragma unroll
+      for (int t = t0 + 2; t < H; t += 2) { madc_lo_cc(o[t + j - 1], x[t], yj); madc_hi_cc(o[t + j], x[t], yj); }
+      addc(kc[j + 1 - (j & 1)]);
+   }
+}
+
 /* word k of the accumulator triple of mac_block, as a non-negative 64-bit value */
 template <int H>
 __device__ __forceinline__ int64_t mac_word(const uint32_t (&e)[2 * H + 2], const uint32_t (&o)[2 * H + 2],
@@ -390,7 +411,7 @@ __device__ __forceinline__ void suffix_block_sums(uint32_t (&S)[C + 1], const ui
  * block); b0+b1 is recomputed after every rotation (the complement of a wrapped block is not the
  * complement of its half-sum).  The additions go to the ALU pipe, next to the IMAD pipe the products
  * keep busy. */
-template <int C, bool KARA, int MINB = 1, bool SPLIT = false, int UNR = 4>
+template <int C, bool KARA, int MINB = 1, bool SPLIT = false, int UNR = 4, int KORD = 0>
 __global__ void __launch_bounds__(128, MINB)
 k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
             uint32_t nblk, uint32_t l, uint32_t pitch)
@@ -469,25 +490,55 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
       for (uint32_t s = 0; s < 32; s++)
       {
          uint32_t x[H], y[H];
-#pragma unroll
-         for (int i = 0; i < H; i++) { x[i] = sA[s * C + i]; y[i] = b[i]; }
-         mac_block<H, SPLIT>(eL, oL, kL, x, y);
-#pragma unroll
-         for (int i = 0; i < H; i++) { x[i] = sA[s * C + H + i]; y[i] = b[H + i]; }
-         mac_block<H, SPLIT>(eH, oH, kH, x, y);
-         uint64_t cy = 0;
-#pragma unroll
-         for (int i = 0; i < H; i++)
+         uint32_t cb, ca;
+         if constexpr (KORD == 0)
          {
-            const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
-            y[i] = (uint32_t) v; cy = v >> 32;
-            x[i] = sAs[s * (H + 1) + i];
+#pragma unroll
+            for (int i = 0; i < H; i++) { x[i] = sA[s * C + i]; y[i] = b[i]; }
+            mac_block<H, SPLIT>(eL, oL, kL, x, y);
+#pragma unroll
+            for (int i = 0; i < H; i++) { x[i] = sA[s * C + H + i]; y[i] = b[H + i]; }
+            mac_block<H, SPLIT>(eH, oH, kH, x, y);
+            uint64_t cy = 0;
+#pragma unroll
+            for (int i = 0; i < H; i++)
+            {
+               const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
+               y[i] = (uint32_t) v; cy = v >> 32;
+               x[i] = sAs[s * (H + 1) + i];
+            }
+            cb = (uint32_t) cy; ca = sAs[s * (H + 1) + H];
+            mac_block<H, SPLIT>(eM, oM, kM, x, y);
+         } else
+         {  /* rows of the independent products next to each other in program order: more carry
+               chains for ptxas to interleave (2 warps per scheduler do not hide the IMAD latency) */
+            uint32_t x0[H], x1[H];
+#pragma unroll
+            for (int i = 0; i < H; i++) { x0[i] = sA[s * C + i]; x1[i] = sA[s * C + H + i]; }
+            uint64_t cy = 0;
+#pragma unroll
+            for (int i = 0; i < H; i++)
+            {
+               const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
+               y[i] = (uint32_t) v; cy = v >> 32;
+               x[i] = sAs[s * (H + 1) + i];
+            }
+            cb = (uint32_t) cy; ca = sAs[s * (H + 1) + H];
+            if constexpr (KORD == 1)
+            {
+#pragma unroll
+               for (int j = 0; j < H; j++) { mac_row<H>(eL, oL, kL, x0, b[j], j); mac_row<H>(eH, oH, kH, x1, b[H + j], j); }
+               mac_block<H, SPLIT>(eM, oM, kM, x, y);
+            } else
+            {
+#pragma unroll
+               for (int j = 0; j < H; j++)
+               { mac_row<H>(eL, oL, kL, x0, b[j], j); mac_row<H>(eH, oH, kH, x1, b[H + j], j); mac_row<H>(eM, oM, kM, x, y[j], j); }
+            }
          }
-         const uint32_t cb = (uint32_t) cy, ca = sAs[s * (H + 1) + H];
-         mac_block<H, SPLIT>(eM, oM, kM, x, y);
          /* carry bits of the two sums: UV += ca*ys + cb*xs, n2 += ca*cb */
          const uint32_t ma = 0u - ca, mb = 0u - cb;
-         cy = 0;
+         uint64_t cy = 0;
 #pragma unroll
          for (int i = 0; i < H; i++)
          {
@@ -1784,7 +1835,11 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
    else if (l == 256)
    {
 #define PW256(KA, SP, UN) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, KA, 1, SP, UN>), grid, 128, 4 * 32 * (KA ? 25 : 16) * 4, st, a, b, d_blocks, nblk, l, pitch)
-      if (g_pw_mode == 5) PW256(true, true, 4);
+      if (g_pw_mode == 6) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 1, false, 4, 1>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
+      else if (g_pw_mode == 7) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 1, false, 4, 2>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
+      else if (g_pw_mode == 8) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 1, false, 2, 1>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
+      else if (g_pw_mode == 9) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 1, false, 2, 2>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
+      else if (g_pw_mode == 5) PW256(true, true, 4);
       else if (g_pw_mode == 4) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 3>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
       else if (kara) { if (u == 1) PW256(true, false, 1); else if (u == 2) PW256(true, false, 2); else if (u == 8) PW256(true, false, 8); else PW256(true, false, 4); }
       else { if (u == 1) PW256(false, false, 1); else if (u == 2) PW256(false, false, 2); else if (u == 8) PW256(false, false, 8); else PW256(false, false, 4); }
