@@ -235,8 +235,8 @@ mp_limb_t *mpirfft_smul_tail_blocks(mpirfft_smul_plan *plan, unsigned count);
  * kernel; its block products are Karatsuba-split at l = 128 and 256, schoolbook otherwise),
  * 1 = nested Schoenhage-Strassen step inside a warp (the fft_mulmod_2expp1 idea, mul_fft.c:3125-3167)
  * for l in {64,128,256,512}, 2 = Karatsuba-split blocks wherever built (l = 64, 128, 256),
- * 3 = schoolbook blocks everywhere.  4 and 5 are tuning variants of 2 at l = 256.  Every mode is
- * bit-exact; the choice only moves time.  Environment: MPIRFFT_POINTWISE = s | k | d. */
+ * 3 = schoolbook blocks everywhere.  Every mode is bit-exact; the choice only moves time.
+ * Environment: MPIRFFT_POINTWISE = s | k | d. */
 void mpirfft_set_pointwise_mode(int mode);
 
 /* device memory helpers (so that a host language needs nothing but this ABI) */

@@ -263,8 +263,6 @@ static inline void madc_lo_cc(uint32_t &d, uint32_t a, uint32_t b)
 static inline void madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b)
 { uint64_t v = (((uint64_t) a * b) >> 32) + d + emu_cc; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
 static inline void addc(uint32_t &d) { d += emu_cc; }
-static inline void add_cc(uint32_t &d, uint32_t a) { uint64_t v = (uint64_t) d + a; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
-static inline void addc_cc(uint32_t &d, uint32_t a) { uint64_t v = (uint64_t) d + a + emu_cc; d = (uint32_t) v; emu_cc = (uint32_t)(v >> 32); }
 #else
 __device__ __forceinline__ void mad_lo_cc(uint32_t &d, uint32_t a, uint32_t b)
 { asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(a), "r"(b)); }
@@ -274,15 +272,11 @@ __device__ __forceinline__ void madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b)
 { asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(a), "r"(b)); }
 __device__ __forceinline__ void addc(uint32_t &d)
 { asm volatile("addc.u32 %0, %0, 0;" : "+r"(d)); }
-__device__ __forceinline__ void add_cc(uint32_t &d, uint32_t a)
-{ asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(d) : "r"(a)); }
-__device__ __forceinline__ void addc_cc(uint32_t &d, uint32_t a)
-{ asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(d) : "r"(a)); }
 #endif
 
 /* P += x*y for two H-word blocks (H even), P = sum e[k] 2^(32k) + sum o[k] 2^(32(k+1)) + sum kc[i] 2^(32(H+i)):
  * H rows of two IMAD.WIDE.U32.X chains (even / odd word offsets), final carries counted in kc[] */
-template <int H, bool SPLIT = false>
+template <int H>
 __device__ __forceinline__ void mac_block(uint32_t (&e)[2 * H + 2], uint32_t (&o)[2 * H + 2], uint32_t (&kc)[H + 2],
                                           const uint32_t (&x)[H], const uint32_t (&y)[H])
 {
@@ -290,28 +284,6 @@ __device__ __forceinline__ void mac_block(uint32_t (&e)[2 * H + 2], uint32_t (&o
    for (int j = 0; j < H; j++)
    {
       const uint32_t yj = y[j];
-      if constexpr (SPLIT)
-      {  /* experiment: plain IMAD.WIDE.U32 products (twice the issue rate of the .X carry-chain form)
-            and the carry chains as IADD3.X on the ALU pipe */
-         uint64_t p[H];
-#pragma unroll
-         for (int t = 0; t < H; t++) p[t] = (uint64_t) x[t] * yj;
-         {
-            const int t0 = j & 1;
-            add_cc(e[t0 + j], (uint32_t) p[t0]); addc_cc(e[t0 + j + 1], (uint32_t)(p[t0] >> 32));
-#pragma unroll
-            for (int t = t0 + 2; t < H; t += 2) { addc_cc(e[t + j], (uint32_t) p[t]); addc_cc(e[t + j + 1], (uint32_t)(p[t] >> 32)); }
-            addc(kc[j + (j & 1)]);
-         }
-         {
-            const int t0 = 1 - (j & 1);
-            add_cc(o[t0 + j - 1], (uint32_t) p[t0]); addc_cc(o[t0 + j], (uint32_t)(p[t0] >> 32));
-#pragma unroll
-            for (int t = t0 + 2; t < H; t += 2) { addc_cc(o[t + j - 1], (uint32_t) p[t]); addc_cc(o[t + j], (uint32_t)(p[t] >> 32)); }
-            addc(kc[j + 1 - (j & 1)]);
-         }
-         continue;
-      }
       {
          const int t0 = j & 1;
          mad_lo_cc(e[t0 + j], x[t0], yj); madc_hi_cc(e[t0 + j + 1], x[t0], yj);
@@ -326,27 +298,6 @@ __device__ __forceinline__ void mac_block(uint32_t (&e)[2 * H + 2], uint32_t (&o
          for (int t = t0 + 2; t < H; t += 2) { madc_lo_cc(o[t + j - 1], x[t], yj); madc_hi_cc(o[t + j], x[t], yj); }
          addc(kc[j + 1 - (j & 1)]);
       }
-   }
-}
-
-/* row j of mac_block (two carry chains) */
-template <int H>
-__device__ __forceinline__ void mac_row(uint32_t (&e)[2 * H + 2], uint32_t (&o)[2 * H + 2], uint32_t (&kc)[H + 2],
-                                        const uint32_t (&x)[H], const uint32_t yj, const int j)
-{
-   {
-      const int t0 = j & 1;
-      mad_lo_cc(e[t0 + j], x[t0], yj); madc_hi_cc(e[t0 + j + 1], x[t0], yj);
-#pragma unroll
-      for (int t = t0 + 2; t < H; t += 2) { madc_lo_cc(e[t + j], x[t], yj); madc_hi_cc(e[t + j + 1], x[t], yj); }
-      addc(kc[j + (j & 1)]);
-   }
-   {
-      const int t0 = 1 - (j & 1);
-      mad_lo_cc(o[t0 + j - 1], x[t0], yj); madc_hi_cc(o[t0 + j], x[t0], yj);
-#pragma unroll
-      for (int t = t0 + 2; t < H; t += 2) { madc_lo_cc(o[t + j - 1], x[t], yj); madc_hi_cc(o[t + j], x[t], yj); }
-      addc(kc[j + 1 - (j & 1)]);
    }
 }
 
@@ -411,8 +362,8 @@ __device__ __forceinline__ void suffix_block_sums(uint32_t (&S)[C + 1], const ui
  * block); b0+b1 is recomputed after every rotation (the complement of a wrapped block is not the
  * complement of its half-sum).  The additions go to the ALU pipe, next to the IMAD pipe the products
  * keep busy. */
-template <int C, bool KARA, int MINB = 1, bool SPLIT = false, int UNR = 4, int KORD = 0>
-__global__ void __launch_bounds__(128, MINB)
+template <int C, bool KARA, int UNR>
+__global__ void __launch_bounds__(128, 1)
 k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
             uint32_t nblk, uint32_t l, uint32_t pitch)
 {
@@ -490,55 +441,25 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
       for (uint32_t s = 0; s < 32; s++)
       {
          uint32_t x[H], y[H];
-         uint32_t cb, ca;
-         if constexpr (KORD == 0)
+#pragma unroll
+         for (int i = 0; i < H; i++) { x[i] = sA[s * C + i]; y[i] = b[i]; }
+         mac_block<H>(eL, oL, kL, x, y);
+#pragma unroll
+         for (int i = 0; i < H; i++) { x[i] = sA[s * C + H + i]; y[i] = b[H + i]; }
+         mac_block<H>(eH, oH, kH, x, y);
+         uint64_t cy = 0;
+#pragma unroll
+         for (int i = 0; i < H; i++)
          {
-#pragma unroll
-            for (int i = 0; i < H; i++) { x[i] = sA[s * C + i]; y[i] = b[i]; }
-            mac_block<H, SPLIT>(eL, oL, kL, x, y);
-#pragma unroll
-            for (int i = 0; i < H; i++) { x[i] = sA[s * C + H + i]; y[i] = b[H + i]; }
-            mac_block<H, SPLIT>(eH, oH, kH, x, y);
-            uint64_t cy = 0;
-#pragma unroll
-            for (int i = 0; i < H; i++)
-            {
-               const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
-               y[i] = (uint32_t) v; cy = v >> 32;
-               x[i] = sAs[s * (H + 1) + i];
-            }
-            cb = (uint32_t) cy; ca = sAs[s * (H + 1) + H];
-            mac_block<H, SPLIT>(eM, oM, kM, x, y);
-         } else
-         {  /* rows of the independent products next to each other in program order: more carry
-               chains for ptxas to interleave (2 warps per scheduler do not hide the IMAD latency) */
-            uint32_t x0[H], x1[H];
-#pragma unroll
-            for (int i = 0; i < H; i++) { x0[i] = sA[s * C + i]; x1[i] = sA[s * C + H + i]; }
-            uint64_t cy = 0;
-#pragma unroll
-            for (int i = 0; i < H; i++)
-            {
-               const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
-               y[i] = (uint32_t) v; cy = v >> 32;
-               x[i] = sAs[s * (H + 1) + i];
-            }
-            cb = (uint32_t) cy; ca = sAs[s * (H + 1) + H];
-            if constexpr (KORD == 1)
-            {
-#pragma unroll
-               for (int j = 0; j < H; j++) { mac_row<H>(eL, oL, kL, x0, b[j], j); mac_row<H>(eH, oH, kH, x1, b[H + j], j); }
-               mac_block<H, SPLIT>(eM, oM, kM, x, y);
-            } else
-            {
-#pragma unroll
-               for (int j = 0; j < H; j++)
-               { mac_row<H>(eL, oL, kL, x0, b[j], j); mac_row<H>(eH, oH, kH, x1, b[H + j], j); mac_row<H>(eM, oM, kM, x, y[j], j); }
-            }
+            const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
+            y[i] = (uint32_t) v; cy = v >> 32;
+            x[i] = sAs[s * (H + 1) + i];
          }
+         const uint32_t cb = (uint32_t) cy, ca = sAs[s * (H + 1) + H];
+         mac_block<H>(eM, oM, kM, x, y);
          /* carry bits of the two sums: UV += ca*ys + cb*xs, n2 += ca*cb */
          const uint32_t ma = 0u - ca, mb = 0u - cb;
-         uint64_t cy = 0;
+         cy = 0;
 #pragma unroll
          for (int i = 0; i < H; i++)
          {
@@ -1781,7 +1702,7 @@ int mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, 
 }
 
 static limb_t *g_pw_scratch = NULL; static size_t g_pw_scratch_bytes = 0;
-static int g_pw_mode = -1;     /* 0 auto, 1 nested SS, 2 Karatsuba blocks, 3 schoolbook blocks */
+static int g_pw_mode = -1;     /* 0 auto, 1 nested SS, 2 Karatsuba-split blocks, 3 schoolbook blocks */
 #define PW_KARA_DEFAULT(l) ((l) == 256 || (l) == 128)
 void mfft_dev_pointwise_mode(int mode) { g_pw_mode = mode; }
 
@@ -1799,7 +1720,7 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
          slower, 0.91 ms: ptxas never emits IMAD.WIDE with a non-zero 64-bit addend on sm_100a, it
          splits every mad.wide.u32 into IMAD.WIDE(.., RZ) + IADD3 + IADD3.X, so the real ceiling for
          32x32->64 multiply-ADDs is the ~31/clk/SM of the IMAD.WIDE.U32.X chains used here.) */
-      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = !e ? 0 : e[0] == 's' ? 1 : e[0] == 'k' ? 2 : e[0] == 'd' ? 3 : e[0] == 'K' ? 4 : e[0] == 'a' ? 5 : 0; }
+      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = !e ? 0 : e[0] == 's' ? 1 : e[0] == 'k' ? 2 : e[0] == 'd' ? 3 : 0; }
       uint32_t np = 0, lp = 0;
       if (g_pw_mode == 1)
       {
@@ -1823,29 +1744,18 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
          return 0;
       }
    }
-   static int unr = -1;        /* step-loop unroll factor (tuning aid): MPIRFFT_PW_UNROLL = 1, 2, 4, 8; default 4 */
+   static int unr = -1;        /* step-loop unroll factor (tuning aid): MPIRFFT_PW_UNROLL = 1 or 4; default 4 */
    if (unr < 0) { const char *e = getenv("MPIRFFT_PW_UNROLL"); unr = e ? atoi(e) : 0; }
    const int u = (unr == 0 && l == 512) ? 1 : unr;   /* l = 512: 252 registers already, unrolling only adds spills (measured: no gain) */
-#define PW_SCHOOL(CC) do { if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, false, 1, false, 1>), grid, 128, 4 * 32 * CC * 4, st, a, b, d_blocks, nblk, l, pitch); \
-                           else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, false, 1, false, 4>), grid, 128, 4 * 32 * CC * 4, st, a, b, d_blocks, nblk, l, pitch); } while (0)
-#define PW_KARA(CC)   MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, true>), grid, 128, 4 * 32 * (CC + CC / 2 + 1) * 4, st, a, b, d_blocks, nblk, l, pitch)
+#define PW_LAUNCH(CC, KA) do { \
+      const size_t sm__ = (size_t) 4 * 32 * ((KA) ? (CC + CC / 2 + 1) : CC) * 4; \
+      if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 1>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); \
+      else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 4>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
    const bool kara = (g_pw_mode == 2) || (g_pw_mode == 0 && PW_KARA_DEFAULT(l));
-   if (l == 64)       { if (kara) PW_KARA(4); else PW_SCHOOL(4); }
-   else if (l == 128) { if (kara) PW_KARA(8); else PW_SCHOOL(8); }
-   else if (l == 256)
-   {
-#define PW256(KA, SP, UN) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, KA, 1, SP, UN>), grid, 128, 4 * 32 * (KA ? 25 : 16) * 4, st, a, b, d_blocks, nblk, l, pitch)
-      if (g_pw_mode == 6) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 1, false, 4, 1>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
-      else if (g_pw_mode == 7) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 1, false, 4, 2>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
-      else if (g_pw_mode == 8) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 1, false, 2, 1>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
-      else if (g_pw_mode == 9) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 1, false, 2, 2>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
-      else if (g_pw_mode == 5) PW256(true, true, 4);
-      else if (g_pw_mode == 4) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<16, true, 3>), grid, 128, 4 * 32 * 25 * 4, st, a, b, d_blocks, nblk, l, pitch);
-      else if (kara) { if (u == 1) PW256(true, false, 1); else if (u == 2) PW256(true, false, 2); else if (u == 8) PW256(true, false, 8); else PW256(true, false, 4); }
-      else { if (u == 1) PW256(false, false, 1); else if (u == 2) PW256(false, false, 2); else if (u == 8) PW256(false, false, 8); else PW256(false, false, 4); }
-#undef PW256
-   }
-   else if (l == 512) PW_SCHOOL(32);
+   if (l == 64)       { if (kara) PW_LAUNCH(4, true); else PW_LAUNCH(4, false); }
+   else if (l == 128) { if (kara) PW_LAUNCH(8, true); else PW_LAUNCH(8, false); }
+   else if (l == 256) { if (kara) PW_LAUNCH(16, true); else PW_LAUNCH(16, false); }
+   else if (l == 512) PW_LAUNCH(32, false);
    else
    {
       const size_t need = (size_t) nblk * 3 * l * sizeof(limb_t);

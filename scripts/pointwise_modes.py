@@ -1,5 +1,5 @@
 """A/B of the product kernels inside new_mpn_mul on one B200: schoolbook blocks (mode 3), Karatsuba
-blocks (mode 2), Karatsuba blocks at 3 CTAs/SM (mode 4, l = 256 only).  Prints one JSON line per
+blocks (mode 2); MPIRFFT_PW_UNROLL=1|4 selects the step-loop unrolling.  Prints one JSON line per
 (workload, mode): pointwise ms per product from the library's per-class CUDA events, the whole
 product from CUDA events, and bit-exactness vs GMP.   python scripts/pointwise_modes.py"""
 import ctypes as C
@@ -29,9 +29,7 @@ for name, (n1, n2, depth, w) in CASES.items():
     a = torch.from_numpy(a_h.view(np.int64)).cuda(); b = torch.from_numpy(b_h.view(np.int64)).cuda()
     r = torch.zeros(n1 + n2, dtype=torch.int64, device="cuda")
     plan = M.MulPlan(n1, n2, depth, w)
-    for mode in ((3, 2) if (len(sys.argv) > 1 and sys.argv[1] == "others") else ((2, 6, 7, 8, 9) if (len(sys.argv) > 2 and sys.argv[2] == "order") else (3, 2, 4, 5))):
-        if mode in (4, 5, 6, 7, 8, 9) and plan.params["limbs"] != 256:
-            continue
+    for mode in (3, 2):
         L.mpirfft_set_pointwise_mode(mode)
         for _ in range(3):
             plan.exec_device(r.data_ptr(), a.data_ptr(), b.data_ptr(), None)
@@ -49,9 +47,7 @@ for name, (n1, n2, depth, w) in CASES.items():
             flush.zero_(); plan.exec_device(r.data_ptr(), a.data_ptr(), b.data_ptr(), None)
         L.mpirfft_profile_read(ms, ln, by, 6); L.mpirfft_profile_enable(0)
         print(json.dumps({"workload": name, "limbs": plan.params["limbs"], "products": plan.params["trunc"],
-                          "mode": {3: "schoolbook", 2: "karatsuba", 4: "karatsuba, 3 CTAs/SM", 5: "karatsuba, IMAD.WIDE + IADD3.X chains", 6: "karatsuba, L/H rows paired, unroll 4",
-                                   7: "karatsuba, L/H/M rows together, unroll 4", 8: "karatsuba, L/H rows paired, unroll 2",
-                                   9: "karatsuba, L/H/M rows together, unroll 2"}[mode],
+                          "mode": {3: "schoolbook", 2: "karatsuba"}[mode],
                           "unroll": os.environ.get("MPIRFFT_PW_UNROLL", "4"), "pointwise_ms": ms[2] / 5, "product_ms": tot / reps, "bit_exact_vs_gmp": ok}), flush=True)
     L.mpirfft_set_pointwise_mode(0)
     plan.close()

@@ -38,7 +38,7 @@ def test_emulated_new_mpn_mul(emu, case):
     assert np.array_equal(r, L.gmp_mul(a, b))
 
 
-@pytest.mark.parametrize("mode", [2, 3, 5, 6, 7])
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("case", [
     (1500, 1500, 6, 64, "ones"), (3000, 2000, 6, 128, "uniform"), (3000, 3000, 6, 128, "ones"),
     (6000, 6000, 6, 256, "ones"), (6000, 6000, 6, 256, "uniform"), (6000, 700, 6, 256, "runs"),
