@@ -57,12 +57,6 @@ __device__ __forceinline__ void pdl_wait()
    asm volatile("griddepcontrol.launch_dependents;");
 #endif
 }
-static int tiles_ctas(void)
-{
-   static int v = -1;
-   if (v < 0) { const char *e = getenv("MPIRFFT_TILES_CTAS"); v = e ? atoi(e) : 4; }
-   return v;
-}
 static int g_pdl = -1;
 static int pdl_on(void)
 {
@@ -1650,14 +1644,7 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
       case 1: RUN_TILES(1, 128); break;
       case 2: RUN_TILES(2, 128); break;
       case 3: RUN_TILES(3, 128); break;
-      default:
-         if (tiles_ctas() == 5 && 5 * (smem + 1024) <= 227 * 1024)
-         {  /* tuning aid (MPIRFFT_TILES_CTAS=5): five CTAs per SM at <= 102 registers */
-            CK(cudaFuncSetAttribute(k_run_tiles<4, 128, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            MFFT_LAUNCH_PDL(pdl, (k_run_tiles<4, 128, 5>), grid, 128, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch,
-                            dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff, g_tile_timing, tp);
-         } else RUN_TILES(4, 128);
-         break;
+      default: RUN_TILES(4, 128); break;
       }
    else if (heavy && NT <= 4)
       switch (NT)

@@ -627,8 +627,8 @@ struct tile_params {
 };
 
 /* ---- the kernel ----------------------------------------------------------------------------- */
-template <int NT, int NTHREADS, int MINB = ((NTHREADS == 128) ? 4 : 2)>
-__global__ void __launch_bounds__(NTHREADS, MINB)
+template <int NT, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, (NTHREADS == 128) ? 4 : 2)
 k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
             const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
             limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,

@@ -23,5 +23,5 @@ for f in ("bench_cfg1", "bench_cfg3", "bench_cfg4"):
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pointwise -s 3 -c 1 -o gpurun_out/prof_pw -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_pw.log 2>&1; echo "ncu pw rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_run_tiles -s 39 -c 6 -o gpurun_out/prof_tiles -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu tiles rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_run_tiles -s 44 -c 5 -o gpurun_out/prof_tiles -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu tiles rc=$?"
 ls -la gpurun_out/*.ncu-rep; du -sh gpurun_out
