@@ -364,7 +364,7 @@ def main():
             roofline = {"kernel": "k_run_tiles (one fused MFA pass: several radix-2 layers in shared memory)", "bound": "hbm",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_source": "profiles/r01_ncu_tiles_summary.csv: mean dram read+write bytes "
-                        "per launch over 6 captured passes (ncu --set full, cold L2)" if traffic else None,
+                        "per launch over the captured passes (ncu --set full, cold L2)" if traffic else None,
                         "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
                         "alg_bytes_per_launch": by[0] / ln[0], "avg_launch_us": avg_ms * 1e3,
                         "share_of_step": (ms[0] / reps) / ms_per_step}
