@@ -330,6 +330,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_value = world * e2e_steps * (n1 + n2) / e2e_dt / 1e6
+    e2e_check = None
+    if rank == 0 and check is True:      # what the timed host-buffer calls returned, against the same GMP product
+        e2e_check = bool(np.array_equal(hr.numpy().view(np.uint64), want))
 
     # ---- profiling leg: per-kernel-class CUDA events (not part of the numbers above) ----
     roofline, phases, roofline_pw = None, None, None
@@ -424,7 +427,8 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (n1 + n2),
                     "d2h_bytes_per_step": 8 * (n1 + n2), "ms_per_step": e2e_dt / e2e_steps * 1e3,
-                    "api": "new_mpn_mul(r, i1, n1, i2, n2, depth, w) with pinned host buffers"},
+                    "api": "new_mpn_mul(r, i1, n1, i2, n2, depth, w) with pinned host buffers",
+                    "bit_exact_vs_gmp": e2e_check},
             "roofline": roofline, "roofline_pointwise": roofline_pw, "cpu_baseline": cpu, "phases": phases,
             "bit_exact_vs_gmp": check, "wall_s_timed_region": wall,
             "step_ms_min_max": [min(step_ms), max(step_ms)],
