@@ -43,6 +43,7 @@
 
 #define FULL 0xffffffffu
 #define MFFT_PDL_DEFAULT 1
+#define MFFT_COMBINE_FUSED_DEFAULT 0
 #ifndef PW_UNROLL
 #define PW_UNROLL 4
 #endif
@@ -1055,19 +1056,13 @@ k_add_small(limb_t *res, uint64_t total, uint32_t c, uint32_t *carry_out)
    if (lane == 0) *carry_out = cin;
 }
 
-/* res[k] = low 64 bits of the sum of all coefficient windows covering limb k; cvec[k+1] = the
- * high part of that sum (a small count) */
-__global__ void __launch_bounds__(256)
-k_combine_sum(limb_t *res, uint32_t *cvec, uint64_t total, const limb_t *__restrict__ slab,
-              uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef, uint64_t base_bit, int small)
+/* sum of all coefficient windows covering limb k of the result window: coefficient i occupies bits
+ * [i*bits, i*bits + NW) of the full result; limb 0 of the window is the limb at bit base_bit (a
+ * multiple of 64) -- the window form used by the sharded recombine */
+__device__ __forceinline__ mfft_u128 combine_limb_sum(uint64_t k, const limb_t *__restrict__ slab, uint32_t l,
+                                                      uint32_t pitch, uint64_t bits, uint64_t ncoef,
+                                                      uint64_t base_bit, int small)
 {
-   pdl_wait();
-   const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-   if (k > total) return;
-   if (k == 0) cvec[0] = 0;
-   if (k == total) return;
-   /* coefficient i occupies bits [i*bits, i*bits + NW) of the full result; res[0] is the limb
-      at bit base_bit (a multiple of 64) -- the window form used by the sharded recombine */
    const uint64_t lo_bit = base_bit + k * 64, NWb = (uint64_t) l * 64;
    /* coefficients i with i*bits <= lo_bit+63 and i*bits + NW > lo_bit */
    uint64_t imax, imin;
@@ -1092,6 +1087,21 @@ k_combine_sum(limb_t *res, uint32_t *cvec, uint64_t total, const limb_t *__restr
       else v = c[0] << (start - lo_bit);          /* coefficient begins inside this limb */
       acc += v;
    }
+   return acc;
+}
+
+/* res[k] = low 64 bits of the sum of all coefficient windows covering limb k; cvec[k+1] = the
+ * high part of that sum (a small count) */
+__global__ void __launch_bounds__(256)
+k_combine_sum(limb_t *res, uint32_t *cvec, uint64_t total, const limb_t *__restrict__ slab,
+              uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef, uint64_t base_bit, int small)
+{
+   pdl_wait();
+   const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+   if (k > total) return;
+   if (k == 0) cvec[0] = 0;
+   if (k == total) return;
+   const mfft_u128 acc = combine_limb_sum(k, slab, l, pitch, bits, ncoef, base_bit, small);
    res[k] = (limb_t) acc;
    cvec[k + 1] = (uint32_t)(acc >> 64);
 }
@@ -1132,6 +1142,66 @@ k_combine_add(limb_t *res, const uint32_t *__restrict__ cvec, uint64_t total, ui
       s[i] = v;
    }
    /* tile generates iff carry out with cin 0; propagates iff every limb is now all ones */
+   bool all1 = true;
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++) all1 = all1 && (kb + i >= total || s[i] == ~(limb_t) 0);
+   const bool tp = __all_sync(FULL, all1);
+   if (lane == 0) { tileG[tile] = (uint32_t)(la >> 32) & 1u; tileP[tile] = tp ? 1u : 0u; }
+}
+
+/* passes 1 + 2 in one kernel (MPIRFFT_COMBINE_FUSED=1): a lane sums the windows of its CMB_M
+ * consecutive limbs in registers, takes the high part of the limb before its first one from the
+ * previous lane (lane 0 recomputes that one limb) and runs the tile-local carry pass of
+ * k_combine_add on the spot -- no cvec array, no intermediate result.  cvec_last[0] receives the high
+ * part of limb total-1 (what k_combine_scan reads at cvec[total]). */
+__global__ void __launch_bounds__(128)
+k_combine_sumadd(limb_t *res, uint32_t *cvec_last, uint64_t total, const limb_t *__restrict__ slab,
+                 uint32_t l, uint32_t pitch, uint64_t bits, uint64_t ncoef, uint64_t base_bit, int small,
+                 uint32_t *tileG, uint32_t *tileP, uint64_t ntiles)
+{
+   pdl_wait();
+   const uint64_t tile = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const uint32_t lane = threadIdx.x & 31;
+   if (tile >= ntiles) return;
+   const uint64_t kb = tile * (32 * CMB_M) + (uint64_t) lane * CMB_M;
+   limb_t lo[CMB_M]; uint32_t hi[CMB_M];
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++)
+   {
+      const uint64_t k = kb + i;
+      lo[i] = ~(limb_t) 0; hi[i] = 0;
+      if (k < total)
+      {
+         const mfft_u128 acc = combine_limb_sum(k, slab, l, pitch, bits, ncoef, base_bit, small);
+         lo[i] = (limb_t) acc; hi[i] = (uint32_t)(acc >> 64);
+         if (k + 1 == total) cvec_last[0] = hi[i];
+      }
+   }
+   uint32_t hprev = __shfl_up_sync(FULL, hi[CMB_M - 1], 1);
+   if (lane == 0)
+      hprev = (kb > 0 && kb - 1 < total) ? (uint32_t)(combine_limb_sum(kb - 1, slab, l, pitch, bits, ncoef, base_bit, small) >> 64) : 0u;
+   limb_t s[CMB_M]; uint32_t c = 0; bool ones_all = true;
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++)
+   {
+      const uint64_t k = kb + i;
+      const uint32_t z = (k < total) ? (i ? hi[i - 1] : hprev) : 0u;
+      const mfft_u128 acc = (mfft_u128) lo[i] + z + c;
+      s[i] = (limb_t) acc; c = (uint32_t)(acc >> 64);
+      ones_all = ones_all && (s[i] == ~(limb_t) 0);
+   }
+   const uint32_t G = __ballot_sync(FULL, c != 0), P = __ballot_sync(FULL, ones_all);
+   const uint64_t la = mfft_lookahead(G, P, 0);
+   uint32_t myc = (uint32_t)(la >> lane) & 1u;
+#pragma unroll
+   for (int i = 0; i < CMB_M; i++)
+   {
+      const uint64_t k = kb + i;
+      const limb_t v = s[i] + myc;
+      myc = (myc && v == 0) ? 1u : 0u;
+      if (k < total) res[k] = v;
+      s[i] = v;
+   }
    bool all1 = true;
 #pragma unroll
    for (int i = 0; i < CMB_M; i++) all1 = all1 && (kb + i >= total || s[i] == ~(limb_t) 0);
@@ -1844,11 +1914,21 @@ int mfft_dev_combine_window(limb_t *res, uint64_t total, const limb_t *slab, uin
    uint32_t *tileP = tileG + ntiles + 32 - (ntiles % 32);
    uint32_t *tileC = tileP + ntiles + 32 - (ntiles % 32);
    PROF(PC_COMBINE, st);
-   MFFT_LAUNCH_PDL(pdl_on(), k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef, base_bit,
-               (int)(base_bit + (total + 2) * 64 < 0xffffff00ull && bits < 0xffffffffull));
-   CKL();
-   MFFT_LAUNCH_PDL(pdl_on(), k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);
-   CKL();
+   static int fused = -1;
+   if (fused < 0) { const char *e = getenv("MPIRFFT_COMBINE_FUSED"); fused = e ? (e[0] != '0') : MFFT_COMBINE_FUSED_DEFAULT; }
+   const int small = (int)(base_bit + (total + 2) * 64 < 0xffffff00ull && bits < 0xffffffffull);
+   if (fused)
+   {
+      MFFT_LAUNCH_PDL(pdl_on(), k_combine_sumadd, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec + total, total, slab, l, pitch,
+                      bits, ncoef, base_bit, small, tileG, tileP, ntiles);
+      CKL();
+   } else
+   {
+      MFFT_LAUNCH_PDL(pdl_on(), k_combine_sum, (unsigned)((total + 1 + 255) / 256), 256, 0, st, res, cvec, total, slab, l, pitch, bits, ncoef, base_bit, small);
+      CKL();
+      MFFT_LAUNCH_PDL(pdl_on(), k_combine_add, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, cvec, total, tileG, tileP, ntiles);
+      CKL();
+   }
    MFFT_LAUNCH_PDL(pdl_on(), k_combine_scan, 1, 1024, 0, st, tileG, tileP, tileC, ntiles, cvec + total, d_carry_out);
    CKL();
    MFFT_LAUNCH_PDL(pdl_on(), k_combine_fix, (unsigned)((ntiles + 3) / 4), 128, 0, st, res, total, tileC, ntiles);
