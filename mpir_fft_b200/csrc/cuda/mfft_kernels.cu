@@ -1499,6 +1499,14 @@ int mfft_dev_count(void)
    return n;
 }
 
+static int g_device = -1;
+int mfft_dev_bind(void)
+{  /* the current device is per host thread: every entry point rebinds before it allocates or launches */
+   if (g_device < 0) { snprintf(g_err, sizeof g_err, "device not initialised"); return -1; }
+   CK(cudaSetDevice(g_device));
+   return 0;
+}
+
 int mfft_dev_init(int device)
 {
    int n = mfft_dev_count();
@@ -1506,6 +1514,7 @@ int mfft_dev_init(int device)
    if (device < 0 || device >= n) { snprintf(g_err, sizeof g_err, "device %d out of range (%d visible)", device, n); return -1; }
    CK(cudaSetDevice(device));
    CK(cudaFree(0));
+   g_device = device;
    return 0;
 }
 
@@ -1584,12 +1593,6 @@ int mfft_dev_run_stage(limb_t *slab, const mfft_geom *g, const mfft_op *d_ops, u
 static unsigned long long *g_tile_timing = NULL;
 extern "C" void mfft_dev_tile_timing(void *buf) { g_tile_timing = (unsigned long long *) buf; }
 
-/* the next mfft_dev_run_tiles launch cuts the coefficients it loads out of {src, nlimbs} itself
- * (block k = bits [k*bits, (k+1)*bits), zero for k >= ncoef) instead of reading the slab */
-static uint32_t g_split_on = 0; static const limb_t *g_split_src = NULL;
-static uint64_t g_split_nlimbs = 0, g_split_bits = 0, g_split_ncoef = 0;
-void mfft_dev_tiles_fuse_split(const limb_t *src, uint64_t nlimbs, uint64_t bits, uint64_t ncoef)
-{ g_split_on = 1; g_split_src = src; g_split_nlimbs = nlimbs; g_split_bits = bits; g_split_ncoef = ncoef; }
 
 /* ---- carry-save stage path (mfft_cs_stage.h): any even l; cw = side array of l/2 carry words per block ---- */
 int mfft_dev_cs_init(const limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_batch *d_batch, uint32_t nbatch, void *stream)
@@ -1666,7 +1669,7 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
                        limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
                        uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy,
                         const mfft_tile *h_tiles, const uint32_t *h_pos, const uint32_t *h_stoff,
-                        const mfft_batch *h_batch, void *stream)
+                        const mfft_batch *h_batch, const mfft_split *split, void *stream)
 {
    int NT = 0;
    if (!ntiles || !nbatch) return 0;
@@ -1677,11 +1680,10 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    const unsigned grid = ntiles * nbatch;
    cudaStream_t st = (cudaStream_t) stream;
    /* small passes: tile descriptors, position lists and stage offsets travel as kernel parameters */
-   static tile_params tp;
+   tile_params tp;                                      /* per call: launches from several host threads do not share it */
    tp.valid = 0; tp.batch_valid = 0;
-   tp.split = g_split_on; tp.split_src = g_split_src; tp.split_nlimbs = g_split_nlimbs;
-   tp.split_bits = g_split_bits; tp.split_ncoef = g_split_ncoef;
-   g_split_on = 0;                                      /* consumed by this launch */
+   tp.split = split ? 1u : 0u; tp.split_src = split ? split->src : NULL; tp.split_nlimbs = split ? split->nlimbs : 0;
+   tp.split_bits = split ? split->bits : 0; tp.split_ncoef = split ? split->ncoef : 0;
    if (h_tiles && h_pos && h_stoff && ntiles <= TP_MAXT)
    {
       uint32_t t, ok = 1;

@@ -381,15 +381,15 @@ int mpirfft_mulmod_batch_device(mp_limb_t *d_a, const mp_limb_t *d_b, size_t cou
          fft_mulmod_2expp1 from 250 limbs up (mul_fft.c:3135-3164); 256 and 512 limbs are served
          directly by the warp-level product kernel */
       mpirfft_mulmod_plan *pl = NULL; int i;
+      mfft_lock();                 /* held across cache lookup, eviction and execution */
       for (i = 0; i < MM_CACHE; i++) if (g_mm[i] && g_mm_l[i] == l && g_mm_count[i] == count) pl = g_mm[i];
       if (!pl)
       {
-         if ((rc = mpirfft_mulmod_plan_create(&pl, (mp_size_t) l, depth, w, count)) != 0) return rc;
+         if ((rc = mpirfft_mulmod_plan_create(&pl, (mp_size_t) l, depth, w, count)) != 0) { mfft_unlock(); return rc; }
          i = (int)(g_mm_next++ % MM_CACHE);
          if (g_mm[i]) mpirfft_mulmod_plan_destroy(g_mm[i]);
          g_mm[i] = pl; g_mm_l[i] = l; g_mm_count[i] = count;
       }
-      mfft_lock();
       rc = mpirfft_mulmod_plan_exec(pl, d_a, d_a, d_b, pitch, -1, stream);
       if (rc == 0 && mfft_dev_sync(stream)) rc = MPIRFFT_ENODEV;
       mfft_unlock();

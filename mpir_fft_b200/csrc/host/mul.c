@@ -146,8 +146,25 @@ uint64_t mpirfft_mul_plan_launches(const mpirfft_mul_plan *pl)
    return 2*((mfft_mfa_can_fuse_split(&pl->fwd) ? 0 : 1) + mfft_mfa_launches(&pl->fwd)) + 1 + mfft_mfa_launches(&pl->inv) + 4;
 }
 
+static int exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, const mp_limb_t *d_i1,
+                      const mp_limb_t *d_i2, void *stream);
+
+/* Thread contract: the launches of a phase are issued under the library lock with the library's
+ * device made current in the calling thread, so plans may be driven from any host thread.  One
+ * plan owns one set of slabs: do not run the same plan concurrently on two streams. */
 int mpirfft_mul_exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, const mp_limb_t *d_i1,
                            const mp_limb_t *d_i2, void *stream)
+{
+   int rc;
+   mfft_lock();
+   rc = mfft_try_device();
+   if (rc == 0) rc = exec_phase(pl, phase, d_r, d_i1, d_i2, stream);
+   mfft_unlock();
+   return rc;
+}
+
+static int exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, const mp_limb_t *d_i1,
+                      const mp_limb_t *d_i2, void *stream)
 {
    const mpirfft_mul_params *p = &pl->p;
    int rc = 0;
@@ -184,17 +201,21 @@ int mpirfft_mul_exec_device(mpirfft_mul_plan *pl, mp_limb_t *d_r, const mp_limb_
                             const mp_limb_t *d_i2, void *stream)
 {
    int ph, rc;
+   mfft_lock();
+   if ((rc = mfft_try_device()) != 0) goto done;
    if (d_i1 == d_i2 && pl->n1 == pl->n2)
    {  /* squaring: one forward transform, the spectrum multiplied by itself */
-      if ((rc = mpirfft_mul_exec_phase(pl, 0, d_r, d_i1, d_i2, stream)) != 0) return rc;
-      if (mfft_dev_pointwise(pl->Z, pl->Z, pl->d_pw_blocks, pl->npw, pl->l, pl->pitch, stream)) return MPIRFFT_ENODEV;
+      if ((rc = exec_phase(pl, 0, d_r, d_i1, d_i2, stream)) != 0) goto done;
+      if (mfft_dev_pointwise(pl->Z, pl->Z, pl->d_pw_blocks, pl->npw, pl->l, pl->pitch, stream)) { rc = MPIRFFT_ENODEV; goto done; }
       for (ph = 3; ph < 5; ph++)
-         if ((rc = mpirfft_mul_exec_phase(pl, ph, d_r, d_i1, d_i2, stream)) != 0) return rc;
-      return 0;
+         if ((rc = exec_phase(pl, ph, d_r, d_i1, d_i2, stream)) != 0) goto done;
+      goto done;
    }
    for (ph = 0; ph < 5; ph++)
-      if ((rc = mpirfft_mul_exec_phase(pl, ph, d_r, d_i1, d_i2, stream)) != 0) return rc;
-   return 0;
+      if ((rc = exec_phase(pl, ph, d_r, d_i1, d_i2, stream)) != 0) break;
+done:
+   mfft_unlock();
+   return rc;
 }
 
 int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i1, const mp_limb_t *i2)
@@ -202,6 +223,7 @@ int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i
    int rc;
    size_t b1 = (size_t) pl->n1*8, b2 = (size_t) pl->n2*8;
    mfft_lock();
+   if ((rc = mfft_try_device()) != 0) { mfft_unlock(); return rc; }
    if (!pl->d_i1)
    {
       pl->d_i1 = (limb_t *) mfft_dev_alloc(b1); pl->d_i2 = (limb_t *) mfft_dev_alloc(b2);
@@ -246,7 +268,9 @@ void new_mpn_mul(mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_s
    if (mpirfft_mul_params_get(&p, n1, n2, depth, w) != 0)
       mfft_die("new_mpn_mul", "illegal parameters n1=%ld n2=%ld depth=%lu w=%lu: need 64 | 2^depth*w and "
                "j1+j2-1 <= 2^(depth+1) (mul_fft.c:3186-3187)", (long) n1, (long) n2, (unsigned long) depth, (unsigned long) w);
-   mfft_lock(); mfft_require_device("new_mpn_mul"); mfft_unlock();
+   /* the lock is held across lookup, eviction and execution: a concurrent call with another shape
+      cannot destroy the plan this thread is executing (the reference is re-entrant) */
+   mfft_lock(); mfft_require_device("new_mpn_mul");
    for (k = 0; k < PLAN_CACHE; k++)
       if (g_cache[k] && g_cache[k]->n1 == n1 && g_cache[k]->n2 == n2 && g_cache[k]->depth == depth && g_cache[k]->w == w)
          pl = g_cache[k];
@@ -260,6 +284,7 @@ void new_mpn_mul(mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_s
    }
    if ((rc = mpirfft_mul_exec_host(pl, r1, i1, i2)) != 0)
       mfft_die("new_mpn_mul", "device execution failed (code %d): %s", rc, mfft_dev_last_error());
+   mfft_unlock();
 }
 
 /* mpn_mul-shaped entry (what the FIXME at mul_fft.c:3177-3178 asks for): chooses (depth, w) itself */

@@ -8,10 +8,24 @@
 #include <stdlib.h>
 #include <string.h>
 
-static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+/* One recursive lock serialises everything that touches library-global state: the device binding,
+ * the plan caches of the drop-in symbols, plan creation / destruction and the issuing of a plan's
+ * launches.  Recursive, because the drop-in symbols hold it across a whole call (cache lookup,
+ * eviction, execution) and call the plan API, which takes it again. */
+static pthread_mutex_t g_mu;
+static pthread_once_t g_mu_once = PTHREAD_ONCE_INIT;
 static int g_ready = 0;
 
-void mfft_lock(void) { pthread_mutex_lock(&g_mu); }
+static void mu_init(void)
+{
+   pthread_mutexattr_t a;
+   pthread_mutexattr_init(&a);
+   pthread_mutexattr_settype(&a, PTHREAD_MUTEX_RECURSIVE);
+   pthread_mutex_init(&g_mu, &a);
+   pthread_mutexattr_destroy(&a);
+}
+
+void mfft_lock(void) { pthread_once(&g_mu_once, mu_init); pthread_mutex_lock(&g_mu); }
 void mfft_unlock(void) { pthread_mutex_unlock(&g_mu); }
 
 void mfft_die(const char *fn, const char *fmt, ...)
@@ -26,14 +40,17 @@ void mfft_die(const char *fn, const char *fmt, ...)
 
 int mfft_try_device(void)
 {
+   int rc = 0;
+   mfft_lock();
    if (!g_ready)
    {
       const char *e = getenv("MPIRFFT_DEVICE");
       int dev = e ? atoi(e) : 0;
-      if (mfft_dev_init(dev) != 0) return MPIRFFT_ENODEV;
-      g_ready = 1;
+      if (mfft_dev_init(dev) != 0) rc = MPIRFFT_ENODEV; else g_ready = 1;
    }
-   return 0;
+   else if (mfft_dev_bind() != 0) rc = MPIRFFT_ENODEV;     /* the current device is per host thread */
+   mfft_unlock();
+   return rc;
 }
 
 void mfft_require_device(const char *fn)
@@ -254,8 +271,10 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
          if (pi > 0)
             for (k = 0; k < p->npos_total; k++)
                if ((p->pos[k] & MFFT_TILE_LOAD) && !wr[p->pos[k] & MFFT_TILE_POSMASK]) ok = 0;
+         /* with the split fused, the first pass loads from the operand and the slab holds only what a
+            pass has STORED */
          for (k = 0; k < p->npos_total; k++)
-            if (p->pos[k] & (MFFT_TILE_STORE | MFFT_TILE_LOAD)) wr[p->pos[k] & MFFT_TILE_POSMASK] = 1;
+            if (p->pos[k] & MFFT_TILE_STORE) wr[p->pos[k] & MFFT_TILE_POSMASK] = 1;
       }
       free(wr);
       m->fuse_split_ok = ok;
@@ -328,27 +347,28 @@ mfft_move *mfft_mfa_debug_moves(mfft_mfa *m, uint32_t *count, uint32_t *dst_stri
 uint32_t *mfft_mfa_debug_dst_base(mfft_mfa *m, uint32_t *count) { *count = m->ndst; return m->h_dst_base; }
 uint32_t *mfft_mfa_debug_rows(mfft_mfa *m, uint32_t *count) { *count = m->nrows; return m->rows; }
 
-/* algorithmic traffic of a fused pass: every position of every tile is read and/or written once */
-static double pass_bytes(const mfft_pass *p, uint32_t nbatch, uint32_t l)
+/* algorithmic traffic of one MFA pass by SURVEY 8(d): one read and one write of the live slab,
+ * 2 T S bytes with T = trunc live coefficients and S = 8 (l+1) -- NOT what the executor happens to
+ * move (rows the truncation synthesises, operand bytes of a split-fused first pass), so that
+ * bytes / time is comparable across implementations */
+static double pass_bytes(const mfft_mfa *m)
 {
-   double blocks = 0; uint32_t i;
-   for (i = 0; i < p->npos_total; i++)
-      blocks += ((p->pos[i] & MFFT_TILE_LOAD) ? 1 : 0) + ((p->pos[i] & MFFT_TILE_STORE) ? 1 : 0);
-   return blocks * nbatch * 8.0 * (l + 1);
+   return 2.0 * (double) m->trunc_rows * (double) m->n1 * 8.0 * (m->l + 1);
 }
 
 static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft_dpass *d, limb_t *slab,
-                      const mfft_geom *g, const mfft_batch *d_batch, const mfft_batch *h_batch, uint32_t nbatch, limb_t *dst, void *stream)
+                      const mfft_geom *g, const mfft_batch *d_batch, const mfft_batch *h_batch, uint32_t nbatch, limb_t *dst,
+                      const mfft_split *split, void *stream)
 {
    uint32_t i;
    for (i = 0; i < P->npasses; i++)
    {
       const mfft_pass *p = &P->pass[i];
       const int lastp = (i + 1 == P->npasses) && dst != NULL;
-      mfft_dev_profile_bytes(pass_bytes(p, nbatch, g->l));
+      mfft_dev_profile_bytes(pass_bytes(m));
       if (mfft_dev_run_tiles(slab, g, d[i].d_tiles, p->ntiles, d[i].d_pos, d[i].d_ops, p->max_npos, p->max_nops, d_batch, nbatch,
                              lastp ? dst : NULL, m->d_dstpos, m->d_dst_base, m->dst_stride,
-                             lastp ? m->normalise : 0, d[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, p->tiles, p->pos, p->stoff, h_batch, stream) != 0) return MPIRFFT_ENODEV;
+                             lastp ? m->normalise : 0, d[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, p->tiles, p->pos, p->stoff, h_batch, (i == 0) ? split : NULL, stream) != 0) return MPIRFFT_ENODEV;
    }
    return 0;
 }
@@ -358,26 +378,31 @@ static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft
  * caller still has to run the split kernel */
 int mfft_mfa_can_fuse_split(const mfft_mfa *m) { return m->fused && !m->inverse && m->pcol.npasses > 0 && m->fuse_split_ok; }
 
+static int mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, const mfft_split *split, void *stream);
+
 int mfft_mfa_exec_split(const mfft_mfa *m, limb_t *slab, limb_t *dst, const limb_t *src, uint64_t nlimbs,
                         uint64_t bits, uint64_t ncoef, void *stream)
 {
+   mfft_split sp;
    if (!mfft_mfa_can_fuse_split(m)) return MPIRFFT_EINVAL;
-   mfft_dev_tiles_fuse_split(src, nlimbs, bits, ncoef);
-   return mfft_mfa_exec(m, slab, dst, stream);
+   sp.src = src; sp.nlimbs = nlimbs; sp.bits = bits; sp.ncoef = ncoef;
+   return mfa_exec(m, slab, dst, &sp, stream);
 }
 
-int mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, void *stream)
+int mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, void *stream) { return mfa_exec(m, slab, dst, NULL, stream); }
+
+static int mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, const mfft_split *split, void *stream)
 {
    int rc;
    if (m->fused)
    {
       if (!m->inverse)
       {
-         if ((rc = run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, NULL, stream)) != 0) return rc;
-         return run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, dst, stream);
+         if ((rc = run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, NULL, split, stream)) != 0) return rc;
+         return run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, dst, NULL, stream);
       }
-      if ((rc = run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, NULL, stream)) != 0) return rc;
-      return run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, dst, stream);
+      if ((rc = run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, NULL, NULL, stream)) != 0) return rc;
+      return run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, dst, NULL, stream);
    }
    if (!m->inverse)
    {

@@ -88,7 +88,9 @@ int mpirfft_smul_plan_create(mpirfft_smul_plan **out, mp_size_t n1, mp_size_t n2
    if (pl->limb_hi > (uint64_t)(n1 + n2)) pl->limb_hi = (uint64_t)(n1 + n2);
    if (pl->limb_lo > pl->limb_hi) pl->limb_lo = pl->limb_hi;
    pl->halo = pl->rank ? (uint32_t)(NW/pl->p.bits1 + 2) : 0;
-   if (pl->halo > sq) { free(pl); return MPIRFFT_EINVAL; }
+   /* every rank hands its last NW/bits1 + 2 coefficients to its successor (the halo all-gather takes
+      them from every rank, rank 0 and the last one included): each rank must own at least that many */
+   if (NW/pl->p.bits1 + 2 > (tr/(uint64_t) world)*sq) { free(pl); return MPIRFFT_EINVAL; }
 
    mfft_lock();
    if ((rc = mfft_try_device()) != 0) goto fail;
@@ -273,4 +275,5 @@ int mpirfft_smul_carry(mpirfft_smul_plan *pl, unsigned carry_in, unsigned *carry
 
 /* the last `count` coefficients I own (what the next rank needs as its halo) / my halo slots */
 mp_limb_t *mpirfft_smul_tail_blocks(mpirfft_smul_plan *pl, unsigned count)
-{ return (mp_limb_t *)(pl->unp + ((size_t) pl->halo + pl->recv_blocks - count)*pl->pitch); }
+{ if ((size_t) count > pl->recv_blocks) return NULL;
+  return (mp_limb_t *)(pl->unp + ((size_t) pl->halo + pl->recv_blocks - count)*pl->pitch); }

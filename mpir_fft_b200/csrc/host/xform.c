@@ -162,7 +162,7 @@ int mfft_xform_exec(const mfft_xform *x, limb_t *slab, limb_t *dst, void *stream
          const int lastp = (i + 1 == x->P.npasses);
          if (mfft_dev_run_tiles(slab, &x->g, x->dp[i].d_tiles, p->ntiles, x->dp[i].d_pos, x->dp[i].d_ops, p->max_npos,
                                 p->max_nops, x->d_batch, x->nbatch, lastp ? dst : NULL, x->d_dstpos, x->d_dst_base,
-                                x->dst_stride, lastp ? x->normalise : 0, x->dp[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, p->tiles, p->pos, p->stoff, x->h_batch, stream) != 0) return MPIRFFT_ENODEV;
+                                x->dst_stride, lastp ? x->normalise : 0, x->dp[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, p->tiles, p->pos, p->stoff, x->h_batch, NULL, stream) != 0) return MPIRFFT_ENODEV;
       }
       return 0;
    }

@@ -117,6 +117,7 @@ typedef struct {
  * returns 0 on success or a negative mfft error code; none of them ever falls back to the CPU.
  * ------------------------------------------------------------------------------------------ */
 int  mfft_dev_init(int device);                       /* select device, create context; <0 if no GPU */
+int  mfft_dev_bind(void);                             /* make the device of mfft_dev_init current in the calling thread */
 int  mfft_dev_count(void);
 void *mfft_dev_alloc(size_t bytes);                   /* NULL on failure */
 void mfft_dev_free(void *p);
@@ -152,6 +153,11 @@ int  mfft_dev_finalize_cs(limb_t *dst, uint32_t dst_stride, const uint32_t *d_ds
                           const mfft_geom *g, const mfft_move *d_moves, uint32_t nmoves, const mfft_batch *d_batch,
                           uint32_t nbatch, int normalise, void *stream);
 
+/* split != NULL in mfft_dev_run_tiles: the launch cuts the coefficients it loads out of the operand
+ * {src, nlimbs} (block k of slab half 0 = bits [k*bits, (k+1)*bits), zero for k >= ncoef;
+ * FFT_split_bits, mul_fft.c:115-170 and the zero fill 3235-3236) instead of reading them from the slab */
+typedef struct { const limb_t *src; uint64_t nlimbs, bits, ncoef; } mfft_split;
+
 /* One fused pass: CTA (tile, batch entry) loads the tile's positions into shared memory, runs
  * all its stages there and stores the written positions back in place -- or, if dst != NULL,
  * to dst[(dst_base[b] + dstpos[i]*dst_stride)*pitch] (dstpos parallel to the position list,
@@ -165,11 +171,7 @@ int  mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_til
                         limb_t *dst, const uint32_t *d_dstpos, const uint32_t *d_dst_base,
                         uint32_t dst_stride, int normalise, const uint32_t *d_stoff, int heavy,
                         const mfft_tile *h_tiles, const uint32_t *h_pos, const uint32_t *h_stoff,
-                        const mfft_batch *h_batch, void *stream);
-/* the NEXT mfft_dev_run_tiles launch cuts the coefficients it loads out of the operand {src, nlimbs}
- * (block k of slab half 0 = bits [k*bits, (k+1)*bits), zero for k >= ncoef; FFT_split_bits,
- * mul_fft.c:115-170 and the zero fill 3235-3236) instead of reading them from the slab */
-void mfft_dev_tiles_fuse_split(const limb_t *src, uint64_t nlimbs, uint64_t bits, uint64_t ncoef);
+                        const mfft_batch *h_batch, const mfft_split *split, void *stream);
 /* 1 if the fused executor supports coefficient size l (else use mfft_dev_run_stage) */
 int  mfft_dev_tiles_supported(uint32_t l);
 uint32_t mfft_dev_tiles_max_npos(uint32_t l);
