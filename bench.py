@@ -48,6 +48,7 @@ WORKLOADS = {
     "big": (8000000, 8000000, 15, 1),          # l = 512: the largest ring of the fused path
 }
 METRIC, UNIT = "new_mpn_mul Mlimb/s", "Mlimb/s"
+SHARDED_LEG_TIMEOUT_S = 420
 
 
 def splitmix64(seed, n):
@@ -225,6 +226,7 @@ def main():
     ap.add_argument("--sharded", action="store_true", help="one product spread over the ranks (strong scaling)")
     ap.add_argument("--count", type=int, default=4096, help="cfg4: products per batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded-leg", action="store_true", help="skip the large sharded product that the default workload appends")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -333,6 +335,23 @@ def main():
     e2e_check = None
     if rank == 0 and check is True:      # what the timed host-buffer calls returned, against the same GMP product
         e2e_check = bool(np.array_equal(hr.numpy().view(np.uint64), want))
+    # the same symbol on plain malloc'ed (pageable) buffers -- what a caller that swaps libraries hands in
+    na, nb = splitmix64(0x5EED0001 + 1000 * rank, n1), splitmix64(0x5EED0002 + 1000 * rank, n2)
+    nr = np.zeros(n1 + n2, dtype=np.uint64)
+    for _ in range(2):
+        f(nr.ctypes.data, na.ctypes.data, n1, nb.ctypes.data, n2, depth, w)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        f(nr.ctypes.data, na.ctypes.data, n1, nb.ctypes.data, n2, depth, w)
+    e2e_pg_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_pg_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_pg_dt = float(t.item())
+    e2e_pg_value = world * e2e_steps * (n1 + n2) / e2e_pg_dt / 1e6
+    e2e_pg_check = bool(np.array_equal(nr, want)) if (rank == 0 and check is True) else None
 
     # ---- profiling leg: per-kernel-class CUDA events (not part of the numbers above) ----
     roofline, phases, roofline_pw = None, None, None
@@ -414,13 +433,14 @@ def main():
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": str(e)}
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "new_mpn_mul %d x %d limbs, depth %d, w %d (BASELINE configs[%s])" % (
-                           n1, n2, depth, w, {"cfg1": 0, "cfg2": 1, "cfg3": 2, "big": "-"}[args.workload]),
+            "config": {"workload": "new_mpn_mul %d x %d limbs, depth %d, w %d" % (n1, n2, depth, w),
+                       "baseline_config_index": {"cfg1": 0, "cfg2": 1, "cfg3": 2, "big": None}[args.workload],
                        "coefficients": prm["trunc"], "limbs_per_coefficient": prm["limbs"],
                        "l2": "flushed between timed steps (256 MiB write)",
                        "multi_gpu": "independent products per rank" if world > 1 else "single GPU"},
@@ -429,11 +449,49 @@ def main():
                     "d2h_bytes_per_step": 8 * (n1 + n2), "ms_per_step": e2e_dt / e2e_steps * 1e3,
                     "api": "new_mpn_mul(r, i1, n1, i2, n2, depth, w) with pinned host buffers",
                     "bit_exact_vs_gmp": e2e_check},
+            "e2e_pageable": {"value": e2e_pg_value, "unit": UNIT, "ms_per_step": e2e_pg_dt / e2e_steps * 1e3,
+                             "api": "new_mpn_mul(r, i1, n1, i2, n2, depth, w) with malloc'ed (pageable) host buffers",
+                             "bit_exact_vs_gmp": e2e_pg_check},
             "roofline": roofline, "roofline_pointwise": roofline_pw, "cpu_baseline": cpu, "phases": phases,
             "bit_exact_vs_gmp": check, "wall_s_timed_region": wall,
             "step_ms_min_max": [min(step_ms), max(step_ms)],
         }
-        print(json.dumps(line))
+
+    # ---- the collective path: ONE large product sharded over all ranks (strong scaling) ----
+    # Appended to the same line as "sharded".  A watchdog prints the line without it if a rank gets
+    # stuck, so the headline numbers above can never be lost to the large leg.
+    if args.workload == "cfg2" and not args.no_sharded_leg:
+        def bail():
+            if rank == 0:
+                line["sharded"] = {"error": "the sharded leg did not finish within %d s" % SHARDED_LEG_TIMEOUT_S}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(SHARDED_LEG_TIMEOUT_S, bail)
+        dog.daemon = True
+        dog.start()
+        recs = []
+        try:
+            del a, b, r, flush
+            plan.close() if hasattr(plan, "close") else None
+            torch.cuda.empty_cache()
+            peaks, _ = load_peaks()
+            for lg in SHARDED_SIZES.get(world, (26,)):
+                rec = sharded_leg(torch, dist, M, rank, world, lg, steps=2, peak_gbs=float(peaks.get("hbm_gbs", 6650.0)))
+                if rank == 0:
+                    recs.append(rec)
+        except Exception as e:      # peers may now be waiting in a collective: the watchdog ends the run
+            import traceback
+            recs.append({"error": "%s: %s" % (type(e).__name__, e), "trace": traceback.format_exc()[-600:]})
+            if world > 1:
+                if rank == 0:
+                    line["sharded"] = recs
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+        dog.cancel()
+        if rank == 0:
+            line["sharded"] = recs
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -459,6 +517,155 @@ def _timed_steps(torch, dist, world, steps, flush, fn):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total = float(t.item())
     return total / steps, ms
+
+
+# one large product spread over the ranks (SURVEY 8e / BASELINE configs[4]); log2 limbs -> (depth, w)
+SHARDED_PARAMS = {24: (16, 1), 26: (17, 1), 28: (18, 1), 30: (19, 1)}
+# which sizes a run with `world` ranks measures: 2^26 everywhere (1-GPU baseline on rank 0 for the
+# strong-scaling efficiency), plus the largest size the box holds
+SHARDED_SIZES = {1: (26,), 2: (26,), 4: (26, 28), 8: (26, 30)}
+
+
+def splitmix64_dev(torch, seed, n, dev, chunk=1 << 26):
+    """limb[k] = splitmix64(seed + k) as int64 bit patterns, generated on the device in chunks"""
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+
+    def lsr(z, sh):
+        return (z >> sh) & ((1 << (64 - sh)) - 1)
+
+    def c64(v):
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        z = torch.arange(lo, hi, dtype=torch.int64, device=dev) + c64(seed & ((1 << 64) - 1))
+        z = z * c64(0x9E3779B97F4A7C15) + c64(0x9E3779B97F4A7C15)
+        z = (z ^ lsr(z, 30)) * c64(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * c64(0x94D049BB133111EB)
+        out[lo:hi] = z ^ lsr(z, 31)
+    return out
+
+
+def _phase_table(torch, timing):
+    """[(name, event)] -> {name: ms} summed over repeated phases (device time on the current stream)"""
+    out = {}
+    for (_, e0), (name, e1) in zip(timing[:-1], timing[1:]):
+        out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+    return out
+
+
+def sharded_leg(torch, dist, M, rank, world, log2, steps=2, baseline_1gpu=True, peak_gbs=None):
+    """ONE product of 2^log2 x 2^log2 limbs over all ranks: time, phases, all-to-all rate, bit-exactness
+    through residues modulo six 31-bit primes (mpir_fft_b200/residues.py) and, at 2^26, equality of the
+    sharded result's fingerprint with the same product computed on rank 0 alone."""
+    from mpir_fft_b200.sharded import ShardedMul
+    from mpir_fft_b200 import residues as RES
+    depth, w = SHARDED_PARAMS[log2]
+    n = 1 << log2
+    dev = torch.device("cuda", torch.cuda.current_device())
+    a = splitmix64_dev(torch, 0x5EED0001, n, dev)
+    b = splitmix64_dev(torch, 0x5EED0002, n, dev)
+    # residues of the operands: every rank reduces its slice
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    ra, rb = RES.residues(a[lo:hi], lo), RES.residues(b[lo:hi], lo)
+
+    def allsum(vals):
+        if world == 1:
+            return [v % p for v, p in zip(vals, RES.PRIMES)]
+        t = torch.tensor(vals, dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        return [int(v) % p for v, p in zip(t.cpu().tolist(), RES.PRIMES)]
+
+    ra, rb = allsum(ra), allsum(rb)
+    sm = ShardedMul(n, n, depth, w, cuda=True)
+    lay = sm.lay
+    sm.multiply(a.data_ptr(), b.data_ptr())             # warm-up (NCCL channels, plan buffers)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sm.multiply(a.data_ptr(), b.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    rr = allsum(RES.residues(sm.out, int(lay.limb_lo)))
+    ok = RES.product_matches(ra, rb, rr)
+    # one more product with a CUDA event after every phase
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    timing = []
+    sm.multiply(a.data_ptr(), b.data_ptr(), timing=timing)
+    torch.cuda.synchronize()
+    phases = _phase_table(torch, timing)
+    pt = torch.tensor([phases.get(k, 0.0) for k in sorted(phases)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+    phases = {k: float(v) for k, v in zip(sorted(phases), pt.cpu().tolist())}
+    a2a_bytes = int(lay.trunc_rows * lay.ncl * lay.block_limbs * 8)          # one rank's buffer per exchange
+    sent = a2a_bytes * (world - 1) // world                                  # what actually leaves the GPU
+    mem = torch.cuda.max_memory_allocated() / 1e9
+    sm.close()
+    del sm
+    base = None
+    if baseline_1gpu and world > 1:
+        # the same product on rank 0 alone: strong-scaling denominator and world-size independence
+        same = None
+        if rank == 0:
+            s1 = ShardedMul(n, n, depth, w, cuda=True, single=True)
+            s1.multiply(a.data_ptr(), b.data_ptr())
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s1.multiply(a.data_ptr(), b.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            base = e0.elapsed_time(e1)
+            same = (RES.residues(s1.out, 0) == rr)
+            s1.close()
+            del s1
+        dist.barrier()
+    else:
+        same = None
+    del a, b
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    ms = min(times)
+    S = int(lay.block_limbs - 1) * 8        # pitch = l + 2 limbs; S = 8 (l + 1)
+    T = int(lay.trunc_rows) * int(lay.n1cols)
+    b_alg = 18 * T * S + 16 * 2 * n
+    a2a_ms = phases.get("all_to_all", 0.0)
+    rec = {
+        "workload": "new_mpn_mul 2^%d x 2^%d limbs, depth %d, w %d, ONE product sharded over %d rank(s)" % (log2, log2, depth, w, world),
+        "n_gpus": world, "ms_per_step": ms, "all_steps_ms": times, "value": 2 * n / (ms * 1e-3) / 1e6, "unit": UNIT,
+        "coefficient_limbs": int(lay.block_limbs) - 2, "coefficients": T,
+        "phases_ms": phases,
+        "all_to_all": {"exchanges_per_product": 3, "buffer_bytes_per_rank_per_exchange": a2a_bytes,
+                       "sent_bytes_per_rank_per_exchange": sent, "ms_total": a2a_ms,
+                       "GBs_per_rank_unidirectional": (3 * sent / (a2a_ms * 1e-3) / 1e9) if (a2a_ms > 0 and world > 1) else None},
+        "ms_1gpu_same_product": base,
+        "strong_efficiency_vs_1gpu": (base / (world * ms)) if base else None,
+        "roofline": {"bound": "hbm", "what": "whole product: SURVEY 8(d) algorithmic bytes 18 T S + 16 (n1+n2) over all ranks",
+                     "alg_bytes": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                     "peak": (peak_gbs * world) if peak_gbs else None,
+                     "frac": (b_alg / (ms * 1e-3) / 1e9 / (peak_gbs * world)) if peak_gbs else None},
+        "bit_exact": bool(ok and (same is not False)),
+        "check": {"residues": "a*b == r modulo the six 31-bit primes of mpir_fft_b200/residues.py (weights 2^(64k) mod p, "
+                              "order of 2 > 3e8: position-sensitive), result limbs reduced where they live",
+                  "residues_match": bool(ok), "result_fingerprint": rr,
+                  "equals_1gpu_result": same,
+                  "full_compare": "2^26 x 2^26 against GMP mpn_mul limb for limb: profiles/r02_full_compare_2p26.json (scripts/full_compare.py)"},
+        "device_mem_gb": mem,
+    }
+    return rec
 
 
 def run_cfg4(args, rank, local_rank, world, torch, dist, M):

@@ -59,15 +59,18 @@ def _view(ptr, n, cuda):
 class ShardedMul:
     """One rank's part of a sharded product n1 x n2 limbs at (depth, w).
 
-    `L`: the bound library (default: the product library); `group`: the process group of the box.
+    `L`: the bound library (default: the product library); `group`: the process group of the box;
+    `single`: ignore the process group and run the whole product on this rank.
     Operands are given to every rank in full (device pointers, or numpy arrays for the emulated
     library); a rank reads only the pieces of its own columns."""
 
-    def __init__(self, n1, n2, depth, w, L=None, group=None, cuda=None):
+    def __init__(self, n1, n2, depth, w, L=None, group=None, cuda=None, single=False):
         self.L = bind_smul(L if L is not None else _default_lib())
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if single:               # the whole product on this rank, no collectives (1-GPU baseline inside a multi-rank job)
+            self.rank, self.world = 0, 1
         self.cuda = torch.cuda.is_available() if cuda is None else cuda
         self.n1, self.n2 = n1, n2
         h = C.c_void_p()
@@ -114,42 +117,83 @@ class ShardedMul:
             return
         dist.all_to_all_single(out, inp, out_split, in_split, group=self.group)
 
-    def multiply(self, d_i1, d_i2):
-        """run the product; afterwards self.out holds limbs [limb_lo, limb_hi) of it"""
+    def _mark(self, timing, name):
+        """phase boundary for the per-phase CUDA-event timing (bench.py); nothing when timing is off"""
+        if timing is None or not self.cuda:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        timing.append((name, ev))
+
+    def multiply(self, d_i1, d_i2, timing=None):
+        """run the product; afterwards self.out holds limbs [limb_lo, limb_hi) of it.
+        timing: a list that receives (phase name, CUDA event recorded when the phase has been issued)
+        pairs on the current stream (the NCCL collectives are ordered against it)"""
         lay, P = self.lay, self.P
+        self._mark(timing, "start")
         for which, d_in in ((0, d_i1), (1, d_i2)):
             self._phase(0, which, d_in)
+            self._mark(timing, "fwd_cols")
             self._a2a(self.recv[:sum(self.a_out)], self.send[:self.tr_limbs], self.a_out, self.a_in)
+            self._mark(timing, "all_to_all")
             self._phase(1, which)
+            self._mark(timing, "fwd_rows")
         self._phase(2)
+        self._mark(timing, "pointwise")
         self._phase(3)
+        self._mark(timing, "inv_rows")
         self._a2a(self.work[:self.tr_limbs], self.send[:sum(self.b_in)], self.b_out, self.b_in)
+        self._mark(timing, "all_to_all")
         self._phase(4)
+        self._mark(timing, "inv_cols")
         self._a2a(self.recv[:sum(self.a_out)], self.send[:self.tr_limbs], self.a_out, self.a_in)
+        self._mark(timing, "all_to_all")
         self._phase(5)
         if self.world > 1:
+            # halo: my last `halo_send` coefficients go to the next rank only, straight from the
+            # plan's row buffer into the successor's halo slots (no staging copy)
             hs = lay.halo_send
-            tail = _view(self.L.mpirfft_smul_tail_blocks(self.h, hs), hs * P, self.cuda)
-            if self.halo_buf is None:
-                self.halo_buf = torch.empty(self.world * hs * P, dtype=torch.int64, device=tail.device)
-            dist.all_gather_into_tensor(self.halo_buf, tail.clone(), group=self.group)
-            if self.rank > 0:
-                assert lay.halo == hs
-                unp = _view(lay.unp, hs * P, self.cuda)
-                unp.copy_(self.halo_buf[(self.rank - 1) * hs * P:self.rank * hs * P])
+            n = hs * P
+            tail = _view(self.L.mpirfft_smul_tail_blocks(self.h, hs), n, self.cuda)
+            unp = _view(lay.unp, n, self.cuda)
+            last = self.rank + 1 == self.world
+            in_split = [n if (g == self.rank + 1) else 0 for g in range(self.world)]
+            out_split = [n if (g == self.rank - 1) else 0 for g in range(self.world)]
+            dist.all_to_all_single(unp[:0 if self.rank == 0 else n], tail[:0 if last else n], out_split, in_split, group=self.group)
         self._phase(6)
-        # carry hand-off along the ranks (a few bits; the ripple is almost always zero limbs long)
-        carry = torch.zeros(1, dtype=torch.int64, device=self.out.device if self.world > 1 else "cpu")
-        for r in range(self.world):
-            if self.rank == r:
-                co = C.c_uint(0)
-                rc = self.L.mpirfft_smul_carry(self.h, int(carry.item()), C.byref(co), self._stream())
-                if rc != 0:
-                    raise RuntimeError("mpirfft_smul_carry failed (%d)" % rc)
-                carry.fill_(co.value)
-            if self.world > 1:
-                dist.broadcast(carry, src=dist.get_global_rank(self.group, r) if self.group is not None else r, group=self.group)
+        self._mark(timing, "recombine")
+        self._carry_handoff()
+        self._mark(timing, "carry")
         return self.out
+
+    def _carry(self, carry_in):
+        co = C.c_uint(0)
+        rc = self.L.mpirfft_smul_carry(self.h, int(carry_in), C.byref(co), self._stream())
+        if rc != 0:
+            raise RuntimeError("mpirfft_smul_carry failed (%d)" % rc)
+        return int(co.value)
+
+    def _carry_handoff(self):
+        """carries between the rank windows (FFT_combine_bits' carry to the end of r1, mul_fft.c:207-267).
+        Every rank publishes the carry that left its window (one all-gather); rank r adds the carry of
+        rank r-1.  Such an addition ripples out of a whole window only if every limb of it is all ones,
+        so a second all-gather of the ripples almost always finds zeros; otherwise the ripples are handed
+        on the same way until none is left (additions commute, so the result is exact)."""
+        own = self._carry(0)                      # what left my window in phase 6 (synchronises my stream)
+        if self.world == 1:
+            return
+        dev = self.out.device
+        pend = own
+        for _ in range(self.world + 1):
+            mine = torch.tensor([pend], dtype=torch.int64, device=dev)
+            every = torch.empty(self.world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(every, mine, group=self.group)
+            every = every.cpu().tolist()
+            if not any(every[:-1]):               # what leaves the last window is beyond n1 + n2 limbs: always 0
+                return
+            cin = every[self.rank - 1] if self.rank > 0 else 0
+            pend = (self._carry(cin) - own) if cin else 0     # the ripple of this addition only
+        raise RuntimeError("carry hand-off did not settle")
 
     def gather_result(self):
         """the whole product on every rank (testing / small sizes): limbs as a uint64 numpy array"""
