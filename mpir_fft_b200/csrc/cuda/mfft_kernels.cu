@@ -1644,8 +1644,9 @@ int mfft_dev_tiles_supported(uint32_t l) { int nt; return tiles_cfg(l, &nt); }
 
 static size_t tiles_coeff_bytes(uint32_t l)
 {
-   /* l body limbs + l/2 chunks with a 32-bit carry word each (mfft_tiles.h) */
-   return (size_t) l * 8 + (size_t)(l / 2) * 4;
+   /* the block image (l body limbs, top limb, pad limb: one 16-byte aligned slab pitch) + l/2 chunks
+      with a 32-bit carry word each (mfft_tiles.h: tile_cfg) */
+   return (size_t) l * 8 + 16 + (size_t)(l / 2) * 4;
 }
 
 uint32_t mfft_dev_tiles_max_npos(uint32_t l)
@@ -1675,7 +1676,7 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    if (!ntiles || !nbatch) return 0;
    if (!tiles_cfg(g->l, &NT)) { snprintf(g_err, sizeof g_err, "run_tiles: l=%u unsupported", g->l); return -2; }
    /* descriptor area (ops + position list), rounded to 16 bytes, then coefficients */
-   const uint32_t desc = (uint32_t)(((size_t) max_nops * sizeof(mfft_tileop) + (size_t) max_npos * 4 + 4 * 64 + 15) & ~(size_t) 15);
+   const uint32_t desc = (uint32_t)((MBAR_BYTES + (size_t) max_nops * sizeof(mfft_tileop) + (size_t) max_npos * 4 + 4 * 64 + 15) & ~(size_t) 15);
    const size_t smem = desc + (size_t) max_npos * tiles_coeff_bytes(g->l);
    const unsigned grid = ntiles * nbatch;
    cudaStream_t st = (cudaStream_t) stream;

@@ -108,7 +108,9 @@ __device__ __forceinline__ void st2(limb_t *p, limb_t x0, limb_t x1)
 template <int NT> struct tile_cfg {
    static constexpr uint32_t L = 64u * NT;           /* body limbs */
    static constexpr uint32_t NCH = 32u * NT;         /* chunks */
-   static constexpr uint32_t SP = L + NCH / 2;       /* limbs per coefficient: body + int32 carry words */
+   static constexpr uint32_t CW = L + 2;             /* limb offset of the carry words: behind the block image (body, top limb, pad) */
+   static constexpr uint32_t SP = CW + NCH / 2;      /* limbs per coefficient: block image (one 16-byte aligned pitch of the slab,
+                                                        so that a bulk copy of a whole block lands in place) + int32 carry words */
 };
 
 /* one term of an op after folding e >= NW into the sign */
@@ -161,7 +163,7 @@ __device__ __forceinline__ void aligned_out(limb_t *out, const tterm &ta, const 
 #else
    *reinterpret_cast<ulonglong2 *>(out + 2 * och) = make_ulonglong2(r0, r1);
 #endif
-   reinterpret_cast<int32_t *>(out + L)[och] = k;
+   reinterpret_cast<int32_t *>(out + tile_cfg<NT>::CW)[och] = k;
 }
 
 /* ---- general path ------------------------------------------------------------------------- */
@@ -194,7 +196,7 @@ __device__ __forceinline__ void general_term(limb_t &x0, limb_t &x1, limb_t &e0,
    x0 ^= m0 ^ nm; x1 ^= m1 ^ nm;
    const uint32_t wrapped = (ch <= t.yc);
    const uint32_t j = wrapped ? ch + NCH - 1 - t.yc : ch - 1 - t.yc;
-   int64_t c = (int64_t) reinterpret_cast<const int32_t *>(X + L)[j];
+   int64_t c = (int64_t) reinterpret_cast<const int32_t *>(X + tile_cfg<NT>::CW)[j];
    if (wrapped) c = -c;
    if (ch == t.yc) c -= 1;
    const int64_t V = t.neg ? -c : c;
@@ -229,7 +231,7 @@ template <int NT>
 __device__ __forceinline__ int64_t resolve_carries(limb_t *sblk, uint32_t lane)
 {
    constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH;
-   const int32_t *cw = reinterpret_cast<const int32_t *>(sblk + L);
+   const int32_t *cw = reinterpret_cast<const int32_t *>(sblk + tile_cfg<NT>::CW);
    limb_t r[2 * NT];
    int64_t cy = 0;
 #pragma unroll
@@ -323,7 +325,7 @@ template <int NT>
 __device__ __forceinline__ int64_t resolve_regs(limb_t (&r0)[NT], limb_t (&r1)[NT], const limb_t *sblk, uint32_t lane)
 {
    constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH;
-   const int32_t *cw = reinterpret_cast<const int32_t *>(sblk + L);
+   const int32_t *cw = reinterpret_cast<const int32_t *>(sblk + tile_cfg<NT>::CW);
    int32_t d[NT];
 #pragma unroll
    for (int ti = 0; ti < NT; ti++)
@@ -373,6 +375,52 @@ __device__ __forceinline__ limb_t *tile_block_ptr(limb_t *slab, const mfft_geom 
    const uint64_t idx = (uint64_t) b.parity * g.half_blocks + b.base + (uint64_t) pos * g.slot_stride;
    return slab + idx * g.pitch;
 }
+
+/* ---- bulk asynchronous copies (TMA engine, cp.async.bulk -> UBLKCP) completing on an mbarrier ---- */
+/* A tile is fetched by a handful of bulk copies -- one whole (l+2)-limb block image per coefficient
+ * plus the tile's op descriptors -- issued by the lanes of one warp; the copy engine moves the data
+ * while no thread of the CTA spends issue slots on it, and every thread then waits on the barrier's
+ * phase.  MBAR_BYTES of shared memory are reserved for the barrier object. */
+#define MBAR_BYTES 32
+#ifdef MFFT_EMU
+typedef emu_mbar tile_mbar;
+__device__ __forceinline__ void mbar_init(tile_mbar *m, uint32_t count) { emu_mbar_init(m, count); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(tile_mbar *m, uint32_t bytes) { emu_mbar_arrive_expect_tx(m, bytes); }
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, tile_mbar *m) { emu_bulk_copy(sdst, gsrc, bytes, m); }
+__device__ __forceinline__ void mbar_wait(tile_mbar *m, uint32_t parity) { emu_mbar_wait(m, parity); }
+__device__ __forceinline__ void fence_async_smem() { }
+#else
+typedef unsigned long long tile_mbar;
+__device__ __forceinline__ void mbar_init(tile_mbar *m, uint32_t count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t) __cvta_generic_to_shared(m)), "r"(count) : "memory");
+   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(tile_mbar *m, uint32_t bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                :: "r"((uint32_t) __cvta_generic_to_shared(m)), "r"(bytes) : "memory");
+}
+/* bytes: a multiple of 16; both addresses 16-byte aligned */
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, uint32_t bytes, tile_mbar *m)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                :: "r"((uint32_t) __cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes),
+                   "r"((uint32_t) __cvta_generic_to_shared(m)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(tile_mbar *m, uint32_t parity)
+{
+   asm volatile("{\n\t.reg .pred p;\n\t"
+                "MBAR_WAIT_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra MBAR_DONE_%=;\n\t"
+                "bra MBAR_WAIT_%=;\n\t"
+                "MBAR_DONE_%=:\n\t}"
+                :: "r"((uint32_t) __cvta_generic_to_shared(m)), "r"(parity) : "memory");
+}
+/* orders earlier generic-proxy accesses to shared memory before later asynchronous-proxy ones */
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 /* 16-byte asynchronous copy global -> shared (LDGSTS), L2 only: the tile is read exactly once */
 __device__ __forceinline__ void cp_async16(limb_t *sdst, const limb_t *gsrc)
@@ -427,10 +475,10 @@ __device__ __forceinline__ cval cv_add(const cval &a, const cval &b)
 { cval r; r.c = add2(r.x0, r.x1, a.x0, a.x1, b.x0, b.x1) + a.c + b.c; return r; }
 __device__ __forceinline__ cval cv_sub(const cval &a, const cval &b)
 { cval r; r.c = sub2(r.x0, r.x1, a.x0, a.x1, b.x0, b.x1) + a.c - b.c; return r; }
-__device__ __forceinline__ cval cv_load(const limb_t *P, uint32_t L, uint32_t ch)
-{ cval r; ld2(r.x0, r.x1, P + 2 * ch); r.c = reinterpret_cast<const int32_t *>(P + L)[ch]; return r; }
-__device__ __forceinline__ void cv_store(limb_t *P, uint32_t L, uint32_t ch, const cval &v)
-{ st2(P + 2 * ch, v.x0, v.x1); reinterpret_cast<int32_t *>(P + L)[ch] = v.c; }
+__device__ __forceinline__ cval cv_load(const limb_t *P, uint32_t cwoff, uint32_t ch)      /* cwoff = tile_cfg<NT>::CW */
+{ cval r; ld2(r.x0, r.x1, P + 2 * ch); r.c = reinterpret_cast<const int32_t *>(P + cwoff)[ch]; return r; }
+__device__ __forceinline__ void cv_store(limb_t *P, uint32_t cwoff, uint32_t ch, const cval &v)
+{ st2(P + 2 * ch, v.x0, v.x1); reinterpret_cast<int32_t *>(P + cwoff)[ch] = v.c; }
 
 /* Two forward layers on positions P0..P3 in place (FFT_radix2 786-827, two levels of the recursion):
  *    layer 1:  (P0,P2) -> P0+P2, +-(P0-P2) 2^(128 y1)      (P1,P3) -> P1+P3, +-(P1-P3) 2^(128 y1')
@@ -450,7 +498,7 @@ __device__ __forceinline__ void fwd4_unit(limb_t *P0, limb_t *P1, limb_t *P2, li
    for (int ti = 0; ti < NT; ti++)
    {
       const uint32_t i = ti * 32u + lane;
-      a0[ti] = cv_load(P0, L, i); a1[ti] = cv_load(P1, L, i); a2[ti] = cv_load(P2, L, i); a3[ti] = cv_load(P3, L, i);
+      a0[ti] = cv_load(P0, tile_cfg<NT>::CW, i); a1[ti] = cv_load(P1, tile_cfg<NT>::CW, i); a2[ti] = cv_load(P2, tile_cfg<NT>::CW, i); a3[ti] = cv_load(P3, tile_cfg<NT>::CW, i);
    }
    __syncwarp();
    /* layer 1 in place: a0 <- a0+a2, a2 <- +-(a0-a2) (the chunk that lands at i+y1), same for a1,a3 */
@@ -472,18 +520,18 @@ __device__ __forceinline__ void fwd4_unit(limb_t *P0, limb_t *P1, limb_t *P2, li
       const uint32_t i = ti * 32u + lane;
       constexpr int dummy = 0; (void) dummy;
       const int tp = (ti + H) % NT;                         /* a3's chunk that lands where a2[ti] does */
-      cv_store(P0, L, i, cv_add(a0[ti], a1[ti]));
+      cv_store(P0, tile_cfg<NT>::CW, i, cv_add(a0[ti], a1[ti]));
       {
          uint32_t o = i + y2, n = n2;
          if (o >= NCH) { o -= NCH; n ^= 1u; }
-         cv_store(P1, L, o, n ? cv_sub(a1[ti], a0[ti]) : cv_sub(a0[ti], a1[ti]));
+         cv_store(P1, tile_cfg<NT>::CW, o, n ? cv_sub(a1[ti], a0[ti]) : cv_sub(a0[ti], a1[ti]));
       }
       uint32_t j = i + y1; if (j >= NCH) j -= NCH;
-      cv_store(P2, L, j, cv_add(a2[ti], a3[tp]));
+      cv_store(P2, tile_cfg<NT>::CW, j, cv_add(a2[ti], a3[tp]));
       {
          uint32_t o = j + y2p, n = n2p;
          if (o >= NCH) { o -= NCH; n ^= 1u; }
-         cv_store(P3, L, o, n ? cv_sub(a3[tp], a2[ti]) : cv_sub(a2[ti], a3[tp]));
+         cv_store(P3, tile_cfg<NT>::CW, o, n ? cv_sub(a3[tp], a2[ti]) : cv_sub(a2[ti], a3[tp]));
       }
    }
 }
@@ -508,7 +556,7 @@ __device__ __forceinline__ void inv4_unit(limb_t *P0, limb_t *P1, limb_t *P2, li
       const uint32_t jb = (i >= y2) ? i - y2 : i + NCH - y2;
       const uint32_t m = (i >= y1) ? i - y1 : i + NCH - y1;
       const uint32_t mb = (m >= y2p) ? m - y2p : m + NCH - y2p;
-      u0[ti] = cv_load(P0, L, i); u1[ti] = cv_load(P1, L, jb); u2[ti] = cv_load(P2, L, m); u3[ti] = cv_load(P3, L, mb);
+      u0[ti] = cv_load(P0, tile_cfg<NT>::CW, i); u1[ti] = cv_load(P1, tile_cfg<NT>::CW, jb); u2[ti] = cv_load(P2, tile_cfg<NT>::CW, m); u3[ti] = cv_load(P3, tile_cfg<NT>::CW, mb);
    }
    __syncwarp();
 #pragma unroll
@@ -535,14 +583,14 @@ __device__ __forceinline__ void inv4_unit(limb_t *P0, limb_t *P1, limb_t *P2, li
       {
          const bool ng = ((i < y1) ? 1u : 0u) != n1;       /* P2's chunk enters negated */
          limb_t *ds = ng ? P2 : P0, *dt = ng ? P0 : P2;
-         cv_store(ds, L, i, cv_add(u0[ti], u2[ti]));
-         cv_store(dt, L, i, cv_sub(u0[ti], u2[ti]));
+         cv_store(ds, tile_cfg<NT>::CW, i, cv_add(u0[ti], u2[ti]));
+         cv_store(dt, tile_cfg<NT>::CW, i, cv_sub(u0[ti], u2[ti]));
       }
       {
          const bool ng = ((i < y1p) ? 1u : 0u) != n1p;
          limb_t *ds = ng ? P3 : P1, *dt = ng ? P1 : P3;
-         cv_store(ds, L, i, cv_add(u1[ti], u3[tp]));
-         cv_store(dt, L, i, cv_sub(u1[ti], u3[tp]));
+         cv_store(ds, tile_cfg<NT>::CW, i, cv_add(u1[ti], u3[tp]));
+         cv_store(dt, tile_cfg<NT>::CW, i, cv_sub(u1[ti], u3[tp]));
       }
    }
 }
@@ -572,7 +620,7 @@ __device__ __forceinline__ void rotg_unit(limb_t *S, const limb_t *A, uint32_t t
    uint32_t yc1 = (t + 127u) >> 7;
    const uint32_t s = 128u * yc1 - t;                       /* 0..127 */
    if (yc1 == NCH) { yc1 = 0; neg ^= 1u; }                  /* a full turn is a factor -1 */
-   const int32_t *cwA = reinterpret_cast<const int32_t *>(A + L);
+   const int32_t *cwA = reinterpret_cast<const int32_t *>(A + tile_cfg<NT>::CW);
    cval r[NT]; limb_t y0[NT], y1[NT];
 #pragma unroll
    for (int ti = 0; ti < NT; ti++)
@@ -591,7 +639,7 @@ __device__ __forceinline__ void rotg_unit(limb_t *S, const limb_t *A, uint32_t t
       }
    }
    __syncwarp();
-   int32_t *cwS = reinterpret_cast<int32_t *>(S + L);
+   int32_t *cwS = reinterpret_cast<int32_t *>(S + tile_cfg<NT>::CW);
 #pragma unroll
    for (int ti = 0; ti < NT; ti++)
    {
@@ -609,166 +657,29 @@ __device__ __forceinline__ void rotg_unit(limb_t *S, const limb_t *A, uint32_t t
    }
 }
 
-/* tile descriptors of a small pass as kernel parameters (constant bank): no dependent global loads
- * before a CTA can start fetching its coefficients */
-#define TP_MAXT 16
-#define TP_MAXP 32
-#define TP_MAXS 12
-#define TP_MAXB 256
-struct tile_params {
-   uint32_t valid, batch_valid;
-   /* split fused into the tile load (FFT_split_bits, mul_fft.c:115-170): block k of the slab is
-      coefficient k = bits [k*bits, (k+1)*bits) of {src, nlimbs}, zero beyond ncoef */
-   uint32_t split; const limb_t *split_src; uint64_t split_nlimbs, split_bits, split_ncoef;
-   mfft_batch batch[TP_MAXB];
-   mfft_tile tiles[TP_MAXT];
-   uint32_t pos[TP_MAXT * TP_MAXP];
-   uint32_t stoff[TP_MAXT * TP_MAXS];
-};
-
-/* ---- the kernel ----------------------------------------------------------------------------- */
-template <int NT, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, (NTHREADS == 128) ? 4 : 2)
-k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
-            const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
-            limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
-            uint32_t dst_stride, int normalise, uint32_t desc_bytes, const uint32_t *__restrict__ stoff,
-            unsigned long long *timing, const __grid_constant__ tile_params TP)
+/* barrier of the threads that work on one tile: the whole CTA (bar_id 0) or one warp group of a
+   persistent CTA (named barrier bar_id, bar_threads threads) */
+__device__ __forceinline__ void tile_sync(uint32_t bar_id, uint32_t bar_threads)
 {
-#ifndef MFFT_EMU
-#define TILE_STAMP(k) do { if (timing && threadIdx.x == 0) { unsigned long long t__; \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); timing[(size_t) blockIdx.x * 8 + (k)] = t__; } } while (0)
+#ifdef MFFT_EMU
+   if (bar_id == 0) __syncthreads(); else emu_bar_sync(bar_id, bar_threads);
 #else
-#define TILE_STAMP(k) do { } while (0)
+   if (bar_id == 0) __syncthreads();
+   else asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(bar_threads) : "memory");
 #endif
-   TILE_STAMP(0);
-   MFFT_DYN_SMEM(limb_t, sm);
-   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP;
+}
+
+/* all stages of a tile on the coefficients in shared memory (sops sorted by stage, sst[k] = first op
+   of stage k); warp `warp` of `nwarps` takes every nwarps-th op of a stage */
+template <int NT>
+__device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sops, const uint32_t *sst, uint32_t nstages,
+                                            const mfft_batch &b, uint32_t warp, uint32_t nwarps, uint32_t lane,
+                                            uint32_t bar_id, uint32_t bar_threads)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP, CW = tile_cfg<NT>::CW;
    constexpr uint32_t NW = 64u * L, M2 = 2u * NW;
    constexpr uint32_t AMASK = 127u;                           /* exponent bits that break chunk alignment */
-   const uint32_t bi = blockIdx.x % nbatch, tix = blockIdx.x / nbatch;
-   const mfft_tile T = TP.valid ? TP.tiles[tix] : tiles[tix];
-   const mfft_batch b = TP.batch_valid ? TP.batch[bi] : batch[bi];
-   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-   /* shared memory: [op descriptors | position list | stage offsets] [coefficients] */
-   mfft_tileop *sops = (mfft_tileop *) sm;
-   uint32_t *spos = (uint32_t *)(sops + T.nops);
-   uint32_t *sst = spos + T.npos;                      /* [nstages+1] first op of each stage */
-   limb_t *coef = sm + desc_bytes / 8;
-
-   {  /* descriptors: asynchronous copies that land together with the tile's coefficients */
-      static_assert(sizeof(mfft_tileop) % 16 == 0, "op descriptors are copied in 16-byte pieces");
-      const limb_t *src = (const limb_t *)(ops + T.op_off);
-      limb_t *d = (limb_t *) sops;
-      for (uint32_t k = tid; k < T.nops * (uint32_t)(sizeof(mfft_tileop) / 16); k += blockDim.x) cp_async16(d + 2 * k, src + 2 * k);
-      if (TP.valid)
-      {
-         for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = TP.pos[tix * TP_MAXP + k];
-         for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = TP.stoff[tix * TP_MAXS + k];
-      } else
-      {
-         for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = pos[T.pos_off + k];
-         for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = stoff[T.pad + k];
-      }
-   }
-   __syncthreads();                                   /* the position list is read by everybody below */
-#ifndef MFFT_EMU
-   /* programmatic dependent launch: when the launch carries the stream-serialisation attribute this
-      CTA may have been scheduled (and its descriptors staged) while the previous pass was still
-      draining; nothing written by that pass is read above.  Without the attribute both are no-ops. */
-   asm volatile("griddepcontrol.wait;" ::: "memory");
-   asm volatile("griddepcontrol.launch_dependents;");
-#endif
-   /* load the positions that are read before being written: the body as it is, carry words 0
-      except the last one, which is the block's signed top limb */
-   const bool al16 = ((g.pitch & 1u) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15u) == 0) &&
-                     (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
-   if (TP.split)
-   {  /* the tile's coefficients are cut straight out of the operand: no split kernel, no slab read */
-      /* limb k of coefficient i = bits [i*bits + 64k, +64) of the operand: two loads and a funnel
-         shift with the same shift count for the whole coefficient; consecutive threads read
-         consecutive limbs, four coefficients are in flight per thread */
-      const uint32_t blimbs = (uint32_t)((TP.split_bits + 63) >> 6);     /* limbs that receive bits */
-      const limb_t lastmask = (TP.split_bits & 63) ? (((limb_t) 1 << (TP.split_bits & 63)) - 1) : ~(limb_t) 0;
-      for (uint32_t p0 = 0; p0 < T.npos; p0 += 4)
-      {
-         uint64_t qb[4]; uint32_t rr[4]; bool ld[4], nz[4];
-#pragma unroll
-         for (int u = 0; u < 4; u++)
-         {
-            const uint32_t p = p0 + u;
-            const uint32_t pp = (p < T.npos) ? spos[p] : 0u;
-            ld[u] = (pp & MFFT_TILE_LOAD) != 0;
-            const uint64_t i = (uint64_t) b.base + (uint64_t)(pp & MFFT_TILE_POSMASK) * g.slot_stride;
-            const uint64_t off = i * TP.split_bits;
-            nz[u] = ld[u] && i < TP.split_ncoef;
-            qb[u] = off >> 6; rr[u] = (uint32_t)(off & 63);
-         }
-         for (uint32_t k = tid; k < L; k += blockDim.x)
-         {
-            limb_t lo[4], hi[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-            {
-               lo[u] = 0; hi[u] = 0;
-               if (nz[u] && k < blimbs)
-               {
-                  const uint64_t q = qb[u] + k;
-                  if (q < TP.split_nlimbs) lo[u] = TP.split_src[q];
-                  if (q + 1 < TP.split_nlimbs) hi[u] = TP.split_src[q + 1];
-               }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-            {
-               if (!ld[u]) continue;
-               limb_t v = lo[u] >> rr[u];
-               if (rr[u]) v |= hi[u] << (64 - rr[u]);
-               if (k + 1 == blimbs) v &= lastmask;
-               coef[(size_t)(p0 + u) * SP + k] = v;
-            }
-         }
-      }
-      for (uint32_t t = tid; t < T.npos * NCH; t += blockDim.x)
-         if (spos[t / NCH] & MFFT_TILE_LOAD) reinterpret_cast<int32_t *>(coef + (size_t)(t / NCH) * SP + L)[t % NCH] = 0;
-   } else
-   if (al16)
-   {  /* 16-byte aligned blocks: every thread fires its share of asynchronous 16-byte copies, one wait.
-         The signed top limbs (one global load per loaded coefficient) are requested first so that
-         their latency hides behind the copy loop. */
-      limb_t topv = 0; bool have_top = false;
-      if (tid < T.npos && (spos[tid] & MFFT_TILE_LOAD))
-      { topv = tile_block_ptr(slab, g, spos[tid] & MFFT_TILE_POSMASK, b)[L]; have_top = true; }
-      for (uint32_t t = tid; t < T.npos * NCH; t += blockDim.x)
-      {
-         const uint32_t p = t / NCH, c = t % NCH;
-         const uint32_t pp = spos[p];
-         if (!(pp & MFFT_TILE_LOAD)) continue;
-         const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
-         limb_t *d = coef + (size_t) p * SP;
-         cp_async16(d + 2 * c, src + 2 * c);
-         if (c != NCH - 1) reinterpret_cast<int32_t *>(d + L)[c] = 0;
-      }
-      if (have_top) reinterpret_cast<int32_t *>(coef + (size_t) tid * SP + L)[NCH - 1] = (int32_t)(int64_t) topv;
-   } else
-   for (uint32_t p = warp; p < T.npos; p += nwarps)
-   {
-      const uint32_t pp = spos[p];
-      if (!(pp & MFFT_TILE_LOAD)) continue;
-      const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
-      limb_t *d = coef + (size_t) p * SP;
-#pragma unroll 4
-      for (uint32_t k = lane; k < L; k += 32) d[k] = src[k];
-      int32_t *cw = reinterpret_cast<int32_t *>(d + L);
-#pragma unroll
-      for (uint32_t ch = lane; ch < NCH; ch += 32) cw[ch] = (ch == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
-   }
-   TILE_STAMP(1);
-   cp_async_wait_all();
-   __syncthreads();
-   TILE_STAMP(2);
-
-   for (uint32_t st = 0; st < T.nstages; st++)
+   for (uint32_t st = 0; st < nstages; st++)
    {
       const uint32_t o0 = sst[st], o1 = sst[st + 1];
       for (uint32_t oi = o0 + warp; oi < o1; oi += nwarps)
@@ -794,9 +705,9 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
          if (op.kind != MFFT_K_ANY)
          {  /* host-classified aligned shapes: lane-local chunk arithmetic, nothing to decode */
             const uint32_t yc = op.kparam & 0x7fffffffu, neg = op.kparam >> 31;
-            const int32_t *cwA = reinterpret_cast<const int32_t *>(A + L);
-            const int32_t *cwB = reinterpret_cast<const int32_t *>(B + L);
-            int32_t *cwS = reinterpret_cast<int32_t *>(S + L), *cwT = reinterpret_cast<int32_t *>(Tt + L);
+            const int32_t *cwA = reinterpret_cast<const int32_t *>(A + tile_cfg<NT>::CW);
+            const int32_t *cwB = reinterpret_cast<const int32_t *>(B + tile_cfg<NT>::CW);
+            int32_t *cwS = reinterpret_cast<int32_t *>(S + tile_cfg<NT>::CW), *cwT = reinterpret_cast<int32_t *>(Tt + tile_cfg<NT>::CW);
             limb_t a0[NT], a1[NT], b0[NT], b1[NT]; int32_t ca[NT], cb[NT];
             if (op.kind == MFFT_K_FWD)
             {
@@ -840,9 +751,9 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
                   limb_t *ds = n ? Tt : S, *dt = n ? S : Tt;
                   limb_t r0, r1; int32_t k;
                   k = add2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]);
-                  st2(ds + 2 * i, r0, r1); reinterpret_cast<int32_t *>(ds + L)[i] = k + ca[ti] + cb[ti];
+                  st2(ds + 2 * i, r0, r1); reinterpret_cast<int32_t *>(ds + tile_cfg<NT>::CW)[i] = k + ca[ti] + cb[ti];
                   k = sub2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]);
-                  st2(dt + 2 * i, r0, r1); reinterpret_cast<int32_t *>(dt + L)[i] = k + ca[ti] - cb[ti];
+                  st2(dt + 2 * i, r0, r1); reinterpret_cast<int32_t *>(dt + tile_cfg<NT>::CW)[i] = k + ca[ti] - cb[ti];
                }
             } else if (op.kind == MFFT_K_ROT)
             {
@@ -972,8 +883,8 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
             const tterm &ref = sb.present ? sa : ta, &refb = sb.present ? sb : tb;
             const uint32_t dB = (ref.yc + NCH - refb.yc) % NCH;       /* B's chunk = A's chunk + dB */
             const bool useB = sb.present || tb.present;
-            const int32_t *cwA = reinterpret_cast<const int32_t *>(A + L);
-            const int32_t *cwB = reinterpret_cast<const int32_t *>(B + L);
+            const int32_t *cwA = reinterpret_cast<const int32_t *>(A + tile_cfg<NT>::CW);
+            const int32_t *cwB = reinterpret_cast<const int32_t *>(B + tile_cfg<NT>::CW);
             limb_t xa[NT][2], xb[NT][2]; int32_t ca[NT], cb[NT];
 #pragma unroll
             for (int ti = 0; ti < NT; ti++)
@@ -1017,7 +928,7 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
                if (hasT) kt[ti] = general_out<NT>(rt[ti][0], rt[ti][1], ta, A, tb, B, ch);
             }
             __syncwarp();
-            int32_t *cwS = reinterpret_cast<int32_t *>(S + L), *cwT = reinterpret_cast<int32_t *>(Tt + L);
+            int32_t *cwS = reinterpret_cast<int32_t *>(S + tile_cfg<NT>::CW), *cwT = reinterpret_cast<int32_t *>(Tt + tile_cfg<NT>::CW);
 #pragma unroll
             for (int ti = 0; ti < NT; ti++)
             {
@@ -1027,12 +938,19 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
             }
          }
       }
-      __syncthreads();
+      tile_sync(bar_id, bar_threads);
    }
+}
 
-   TILE_STAMP(3);
-   /* store what was written: in place, or gathered (and normalised) into dst */
-   for (uint32_t p = warp; p < T.npos; p += nwarps)
+/* store what was written: in place, or gathered (and normalised) into dst */
+template <int NT>
+__device__ __forceinline__ void tile_store(limb_t *coef, const uint32_t *spos, uint32_t npos, limb_t *slab, const mfft_geom &g,
+                                           const mfft_batch &b, uint32_t bi, limb_t *dst, const uint32_t *__restrict__ dstpos,
+                                           const uint32_t *__restrict__ dst_base, uint32_t dst_stride, int normalise, bool al16,
+                                           uint32_t warp, uint32_t nwarps, uint32_t lane)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, SP = tile_cfg<NT>::SP;
+   for (uint32_t p = warp; p < npos; p += nwarps)
    {
       const uint32_t pp = spos[p];
       if (!(pp & MFFT_TILE_STORE)) continue;
@@ -1060,6 +978,188 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
       for (uint32_t k = lane; k < L; k += 32) out[k] = sblk[k];
       if (lane == 0) out[L] = (limb_t) top;
    }
+}
+
+/* tile descriptors of a small pass as kernel parameters (constant bank): no dependent global loads
+ * before a CTA can start fetching its coefficients */
+#define TP_MAXT 16
+#define TP_MAXP 32
+#define TP_MAXS 12
+#define TP_MAXB 256
+struct tile_params {
+   uint32_t valid, batch_valid;
+   /* split fused into the tile load (FFT_split_bits, mul_fft.c:115-170): block k of the slab is
+      coefficient k = bits [k*bits, (k+1)*bits) of {src, nlimbs}, zero beyond ncoef */
+   uint32_t split; const limb_t *split_src; uint64_t split_nlimbs, split_bits, split_ncoef;
+   mfft_batch batch[TP_MAXB];
+   mfft_tile tiles[TP_MAXT];
+   uint32_t pos[TP_MAXT * TP_MAXP];
+   uint32_t stoff[TP_MAXT * TP_MAXS];
+};
+
+/* ---- the kernel ----------------------------------------------------------------------------- */
+template <int NT, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, (NTHREADS == 128) ? 4 : 2)
+k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
+            const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
+            limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
+            uint32_t dst_stride, int normalise, uint32_t desc_bytes, const uint32_t *__restrict__ stoff,
+            unsigned long long *timing, const __grid_constant__ tile_params TP)
+{
+#ifndef MFFT_EMU
+#define TILE_STAMP(k) do { if (timing && threadIdx.x == 0) { unsigned long long t__; \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); timing[(size_t) blockIdx.x * 8 + (k)] = t__; } } while (0)
+#else
+#define TILE_STAMP(k) do { } while (0)
+#endif
+   TILE_STAMP(0);
+   MFFT_DYN_SMEM(limb_t, sm);
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP;
+   constexpr uint32_t NW = 64u * L, M2 = 2u * NW;
+   constexpr uint32_t AMASK = 127u;                           /* exponent bits that break chunk alignment */
+   const uint32_t bi = blockIdx.x % nbatch, tix = blockIdx.x / nbatch;
+   const mfft_tile T = TP.valid ? TP.tiles[tix] : tiles[tix];
+   const mfft_batch b = TP.batch_valid ? TP.batch[bi] : batch[bi];
+   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+   /* shared memory: [mbarrier] [op descriptors | position list | stage offsets] [coefficients] */
+   tile_mbar *mbar = (tile_mbar *) sm;
+   mfft_tileop *sops = (mfft_tileop *)(sm + MBAR_BYTES / 8);
+   uint32_t *spos = (uint32_t *)(sops + T.nops);
+   uint32_t *sst = spos + T.npos;                      /* [nstages+1] first op of each stage */
+   limb_t *coef = sm + desc_bytes / 8;
+
+   {  /* the barrier all of the tile's bulk copies complete on; position list and stage offsets */
+      static_assert(sizeof(mfft_tileop) % 16 == 0, "op descriptors are fetched by one bulk copy");
+      if (tid == 0) mbar_init(mbar, 1);
+      if (TP.valid)
+      {
+         for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = TP.pos[tix * TP_MAXP + k];
+         for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = TP.stoff[tix * TP_MAXS + k];
+      } else
+      {
+         for (uint32_t k = tid; k < T.npos; k += blockDim.x) spos[k] = pos[T.pos_off + k];
+         for (uint32_t k = tid; k <= T.nstages; k += blockDim.x) sst[k] = stoff[T.pad + k];
+      }
+   }
+   __syncthreads();                                   /* the position list is read by everybody below */
+#ifndef MFFT_EMU
+   /* programmatic dependent launch: when the launch carries the stream-serialisation attribute this
+      CTA may have been scheduled (and its descriptors staged) while the previous pass was still
+      draining; nothing written by that pass is read above.  Without the attribute both are no-ops. */
+   asm volatile("griddepcontrol.wait;" ::: "memory");
+   asm volatile("griddepcontrol.launch_dependents;");
+#endif
+   /* load the positions that are read before being written: the body as it is, carry words 0
+      except the last one, which is the block's signed top limb */
+   const bool al16 = ((g.pitch & 1u) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15u) == 0) &&
+                     (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+   const bool bulk_tile = al16 && !TP.split && g.pitch >= L + 2;      /* whole block images by bulk copy */
+   if (warp == 0)
+   {  /* one warp issues the tile's copies: the op descriptors and, for 16-byte aligned slabs, one
+         (l+2)-limb block image per coefficient that is read before it is written */
+      uint32_t nload = 0;
+      if (bulk_tile) for (uint32_t p = lane; p < T.npos; p += 32) nload += (spos[p] & MFFT_TILE_LOAD) ? 1u : 0u;
+#pragma unroll
+      for (int off = 16; off; off >>= 1) nload += __shfl_xor_sync(FULL, nload, off);
+      if (lane == 0)
+      {
+         mbar_arrive_expect_tx(mbar, T.nops * (uint32_t) sizeof(mfft_tileop) + nload * (L + 2) * 8u);
+         if (T.nops) bulk_g2s(sops, ops + T.op_off, T.nops * (uint32_t) sizeof(mfft_tileop), mbar);
+      }
+      __syncwarp();
+      if (bulk_tile)
+         for (uint32_t p = lane; p < T.npos; p += 32)
+         {
+            const uint32_t pp = spos[p];
+            if (pp & MFFT_TILE_LOAD) bulk_g2s(coef + (size_t) p * SP, tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b), (L + 2) * 8u, mbar);
+         }
+   }
+   if (TP.split)
+   {  /* the tile's coefficients are cut straight out of the operand: no split kernel, no slab read */
+      /* limb k of coefficient i = bits [i*bits + 64k, +64) of the operand: two loads and a funnel
+         shift with the same shift count for the whole coefficient; consecutive threads read
+         consecutive limbs, four coefficients are in flight per thread */
+      const uint32_t blimbs = (uint32_t)((TP.split_bits + 63) >> 6);     /* limbs that receive bits */
+      const limb_t lastmask = (TP.split_bits & 63) ? (((limb_t) 1 << (TP.split_bits & 63)) - 1) : ~(limb_t) 0;
+      for (uint32_t p0 = 0; p0 < T.npos; p0 += 4)
+      {
+         uint64_t qb[4]; uint32_t rr[4]; bool ld[4], nz[4];
+#pragma unroll
+         for (int u = 0; u < 4; u++)
+         {
+            const uint32_t p = p0 + u;
+            const uint32_t pp = (p < T.npos) ? spos[p] : 0u;
+            ld[u] = (pp & MFFT_TILE_LOAD) != 0;
+            const uint64_t i = (uint64_t) b.base + (uint64_t)(pp & MFFT_TILE_POSMASK) * g.slot_stride;
+            const uint64_t off = i * TP.split_bits;
+            nz[u] = ld[u] && i < TP.split_ncoef;
+            qb[u] = off >> 6; rr[u] = (uint32_t)(off & 63);
+         }
+         for (uint32_t k = tid; k < L; k += blockDim.x)
+         {
+            limb_t lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+               lo[u] = 0; hi[u] = 0;
+               if (nz[u] && k < blimbs)
+               {
+                  const uint64_t q = qb[u] + k;
+                  if (q < TP.split_nlimbs) lo[u] = TP.split_src[q];
+                  if (q + 1 < TP.split_nlimbs) hi[u] = TP.split_src[q + 1];
+               }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+               if (!ld[u]) continue;
+               limb_t v = lo[u] >> rr[u];
+               if (rr[u]) v |= hi[u] << (64 - rr[u]);
+               if (k + 1 == blimbs) v &= lastmask;
+               coef[(size_t)(p0 + u) * SP + k] = v;
+            }
+         }
+      }
+      for (uint32_t t = tid; t < T.npos * NCH; t += blockDim.x)
+         if (spos[t / NCH] & MFFT_TILE_LOAD) reinterpret_cast<int32_t *>(coef + (size_t)(t / NCH) * SP + tile_cfg<NT>::CW)[t % NCH] = 0;
+   } else
+   if (bulk_tile)
+   {  /* the block images are on their way; meanwhile zero the carry words (they live behind the image) */
+      for (uint32_t t = tid; t < T.npos * (NCH / 4); t += blockDim.x)
+      {
+         const uint32_t p = t / (NCH / 4), c = t % (NCH / 4);
+         if (!(spos[p] & MFFT_TILE_LOAD)) continue;
+         st2(coef + (size_t) p * SP + tile_cfg<NT>::CW + 2 * c, 0, 0);
+      }
+   } else
+   for (uint32_t p = warp; p < T.npos; p += nwarps)
+   {
+      const uint32_t pp = spos[p];
+      if (!(pp & MFFT_TILE_LOAD)) continue;
+      const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
+      limb_t *d = coef + (size_t) p * SP;
+#pragma unroll 4
+      for (uint32_t k = lane; k < L; k += 32) d[k] = src[k];
+      int32_t *cw = reinterpret_cast<int32_t *>(d + tile_cfg<NT>::CW);
+#pragma unroll
+      for (uint32_t ch = lane; ch < NCH; ch += 32) cw[ch] = (ch == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
+   }
+   TILE_STAMP(1);
+   mbar_wait(mbar, 0);
+   if (bulk_tile)
+   {  /* last carry word = the block's signed top limb, which arrived with the image */
+      __syncthreads();
+      if (tid < T.npos && (spos[tid] & MFFT_TILE_LOAD))
+         reinterpret_cast<int32_t *>(coef + (size_t) tid * SP + tile_cfg<NT>::CW)[NCH - 1] = (int32_t)(int64_t) coef[(size_t) tid * SP + L];
+   }
+   __syncthreads();
+   TILE_STAMP(2);
+
+   tile_stages<NT>(coef, sops, sst, T.nstages, b, warp, nwarps, lane, 0u, 0u);
+
+   TILE_STAMP(3);
+   /* store what was written: in place, or gathered (and normalised) into dst */
+   tile_store<NT>(coef, spos, T.npos, slab, g, b, bi, dst, dstpos, dst_base, dst_stride, normalise, al16, warp, nwarps, lane);
 #ifndef MFFT_EMU
    if (timing)
    {

@@ -258,8 +258,20 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
          for (k = 0; k < nout; k++)
             mfft_sched_emit_op(last, k, MFFT_NONE, k, 1, m->final_shift, 0, 0, MFFT_NONE, 0, 0, 0, 0);
       for (k = 0; k < nout; k++) { m->h_must_store[last->phys[k]] = 1; m->h_dstpos[last->phys[k]] = k; }
-      if (mfft_passes_build(&m->pcol, cs, pmax, last == cs ? m->h_must_store : NULL) != 0 ||
-          mfft_passes_build(&m->prow, rs, pmax, last == rs ? m->h_must_store : NULL) != 0) { rc = MPIRFFT_ENOMEM; goto fail; }
+      {  /* what the first schedule has to leave behind: forward, the rows the row pass will read
+            (2392-2394); inverse, every column of the valid rows (all positions of the row schedule) */
+         uint8_t *live_first = NULL;
+         if (!inverse)
+         {
+            live_first = (uint8_t *) calloc(cs->S, 1);
+            if (!live_first) { rc = MPIRFFT_ENOMEM; goto fail; }
+            for (i = 0; i < m->nrows; i++) live_first[cs->phys[m->rows[i]]] = 1;
+         }
+         if (mfft_passes_build(&m->pcol, cs, pmax, last == cs ? m->h_must_store : NULL, last == cs ? m->h_must_store : live_first) != 0 ||
+             mfft_passes_build(&m->prow, rs, pmax, last == rs ? m->h_must_store : NULL, last == rs ? m->h_must_store : NULL) != 0)
+         { free(live_first); rc = MPIRFFT_ENOMEM; goto fail; }
+         free(live_first);
+      }
    }
    if (m->fused && !inverse)
    {  /* may the first column pass split while it loads?  Only if no later pass reads a block that

@@ -148,7 +148,8 @@ static void fuse_radix4(mfft_tileop *ops, uint32_t nops, uint32_t nstages, uint3
 /* build one pass from ops[lo..hi) (sorted by pstage; window = stages s0..s1) */
 static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, uint32_t S,
                       uint32_t s0, uint32_t max_npos, const uint32_t *par_in, uint32_t *scratch,
-                      const uint8_t *must_store, uint64_t NW)
+                      const uint8_t *must_store, uint64_t NW, uint32_t s1, const uint32_t *last_read,
+                      const uint8_t *live_out)
 {
    /* scratch: 6*S uint32: root->tile map, first-access kind, written flag, local index, order */
    uint32_t *root_tile = scratch, *first = scratch + S, *written = scratch + 2*S, *local = scratch + 3*S;
@@ -218,7 +219,11 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
       if (!first[p]) continue;
       t = root_tile[uf_find(par, p)];
       local[p] = pos_cursor[t] - out->tiles[t].pos_off;
-      out->pos[pos_cursor[t]++] = p | (first[p] == 1 ? MFFT_TILE_LOAD : 0) | (written[p] ? MFFT_TILE_STORE : 0);
+      {  /* a value nobody reads after this pass and that is not an output of the schedule is dead:
+            the truncated transforms leave many of those behind (rows they synthesise and fold away) */
+         const int live = (last_read[p] > s1) || !live_out || live_out[p] || (must_store && must_store[p]);
+         out->pos[pos_cursor[t]++] = p | (first[p] == 1 ? MFFT_TILE_LOAD : 0) | ((written[p] && live) ? MFFT_TILE_STORE : 0);
+      }
    }
    for (k = lo; k < hi; k++)      /* ops are in pstage order, so each tile's list is too */
    {
@@ -281,13 +286,21 @@ static int build_pass(mfft_pass *out, const mfft_op *ops, size_t lo, size_t hi, 
    return 0;
 }
 
-int mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, const uint8_t *must_store)
+int mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, const uint8_t *must_store, const uint8_t *live_out)
 {
    uint32_t S = s->S, maxst = s->npstages, s0, p;
-   mfft_op *ops; uint32_t *par, *sz, *par2, *sz2, *scratch; size_t *st_off; size_t k;
+   mfft_op *ops; uint32_t *par, *sz, *par2, *sz2, *scratch, *last_read; size_t *st_off; size_t k;
    int rc = -1;
    memset(P, 0, sizeof(*P));
    if (max_npos < 4) return -1;
+   last_read = (uint32_t *) calloc(S ? S : 1, sizeof(uint32_t));       /* latest pstage that reads a position */
+   if (!last_read) return -1;
+   for (k = 0; k < s->nops; k++)
+   {
+      const mfft_op *o = &s->ops[k];
+      if (o->pstage > last_read[o->pA]) last_read[o->pA] = o->pstage;
+      if (o->pB != MFFT_NONE && o->pstage > last_read[o->pB]) last_read[o->pB] = o->pstage;
+   }
    ops = (mfft_op *) malloc(sizeof(mfft_op) * (s->nops ? s->nops : 1));
    par = (uint32_t *) malloc(sizeof(uint32_t) * 4 * (size_t) S);
    scratch = (uint32_t *) malloc(sizeof(uint32_t) * 6 * (size_t) S);
@@ -329,13 +342,13 @@ int mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, co
          s1++;
       }
       if (build_pass(&P->pass[P->npasses], ops, st_off[s0], st_off[s1 + 1], S, s0, max_npos, par, scratch,
-                     (s1 == maxst) ? must_store : NULL, s->NW) != 0) goto done;
+                     (s1 == maxst) ? must_store : NULL, s->NW, s1, last_read, live_out) != 0) goto done;
       P->npasses++;
       s0 = s1 + 1;
    }
    rc = 0;
 done:
-   free(ops); free(par); free(scratch); free(st_off);
+   free(ops); free(par); free(scratch); free(st_off); free(last_read);
    if (rc != 0) mfft_passes_free(P);
    return rc;
 }

@@ -22,7 +22,9 @@ typedef struct { uint32_t npasses; mfft_pass *pass; } mfft_passes;
 /* cut schedule s (position-based view) into passes whose tiles hold <= max_npos coefficients.
  * must_store (may be NULL): [S] flags of physical positions the LAST pass has to store even if no
  * op of its window writes them (the outputs of a transform whose last pass gathers into dst). */
-int  mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, const uint8_t *must_store);
+/* live_out (may be NULL = all): [S] flags of the physical positions whose final value somebody needs
+ * after the schedule; a position written by a pass is stored only if a later op reads it or it is live. */
+int  mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, const uint8_t *must_store, const uint8_t *live_out);
 void mfft_passes_free(mfft_passes *P);
 
 #ifdef __cplusplus

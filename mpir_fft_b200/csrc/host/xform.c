@@ -99,7 +99,7 @@ int mfft_xform_build(mfft_xform *x, mfft_sched *s, uint32_t l, uint32_t slot_str
       if (x->shift)
          for (k = 0; k < nout; k++) mfft_sched_emit_op(s, k, MFFT_NONE, k, 1, x->shift, 0, 0, MFFT_NONE, 0, 0, 0, 0);
       for (k = 0; k < nout; k++) { must[s->phys[k]] = 1; dstpos[s->phys[k]] = dst_of[k]; }
-      if (mfft_passes_build(&x->P, s, mfft_dev_tiles_max_npos(l), must) != 0) { free(must); free(dstpos); goto fail; }
+      if (mfft_passes_build(&x->P, s, mfft_dev_tiles_max_npos(l), must, must) != 0) { free(must); free(dstpos); goto fail; }
       x->d_dstpos = (uint32_t *) mfft_upload(dstpos, sizeof(uint32_t)*S);
       free(must); free(dstpos);
       x->dp = (struct mfft_dpass *) calloc(x->P.npasses ? x->P.npasses : 1, sizeof(*x->dp));

@@ -11,6 +11,7 @@ ucontext_t g_sched;
 fiber *g_cur = nullptr;
 std::vector<emu_warp> g_warps;
 emu_block_sync g_block;
+emu_named_bar g_named[16];
 void *g_smem = nullptr;
 const std::function<void()> *g_body = nullptr;
 unsigned long g_progress = 0;
@@ -31,6 +32,7 @@ void emu_yield() { swapcontext(&g_cur->ctx, &g_sched); }
 void *emu_dyn_smem() { return g_smem; }
 emu_warp *emu_cur_warp() { return &g_warps[g_cur->tid >> 5]; }
 emu_block_sync *emu_cur_block() { return &g_block; }
+emu_named_bar *emu_cur_named_bar(unsigned id) { return &g_named[id & 15]; }
 
 void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body)
 {
@@ -49,6 +51,7 @@ void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<
       g_warps.assign(nwarps, emu_warp());
       for (unsigned w = 0; w < nwarps; w++) { g_warps[w].gen = 0; g_warps[w].arrived = 0; g_warps[w].tag[0] = g_warps[w].tag[1] = 0xffffffffu; g_warps[w].nlanes = (w == nwarps - 1 && block % 32) ? block % 32 : 32; }
       g_block.gen = 0; g_block.arrived = 0; g_block.nthreads = block;
+      memset(g_named, 0, sizeof g_named);
       g_smem = smem_buf.data();
       for (unsigned t = 0; t < block; t++)
       {

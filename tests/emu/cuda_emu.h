@@ -128,6 +128,13 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d)
    const unsigned lane = threadIdx.x & 31;
    T out; uint64_t r = (lane + d < 32) ? s[lane + d] : raw; memcpy(&out, &r, sizeof(T)); return out;
 }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, unsigned m)
+{
+   uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
+   const uint64_t *s = emu_warp_exchange(raw);
+   const unsigned lane = threadIdx.x & 31;
+   T out; uint64_t r = s[(lane ^ m) & 31]; memcpy(&out, &r, sizeof(T)); return out;
+}
 static inline void __syncthreads()
 {
    emu_block_sync *b = emu_cur_block();
@@ -135,6 +142,29 @@ static inline void __syncthreads()
    if (++b->arrived == b->nthreads) { b->arrived = 0; b->gen = g + 1; }
    else while (b->gen == g) emu_yield();
 }
+
+/* named barrier (bar.sync id, nthreads): the nthreads threads that name the same id rendezvous */
+struct emu_named_bar { uint32_t gen, arrived; };
+emu_named_bar *emu_cur_named_bar(unsigned id);
+static inline void emu_bar_sync(unsigned id, unsigned nthreads)
+{
+   emu_named_bar *b = emu_cur_named_bar(id);
+   const uint32_t g = b->gen;
+   if (++b->arrived == nthreads) { b->arrived = 0; b->gen = g + 1; }
+   else while (b->gen == g) emu_yield();
+}
+
+/* mbarrier + bulk asynchronous copy (cp.async.bulk ... mbarrier::complete_tx): the emulated copy is
+   done at issue; the barrier's phase completes when its arrival count is reached and the expected
+   bytes have been delivered */
+struct emu_mbar { uint32_t phase, count, arrived; int64_t pending; };
+static inline void emu_mbar_try_complete(emu_mbar *m)
+{ if (m->arrived >= m->count && m->pending == 0) { m->arrived = 0; m->phase ^= 1u; } }
+static inline void emu_mbar_init(emu_mbar *m, uint32_t count) { m->phase = 0; m->count = count; m->arrived = 0; m->pending = 0; }
+static inline void emu_mbar_arrive_expect_tx(emu_mbar *m, uint32_t bytes) { m->pending += bytes; m->arrived++; emu_mbar_try_complete(m); }
+static inline void emu_bulk_copy(void *dst, const void *src, uint32_t bytes, emu_mbar *m)
+{ memcpy(dst, src, bytes); m->pending -= bytes; emu_mbar_try_complete(m); }
+static inline void emu_mbar_wait(emu_mbar *m, uint32_t parity) { while (m->phase == parity) emu_yield(); }
 
 #define MFFT_LAUNCH(kern, grid, block, smem, stream, ...) \
    emu_launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
