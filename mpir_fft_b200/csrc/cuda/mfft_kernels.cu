@@ -1472,6 +1472,7 @@ double mfft_dev_imad_rate(int) { return -1.0; }     /* the microbenchmark lives 
 const char *mfft_dev_last_error(void) { return g_err; }
 
 void mfft_dev_profile_enable(int on) { g_prof_on = on; }
+int  mfft_dev_profile_is_on(void) { return g_prof_on; }
 void mfft_dev_profile_bytes(double bytes) { if (g_prof_on) g_prof_bytes_next = bytes; }
 /* drain the recorded launches: per class total ms, launch count, algorithmic bytes */
 int mfft_dev_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass)
@@ -1683,6 +1684,7 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    /* small passes: tile descriptors, position lists and stage offsets travel as kernel parameters */
    tile_params tp;                                      /* per call: launches from several host threads do not share it */
    tp.valid = 0; tp.batch_valid = 0;
+   { static int dbg = -1; if (dbg < 0) { const char *e = getenv("MPIRFFT_TILE_DEBUG"); dbg = e ? atoi(e) : 0; } tp.debug = (uint32_t) dbg; }
    tp.split = split ? 1u : 0u; tp.split_src = split ? split->src : NULL; tp.split_nlimbs = split ? split->nlimbs : 0;
    tp.split_bits = split ? split->bits : 0; tp.split_ncoef = split ? split->ncoef : 0;
    if (h_tiles && h_pos && h_stoff && ntiles <= TP_MAXT)
@@ -1705,37 +1707,78 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    PROF(PC_STAGE, st);
    /* two CTAs per SM: 16 warps x 64 registers while a lane holds <= 4 chunk pairs of an op, else
       8 warps x 128 registers (fewer, larger coefficients per tile) */
-#define RUN_TILES(NN, TH)                                                                          \
+#define RUN_TILES(NN, TH, WS)                                                                      \
    do {                                                                                            \
-      CK(cudaFuncSetAttribute(k_run_tiles<NN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-      MFFT_LAUNCH_PDL(pdl, (k_run_tiles<NN, TH>), grid, TH, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
+      CK(cudaFuncSetAttribute(k_run_tiles<NN, TH, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+      MFFT_LAUNCH_PDL(pdl, (k_run_tiles<NN, TH, WS>), grid, TH, smem, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
                   dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff, g_tile_timing, tp); \
    } while (0)
-   if (max_npos <= 16 && NT <= 4 && smem <= 56 * 1024)
-      switch (NT)          /* small tiles: four 4-warp CTAs per SM */
+   static int wsplit = -1;       /* MPIRFFT_TILE_WSPLIT=0: one warp per op at l = 256 (the 4-warp CTAs of round 1) */
+   if (wsplit < 0) { const char *e = getenv("MPIRFFT_TILE_WSPLIT"); wsplit = e ? atoi(e) : 1; }
+   {  /* persistent pipelined variant (k_run_tiles_p): one CTA per SM, a ring of tile buffers filled by
+         bulk copies while the warp groups work.  Needs at least two tiles per SM to have anything to
+         overlap, four-warp tiles (NT <= 4), and room for the ring.  MPIRFFT_TILE_PERSIST=0 turns it off. */
+      static int persist = -1, nsm = 0;
+      if (persist < 0)
       {
-      case 1: RUN_TILES(1, 128); break;
-      case 2: RUN_TILES(2, 128); break;
-      case 3: RUN_TILES(3, 128); break;
-      default: RUN_TILES(4, 128); break;
+         const char *e = getenv("MPIRFFT_TILE_PERSIST"); persist = e ? atoi(e) : 1;
+#ifndef MFFT_EMU
+         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+#else
+         nsm = 2;
+#endif
+         if (nsm <= 0) nsm = 148;
+      }
+      const size_t buf = desc + (size_t) max_npos * tiles_coeff_bytes(g->l);
+      const size_t smem_p = TPP_CTL_BYTES + TPP_NBUF * buf;
+      const int emu_force = (persist == 2);          /* tests: also for small launches */
+      if (persist && NT <= 4 && smem_p <= 227 * 1024 && (grid >= 2u * (unsigned) nsm || emu_force) &&
+          (((g->pitch & 1u) == 0) || emu_force))
+      {
+         const unsigned gp = grid < (unsigned) nsm ? grid : (unsigned) nsm;
+#define RUN_TILES_P(NN)                                                                            \
+         do {                                                                                      \
+            CK(cudaFuncSetAttribute(k_run_tiles_p<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_p)); \
+            MFFT_LAUNCH_PDL(pdl, (k_run_tiles_p<NN>), gp, TPP_GROUPS * 128, smem_p, st, slab, *g, d_tiles, d_pos, d_ops, d_batch, nbatch, \
+                        dst, d_dstpos, d_dst_base, dst_stride, normalise, desc, d_stoff, grid, (uint32_t) buf, tp); \
+         } while (0)
+         switch (NT)
+         {
+         case 1: RUN_TILES_P(1); break;
+         case 2: RUN_TILES_P(2); break;
+         case 3: RUN_TILES_P(3); break;
+         default: RUN_TILES_P(4); break;
+         }
+#undef RUN_TILES_P
+         CKL();
+         return 0;
+      }
+   }
+   if (max_npos <= 16 && NT <= 4 && smem <= 56 * 1024)
+      switch (NT)          /* small tiles: four CTAs per SM */
+      {
+      case 1: RUN_TILES(1, 128, 1); break;
+      case 2: RUN_TILES(2, 128, 1); break;
+      case 3: RUN_TILES(3, 128, 1); break;
+      default: if (wsplit) RUN_TILES(4, 256, 2); else RUN_TILES(4, 128, 1); break;
       }
    else if (heavy && NT <= 4)
       switch (NT)
       {
-      case 1: RUN_TILES(1, 256); break;
-      case 2: RUN_TILES(2, 256); break;
-      case 3: RUN_TILES(3, 256); break;
-      default: RUN_TILES(4, 256); break;
+      case 1: RUN_TILES(1, 256, 1); break;
+      case 2: RUN_TILES(2, 256, 1); break;
+      case 3: RUN_TILES(3, 256, 1); break;
+      default: RUN_TILES(4, 256, 1); break;
       }
    else
    switch (NT)
    {
-   case 1: RUN_TILES(1, 512); break;
-   case 2: RUN_TILES(2, 512); break;
-   case 3: RUN_TILES(3, 512); break;
-   case 4: RUN_TILES(4, 512); break;
-   case 6: RUN_TILES(6, 256); break;
-   default: RUN_TILES(8, 256); break;
+   case 1: RUN_TILES(1, 512, 1); break;
+   case 2: RUN_TILES(2, 512, 1); break;
+   case 3: RUN_TILES(3, 512, 1); break;
+   case 4: RUN_TILES(4, 512, 1); break;
+   case 6: RUN_TILES(6, 256, 1); break;
+   default: RUN_TILES(8, 256, 1); break;
    }
 #undef RUN_TILES
    if (g_tile_timing) g_tile_timing += (size_t) grid * 8;       /* next launch stamps behind this one */

@@ -468,6 +468,19 @@ __device__ __forceinline__ int64_t normalise_tile(limb_t *sblk, uint32_t l, int6
    return top;
 }
 
+/* rendezvous of the W warps that share an op (between "everybody has read its operand chunks" and the
+   in-place stores): the warp itself, or a named barrier of the W consecutive warps */
+template <int W>
+__device__ __forceinline__ void op_sync(uint32_t warp)
+{
+   if (W == 1) { __syncwarp(); return; }
+#ifdef MFFT_EMU
+   emu_bar_sync(1 + warp / W, 32 * W);
+#else
+   asm volatile("bar.sync %0, %1;" :: "r"(1u + warp / W), "r"(32u * W) : "memory");
+#endif
+}
+
 /* ---- radix-4 units: two radix-2 layers per shared-memory round trip -------------------------- */
 /* signed chunk value = 2 limbs + carry word */
 struct cval { limb_t x0, x1; int32_t c; };
@@ -486,52 +499,52 @@ __device__ __forceinline__ void cv_store(limb_t *P, uint32_t cwoff, uint32_t ch,
  * with y1' = y1 + NCH/2 (the two layer-1 twiddles differ by the quarter turn 2^(NW/2)).  A rotation by
  * NCH/2 = 16 NT chunks maps a lane's chunk ti to its own chunk ti +- NT/2, so the whole unit is
  * lane-local: 4 chunk loads and 4 chunk stores per lane and ti instead of 8 + 8.  q[k] = y | neg << 31. */
-template <int NT>
+template <int NT, int W>
 __device__ __forceinline__ void fwd4_unit(limb_t *P0, limb_t *P1, limb_t *P2, limb_t *P3,
-                                          uint32_t q1, uint32_t q1p, uint32_t q2, uint32_t q2p, uint32_t lane)
+                                          uint32_t q1, uint32_t q1p, uint32_t q2, uint32_t q2p, uint32_t lane, uint32_t warp)
 {
-   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH; constexpr int H = NT / 2;
+   constexpr uint32_t NCH = tile_cfg<NT>::NCH; constexpr int NTS = NT / W; const uint32_t half = warp % W;
    const uint32_t y1 = q1 & 0x7fffffffu, y1p = q1p & 0x7fffffffu, y2 = q2 & 0x7fffffffu, y2p = q2p & 0x7fffffffu;
    const uint32_t n1 = q1 >> 31, n1p = q1p >> 31, n2 = q2 >> 31, n2p = q2p >> 31;
-   cval a0[NT], a1[NT], a2[NT], a3[NT];
+   cval a0[NTS], a1[NTS], a2[NTS], a3[NTS];
 #pragma unroll
-   for (int ti = 0; ti < NT; ti++)
+   for (int tj = 0; tj < NTS; tj++)
    {
-      const uint32_t i = ti * 32u + lane;
-      a0[ti] = cv_load(P0, tile_cfg<NT>::CW, i); a1[ti] = cv_load(P1, tile_cfg<NT>::CW, i); a2[ti] = cv_load(P2, tile_cfg<NT>::CW, i); a3[ti] = cv_load(P3, tile_cfg<NT>::CW, i);
+      const uint32_t i = (half + W * tj) * 32u + lane;
+      a0[tj] = cv_load(P0, tile_cfg<NT>::CW, i); a1[tj] = cv_load(P1, tile_cfg<NT>::CW, i); a2[tj] = cv_load(P2, tile_cfg<NT>::CW, i); a3[tj] = cv_load(P3, tile_cfg<NT>::CW, i);
    }
-   __syncwarp();
+   op_sync<W>(warp);
    /* layer 1 in place: a0 <- a0+a2, a2 <- +-(a0-a2) (the chunk that lands at i+y1), same for a1,a3 */
 #pragma unroll
-   for (int ti = 0; ti < NT; ti++)
+   for (int tj = 0; tj < NTS; tj++)
    {
-      const uint32_t i = ti * 32u + lane;
-      const cval s = cv_add(a0[ti], a2[ti]);
-      a2[ti] = (((i + y1 >= NCH) ? 1u : 0u) != n1) ? cv_sub(a2[ti], a0[ti]) : cv_sub(a0[ti], a2[ti]);
-      a0[ti] = s;
-      const cval sp = cv_add(a1[ti], a3[ti]);
-      a3[ti] = (((i + y1p >= NCH) ? 1u : 0u) != n1p) ? cv_sub(a3[ti], a1[ti]) : cv_sub(a1[ti], a3[ti]);
-      a1[ti] = sp;
+      const uint32_t i = (half + W * tj) * 32u + lane;
+      const cval s = cv_add(a0[tj], a2[tj]);
+      a2[tj] = (((i + y1 >= NCH) ? 1u : 0u) != n1) ? cv_sub(a2[tj], a0[tj]) : cv_sub(a0[tj], a2[tj]);
+      a0[tj] = s;
+      const cval sp = cv_add(a1[tj], a3[tj]);
+      a3[tj] = (((i + y1p >= NCH) ? 1u : 0u) != n1p) ? cv_sub(a3[tj], a1[tj]) : cv_sub(a1[tj], a3[tj]);
+      a1[tj] = sp;
    }
    /* layer 2 */
 #pragma unroll
-   for (int ti = 0; ti < NT; ti++)
+   for (int tj = 0; tj < NTS; tj++)
    {
-      const uint32_t i = ti * 32u + lane;
+      const uint32_t i = (half + W * tj) * 32u + lane;
       constexpr int dummy = 0; (void) dummy;
-      const int tp = (ti + H) % NT;                         /* a3's chunk that lands where a2[ti] does */
-      cv_store(P0, tile_cfg<NT>::CW, i, cv_add(a0[ti], a1[ti]));
+      const int tp = (tj + NTS / 2) % NTS;                        /* a3's chunk that lands where a2[tj] does */
+      cv_store(P0, tile_cfg<NT>::CW, i, cv_add(a0[tj], a1[tj]));
       {
          uint32_t o = i + y2, n = n2;
          if (o >= NCH) { o -= NCH; n ^= 1u; }
-         cv_store(P1, tile_cfg<NT>::CW, o, n ? cv_sub(a1[ti], a0[ti]) : cv_sub(a0[ti], a1[ti]));
+         cv_store(P1, tile_cfg<NT>::CW, o, n ? cv_sub(a1[tj], a0[tj]) : cv_sub(a0[tj], a1[tj]));
       }
       uint32_t j = i + y1; if (j >= NCH) j -= NCH;
-      cv_store(P2, tile_cfg<NT>::CW, j, cv_add(a2[ti], a3[tp]));
+      cv_store(P2, tile_cfg<NT>::CW, j, cv_add(a2[tj], a3[tp]));
       {
          uint32_t o = j + y2p, n = n2p;
          if (o >= NCH) { o -= NCH; n ^= 1u; }
-         cv_store(P3, tile_cfg<NT>::CW, o, n ? cv_sub(a3[tp], a2[ti]) : cv_sub(a2[ti], a3[tp]));
+         cv_store(P3, tile_cfg<NT>::CW, o, n ? cv_sub(a3[tp], a2[tj]) : cv_sub(a2[tj], a3[tp]));
       }
    }
 }
@@ -540,57 +553,57 @@ __device__ __forceinline__ void fwd4_unit(limb_t *P0, limb_t *P1, limb_t *P2, li
  *    layer 1:  (P0,P1) -> P0 +- P1 2^(128 y2), P0 -+ ...      (P2,P3) -> P2 +- P3 2^(128 y2'), ...
  *    layer 2:  (P0,P2) -> P0 +- P2 2^(128 y1), ...            (P1,P3) -> P1 +- P3 2^(128 y1'), ...
  * with y1' = y1 + NCH/2; exponents are the negated (inverse) rotations already folded mod 2NW. */
-template <int NT>
+template <int NT, int W>
 __device__ __forceinline__ void inv4_unit(limb_t *P0, limb_t *P1, limb_t *P2, limb_t *P3,
-                                          uint32_t q2, uint32_t q2p, uint32_t q1, uint32_t q1p, uint32_t lane)
+                                          uint32_t q2, uint32_t q2p, uint32_t q1, uint32_t q1p, uint32_t lane, uint32_t warp)
 {
-   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH; constexpr int H = NT / 2;
+   constexpr uint32_t NCH = tile_cfg<NT>::NCH; constexpr int NTS = NT / W; const uint32_t half = warp % W;
    const uint32_t y1 = q1 & 0x7fffffffu, y1p = q1p & 0x7fffffffu, y2 = q2 & 0x7fffffffu, y2p = q2p & 0x7fffffffu;
    const uint32_t n1 = q1 >> 31, n1p = q1p >> 31, n2 = q2 >> 31, n2p = q2p >> 31;
-   cval u0[NT], u1[NT], u2[NT], u3[NT];
+   cval u0[NTS], u1[NTS], u2[NTS], u3[NTS];
    /* u0,u1 at chunk i; u2,u3 at chunk m = i - y1 (what layer 2 adds to chunk i of P0) */
 #pragma unroll
-   for (int ti = 0; ti < NT; ti++)
+   for (int tj = 0; tj < NTS; tj++)
    {
-      const uint32_t i = ti * 32u + lane;
+      const uint32_t i = (half + W * tj) * 32u + lane;
       const uint32_t jb = (i >= y2) ? i - y2 : i + NCH - y2;
       const uint32_t m = (i >= y1) ? i - y1 : i + NCH - y1;
       const uint32_t mb = (m >= y2p) ? m - y2p : m + NCH - y2p;
-      u0[ti] = cv_load(P0, tile_cfg<NT>::CW, i); u1[ti] = cv_load(P1, tile_cfg<NT>::CW, jb); u2[ti] = cv_load(P2, tile_cfg<NT>::CW, m); u3[ti] = cv_load(P3, tile_cfg<NT>::CW, mb);
+      u0[tj] = cv_load(P0, tile_cfg<NT>::CW, i); u1[tj] = cv_load(P1, tile_cfg<NT>::CW, jb); u2[tj] = cv_load(P2, tile_cfg<NT>::CW, m); u3[tj] = cv_load(P3, tile_cfg<NT>::CW, mb);
    }
-   __syncwarp();
+   op_sync<W>(warp);
 #pragma unroll
-   for (int ti = 0; ti < NT; ti++)
+   for (int tj = 0; tj < NTS; tj++)
    {
-      const uint32_t i = ti * 32u + lane;
+      const uint32_t i = (half + W * tj) * 32u + lane;
       const uint32_t m = (i >= y1) ? i - y1 : i + NCH - y1;
       {  /* (u0,u1) <- b0 +- b1', b0 -+ b1' */
-         const cval sm = cv_add(u0[ti], u1[ti]), df = cv_sub(u0[ti], u1[ti]);
+         const cval sm = cv_add(u0[tj], u1[tj]), df = cv_sub(u0[tj], u1[tj]);
          const bool ng = ((i < y2) ? 1u : 0u) != n2;
-         u0[ti] = ng ? df : sm; u1[ti] = ng ? sm : df;
+         u0[tj] = ng ? df : sm; u1[tj] = ng ? sm : df;
       }
       {
-         const cval sm = cv_add(u2[ti], u3[ti]), df = cv_sub(u2[ti], u3[ti]);
+         const cval sm = cv_add(u2[tj], u3[tj]), df = cv_sub(u2[tj], u3[tj]);
          const bool ng = ((m < y2p) ? 1u : 0u) != n2p;
-         u2[ti] = ng ? df : sm; u3[ti] = ng ? sm : df;
+         u2[tj] = ng ? df : sm; u3[tj] = ng ? sm : df;
       }
    }
 #pragma unroll
-   for (int ti = 0; ti < NT; ti++)
+   for (int tj = 0; tj < NTS; tj++)
    {
-      const uint32_t i = ti * 32u + lane;
-      const int tp = (ti + H) % NT;                         /* u3 at chunk i - y1' = (i -+ NCH/2) - y1 */
+      const uint32_t i = (half + W * tj) * 32u + lane;
+      const int tp = (tj + NTS / 2) % NTS;                        /* u3 at chunk i - y1' = (i -+ NCH/2) - y1 */
       {
          const bool ng = ((i < y1) ? 1u : 0u) != n1;       /* P2's chunk enters negated */
          limb_t *ds = ng ? P2 : P0, *dt = ng ? P0 : P2;
-         cv_store(ds, tile_cfg<NT>::CW, i, cv_add(u0[ti], u2[ti]));
-         cv_store(dt, tile_cfg<NT>::CW, i, cv_sub(u0[ti], u2[ti]));
+         cv_store(ds, tile_cfg<NT>::CW, i, cv_add(u0[tj], u2[tj]));
+         cv_store(dt, tile_cfg<NT>::CW, i, cv_sub(u0[tj], u2[tj]));
       }
       {
          const bool ng = ((i < y1p) ? 1u : 0u) != n1p;
          limb_t *ds = ng ? P3 : P1, *dt = ng ? P1 : P3;
-         cv_store(ds, tile_cfg<NT>::CW, i, cv_add(u1[ti], u3[tp]));
-         cv_store(dt, tile_cfg<NT>::CW, i, cv_sub(u1[ti], u3[tp]));
+         cv_store(ds, tile_cfg<NT>::CW, i, cv_add(u1[tj], u3[tp]));
+         cv_store(dt, tile_cfg<NT>::CW, i, cv_sub(u1[tj], u3[tp]));
       }
    }
 }
@@ -613,47 +626,47 @@ __device__ __forceinline__ void shl128(limb_t &h0, limb_t &h1, limb_t x0, limb_t
    else { h1 = (x1 << u) | (x0 >> (64 - u)); h0 = x0 << u; }
 }
 
-template <int NT>
-__device__ __forceinline__ void rotg_unit(limb_t *S, const limb_t *A, uint32_t t, uint32_t neg, uint32_t lane)
+template <int NT, int W>
+__device__ __forceinline__ void rotg_unit(limb_t *S, const limb_t *A, uint32_t t, uint32_t neg, uint32_t lane, uint32_t warp)
 {
-   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH;
+   constexpr uint32_t NCH = tile_cfg<NT>::NCH; constexpr int NTS = NT / W; const uint32_t half = warp % W;
    uint32_t yc1 = (t + 127u) >> 7;
    const uint32_t s = 128u * yc1 - t;                       /* 0..127 */
    if (yc1 == NCH) { yc1 = 0; neg ^= 1u; }                  /* a full turn is a factor -1 */
    const int32_t *cwA = reinterpret_cast<const int32_t *>(A + tile_cfg<NT>::CW);
-   cval r[NT]; limb_t y0[NT], y1[NT];
+   cval r[NTS]; limb_t y0[NTS], y1[NTS];
 #pragma unroll
-   for (int ti = 0; ti < NT; ti++)
+   for (int tj = 0; tj < NTS; tj++)
    {
-      const uint32_t j = ti * 32u + lane;
+      const uint32_t j = (half + W * tj) * 32u + lane;
       {  /* R_j = +-A_(j - yc1) */
          const uint32_t wj = (j < yc1) ? 1u : 0u, sj = wj ? j + NCH - yc1 : j - yc1;
-         ld2(r[ti].x0, r[ti].x1, A + 2 * sj); r[ti].c = cwA[sj];
-         if (wj != neg) { const int32_t b = sub2(r[ti].x0, r[ti].x1, 0, 0, r[ti].x0, r[ti].x1); r[ti].c = b - r[ti].c; }
+         ld2(r[tj].x0, r[tj].x1, A + 2 * sj); r[tj].c = cwA[sj];
+         if (wj != neg) { const int32_t b = sub2(r[tj].x0, r[tj].x1, 0, 0, r[tj].x0, r[tj].x1); r[tj].c = b - r[tj].c; }
       }
       {  /* body of R_(j+1); for the last chunk that is R_0, which enters negated (handled below) */
          const uint32_t j1 = (j + 1 == NCH) ? 0u : j + 1;
          const uint32_t w1 = (j1 < yc1) ? 1u : 0u, s1 = w1 ? j1 + NCH - yc1 : j1 - yc1;
-         ld2(y0[ti], y1[ti], A + 2 * s1);
-         if (w1 != neg) (void) sub2(y0[ti], y1[ti], 0, 0, y0[ti], y1[ti]);
+         ld2(y0[tj], y1[tj], A + 2 * s1);
+         if (w1 != neg) (void) sub2(y0[tj], y1[tj], 0, 0, y0[tj], y1[tj]);
       }
    }
-   __syncwarp();
+   op_sync<W>(warp);
    int32_t *cwS = reinterpret_cast<int32_t *>(S + tile_cfg<NT>::CW);
 #pragma unroll
-   for (int ti = 0; ti < NT; ti++)
+   for (int tj = 0; tj < NTS; tj++)
    {
-      const uint32_t j = ti * 32u + lane;
-      if (s == 0) { st2(S + 2 * j, r[ti].x0, r[ti].x1); cwS[j] = r[ti].c; continue; }
+      const uint32_t j = (half + W * tj) * 32u + lane;
+      if (s == 0) { st2(S + 2 * j, r[tj].x0, r[tj].x1); cwS[j] = r[tj].c; continue; }
       limb_t h0, h1, f0, f1, g0, g1, o0, o1;
-      const int64_t c64 = (int64_t) r[ti].c;
-      shr128(h0, h1, r[ti].x0, r[ti].x1, s);
+      const int64_t c64 = (int64_t) r[tj].c;
+      shr128(h0, h1, r[tj].x0, r[tj].x1, s);
       shl128(f0, f1, (limb_t) c64, (limb_t)(c64 >> 63), 128u - s);
-      shl128(g0, g1, y0[ti], y1[ti], 128u - s);
+      shl128(g0, g1, y0[tj], y1[tj], 128u - s);
       h0 |= f0; h1 |= f1;                                   /* disjoint bit fields */
       const int32_t k = (j + 1 == NCH) ? sub2(o0, o1, h0, h1, g0, g1) : add2(o0, o1, h0, h1, g0, g1);
       st2(S + 2 * j, o0, o1);
-      cwS[j] = ((s >= 31) ? (r[ti].c >> 31) : (r[ti].c >> s)) + k;
+      cwS[j] = ((s >= 31) ? (r[tj].c >> 31) : (r[tj].c >> s)) + k;
    }
 }
 
@@ -671,7 +684,7 @@ __device__ __forceinline__ void tile_sync(uint32_t bar_id, uint32_t bar_threads)
 
 /* all stages of a tile on the coefficients in shared memory (sops sorted by stage, sst[k] = first op
    of stage k); warp `warp` of `nwarps` takes every nwarps-th op of a stage */
-template <int NT>
+template <int NT, int W>
 __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sops, const uint32_t *sst, uint32_t nstages,
                                             const mfft_batch &b, uint32_t warp, uint32_t nwarps, uint32_t lane,
                                             uint32_t bar_id, uint32_t bar_threads)
@@ -679,10 +692,12 @@ __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sop
    constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP, CW = tile_cfg<NT>::CW;
    constexpr uint32_t NW = 64u * L, M2 = 2u * NW;
    constexpr uint32_t AMASK = 127u;                           /* exponent bits that break chunk alignment */
+   /* W warps share an op: warp `warp` works on the chunks ti*32 + lane with ti = half, half + W, ... */
+   constexpr int NTS = NT / W; const uint32_t half = warp % W, wunit = warp / W, nunits = nwarps / W;
    for (uint32_t st = 0; st < nstages; st++)
    {
       const uint32_t o0 = sst[st], o1 = sst[st + 1];
-      for (uint32_t oi = o0 + warp; oi < o1; oi += nwarps)
+      for (uint32_t oi = o0 + wunit; oi < o1; oi += nunits)
       {
          const mfft_tileop op = sops[oi];
          const limb_t *A = coef + (size_t) op.a * SP;
@@ -697,8 +712,8 @@ __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sop
             {
                limb_t *P0 = coef + (size_t) op.a * SP, *P1 = coef + (size_t) op.b * SP;
                limb_t *P2 = coef + (size_t) op.s * SP, *P3 = coef + (size_t) op.t * SP;
-               if (op.kind == MFFT_K_FWD4) fwd4_unit<(NT <= 4 && NT % 2 == 0) ? NT : 2>(P0, P1, P2, P3, op.eSA, op.eSB, op.eTA, op.eTB, lane);
-               else inv4_unit<(NT <= 4 && NT % 2 == 0) ? NT : 2>(P0, P1, P2, P3, op.eSA, op.eSB, op.eTA, op.eTB, lane);
+               if (op.kind == MFFT_K_FWD4) fwd4_unit<(NT <= 4 && NT % 2 == 0) ? NT : 2, (NT <= 4 && NT % 2 == 0) ? W : 1>(P0, P1, P2, P3, op.eSA, op.eSB, op.eTA, op.eTB, lane, warp);
+               else inv4_unit<(NT <= 4 && NT % 2 == 0) ? NT : 2, (NT <= 4 && NT % 2 == 0) ? W : 1>(P0, P1, P2, P3, op.eSA, op.eSB, op.eTA, op.eTB, lane, warp);
             }
             continue;
          }
@@ -708,78 +723,78 @@ __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sop
             const int32_t *cwA = reinterpret_cast<const int32_t *>(A + tile_cfg<NT>::CW);
             const int32_t *cwB = reinterpret_cast<const int32_t *>(B + tile_cfg<NT>::CW);
             int32_t *cwS = reinterpret_cast<int32_t *>(S + tile_cfg<NT>::CW), *cwT = reinterpret_cast<int32_t *>(Tt + tile_cfg<NT>::CW);
-            limb_t a0[NT], a1[NT], b0[NT], b1[NT]; int32_t ca[NT], cb[NT];
+            limb_t a0[NTS], a1[NTS], b0[NTS], b1[NTS]; int32_t ca[NTS], cb[NTS];
             if (op.kind == MFFT_K_FWD)
             {
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
-                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
-                  ld2(b0[ti], b1[ti], B + 2 * i); cb[ti] = cwB[i];
+                  const uint32_t i = (half + W * tj) * 32u + lane;
+                  ld2(a0[tj], a1[tj], A + 2 * i); ca[tj] = cwA[i];
+                  ld2(b0[tj], b1[tj], B + 2 * i); cb[tj] = cwB[i];
                }
-               __syncwarp();
+               op_sync<W>(warp);
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
+                  const uint32_t i = (half + W * tj) * 32u + lane;
                   limb_t r0, r1; int32_t k;
-                  k = add2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]);
-                  st2(S + 2 * i, r0, r1); cwS[i] = k + ca[ti] + cb[ti];
+                  k = add2(r0, r1, a0[tj], a1[tj], b0[tj], b1[tj]);
+                  st2(S + 2 * i, r0, r1); cwS[i] = k + ca[tj] + cb[tj];
                   uint32_t o = i + yc, n = neg;
                   if (o >= NCH) { o -= NCH; n ^= 1u; }
-                  if (n) k = sub2(r0, r1, b0[ti], b1[ti], a0[ti], a1[ti]) + cb[ti] - ca[ti];
-                  else   k = sub2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]) + ca[ti] - cb[ti];
+                  if (n) k = sub2(r0, r1, b0[tj], b1[tj], a0[tj], a1[tj]) + cb[tj] - ca[tj];
+                  else   k = sub2(r0, r1, a0[tj], a1[tj], b0[tj], b1[tj]) + ca[tj] - cb[tj];
                   st2(Tt + 2 * o, r0, r1); cwT[o] = k;
                }
             } else if (op.kind == MFFT_K_INV)
             {
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
+                  const uint32_t i = (half + W * tj) * 32u + lane;
                   const uint32_t j = (i >= yc) ? i - yc : i + NCH - yc;
-                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
-                  ld2(b0[ti], b1[ti], B + 2 * j); cb[ti] = cwB[j];
+                  ld2(a0[tj], a1[tj], A + 2 * i); ca[tj] = cwA[i];
+                  ld2(b0[tj], b1[tj], B + 2 * j); cb[tj] = cwB[j];
                }
-               __syncwarp();
+               op_sync<W>(warp);
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
+                  const uint32_t i = (half + W * tj) * 32u + lane;
                   const bool n = ((i < yc) ? 1u : 0u) != neg;      /* B's chunk enters negated */
                   limb_t *ds = n ? Tt : S, *dt = n ? S : Tt;
                   limb_t r0, r1; int32_t k;
-                  k = add2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]);
-                  st2(ds + 2 * i, r0, r1); reinterpret_cast<int32_t *>(ds + tile_cfg<NT>::CW)[i] = k + ca[ti] + cb[ti];
-                  k = sub2(r0, r1, a0[ti], a1[ti], b0[ti], b1[ti]);
-                  st2(dt + 2 * i, r0, r1); reinterpret_cast<int32_t *>(dt + tile_cfg<NT>::CW)[i] = k + ca[ti] - cb[ti];
+                  k = add2(r0, r1, a0[tj], a1[tj], b0[tj], b1[tj]);
+                  st2(ds + 2 * i, r0, r1); reinterpret_cast<int32_t *>(ds + tile_cfg<NT>::CW)[i] = k + ca[tj] + cb[tj];
+                  k = sub2(r0, r1, a0[tj], a1[tj], b0[tj], b1[tj]);
+                  st2(dt + 2 * i, r0, r1); reinterpret_cast<int32_t *>(dt + tile_cfg<NT>::CW)[i] = k + ca[tj] - cb[tj];
                }
             } else if (op.kind == MFFT_K_ROT)
             {
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
-                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
+                  const uint32_t i = (half + W * tj) * 32u + lane;
+                  ld2(a0[tj], a1[tj], A + 2 * i); ca[tj] = cwA[i];
                }
-               __syncwarp();
+               op_sync<W>(warp);
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
+                  const uint32_t i = (half + W * tj) * 32u + lane;
                   uint32_t o = i + yc, n = neg;
                   if (o >= NCH) { o -= NCH; n ^= 1u; }
-                  limb_t r0 = a0[ti], r1 = a1[ti]; int32_t k = ca[ti];
-                  if (n) k = sub2(r0, r1, 0, 0, a0[ti], a1[ti]) - ca[ti];
+                  limb_t r0 = a0[tj], r1 = a1[tj]; int32_t k = ca[tj];
+                  if (n) k = sub2(r0, r1, 0, 0, a0[tj], a1[tj]) - ca[tj];
                   st2(S + 2 * o, r0, r1); cwS[o] = k;
                }
             } else if (op.kind == MFFT_K_DBL)
             {  /* 2 (x + c B^2) = (2x mod B^2) + (2c + top bit of x) B^2: chunk-local */
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
+                  const uint32_t i = (half + W * tj) * 32u + lane;
                   limb_t x0, x1;
                   ld2(x0, x1, A + 2 * i);
                   const int32_t c = cwA[i];
@@ -789,23 +804,23 @@ __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sop
             } else if (op.kind == MFFT_K_HALF)
             {  /* (A + B) / 2: halve chunk by chunk; a chunk's (and a carry word's) lowest bit is worth
                   2^127 one chunk below, and chunk 0's lowest bit -2^(NW-1) (2^-1 == -2^(NW-1) mod p) */
-               uint32_t lowbit[NT];
+               uint32_t lowbit[NTS];
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane, nx = (i + 1 == NCH) ? 0u : i + 1;
-                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
-                  ld2(b0[ti], b1[ti], B + 2 * i); cb[ti] = cwB[i];
-                  lowbit[ti] = (uint32_t)((A[2 * nx] ^ B[2 * nx]) & 1u);
+                  const uint32_t i = (half + W * tj) * 32u + lane, nx = (i + 1 == NCH) ? 0u : i + 1;
+                  ld2(a0[tj], a1[tj], A + 2 * i); ca[tj] = cwA[i];
+                  ld2(b0[tj], b1[tj], B + 2 * i); cb[tj] = cwB[i];
+                  lowbit[tj] = (uint32_t)((A[2 * nx] ^ B[2 * nx]) & 1u);
                }
-               __syncwarp();
+               op_sync<W>(warp);
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
+                  const uint32_t i = (half + W * tj) * 32u + lane;
                   limb_t t0, t1;
-                  const int32_t ct = add2(t0, t1, a0[ti], a1[ti], b0[ti], b1[ti]) + ca[ti] + cb[ti];
-                  const int32_t e = (ct & 1) + ((i + 1 == NCH) ? -(int32_t) lowbit[ti] : (int32_t) lowbit[ti]);   /* in {-1,0,1,2} */
+                  const int32_t ct = add2(t0, t1, a0[tj], a1[tj], b0[tj], b1[tj]) + ca[tj] + cb[tj];
+                  const int32_t e = (ct & 1) + ((i + 1 == NCH) ? -(int32_t) lowbit[tj] : (int32_t) lowbit[tj]);   /* in {-1,0,1,2} */
                   const limb_t h0 = (t0 >> 1) | (t1 << 63);
                   const limb_t h1 = (t1 >> 1) | ((limb_t)(e & 1) << 63);
                   st2(S + 2 * i, h0, h1);
@@ -816,32 +831,32 @@ __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sop
                   worth 2^(128-s) one chunk below; chunk 0's go to the top negated (2^-s == -2^(NW-s)) */
                const uint32_t sh = op.kparam;
                const limb_t fm = (((limb_t) 1 << sh) - 1);
-               limb_t lowf[NT];
+               limb_t lowf[NTS];
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane, nx = (i + 1 == NCH) ? 0u : i + 1;
-                  ld2(a0[ti], a1[ti], A + 2 * i); ca[ti] = cwA[i];
-                  lowf[ti] = A[2 * nx] & fm;
+                  const uint32_t i = (half + W * tj) * 32u + lane, nx = (i + 1 == NCH) ? 0u : i + 1;
+                  ld2(a0[tj], a1[tj], A + 2 * i); ca[tj] = cwA[i];
+                  lowf[tj] = A[2 * nx] & fm;
                }
-               __syncwarp();
+               op_sync<W>(warp);
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
-                  const int64_t r = (int64_t)((limb_t)(int64_t) ca[ti] & fm);             /* c = q 2^s + r, 0 <= r < 2^s */
-                  const int64_t e = r + ((i + 1 == NCH) ? -(int64_t) lowf[ti] : (int64_t) lowf[ti]);
-                  const limb_t h0 = (a0[ti] >> sh) | (a1[ti] << (64 - sh));
-                  const limb_t h1 = (a1[ti] >> sh) | (((limb_t) e & fm) << (64 - sh));
+                  const uint32_t i = (half + W * tj) * 32u + lane;
+                  const int64_t r = (int64_t)((limb_t)(int64_t) ca[tj] & fm);             /* c = q 2^s + r, 0 <= r < 2^s */
+                  const int64_t e = r + ((i + 1 == NCH) ? -(int64_t) lowf[tj] : (int64_t) lowf[tj]);
+                  const limb_t h0 = (a0[tj] >> sh) | (a1[tj] << (64 - sh));
+                  const limb_t h1 = (a1[tj] >> sh) | (((limb_t) e & fm) << (64 - sh));
                   st2(S + 2 * i, h0, h1);
-                  cwS[i] = (ca[ti] >> sh) + (int32_t)(e >> sh);
+                  cwS[i] = (ca[tj] >> sh) + (int32_t)(e >> sh);
                }
             } else
             {  /* MFFT_K_ADD */
 #pragma unroll
-               for (int ti = 0; ti < NT; ti++)
+               for (int tj = 0; tj < NTS; tj++)
                {
-                  const uint32_t i = ti * 32u + lane;
+                  const uint32_t i = (half + W * tj) * 32u + lane;
                   limb_t x0, x1, y0, y1, r0, r1;
                   ld2(x0, x1, A + 2 * i); ld2(y0, y1, B + 2 * i);
                   const int32_t k = add2(r0, r1, x0, x1, y0, y1) + cwA[i] + cwB[i];
@@ -860,7 +875,7 @@ __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sop
          {  /* one operand, any rotation (the twist layer): chunk-local */
             uint32_t e = eSA, ng = (op.sSA < 0) ? 1u : 0u;
             if (e >= NW) { e -= NW; ng ^= 1u; }
-            rotg_unit<NT>(S, A, e, ng, lane);
+            rotg_unit<NT, W>(S, A, e, ng, lane, warp);
             continue;
          }
          tterm sa, sb, ta, tb;
@@ -885,56 +900,56 @@ __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sop
             const bool useB = sb.present || tb.present;
             const int32_t *cwA = reinterpret_cast<const int32_t *>(A + tile_cfg<NT>::CW);
             const int32_t *cwB = reinterpret_cast<const int32_t *>(B + tile_cfg<NT>::CW);
-            limb_t xa[NT][2], xb[NT][2]; int32_t ca[NT], cb[NT];
+            limb_t xa[NTS][2], xb[NTS][2]; int32_t ca[NTS], cb[NTS];
 #pragma unroll
-            for (int ti = 0; ti < NT; ti++)
+            for (int tj = 0; tj < NTS; tj++)
             {
-               const uint32_t ia = ti * 32u + lane;
+               const uint32_t ia = (half + W * tj) * 32u + lane;
 #ifdef MFFT_EMU
-               xa[ti][0] = A[2 * ia]; xa[ti][1] = A[2 * ia + 1];
+               xa[tj][0] = A[2 * ia]; xa[tj][1] = A[2 * ia + 1];
 #else
-               { const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(A + 2 * ia); xa[ti][0] = v.x; xa[ti][1] = v.y; }
+               { const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(A + 2 * ia); xa[tj][0] = v.x; xa[tj][1] = v.y; }
 #endif
-               ca[ti] = cwA[ia];
-               xb[ti][0] = 0; xb[ti][1] = 0; cb[ti] = 0;
+               ca[tj] = cwA[ia];
+               xb[tj][0] = 0; xb[tj][1] = 0; cb[tj] = 0;
                if (useB)
                {
                   uint32_t jb = ia + dB; if (jb >= NCH) jb -= NCH;
 #ifdef MFFT_EMU
-                  xb[ti][0] = B[2 * jb]; xb[ti][1] = B[2 * jb + 1];
+                  xb[tj][0] = B[2 * jb]; xb[tj][1] = B[2 * jb + 1];
 #else
-                  { const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(B + 2 * jb); xb[ti][0] = v.x; xb[ti][1] = v.y; }
+                  { const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(B + 2 * jb); xb[tj][0] = v.x; xb[tj][1] = v.y; }
 #endif
-                  cb[ti] = cwB[jb];
+                  cb[tj] = cwB[jb];
                }
             }
-            __syncwarp();                   /* every lane has read its operands: in-place stores are safe */
+            op_sync<W>(warp);                   /* every lane has read its operands: in-place stores are safe */
 #pragma unroll
-            for (int ti = 0; ti < NT; ti++)
+            for (int tj = 0; tj < NTS; tj++)
             {
-               const uint32_t ia = ti * 32u + lane;
+               const uint32_t ia = (half + W * tj) * 32u + lane;
                uint32_t jb = ia + dB; if (jb >= NCH) jb -= NCH;
-               aligned_out<NT>(S, sa, sb, ia, jb, xa[ti][0], xa[ti][1], ca[ti], xb[ti][0], xb[ti][1], cb[ti]);
-               if (hasT) aligned_out<NT>(Tt, ta, tb, ia, jb, xa[ti][0], xa[ti][1], ca[ti], xb[ti][0], xb[ti][1], cb[ti]);
+               aligned_out<NT>(S, sa, sb, ia, jb, xa[tj][0], xa[tj][1], ca[tj], xb[tj][0], xb[tj][1], cb[tj]);
+               if (hasT) aligned_out<NT>(Tt, ta, tb, ia, jb, xa[tj][0], xa[tj][1], ca[tj], xb[tj][0], xb[tj][1], cb[tj]);
             }
          } else
          {
-            limb_t rs[NT][2], rt[NT][2]; int32_t ks[NT], kt[NT];
+            limb_t rs[NTS][2], rt[NTS][2]; int32_t ks[NTS], kt[NTS];
 #pragma unroll
-            for (int ti = 0; ti < NT; ti++)
+            for (int tj = 0; tj < NTS; tj++)
             {
-               const uint32_t ch = ti * 32u + lane;
-               ks[ti] = general_out<NT>(rs[ti][0], rs[ti][1], sa, A, sb, B, ch);
-               if (hasT) kt[ti] = general_out<NT>(rt[ti][0], rt[ti][1], ta, A, tb, B, ch);
+               const uint32_t ch = (half + W * tj) * 32u + lane;
+               ks[tj] = general_out<NT>(rs[tj][0], rs[tj][1], sa, A, sb, B, ch);
+               if (hasT) kt[tj] = general_out<NT>(rt[tj][0], rt[tj][1], ta, A, tb, B, ch);
             }
-            __syncwarp();
+            op_sync<W>(warp);
             int32_t *cwS = reinterpret_cast<int32_t *>(S + tile_cfg<NT>::CW), *cwT = reinterpret_cast<int32_t *>(Tt + tile_cfg<NT>::CW);
 #pragma unroll
-            for (int ti = 0; ti < NT; ti++)
+            for (int tj = 0; tj < NTS; tj++)
             {
-               const uint32_t ch = ti * 32u + lane;
-               S[2 * ch] = rs[ti][0]; S[2 * ch + 1] = rs[ti][1]; cwS[ch] = ks[ti];
-               if (hasT) { Tt[2 * ch] = rt[ti][0]; Tt[2 * ch + 1] = rt[ti][1]; cwT[ch] = kt[ti]; }
+               const uint32_t ch = (half + W * tj) * 32u + lane;
+               S[2 * ch] = rs[tj][0]; S[2 * ch + 1] = rs[tj][1]; cwS[ch] = ks[tj];
+               if (hasT) { Tt[2 * ch] = rt[tj][0]; Tt[2 * ch + 1] = rt[tj][1]; cwT[ch] = kt[tj]; }
             }
          }
       }
@@ -988,6 +1003,7 @@ __device__ __forceinline__ void tile_store(limb_t *coef, const uint32_t *spos, u
 #define TP_MAXB 256
 struct tile_params {
    uint32_t valid, batch_valid;
+   uint32_t debug;          /* developer aid (MPIRFFT_TILE_DEBUG): 1 = skip the stages, 2 = skip the stores (timing floors; wrong results) */
    /* split fused into the tile load (FFT_split_bits, mul_fft.c:115-170): block k of the slab is
       coefficient k = bits [k*bits, (k+1)*bits) of {src, nlimbs}, zero beyond ncoef */
    uint32_t split; const limb_t *split_src; uint64_t split_nlimbs, split_bits, split_ncoef;
@@ -997,9 +1013,118 @@ struct tile_params {
    uint32_t stoff[TP_MAXT * TP_MAXS];
 };
 
+/* what the threads of a tile do while (or instead of) the bulk copies: the split-fused load, the plain
+   load of slabs that are not 16-byte aligned, and the zeroing of the carry words */
+template <int NT>
+__device__ __forceinline__ void tile_fill(limb_t *coef, const uint32_t *spos, uint32_t npos, limb_t *slab, const mfft_geom &g,
+                                          const mfft_batch &b, const tile_params &TP, bool bulk_tile,
+                                          uint32_t tid, uint32_t nthreads, uint32_t warp, uint32_t nwarps, uint32_t lane)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP;
+   if (TP.split)
+   {  /* the tile's coefficients are cut straight out of the operand: no split kernel, no slab read */
+      /* limb k of coefficient i = bits [i*bits + 64k, +64) of the operand: two loads and a funnel
+         shift with the same shift count for the whole coefficient; consecutive threads read
+         consecutive limbs, four coefficients are in flight per thread */
+      const uint32_t blimbs = (uint32_t)((TP.split_bits + 63) >> 6);     /* limbs that receive bits */
+      const limb_t lastmask = (TP.split_bits & 63) ? (((limb_t) 1 << (TP.split_bits & 63)) - 1) : ~(limb_t) 0;
+      for (uint32_t p0 = 0; p0 < npos; p0 += 4)
+      {
+         uint64_t qb[4]; uint32_t rr[4]; bool ld[4], nz[4];
+#pragma unroll
+         for (int u = 0; u < 4; u++)
+         {
+            const uint32_t p = p0 + u;
+            const uint32_t pp = (p < npos) ? spos[p] : 0u;
+            ld[u] = (pp & MFFT_TILE_LOAD) != 0;
+            const uint64_t i = (uint64_t) b.base + (uint64_t)(pp & MFFT_TILE_POSMASK) * g.slot_stride;
+            const uint64_t off = i * TP.split_bits;
+            nz[u] = ld[u] && i < TP.split_ncoef;
+            qb[u] = off >> 6; rr[u] = (uint32_t)(off & 63);
+         }
+         for (uint32_t k = tid; k < L; k += nthreads)
+         {
+            limb_t lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+               lo[u] = 0; hi[u] = 0;
+               if (nz[u] && k < blimbs)
+               {
+                  const uint64_t q = qb[u] + k;
+                  if (q < TP.split_nlimbs) lo[u] = TP.split_src[q];
+                  if (q + 1 < TP.split_nlimbs) hi[u] = TP.split_src[q + 1];
+               }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+               if (!ld[u]) continue;
+               limb_t v = lo[u] >> rr[u];
+               if (rr[u]) v |= hi[u] << (64 - rr[u]);
+               if (k + 1 == blimbs) v &= lastmask;
+               coef[(size_t)(p0 + u) * SP + k] = v;
+            }
+         }
+      }
+      for (uint32_t t = tid; t < npos * NCH; t += nthreads)
+         if (spos[t / NCH] & MFFT_TILE_LOAD) reinterpret_cast<int32_t *>(coef + (size_t)(t / NCH) * SP + tile_cfg<NT>::CW)[t % NCH] = 0;
+   } else
+   if (bulk_tile)
+   {  /* the block images are on their way; meanwhile zero the carry words (they live behind the image) */
+      for (uint32_t t = tid; t < npos * (NCH / 4); t += nthreads)
+      {
+         const uint32_t p = t / (NCH / 4), c = t % (NCH / 4);
+         if (!(spos[p] & MFFT_TILE_LOAD)) continue;
+         st2(coef + (size_t) p * SP + tile_cfg<NT>::CW + 2 * c, 0, 0);
+      }
+   } else
+   for (uint32_t p = warp; p < npos; p += nwarps)
+   {
+      const uint32_t pp = spos[p];
+      if (!(pp & MFFT_TILE_LOAD)) continue;
+      const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
+      limb_t *d = coef + (size_t) p * SP;
+#pragma unroll 4
+      for (uint32_t k = lane; k < L; k += 32) d[k] = src[k];
+      int32_t *cw = reinterpret_cast<int32_t *>(d + tile_cfg<NT>::CW);
+#pragma unroll
+      for (uint32_t ch = lane; ch < NCH; ch += 32) cw[ch] = (ch == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
+   }
+}
+
+/* issued by one warp: arm the barrier with the bytes of the tile's op descriptors and block images,
+   then fire the bulk copies (one per coefficient that is read before it is written) */
+template <int NT, class POS>
+__device__ __forceinline__ void tile_issue(tile_mbar *mbar, mfft_tileop *sops, limb_t *coef, const mfft_tile &T, POS posf,
+                                           const mfft_tileop *__restrict__ ops, limb_t *slab, const mfft_geom &g,
+                                           const mfft_batch &b, bool bulk_tile, uint32_t lane)
+{
+   constexpr uint32_t L = tile_cfg<NT>::L, SP = tile_cfg<NT>::SP;
+   uint32_t nload = 0;
+   if (bulk_tile) for (uint32_t p = lane; p < T.npos; p += 32) nload += (posf(p) & MFFT_TILE_LOAD) ? 1u : 0u;
+#pragma unroll
+   for (int off = 16; off; off >>= 1) nload += __shfl_xor_sync(FULL, nload, off);
+   if (lane == 0)
+   {
+      mbar_arrive_expect_tx(mbar, T.nops * (uint32_t) sizeof(mfft_tileop) + nload * (L + 2) * 8u);
+      if (T.nops) bulk_g2s(sops, ops + T.op_off, T.nops * (uint32_t) sizeof(mfft_tileop), mbar);
+   }
+   __syncwarp();
+   if (bulk_tile)
+      for (uint32_t p = lane; p < T.npos; p += 32)
+      {
+         const uint32_t pp = posf(p);
+         if (pp & MFFT_TILE_LOAD) bulk_g2s(coef + (size_t) p * SP, tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b), (L + 2) * 8u, mbar);
+      }
+}
+
 /* ---- the kernel ----------------------------------------------------------------------------- */
-template <int NT, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, (NTHREADS == 128) ? 4 : 2)
+/* WSPLIT = 2: two warps share every op (each takes every other group of 32 chunks), so a tile is worked
+   on by twice as many warps holding half as many chunks each: 8 warps x 64 registers per 16-coefficient
+   tile, four CTAs per SM = 32 resident warps instead of 16 */
+template <int NT, int NTHREADS, int WSPLIT>
+__global__ void __launch_bounds__(NTHREADS, (NTHREADS == 128 || WSPLIT == 2) ? 4 : 2)
 k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
             const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
             limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
@@ -1054,96 +1179,9 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
    const bool al16 = ((g.pitch & 1u) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15u) == 0) &&
                      (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
    const bool bulk_tile = al16 && !TP.split && g.pitch >= L + 2;      /* whole block images by bulk copy */
-   if (warp == 0)
-   {  /* one warp issues the tile's copies: the op descriptors and, for 16-byte aligned slabs, one
-         (l+2)-limb block image per coefficient that is read before it is written */
-      uint32_t nload = 0;
-      if (bulk_tile) for (uint32_t p = lane; p < T.npos; p += 32) nload += (spos[p] & MFFT_TILE_LOAD) ? 1u : 0u;
-#pragma unroll
-      for (int off = 16; off; off >>= 1) nload += __shfl_xor_sync(FULL, nload, off);
-      if (lane == 0)
-      {
-         mbar_arrive_expect_tx(mbar, T.nops * (uint32_t) sizeof(mfft_tileop) + nload * (L + 2) * 8u);
-         if (T.nops) bulk_g2s(sops, ops + T.op_off, T.nops * (uint32_t) sizeof(mfft_tileop), mbar);
-      }
-      __syncwarp();
-      if (bulk_tile)
-         for (uint32_t p = lane; p < T.npos; p += 32)
-         {
-            const uint32_t pp = spos[p];
-            if (pp & MFFT_TILE_LOAD) bulk_g2s(coef + (size_t) p * SP, tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b), (L + 2) * 8u, mbar);
-         }
-   }
-   if (TP.split)
-   {  /* the tile's coefficients are cut straight out of the operand: no split kernel, no slab read */
-      /* limb k of coefficient i = bits [i*bits + 64k, +64) of the operand: two loads and a funnel
-         shift with the same shift count for the whole coefficient; consecutive threads read
-         consecutive limbs, four coefficients are in flight per thread */
-      const uint32_t blimbs = (uint32_t)((TP.split_bits + 63) >> 6);     /* limbs that receive bits */
-      const limb_t lastmask = (TP.split_bits & 63) ? (((limb_t) 1 << (TP.split_bits & 63)) - 1) : ~(limb_t) 0;
-      for (uint32_t p0 = 0; p0 < T.npos; p0 += 4)
-      {
-         uint64_t qb[4]; uint32_t rr[4]; bool ld[4], nz[4];
-#pragma unroll
-         for (int u = 0; u < 4; u++)
-         {
-            const uint32_t p = p0 + u;
-            const uint32_t pp = (p < T.npos) ? spos[p] : 0u;
-            ld[u] = (pp & MFFT_TILE_LOAD) != 0;
-            const uint64_t i = (uint64_t) b.base + (uint64_t)(pp & MFFT_TILE_POSMASK) * g.slot_stride;
-            const uint64_t off = i * TP.split_bits;
-            nz[u] = ld[u] && i < TP.split_ncoef;
-            qb[u] = off >> 6; rr[u] = (uint32_t)(off & 63);
-         }
-         for (uint32_t k = tid; k < L; k += blockDim.x)
-         {
-            limb_t lo[4], hi[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-            {
-               lo[u] = 0; hi[u] = 0;
-               if (nz[u] && k < blimbs)
-               {
-                  const uint64_t q = qb[u] + k;
-                  if (q < TP.split_nlimbs) lo[u] = TP.split_src[q];
-                  if (q + 1 < TP.split_nlimbs) hi[u] = TP.split_src[q + 1];
-               }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-            {
-               if (!ld[u]) continue;
-               limb_t v = lo[u] >> rr[u];
-               if (rr[u]) v |= hi[u] << (64 - rr[u]);
-               if (k + 1 == blimbs) v &= lastmask;
-               coef[(size_t)(p0 + u) * SP + k] = v;
-            }
-         }
-      }
-      for (uint32_t t = tid; t < T.npos * NCH; t += blockDim.x)
-         if (spos[t / NCH] & MFFT_TILE_LOAD) reinterpret_cast<int32_t *>(coef + (size_t)(t / NCH) * SP + tile_cfg<NT>::CW)[t % NCH] = 0;
-   } else
-   if (bulk_tile)
-   {  /* the block images are on their way; meanwhile zero the carry words (they live behind the image) */
-      for (uint32_t t = tid; t < T.npos * (NCH / 4); t += blockDim.x)
-      {
-         const uint32_t p = t / (NCH / 4), c = t % (NCH / 4);
-         if (!(spos[p] & MFFT_TILE_LOAD)) continue;
-         st2(coef + (size_t) p * SP + tile_cfg<NT>::CW + 2 * c, 0, 0);
-      }
-   } else
-   for (uint32_t p = warp; p < T.npos; p += nwarps)
-   {
-      const uint32_t pp = spos[p];
-      if (!(pp & MFFT_TILE_LOAD)) continue;
-      const limb_t *src = tile_block_ptr(slab, g, pp & MFFT_TILE_POSMASK, b);
-      limb_t *d = coef + (size_t) p * SP;
-#pragma unroll 4
-      for (uint32_t k = lane; k < L; k += 32) d[k] = src[k];
-      int32_t *cw = reinterpret_cast<int32_t *>(d + tile_cfg<NT>::CW);
-#pragma unroll
-      for (uint32_t ch = lane; ch < NCH; ch += 32) cw[ch] = (ch == NCH - 1) ? (int32_t)(int64_t) src[L] : 0;
-   }
+   if (warp == 0)     /* one warp issues the tile's copies */
+      tile_issue<NT>(mbar, sops, coef, T, [&](uint32_t p) { return spos[p]; }, ops, slab, g, b, bulk_tile, lane);
+   tile_fill<NT>(coef, spos, T.npos, slab, g, b, TP, bulk_tile, tid, blockDim.x, warp, nwarps, lane);
    TILE_STAMP(1);
    mbar_wait(mbar, 0);
    if (bulk_tile)
@@ -1155,11 +1193,11 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
    __syncthreads();
    TILE_STAMP(2);
 
-   tile_stages<NT>(coef, sops, sst, T.nstages, b, warp, nwarps, lane, 0u, 0u);
+   if (!(TP.debug & 1u)) tile_stages<NT, WSPLIT>(coef, sops, sst, T.nstages, b, warp, nwarps, lane, 0u, 0u);
 
    TILE_STAMP(3);
    /* store what was written: in place, or gathered (and normalised) into dst */
-   tile_store<NT>(coef, spos, T.npos, slab, g, b, bi, dst, dstpos, dst_base, dst_stride, normalise, al16, warp, nwarps, lane);
+   if (!(TP.debug & 2u)) tile_store<NT>(coef, spos, T.npos, slab, g, b, bi, dst, dstpos, dst_base, dst_stride, normalise, al16, warp, nwarps, lane);
 #ifndef MFFT_EMU
    if (timing)
    {
@@ -1169,6 +1207,112 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
    }
 #endif
 #undef TILE_STAMP
+}
+
+
+/* ---- the persistent, pipelined variant ------------------------------------------------------- */
+/* One CTA per SM walks over tiles w = blockIdx.x, blockIdx.x + gridDim.x, ...  The CTA's shared memory
+ * is a ring of TPP_NBUF tile buffers; TPP_GROUPS groups of four warps each work on one tile at a time
+ * (item k of the CTA goes to group k mod TPP_GROUPS and lives in buffer k mod TPP_NBUF), so while the
+ * groups run their stages and stores, the spare buffers are being filled by the copy engine: the
+ * group that finishes item k hands its buffer straight back by issuing the bulk copies of item
+ * k + TPP_NBUF.  Without this, all CTAs of a launch move through load -> stages -> store in lockstep
+ * waves (measured on B200 at 2^20 limbs: load 6 us + stages 12 us + stores 6 us per pass add up instead
+ * of overlapping).  full[b]: mbarrier the copies of buffer b complete on; armed[b]: how many uses of
+ * buffer b have been armed -- a consumer first waits for its use to be armed, then for the phase
+ * (groups consume different buffers, so a phase parity alone could be one lap behind). */
+#define TPP_GROUPS 4
+#define TPP_NBUF 5
+#define TPP_CTL_BYTES 256
+
+template <int NT>
+__global__ void __launch_bounds__(TPP_GROUPS * 128, 1)
+k_run_tiles_p(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, const uint32_t *__restrict__ pos,
+              const mfft_tileop *__restrict__ ops, const mfft_batch *__restrict__ batch, uint32_t nbatch,
+              limb_t *dst, const uint32_t *__restrict__ dstpos, const uint32_t *__restrict__ dst_base,
+              uint32_t dst_stride, int normalise, uint32_t desc_bytes, const uint32_t *__restrict__ stoff,
+              uint32_t total, uint32_t buf_bytes, const __grid_constant__ tile_params TP)
+{
+   MFFT_DYN_SMEM(limb_t, sm);
+   constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP;
+   unsigned char *smb = (unsigned char *) sm;
+   const uint32_t tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127u, lane = tid & 31u, gwarp = gtid >> 5;
+   const uint32_t K = (total > blockIdx.x) ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   /* my items */
+   volatile uint32_t *armed = (volatile uint32_t *)(smb + TPP_NBUF * MBAR_BYTES);
+   static_assert(TPP_NBUF * MBAR_BYTES + TPP_NBUF * 4 <= TPP_CTL_BYTES, "control block");
+   if (tid == 0)
+      for (uint32_t bf = 0; bf < TPP_NBUF; bf++) { mbar_init((tile_mbar *)(smb + bf * MBAR_BYTES), 1); armed[bf] = 0; }
+   __syncthreads();
+#ifndef MFFT_EMU
+   asm volatile("griddepcontrol.wait;" ::: "memory");           /* see k_run_tiles */
+   asm volatile("griddepcontrol.launch_dependents;");
+#endif
+   const bool al16 = ((g.pitch & 1u) == 0) && ((reinterpret_cast<uintptr_t>(slab) & 15u) == 0) &&
+                     (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+   const bool bulk_tile = al16 && !TP.split && g.pitch >= L + 2;
+
+   /* arm and fire the copies of item k (one warp) */
+   auto issue = [&](uint32_t k)
+   {
+      const uint32_t w = blockIdx.x + k * gridDim.x, bi = w % nbatch, tix = w / nbatch, bf = k % TPP_NBUF;
+      const mfft_tile T = TP.valid ? TP.tiles[tix] : tiles[tix];
+      const mfft_batch b = TP.batch_valid ? TP.batch[bi] : batch[bi];
+      unsigned char *bb = smb + TPP_CTL_BYTES + (size_t) bf * buf_bytes;
+      tile_mbar *mbar = (tile_mbar *)(smb + bf * MBAR_BYTES);
+      fence_async_smem();                              /* the buffer was last touched through the generic proxy */
+      if (TP.valid) tile_issue<NT>(mbar, (mfft_tileop *) bb, (limb_t *)(bb + desc_bytes), T, [&](uint32_t p) { return TP.pos[tix * TP_MAXP + p]; }, ops, slab, g, b, bulk_tile, lane);
+      else          tile_issue<NT>(mbar, (mfft_tileop *) bb, (limb_t *)(bb + desc_bytes), T, [&](uint32_t p) { return pos[T.pos_off + p]; }, ops, slab, g, b, bulk_tile, lane);
+      if (lane == 0) { __threadfence_block(); armed[bf] = k / TPP_NBUF + 1; }
+   };
+   if (gwarp == 0)
+      for (uint32_t k = grp; k < K && k < TPP_NBUF; k += TPP_GROUPS) issue(k);
+
+   for (uint32_t k = grp; k < K; k += TPP_GROUPS)
+   {
+      const uint32_t w = blockIdx.x + k * gridDim.x, bi = w % nbatch, tix = w / nbatch, bf = k % TPP_NBUF, use = k / TPP_NBUF;
+      const mfft_tile T = TP.valid ? TP.tiles[tix] : tiles[tix];
+      const mfft_batch b = TP.batch_valid ? TP.batch[bi] : batch[bi];
+      unsigned char *bb = smb + TPP_CTL_BYTES + (size_t) bf * buf_bytes;
+      tile_mbar *mbar = (tile_mbar *)(smb + bf * MBAR_BYTES);
+      mfft_tileop *sops = (mfft_tileop *) bb;
+      uint32_t *spos = (uint32_t *)(sops + T.nops);
+      uint32_t *sst = spos + T.npos;
+      limb_t *coef = (limb_t *)(bb + desc_bytes);
+      /* the buffer is mine once the copies of my item have been armed (its previous user did that
+         after its last access) */
+      while (armed[bf] < use + 1)
+      {
+#ifdef MFFT_EMU
+         emu_yield();
+#else
+         __nanosleep(64);
+#endif
+      }
+      __threadfence_block();
+      if (TP.valid)
+      {
+         for (uint32_t q = gtid; q < T.npos; q += 128) spos[q] = TP.pos[tix * TP_MAXP + q];
+         for (uint32_t q = gtid; q <= T.nstages; q += 128) sst[q] = TP.stoff[tix * TP_MAXS + q];
+      } else
+      {
+         for (uint32_t q = gtid; q < T.npos; q += 128) spos[q] = pos[T.pos_off + q];
+         for (uint32_t q = gtid; q <= T.nstages; q += 128) sst[q] = stoff[T.pad + q];
+      }
+      tile_sync(1 + grp, 128);
+      tile_fill<NT>(coef, spos, T.npos, slab, g, b, TP, bulk_tile, gtid, 128, gwarp, 4, lane);
+      mbar_wait(mbar, use & 1u);
+      if (bulk_tile)
+      {  /* last carry word = the block's signed top limb, which arrived with the image */
+         tile_sync(1 + grp, 128);
+         if (gtid < T.npos && (spos[gtid] & MFFT_TILE_LOAD))
+            reinterpret_cast<int32_t *>(coef + (size_t) gtid * SP + tile_cfg<NT>::CW)[NCH - 1] = (int32_t)(int64_t) coef[(size_t) gtid * SP + L];
+      }
+      tile_sync(1 + grp, 128);
+      if (!(TP.debug & 1u)) tile_stages<NT, 1>(coef, sops, sst, T.nstages, b, gwarp, 4, lane, 1 + grp, 128);
+      if (!(TP.debug & 2u)) tile_store<NT>(coef, spos, T.npos, slab, g, b, bi, dst, dstpos, dst_base, dst_stride, normalise, al16, gwarp, 4, lane);
+      tile_sync(1 + grp, 128);                         /* nobody of the group reads the buffer any more */
+      if (gwarp == 0 && k + TPP_NBUF < K) issue(k + TPP_NBUF);
+   }
 }
 
 #endif

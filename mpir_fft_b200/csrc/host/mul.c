@@ -21,6 +21,8 @@ struct mpirfft_mul_plan {
    uint32_t l, pitch;
    mfft_mfa fwd, inv;
    limb_t *X, *Z, *Y;          /* 2N, 2N, N blocks */
+   limb_t *X2;                 /* work slab of the second forward transform (runs concurrently with the first) */
+   void *s_fwd2, *ev_fork, *ev_join;
    uint32_t *d_pw_blocks; uint32_t npw;
    void *combine_work;
    limb_t *d_i1, *d_i2, *d_r;  /* staging for the host-pointer entry */
@@ -85,7 +87,8 @@ void mpirfft_mul_plan_destroy(mpirfft_mul_plan *pl)
    if (!pl) return;
    mfft_lock();
    mfft_mfa_free(&pl->fwd); mfft_mfa_free(&pl->inv);
-   mfft_dev_free(pl->X); mfft_dev_free(pl->Z); mfft_dev_free(pl->Y);
+   mfft_dev_free(pl->X); mfft_dev_free(pl->Z); mfft_dev_free(pl->Y); mfft_dev_free(pl->X2);
+   mfft_dev_stream_destroy(pl->s_fwd2); mfft_dev_event_destroy(pl->ev_fork); mfft_dev_event_destroy(pl->ev_join);
    mfft_dev_free(pl->d_pw_blocks); mfft_dev_free(pl->combine_work);
    mfft_dev_free(pl->d_i1); mfft_dev_free(pl->d_i2); mfft_dev_free(pl->d_r);
    mfft_dev_stream_destroy(pl->s_copy); mfft_dev_stream_destroy(pl->s_comp);
@@ -118,6 +121,18 @@ int mpirfft_mul_plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, 
    pl->combine_work = mfft_dev_alloc(mfft_dev_combine_work((uint64_t)(n1 + n2)));
    if (!pl->X || !pl->Z || !pl->Y || !pl->combine_work) goto fail;
    pl->dev_bytes = 5*half + mfft_dev_combine_work((uint64_t)(n1 + n2));
+   {  /* The two forward transforms are independent: on two streams their passes interleave on the SMs,
+         one transform's tiles computing while the other's are being fetched (within one launch all
+         CTAs move through load -> stages -> store in lockstep waves).  MPIRFFT_FWD_STREAMS=1 serialises. */
+      const char *e = getenv("MPIRFFT_FWD_STREAMS");
+      if (!(e && e[0] == '1'))
+      {
+         pl->X2 = (limb_t *) mfft_dev_alloc(2*half);
+         pl->s_fwd2 = mfft_dev_stream_create(); pl->ev_fork = mfft_dev_event_create(); pl->ev_join = mfft_dev_event_create();
+         if (!pl->X2 || !pl->s_fwd2 || !pl->ev_fork || !pl->ev_join) goto fail;
+         pl->dev_bytes += 2*half;
+      }
+   }
    /* the rows whose coefficients get multiplied: revbin(s, depth+1-depth/2), s < trunc/sqrt
       (mul_fft.c:3244-3253 with the bit width of 3246 corrected, cf. 3629, 3642) */
    pl->npw = (uint32_t)(pl->p.trunc_rows * pl->p.sqrt);
@@ -177,11 +192,14 @@ static int exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, const mp_
       rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Z, stream);
       break;
    case 1:
+   {
+      limb_t *W = pl->X2 ? pl->X2 : pl->X;
       if (mfft_mfa_can_fuse_split(&pl->fwd))
-      { rc = mfft_mfa_exec_split(&pl->fwd, pl->X, pl->Y, (const limb_t *) d_i2, (uint64_t) pl->n2, p->bits1, p->j2, stream); break; }
-      if (mfft_dev_split(pl->X, pl->l, pl->pitch, (const limb_t *) d_i2, (uint64_t) pl->n2, p->bits1, p->j2, p->trunc, stream)) return MPIRFFT_ENODEV;
-      rc = mfft_mfa_exec(&pl->fwd, pl->X, pl->Y, stream);
+      { rc = mfft_mfa_exec_split(&pl->fwd, W, pl->Y, (const limb_t *) d_i2, (uint64_t) pl->n2, p->bits1, p->j2, stream); break; }
+      if (mfft_dev_split(W, pl->l, pl->pitch, (const limb_t *) d_i2, (uint64_t) pl->n2, p->bits1, p->j2, p->trunc, stream)) return MPIRFFT_ENODEV;
+      rc = mfft_mfa_exec(&pl->fwd, W, pl->Y, stream);
       break;
+   }
    case 2:
       if (mfft_dev_pointwise(pl->Z, pl->Y, pl->d_pw_blocks, pl->npw, pl->l, pl->pitch, stream)) return MPIRFFT_ENODEV;
       break;
@@ -209,6 +227,18 @@ int mpirfft_mul_exec_device(mpirfft_mul_plan *pl, mp_limb_t *d_r, const mp_limb_
       if (mfft_dev_pointwise(pl->Z, pl->Z, pl->d_pw_blocks, pl->npw, pl->l, pl->pitch, stream)) { rc = MPIRFFT_ENODEV; goto done; }
       for (ph = 3; ph < 5; ph++)
          if ((rc = exec_phase(pl, ph, d_r, d_i1, d_i2, stream)) != 0) goto done;
+      goto done;
+   }
+   if (pl->X2 && !mfft_dev_profile_is_on())     /* (per-launch event timing wants the launches one after the other) */
+   {  /* fork: the second operand's transform on its own stream and slab; join before the products */
+      rc = MPIRFFT_ENODEV;
+      if (mfft_dev_event_record(pl->ev_fork, stream) || mfft_dev_stream_wait(pl->s_fwd2, pl->ev_fork)) goto done;
+      if ((rc = exec_phase(pl, 0, d_r, d_i1, d_i2, stream)) != 0) goto done;
+      if ((rc = exec_phase(pl, 1, d_r, d_i1, d_i2, pl->s_fwd2)) != 0) goto done;
+      rc = MPIRFFT_ENODEV;
+      if (mfft_dev_event_record(pl->ev_join, pl->s_fwd2) || mfft_dev_stream_wait(stream, pl->ev_join)) goto done;
+      for (ph = 2; ph < 5; ph++)
+         if ((rc = exec_phase(pl, ph, d_r, d_i1, d_i2, stream)) != 0) break;
       goto done;
    }
    for (ph = 0; ph < 5; ph++)
@@ -240,10 +270,17 @@ int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i
    if (mfft_dev_stream_wait(pl->s_comp, pl->ev1)) goto done;
    if ((rc = mpirfft_mul_exec_phase(pl, 0, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_comp)) != 0) goto done;
    rc = MPIRFFT_ENODEV;
-   if (mfft_dev_stream_wait(pl->s_comp, pl->ev2)) goto done;
+   if (pl->X2)
+   {  /* the second transform starts on its own stream as soon as its operand has arrived */
+      if (mfft_dev_stream_wait(pl->s_fwd2, pl->ev2)) goto done;
+      if ((rc = mpirfft_mul_exec_phase(pl, 1, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_fwd2)) != 0) goto done;
+      rc = MPIRFFT_ENODEV;
+      if (mfft_dev_event_record(pl->ev_join, pl->s_fwd2) || mfft_dev_stream_wait(pl->s_comp, pl->ev_join)) goto done;
+   }
+   else if (mfft_dev_stream_wait(pl->s_comp, pl->ev2)) goto done;
    {
       int ph;
-      for (ph = 1; ph < 5; ph++)
+      for (ph = pl->X2 ? 2 : 1; ph < 5; ph++)
          if ((rc = mpirfft_mul_exec_phase(pl, ph, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_comp)) != 0) goto done;
    }
    rc = MPIRFFT_ENODEV;

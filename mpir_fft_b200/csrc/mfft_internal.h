@@ -230,6 +230,7 @@ int  mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk,
 /* optional per-kernel-class CUDA-event timing (bench.py's roofline leg); classes in order:
  * 0 stage, 1 finalize, 2 pointwise, 3 split, 4 combine, 5 normalise */
 void mfft_dev_profile_enable(int on);
+int  mfft_dev_profile_is_on(void);
 void mfft_dev_profile_bytes(double bytes);     /* algorithmic bytes of the next launch */
 int  mfft_dev_profile_read(double *ms, uint64_t *launches, double *bytes, int nclass);
 

@@ -16,11 +16,18 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = torch.zeros(8 * 16384, dtype=torch.int64, device="cuda")
 for ph, name, grids in ((0, "fwd", (2048, 1152, 1040, 1040)), (3, "inv", (1040, 1040, 1152, 2048, 1280))):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     buf.zero_()
     L.mfft_dev_tile_timing(C.c_void_p(buf.data_ptr()))
     plan.exec_phase(ph, r.data_ptr(), a.data_ptr(), b.data_ptr(), None)
     torch.cuda.synchronize()
     L.mfft_dev_tile_timing(None)
+    e0.record()
+    for _ in range(10):
+        plan.exec_phase(ph, r.data_ptr(), a.data_ptr(), b.data_ptr(), None)
+    e1.record()
+    torch.cuda.synchronize()
+    print("%s: %.1f us per transform (10 back-to-back, un-instrumented)" % (name, e0.elapsed_time(e1) * 100))
     allt = buf.cpu().numpy().reshape(-1, 8)
     off = 0
     for gi, g in enumerate(grids):

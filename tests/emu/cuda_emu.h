@@ -135,6 +135,7 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, unsigned m)
    const unsigned lane = threadIdx.x & 31;
    T out; uint64_t r = s[(lane ^ m) & 31]; memcpy(&out, &r, sizeof(T)); return out;
 }
+static inline void __threadfence_block() { }
 static inline void __syncthreads()
 {
    emu_block_sync *b = emu_cur_block();
