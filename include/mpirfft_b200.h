@@ -40,6 +40,12 @@ typedef unsigned long mp_bitcnt_t;
 void new_mpn_mul(mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2,
                  mp_bitcnt_t depth, mp_bitcnt_t w);
 
+/* mul_fft.c:3573  the same product through the sqrt2 transforms: transform length 4n = 2^(depth+2)
+ * with the 4n-th root of unity sqrt2^w, sqrt2 = 2^(3nw/4) - 2^(nw/4), so a ring of nw bits carries
+ * twice as many coefficients as in new_mpn_mul.  Needs 2^(depth+1) < j1+j2-1 <= 2^(depth+2). */
+void new_mpn_mul6(mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2,
+                  mp_bitcnt_t depth, mp_bitcnt_t w);
+
 /* mul_fft.c:41, 3119  r = i1*i2 mod 2^bits+1; c bit0 <=> i1 == 2^bits, bit1 <=> i2 == 2^bits;
  * returns 1 iff the result is 2^bits.  tt (2*(bits/64+1) limbs) is accepted and unused. */
 mp_limb_t new_mpn_mulmod_2expp1(mp_limb_t *r, mp_limb_t *i1, mp_limb_t *i2, mp_limb_t c,
@@ -64,6 +70,14 @@ void FFT_radix2_mfa_truncate(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb
                              mp_limb_t **t2, mp_limb_t **temp, mp_size_t n1, mp_size_t trunc);
 void IFFT_radix2_mfa_truncate(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
                               mp_limb_t **t2, mp_limb_t **temp, mp_size_t n1, mp_size_t trunc);
+
+/* mul_fft.c:2212 / 2593  length-4n truncated MFA with the sqrt2 trick: ii has 4n blocks (two halves of
+ * n2 = 2n/n1 rows of n1 columns), trunc a multiple of 2*n1 in (2n, 4n]; temp is scratch in the
+ * reference and unused here */
+void FFT_radix2_mfa_truncate_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                                   mp_limb_t **t2, mp_limb_t **temp, mp_size_t n1, mp_size_t trunc);
+void IFFT_radix2_mfa_truncate_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
+                                    mp_limb_t **t2, mp_limb_t **temp, mp_size_t n1, mp_size_t trunc);
 
 /* mul_fft.c:786 / 1444  length-2n radix-2 FFT (output bit-reversed) and its inverse (unscaled) */
 void FFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
@@ -114,6 +128,12 @@ void FFT_radix2_twiddle_butterfly(mp_limb_t *u, mp_limb_t *v, mp_limb_t *s, mp_l
 void FFT_radix2_twiddle_inverse_butterfly(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2,
                                           mp_size_t NW, mp_bitcnt_t b1, mp_bitcnt_t b2);
 void FFT_twiddle(mp_limb_t *r, mp_limb_t *i1, mp_size_t i, mp_size_t n, mp_bitcnt_t w);
+/* mul_fft.c:591, 673, 972  the same with the 4n-th root of unity z1 = sqrt2^w (i and w odd) */
+void FFT_radix2_butterfly_sqrt2(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2, mp_size_t i,
+                                mp_size_t n, mp_bitcnt_t w, mp_limb_t *temp);
+void FFT_radix2_inverse_butterfly_sqrt2(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2,
+                                        mp_size_t i, mp_size_t n, mp_bitcnt_t w, mp_limb_t *temp);
+void FFT_twiddle_sqrt2(mp_limb_t *r, mp_limb_t *i1, mp_size_t i, mp_size_t n, mp_bitcnt_t w, mp_limb_t *temp);
 
 /* mul_fft.c:272, 470, 494, 303, 394  arithmetic mod 2^(64 l)+1 on one block */
 void mpn_normmod_2expp1(mp_limb_t *t, mp_size_t l);
@@ -156,10 +176,16 @@ typedef struct {
 } mpirfft_mul_params;
 int  mpirfft_mul_params_get(mpirfft_mul_params *out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
                             mp_bitcnt_t w);
+/* the same for new_mpn_mul6 (mul_fft.c:3576-3612): n2 = rows per half, trunc_rows = live rows of both halves */
+int  mpirfft_mul6_params_get(mpirfft_mul_params *out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
+                             mp_bitcnt_t w);
 /* Parameter chooser (the reference has none, mul_fft.c:3177-3178): the smallest coefficient ring
  * among 64..512 limbs that is legal for an n1 x n2 limb product (the fused tile executor and the
  * warp-level product kernel), else the smallest legal (depth, w) with w in {1,2}. */
 int  mpirfft_choose_params(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w);
+/* the same with the new_mpn_mul6 shape as a candidate at every ring size (*sqrt2 = 1: use new_mpn_mul6 /
+ * mpirfft_mul6_plan_create): what mpirfft_mpn_mul uses */
+int  mpirfft_choose_params6(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w, int *sqrt2);
 /* r[0..n1+n2) = i1 * i2 with the parameters of mpirfft_choose_params: the mpn_mul-shaped entry the
  * reference leaves as a FIXME (mul_fft.c:3177-3178).  Host pointers; aborts like new_mpn_mul. */
 void mpirfft_mpn_mul(mp_limb_t *r, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2);
@@ -168,6 +194,9 @@ void mpirfft_mpn_mul(mp_limb_t *r, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, m
 typedef struct mpirfft_mul_plan mpirfft_mul_plan;
 int  mpirfft_mul_plan_create(mpirfft_mul_plan **plan, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
                              mp_bitcnt_t w);
+/* the plan of new_mpn_mul6 (sqrt2 transforms); executed and destroyed like any other plan */
+int  mpirfft_mul6_plan_create(mpirfft_mul_plan **plan, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
+                              mp_bitcnt_t w);
 void mpirfft_mul_plan_destroy(mpirfft_mul_plan *plan);
 /* d_r[0..n1+n2) = d_i1 * d_i2, all three device pointers; asynchronous on `stream`
  * (a cudaStream_t, NULL = default stream). */

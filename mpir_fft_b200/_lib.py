@@ -50,7 +50,11 @@ def bind(L):
         "mpirfft_last_error": (C.c_char_p, []),
         "mpirfft_version": (C.c_char_p, []),
         "mpirfft_mul_params_get": (i32, [C.POINTER(MulParams), i64, i64, u64, u64]),
+        "mpirfft_mul6_params_get": (i32, [C.POINTER(MulParams), i64, i64, u64, u64]),
+        "mpirfft_mul6_plan_create": (i32, [C.POINTER(vp), i64, i64, u64, u64]),
+        "new_mpn_mul6": (None, [vp, vp, i64, vp, i64, u64, u64]),
         "mpirfft_choose_params": (i32, [i64, i64, C.POINTER(u64), C.POINTER(u64)]),
+        "mpirfft_choose_params6": (i32, [i64, i64, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]),
         "mpirfft_mul_plan_create": (i32, [C.POINTER(vp), i64, i64, u64, u64]),
         "mpirfft_mul_plan_destroy": (None, [vp]),
         "mpirfft_mul_exec_device": (i32, [vp, vp, vp, vp, vp]),

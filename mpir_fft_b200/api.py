@@ -51,6 +51,20 @@ def new_mpn_mul(i1, i2, depth, w):
     return r
 
 
+def new_mpn_mul6(i1, i2, depth, w):
+    """r = i1 * i2 through the sqrt2 transforms -- the drop-in symbol new_mpn_mul6 (mul_fft.c:3573)."""
+    i1 = np.ascontiguousarray(i1, dtype=np.uint64)
+    i2 = np.ascontiguousarray(i2, dtype=np.uint64)
+    p = MulParams()
+    if lib().mpirfft_mul6_params_get(C.byref(p), len(i1), len(i2), depth, w) != 0:
+        raise ValueError("illegal new_mpn_mul6 parameters n1=%d n2=%d depth=%d w=%d" % (len(i1), len(i2), depth, w))
+    if not have_gpu():
+        raise RuntimeError("no CUDA device: mpir_fft_b200 has no CPU path")
+    r = np.zeros(len(i1) + len(i2), dtype=np.uint64)
+    lib().new_mpn_mul6(_ptr(r), _ptr(i1), len(i1), _ptr(i2), len(i2), depth, w)
+    return r
+
+
 def mpn_mul(i1, i2):
     """r = i1 * i2 with automatically chosen (depth, w) -- mpirfft_mpn_mul"""
     i1 = np.ascontiguousarray(i1, dtype=np.uint64)

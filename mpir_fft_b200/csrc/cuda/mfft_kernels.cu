@@ -1717,11 +1717,11 @@ int mfft_dev_run_tiles(limb_t *slab, const mfft_geom *g, const mfft_tile *d_tile
    if (wsplit < 0) { const char *e = getenv("MPIRFFT_TILE_WSPLIT"); wsplit = e ? atoi(e) : 1; }
    {  /* persistent pipelined variant (k_run_tiles_p): one CTA per SM, a ring of tile buffers filled by
          bulk copies while the warp groups work.  Needs at least two tiles per SM to have anything to
-         overlap, four-warp tiles (NT <= 4), and room for the ring.  MPIRFFT_TILE_PERSIST=0 turns it off. */
+         overlap, four-warp tiles (NT <= 4), and room for the ring.  MPIRFFT_TILE_PERSIST=1 turns it on. */
       static int persist = -1, nsm = 0;
       if (persist < 0)
       {
-         const char *e = getenv("MPIRFFT_TILE_PERSIST"); persist = e ? atoi(e) : 1;
+         const char *e = getenv("MPIRFFT_TILE_PERSIST"); persist = e ? atoi(e) : 0;     /* opt-in: measured slower at 2^20 limbs (7 tiles per SM are too few to pipeline) */
 #ifndef MFFT_EMU
          int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 #else

@@ -158,12 +158,14 @@ void IFFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_siz
 
 /* ------------------------------- MFA on host pointer tables -------------------------------- */
 static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_size_t n1,
-                     mp_size_t trunc, int truncated)
+                     mp_size_t trunc, int truncated, int sqrt2)
 {
    mfft_mfa m; int rc; uint64_t N, k, i, j; size_t half; limb_t *stage, *d_slab, *d_dst; uint32_t pitch;
    check_ring(fn, n, w);
    mfft_lock();
    mfft_require_device(fn);
+   if (sqrt2) rc = mfft_mfa_build_sqrt2(&m, inverse, (uint64_t) n, w, (uint64_t) n1, (uint64_t) trunc, 0, 1);
+   else
    rc = mfft_mfa_build(&m, inverse, (uint64_t) n, w, (uint64_t) n1, truncated ? (uint64_t) trunc : 0, 0, truncated);
    if (rc != 0) mfft_die(fn, "illegal MFA parameters n=%ld w=%lu n1=%ld trunc=%ld (code %d; trunc must be a multiple "
                          "of 2*n1, mul_fft.c:2209-2211)", (long) n, (unsigned long) w, (long) n1, (long) trunc, rc);
@@ -193,19 +195,29 @@ static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, m
 
 void FFT_radix2_mfa(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
                     mp_limb_t **temp, mp_size_t n1)
-{ (void) t1; (void) t2; (void) temp; mfa_host("FFT_radix2_mfa", 0, ii, n, w, n1, 0, 0); }
+{ (void) t1; (void) t2; (void) temp; mfa_host("FFT_radix2_mfa", 0, ii, n, w, n1, 0, 0, 0); }
 
 void IFFT_radix2_mfa(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
                      mp_limb_t **temp, mp_size_t n1)
-{ (void) t1; (void) t2; (void) temp; mfa_host("IFFT_radix2_mfa", 1, ii, n, w, n1, 0, 0); }
+{ (void) t1; (void) t2; (void) temp; mfa_host("IFFT_radix2_mfa", 1, ii, n, w, n1, 0, 0, 0); }
 
 void FFT_radix2_mfa_truncate(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
                              mp_limb_t **temp, mp_size_t n1, mp_size_t trunc)
-{ (void) t1; (void) t2; (void) temp; mfa_host("FFT_radix2_mfa_truncate", 0, ii, n, w, n1, trunc, 1); }
+{ (void) t1; (void) t2; (void) temp; mfa_host("FFT_radix2_mfa_truncate", 0, ii, n, w, n1, trunc, 1, 0); }
 
 void IFFT_radix2_mfa_truncate(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
                               mp_limb_t **temp, mp_size_t n1, mp_size_t trunc)
-{ (void) t1; (void) t2; (void) temp; mfa_host("IFFT_radix2_mfa_truncate", 1, ii, n, w, n1, trunc, 1); }
+{ (void) t1; (void) t2; (void) temp; mfa_host("IFFT_radix2_mfa_truncate", 1, ii, n, w, n1, trunc, 1, 0); }
+
+/* the sqrt2 transforms of length 4n (mul_fft.c:2212, 2593): valid outputs as in the reference -- forward,
+   every row of the first half and rows revbin(s), s < (trunc-2n)/n1, of the second; inverse, ii[0..trunc) */
+void FFT_radix2_mfa_truncate_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                                   mp_limb_t **temp, mp_size_t n1, mp_size_t trunc)
+{ (void) t1; (void) t2; (void) temp; mfa_host("FFT_radix2_mfa_truncate_sqrt2", 0, ii, n, w, n1, trunc, 1, 1); }
+
+void IFFT_radix2_mfa_truncate_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                                    mp_limb_t **temp, mp_size_t n1, mp_size_t trunc)
+{ (void) t1; (void) t2; (void) temp; mfa_host("IFFT_radix2_mfa_truncate_sqrt2", 1, ii, n, w, n1, trunc, 1, 1); }
 
 /* ----------------------------- single-block primitives ------------------------------------- */
 /* positions 0,1 = inputs A,B; outputs S -> position 0, T -> position 1 */
@@ -294,6 +306,56 @@ void FFT_twiddle(mp_limb_t *r, mp_limb_t *i1, mp_size_t i, mp_size_t n, mp_bitcn
    check_ring("FFT_twiddle", n, w);
    l = (uint64_t) n*w/64; e = ((uint64_t) i % (2*(uint64_t) n)) * w;
    two_block_op("FFT_twiddle", (uint32_t) l, r, NULL, i1, NULL, 1, e, 0, 0, 0, 0, 0, 0, 0);
+}
+
+/* ---- sqrt2 butterflies (mul_fft.c:591, 673, 972): z1^i = 2^e (2^(nw/2) - 1), e = (i w - 1)/2 + nw/4 ---- */
+static void sqrt2_check(const char *fn, mp_size_t i, mp_size_t n, mp_bitcnt_t w)
+{
+   check_ring(fn, n, w);
+   if (!(i & 1) || !(w & 1) || i < 0 || i >= 4*n || ((uint64_t) n*w) % 256)
+      mfft_die(fn, "needs odd i < 4n, odd w and 256 | n*w (i=%ld n=%ld w=%lu)", (long) i, (long) n, (unsigned long) w);
+}
+
+void FFT_radix2_butterfly_sqrt2(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2, mp_size_t i,
+                                mp_size_t n, mp_bitcnt_t w, mp_limb_t *temp)
+{
+   uint64_t NW, e; mfft_sched *sc; mp_limb_t *in[2], *out[2];
+   (void) temp;
+   sqrt2_check("FFT_radix2_butterfly_sqrt2", i, n, w);
+   NW = (uint64_t) n*w; e = (((uint64_t) i*w - 1)/2 + NW/4) % (2*NW);
+   if (!(sc = mfft_sched_new(2, NW))) mfft_die("FFT_radix2_butterfly_sqrt2", "out of host memory");
+   in[0] = i1; in[1] = i2; out[0] = s; out[1] = t;
+   mfft_sched_emit_op(sc, 0, 1, 0, 1, 0, 1, 0, 1, 1, e, -1, e);                     /* a + b, 2^e (a - b) */
+   mfft_sched_emit_op(sc, 1, 1, 1, 1, NW/2, -1, 0, MFFT_NONE, 0, 0, 0, 0);          /* x 2^(nw/2) - x */
+   run_on_host_blocks("FFT_radix2_butterfly_sqrt2", sc, (uint32_t)(NW/64), in, out, 0, 0);
+}
+
+void FFT_radix2_inverse_butterfly_sqrt2(mp_limb_t *s, mp_limb_t *t, mp_limb_t *i1, mp_limb_t *i2, mp_size_t i,
+                                        mp_size_t n, mp_bitcnt_t w, mp_limb_t *temp)
+{
+   uint64_t NW, e; mfft_sched *sc; mp_limb_t *in[2], *out[2];
+   (void) temp;
+   sqrt2_check("FFT_radix2_inverse_butterfly_sqrt2", i, n, w);
+   NW = (uint64_t) n*w; e = (4*NW - ((uint64_t) i*w - 1)/2 - 1 + NW/4) % (2*NW);     /* mul_fft.c:653-672 */
+   if (!(sc = mfft_sched_new(2, NW))) mfft_die("FFT_radix2_inverse_butterfly_sqrt2", "out of host memory");
+   in[0] = i1; in[1] = i2; out[0] = s; out[1] = t;
+   mfft_sched_emit_op(sc, 1, MFFT_NONE, 1, 1, e, 0, 0, MFFT_NONE, 0, 0, 0, 0);
+   mfft_sched_emit_op(sc, 1, 1, 1, 1, NW/2, -1, 0, MFFT_NONE, 0, 0, 0, 0);
+   mfft_sched_emit_op(sc, 0, 1, 0, 1, 0, 1, 0, 1, 1, 0, -1, 0);
+   run_on_host_blocks("FFT_radix2_inverse_butterfly_sqrt2", sc, (uint32_t)(NW/64), in, out, 0, 0);
+}
+
+void FFT_twiddle_sqrt2(mp_limb_t *r, mp_limb_t *i1, mp_size_t i, mp_size_t n, mp_bitcnt_t w, mp_limb_t *temp)
+{
+   uint64_t NW, e; mfft_sched *sc; mp_limb_t *in[1], *out[1];
+   (void) temp;
+   sqrt2_check("FFT_twiddle_sqrt2", i, n, w);
+   NW = (uint64_t) n*w; e = (((uint64_t) i*w - 1)/2 + NW/4) % (2*NW);
+   if (!(sc = mfft_sched_new(1, NW))) mfft_die("FFT_twiddle_sqrt2", "out of host memory");
+   in[0] = i1; out[0] = r;
+   mfft_sched_emit_op(sc, 0, MFFT_NONE, 0, 1, e, 0, 0, MFFT_NONE, 0, 0, 0, 0);
+   mfft_sched_emit_op(sc, 0, 0, 0, 1, NW/2, -1, 0, MFFT_NONE, 0, 0, 0, 0);
+   run_on_host_blocks("FFT_twiddle_sqrt2", sc, (uint32_t)(NW/64), in, out, 0, 0);
 }
 
 /* ---------------------------------- split / combine ---------------------------------------- */

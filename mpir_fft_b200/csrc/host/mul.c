@@ -17,6 +17,7 @@
 
 struct mpirfft_mul_plan {
    mp_size_t n1, n2; mp_bitcnt_t depth, w;
+   int sqrt2;                  /* new_mpn_mul6: transform length 4n with the sqrt2 trick (mul_fft.c:3573) */
    mpirfft_mul_params p;
    uint32_t l, pitch;
    mfft_mfa fwd, inv;
@@ -52,24 +53,55 @@ int mpirfft_mul_params_get(mpirfft_mul_params *o, mp_size_t n1, mp_size_t n2, mp
    return 0;
 }
 
-int mpirfft_choose_params(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w)
+/* new_mpn_mul6 (mul_fft.c:3573-3668): transform length 4n, one bit less per coefficient (3578), the
+   first 2n coefficients always live, trunc in (2n, 4n] */
+int mpirfft_mul6_params_get(mpirfft_mul_params *o, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth, mp_bitcnt_t w)
+{
+   uint64_t n, nw;
+   memset(o, 0, sizeof(*o));
+   if (n1 <= 0 || n2 <= 0 || depth < 3 || depth > 25 || w == 0 || w > 4096) return MPIRFFT_EINVAL;
+   n = (uint64_t)1 << depth; nw = n*w;
+   if (nw % 64 || nw % 4) return MPIRFFT_EINVAL;
+   if (nw <= depth + 2) return MPIRFFT_EINVAL;
+   o->n = n;
+   o->bits1 = (nw - (depth + 1))/2;                          /* 3578 */
+   o->sqrt = (uint64_t)1 << (depth/2);                       /* 3577 */
+   o->j1 = ((uint64_t) n1*64 - 1)/o->bits1 + 1;              /* 3581 */
+   o->j2 = ((uint64_t) n2*64 - 1)/o->bits1 + 1;              /* 3582 */
+   o->trunc = 2*o->sqrt*((o->j1 + o->j2 + 2*o->sqrt - 2)/(2*o->sqrt));   /* 3612 */
+   o->limbs = nw/64;
+   o->n2 = 2*n/o->sqrt;
+   if (o->j1 + o->j2 - 1 > 4*n || o->trunc > 4*n) return MPIRFFT_EINVAL;
+   if (o->trunc <= 2*n) return MPIRFFT_EINVAL;   /* the second half would be empty (the reference's truncate1 then recurses forever): use new_mpn_mul */
+   if (o->n2 < 4 || o->sqrt < 2) return MPIRFFT_EINVAL;
+   o->trunc_rows = o->trunc/o->sqrt;                         /* n2 first-half rows + the live second-half rows */
+   return 0;
+}
+
+/* sqrt2 != NULL: the new_mpn_mul6 shape (transform length 4n) is a candidate too; *sqrt2 says which */
+static int choose(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w, int *sqrt2)
 {
    mp_bitcnt_t d, ww;
    mpirfft_mul_params p;
+   if (sqrt2) *sqrt2 = 0;
    /* first choice: the smallest coefficient ring the fused tile executor and the warp-level product
       kernel handle (64, 128, 256, 512 limbs) -- the pointwise work grows with the ring, the transform
-      work shrinks; measured on B200 the smaller ring wins whenever it is legal */
+      work shrinks; measured on B200 the smaller ring wins whenever it is legal.  With the sqrt2 trick a
+      ring carries twice as many coefficients, so a product that would need the next ring size stays
+      one size smaller (a quarter of the multiply work per coefficient, twice the coefficients). */
    {
       static const uint32_t ring[4] = { 64, 128, 256, 512 };
-      int i;
+      int i, sq;
       for (i = 0; i < 4; i++)
-         for (ww = 2; ww >= 1; ww--)                  /* w = 2: one layer less for the same ring */
-         {
-            uint64_t nn = 64ull*ring[i]/ww;
-            if (nn & (nn - 1)) continue;
-            for (d = 0; ((uint64_t)1 << d) < nn; d++) ;
-            if (mpirfft_mul_params_get(&p, n1, n2, d, ww) == 0) { *depth = d; *w = ww; return 0; }
-         }
+         for (sq = 0; sq <= (sqrt2 ? 1 : 0); sq++)
+            for (ww = 2; ww >= 1; ww--)                  /* w = 2: one layer less for the same ring */
+            {
+               uint64_t nn = 64ull*ring[i]/ww;
+               if (nn & (nn - 1)) continue;
+               for (d = 0; ((uint64_t)1 << d) < nn; d++) ;
+               if ((sq ? mpirfft_mul6_params_get(&p, n1, n2, d, ww) : mpirfft_mul_params_get(&p, n1, n2, d, ww)) == 0)
+               { *depth = d; *w = ww; if (sqrt2) *sqrt2 = sq; return 0; }
+            }
    }
    /* smallest coefficient size first: n*w ascending, preferring w = 1 */
    for (d = 6; d <= 26; d++)
@@ -81,6 +113,12 @@ int mpirfft_choose_params(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bit
          }
    return MPIRFFT_EINVAL;
 }
+
+int mpirfft_choose_params(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w)
+{ return choose(n1, n2, depth, w, NULL); }
+
+int mpirfft_choose_params6(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bitcnt_t *w, int *sqrt2)
+{ return choose(n1, n2, depth, w, sqrt2); }
 
 void mpirfft_mul_plan_destroy(mpirfft_mul_plan *pl)
 {
@@ -97,22 +135,40 @@ void mpirfft_mul_plan_destroy(mpirfft_mul_plan *pl)
    free(pl);
 }
 
+static int plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth, mp_bitcnt_t w, int sqrt2);
+
 int mpirfft_mul_plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth, mp_bitcnt_t w)
+{ return plan_create(out, n1, n2, depth, w, 0); }
+
+int mpirfft_mul6_plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth, mp_bitcnt_t w)
+{ return plan_create(out, n1, n2, depth, w, 1); }
+
+static int plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth, mp_bitcnt_t w, int sqrt2)
 {
    mpirfft_mul_plan *pl; int rc; uint64_t N, i, j; size_t half; uint32_t *blocks = NULL;
    *out = NULL;
    pl = (mpirfft_mul_plan *) calloc(1, sizeof(*pl));
    if (!pl) return MPIRFFT_ENOMEM;
-   pl->n1 = n1; pl->n2 = n2; pl->depth = depth; pl->w = w;
-   if ((rc = mpirfft_mul_params_get(&pl->p, n1, n2, depth, w)) != 0) { free(pl); return rc; }
+   pl->n1 = n1; pl->n2 = n2; pl->depth = depth; pl->w = w; pl->sqrt2 = sqrt2;
+   rc = sqrt2 ? mpirfft_mul6_params_get(&pl->p, n1, n2, depth, w) : mpirfft_mul_params_get(&pl->p, n1, n2, depth, w);
+   if (rc != 0) { free(pl); return rc; }
    mfft_lock();
    if ((rc = mfft_try_device()) != 0) goto fail;
    pl->l = (uint32_t) pl->p.limbs; pl->pitch = mfft_pitch(pl->l);
-   N = 2*pl->p.n;
+   N = (sqrt2 ? 4 : 2)*pl->p.n;
+   if (sqrt2)
+   {  /* FFT/IFFT_radix2_mfa_truncate_sqrt2 (3619, 3625, 3656); / 2^(depth+2) and the normalisation
+         (3659-3663) folded into the last inverse pass */
+      if ((rc = mfft_mfa_build_sqrt2(&pl->fwd, 0, pl->p.n, w, pl->p.sqrt, pl->p.trunc, 0, 1)) != 0) goto fail;
+      if ((rc = mfft_mfa_build_sqrt2(&pl->inv, 1, pl->p.n, w, pl->p.sqrt, pl->p.trunc,
+                                     (uint32_t)(128ull*pl->l - (depth + 2)), 1)) != 0) goto fail;
+   } else
+   {
    if ((rc = mfft_mfa_build(&pl->fwd, 0, pl->p.n, w, pl->p.sqrt, pl->p.trunc, 0, 1)) != 0) goto fail;
    /* the inverse is unscaled: fold / 2^(depth+1) and the normalisation into its last pass (3256-3260) */
    if ((rc = mfft_mfa_build(&pl->inv, 1, pl->p.n, w, pl->p.sqrt, pl->p.trunc,
                             (uint32_t)(128ull*pl->l - (depth + 1)), 1)) != 0) goto fail;
+   }
    half = (size_t) N * pl->pitch * sizeof(limb_t);
    rc = MPIRFFT_ENOMEM;
    pl->X = (limb_t *) mfft_dev_alloc(2*half);
@@ -134,7 +190,8 @@ int mpirfft_mul_plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, 
       }
    }
    /* the rows whose coefficients get multiplied: revbin(s, depth+1-depth/2), s < trunc/sqrt
-      (mul_fft.c:3244-3253 with the bit width of 3246 corrected, cf. 3629, 3642) */
+      (mul_fft.c:3244-3253 with the bit width of 3246 corrected, cf. 3629, 3642); for new_mpn_mul6 all
+      rows of the first half and those rows of the second (3630-3653); fwd.rows lists them either way */
    pl->npw = (uint32_t)(pl->p.trunc_rows * pl->p.sqrt);
    blocks = (uint32_t *) malloc(sizeof(uint32_t) * pl->npw);
    if (!blocks) goto fail;
@@ -296,40 +353,55 @@ done:
 static mpirfft_mul_plan *g_cache[PLAN_CACHE];
 static unsigned g_cache_next = 0;
 
+static void mul_dropin(const char *fn, int sqrt2, mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2,
+                       mp_bitcnt_t depth, mp_bitcnt_t w);
+
 void new_mpn_mul(mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2,
                  mp_bitcnt_t depth, mp_bitcnt_t w)
+{ mul_dropin("new_mpn_mul", 0, r1, i1, n1, i2, n2, depth, w); }
+
+/* mul_fft.c:3573  the same product through the sqrt2 transforms of length 4n */
+void new_mpn_mul6(mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2,
+                  mp_bitcnt_t depth, mp_bitcnt_t w)
+{ mul_dropin("new_mpn_mul6", 1, r1, i1, n1, i2, n2, depth, w); }
+
+static void mul_dropin(const char *fn, int sqrt2, mp_limb_t *r1, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2,
+                       mp_bitcnt_t depth, mp_bitcnt_t w)
 {
    mpirfft_mul_plan *pl = NULL; int k, rc;
    mpirfft_mul_params p;
-   if (!r1 || !i1 || !i2) mfft_die("new_mpn_mul", "null operand");
-   if (mpirfft_mul_params_get(&p, n1, n2, depth, w) != 0)
-      mfft_die("new_mpn_mul", "illegal parameters n1=%ld n2=%ld depth=%lu w=%lu: need 64 | 2^depth*w and "
-               "j1+j2-1 <= 2^(depth+1) (mul_fft.c:3186-3187)", (long) n1, (long) n2, (unsigned long) depth, (unsigned long) w);
+   if (!r1 || !i1 || !i2) mfft_die(fn, "null operand");
+   if ((sqrt2 ? mpirfft_mul6_params_get(&p, n1, n2, depth, w) : mpirfft_mul_params_get(&p, n1, n2, depth, w)) != 0)
+      mfft_die(fn, "illegal parameters n1=%ld n2=%ld depth=%lu w=%lu: need 64 | 2^depth*w and %s "
+               "(mul_fft.c:3186-3187)", (long) n1, (long) n2, (unsigned long) depth, (unsigned long) w,
+               sqrt2 ? "2^(depth+1) < j1+j2-1 <= 2^(depth+2)" : "j1+j2-1 <= 2^(depth+1)");
    /* the lock is held across lookup, eviction and execution: a concurrent call with another shape
       cannot destroy the plan this thread is executing (the reference is re-entrant) */
-   mfft_lock(); mfft_require_device("new_mpn_mul");
+   mfft_lock(); mfft_require_device(fn);
    for (k = 0; k < PLAN_CACHE; k++)
-      if (g_cache[k] && g_cache[k]->n1 == n1 && g_cache[k]->n2 == n2 && g_cache[k]->depth == depth && g_cache[k]->w == w)
+      if (g_cache[k] && g_cache[k]->n1 == n1 && g_cache[k]->n2 == n2 && g_cache[k]->depth == depth && g_cache[k]->w == w &&
+          g_cache[k]->sqrt2 == sqrt2)
          pl = g_cache[k];
    if (!pl)
    {
-      if ((rc = mpirfft_mul_plan_create(&pl, n1, n2, depth, w)) != 0)
-         mfft_die("new_mpn_mul", "cannot build the plan (code %d): %s", rc, mfft_dev_last_error());
+      if ((rc = plan_create(&pl, n1, n2, depth, w, sqrt2)) != 0)
+         mfft_die(fn, "cannot build the plan (code %d): %s", rc, mfft_dev_last_error());
       k = (int)(g_cache_next++ % PLAN_CACHE);
       if (g_cache[k]) mpirfft_mul_plan_destroy(g_cache[k]);
       g_cache[k] = pl;
    }
    if ((rc = mpirfft_mul_exec_host(pl, r1, i1, i2)) != 0)
-      mfft_die("new_mpn_mul", "device execution failed (code %d): %s", rc, mfft_dev_last_error());
+      mfft_die(fn, "device execution failed (code %d): %s", rc, mfft_dev_last_error());
    mfft_unlock();
 }
 
 /* mpn_mul-shaped entry (what the FIXME at mul_fft.c:3177-3178 asks for): chooses (depth, w) itself */
 void mpirfft_mpn_mul(mp_limb_t *r, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2)
 {
-   mp_bitcnt_t depth, w;
+   mp_bitcnt_t depth, w; int sqrt2;
    if (n1 <= 0 || n2 <= 0) mfft_die("mpirfft_mpn_mul", "operand sizes must be positive");
-   if (mpirfft_choose_params(n1, n2, &depth, &w) != 0)
+   if (mpirfft_choose_params6(n1, n2, &depth, &w, &sqrt2) != 0)
       mfft_die("mpirfft_mpn_mul", "no legal (depth, w) for %ld x %ld limbs", (long) n1, (long) n2);
-   new_mpn_mul(r, i1, n1, i2, n2, depth, w);
+   if (sqrt2) new_mpn_mul6(r, i1, n1, i2, n2, depth, w);
+   else new_mpn_mul(r, i1, n1, i2, n2, depth, w);
 }

@@ -149,13 +149,37 @@ void mfft_mfa_free(mfft_mfa *m)
    mfft_dsched_free(&m->col); mfft_dsched_free(&m->row);
    if (m->h_col) mfft_sched_free(m->h_col);
    if (m->h_row) mfft_sched_free(m->h_row);
-   dpass_free(m->dcol, m->pcol.npasses); dpass_free(m->drow, m->prow.npasses);
-   mfft_passes_free(&m->pcol); mfft_passes_free(&m->prow);
+   if (m->col2.s) m->h_col2 = NULL;
+   mfft_dsched_free(&m->col2);
+   if (m->h_col2) mfft_sched_free(m->h_col2);
+   dpass_free(m->dcol, m->pcol.npasses); dpass_free(m->drow, m->prow.npasses); dpass_free(m->dcol2, m->pcol2.npasses);
+   mfft_passes_free(&m->pcol); mfft_passes_free(&m->prow); mfft_passes_free(&m->pcol2);
+   mfft_dev_free(m->d_colb2); mfft_dev_free(m->d_dst_base2); free(m->h_colb2); free(m->h_dst_base2);
    mfft_dev_free(m->d_colb); mfft_dev_free(m->d_rowb); mfft_dev_free(m->d_moves); mfft_dev_free(m->d_dst_base);
    mfft_dev_free(m->d_dstpos);
    free(m->rows); free(m->h_colb); free(m->h_rowb); free(m->h_moves); free(m->h_dst_base);
    free(m->h_must_store); free(m->h_dstpos);
    memset(m, 0, sizeof(*m));
+}
+
+/* may the first column pass split while it loads?  Only if no later pass reads a block that
+   nothing has written before (such a block would be an input the split kernel had to provide) */
+static int passes_split_ok(const mfft_passes *P, uint32_t S)
+{
+   uint8_t *wr = (uint8_t *) calloc(S, 1); uint32_t pi, k; int ok = (wr != NULL);
+   for (pi = 0; ok && pi < P->npasses; pi++)
+   {
+      const mfft_pass *p = &P->pass[pi];
+      if (pi > 0)
+         for (k = 0; k < p->npos_total; k++)
+            if ((p->pos[k] & MFFT_TILE_LOAD) && !wr[p->pos[k] & MFFT_TILE_POSMASK]) ok = 0;
+      /* with the split fused, the first pass loads from the operand and the slab holds only what a
+         pass has STORED */
+      for (k = 0; k < p->npos_total; k++)
+         if (p->pos[k] & MFFT_TILE_STORE) wr[p->pos[k] & MFFT_TILE_POSMASK] = 1;
+   }
+   free(wr);
+   return ok;
 }
 
 int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
@@ -273,24 +297,7 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
          free(live_first);
       }
    }
-   if (m->fused && !inverse)
-   {  /* may the first column pass split while it loads?  Only if no later pass reads a block that
-         nothing has written before (such a block would be an input the split kernel had to provide) */
-      uint8_t *wr = (uint8_t *) calloc(cs->S, 1); uint32_t pi, k; int ok = (wr != NULL);
-      for (pi = 0; ok && pi < m->pcol.npasses; pi++)
-      {
-         const mfft_pass *p = &m->pcol.pass[pi];
-         if (pi > 0)
-            for (k = 0; k < p->npos_total; k++)
-               if ((p->pos[k] & MFFT_TILE_LOAD) && !wr[p->pos[k] & MFFT_TILE_POSMASK]) ok = 0;
-         /* with the split fused, the first pass loads from the operand and the slab holds only what a
-            pass has STORED */
-         for (k = 0; k < p->npos_total; k++)
-            if (p->pos[k] & MFFT_TILE_STORE) wr[p->pos[k] & MFFT_TILE_POSMASK] = 1;
-      }
-      free(wr);
-      m->fuse_split_ok = ok;
-   }
+   if (m->fused && !inverse) m->fuse_split_ok = passes_split_ok(&m->pcol, cs->S);
    if (mfft_sched_finish(cs) != 0 || mfft_sched_finish(rs) != 0) { rc = MPIRFFT_ENOMEM; goto fail; }
    return 0;
 fail:
@@ -324,12 +331,24 @@ int mfft_mfa_upload(mfft_mfa *m)
    m->d_moves = (mfft_move *) mfft_upload(m->h_moves, sizeof(mfft_move) * m->nmoves);
    m->d_dst_base = (uint32_t *) mfft_upload(m->h_dst_base, sizeof(uint32_t) * m->ndst);
    if (!m->d_colb || !m->d_rowb || !m->d_moves || !m->d_dst_base) return MPIRFFT_ENODEV;
+   if (m->nclass == 2)
+   {
+      if (mfft_dsched_upload(&m->col2, m->h_col2) != 0) return MPIRFFT_ENODEV;
+      m->d_colb2 = (mfft_batch *) mfft_upload(m->h_colb2, sizeof(mfft_batch) * m->ncolb2);
+      if (!m->d_colb2) return MPIRFFT_ENODEV;
+      if (m->h_dst_base2)
+      {
+         m->d_dst_base2 = (uint32_t *) mfft_upload(m->h_dst_base2, sizeof(uint32_t) * m->ndst2);
+         if (!m->d_dst_base2) return MPIRFFT_ENODEV;
+      }
+   }
    if (m->fused)
    {
       uint32_t S = m->inverse ? m->gcol.S : m->grow.S;
       m->dcol = dpass_upload(&m->pcol); m->drow = dpass_upload(&m->prow);
       m->d_dstpos = (uint32_t *) mfft_upload(m->h_dstpos, sizeof(uint32_t) * S);
       if (!m->dcol || !m->drow || !m->d_dstpos) return MPIRFFT_ENODEV;
+      if (m->nclass == 2 && !(m->dcol2 = dpass_upload(&m->pcol2))) return MPIRFFT_ENODEV;
    }
    return 0;
 }
@@ -343,6 +362,161 @@ int mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1
    return 0;
 }
 
+
+/* ---- sqrt2 MFA (FFT/IFFT_radix2_mfa_truncate_sqrt2, mul_fft.c:2212-2355, 2593-2750) ------------------ */
+int mfft_mfa_plan_sqrt2(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
+                        uint32_t final_shift, int normalise, int mode)
+{
+   uint64_t NW = n*w, n2, trunc2, i, j; uint32_t cl, k;
+   mfft_sched *cs[2] = { NULL, NULL }, *rs, *last; mfft_batch *rowb; mfft_move *mv;
+   int rc = MPIRFFT_EINVAL;
+   const char *env = getenv("MPIRFFT_UNFUSED");
+
+   memset(m, 0, sizeof(*m));
+   if (n == 0 || (n & (n - 1)) || w == 0 || (NW % 64) || (NW % 4) || n1 < 2 || (n1 & (n1 - 1)) || n1 > n) return MPIRFFT_EINVAL;
+   n2 = 2*n/n1;
+   if (n2 < 4) return MPIRFFT_EINVAL;
+   /* trunc: a multiple of 2*n1 in (2n, 4n]  (mul_fft.c:2209-2211) */
+   if (trunc % (2*n1) || trunc <= 2*n || trunc > 4*n) return MPIRFFT_EINVAL;
+   trunc2 = (trunc - 2*n)/n1;
+   m->sqrt2 = 1; m->nclass = (w & 1) ? 2 : 1; m->trunc2 = trunc2;
+   m->inverse = inverse; m->truncated = 1;
+   m->n = n; m->w = w; m->n1 = n1; m->n2 = n2; m->N = 4*n;
+   m->l = (uint32_t)(NW/64); m->pitch = mfft_pitch(m->l);
+   m->depth1 = ilog2(n2); m->depth2 = ilog2(n1);
+   m->final_shift = (uint32_t)(final_shift % (2*NW)); m->normalise = normalise;
+   m->fused = (mode == 0) && mfft_dev_tiles_supported(m->l) && !(env && env[0] == '1');
+   m->trunc_rows = n2 + trunc2;
+
+   /* the valid rows, as positions of a column: all first-half rows, then revbin(s) of the second half */
+   m->nrows = (uint32_t)(n2 + trunc2);
+   m->rows = (uint32_t *) malloc(sizeof(uint32_t) * m->nrows);
+   m->h_row = rs = mfft_sched_new((uint32_t) n1, NW);
+   m->h_rowb = rowb = (mfft_batch *) calloc(m->nrows, sizeof(mfft_batch));
+   if (!m->rows || !rs || !rowb) { rc = MPIRFFT_ENOMEM; goto fail; }
+   for (i = 0; i < n2; i++) m->rows[i] = (uint32_t) i;
+   for (i = 0; i < trunc2; i++) m->rows[n2 + i] = (uint32_t)(n2 + mfft_revbin(i, m->depth1));
+
+   m->gcol.S = (uint32_t)(2*n2); m->gcol.slot_stride = (uint32_t) n1; m->gcol.half_blocks = m->N;
+   m->gcol.l = m->l; m->gcol.pitch = m->pitch;
+   m->grow.S = (uint32_t) n1; m->grow.slot_stride = 1; m->grow.half_blocks = m->N;
+   m->grow.l = m->l; m->grow.pitch = m->pitch;
+   m->nrowb = m->nrows;
+
+   for (cl = 0; cl < (uint32_t) m->nclass; cl++)
+   {
+      const uint32_t ncb = (uint32_t)(m->nclass == 2 ? n1/2 : n1);
+      mfft_batch *cb = (mfft_batch *) calloc(ncb, sizeof(mfft_batch));
+      cs[cl] = mfft_sched_new((uint32_t)(2*n2), NW);
+      if (cl == 0) { m->h_col = cs[0]; m->h_colb = cb; m->ncolb = ncb; } else { m->h_col2 = cs[1]; m->h_colb2 = cb; m->ncolb2 = ncb; }
+      if (!cs[cl] || !cb) { rc = MPIRFFT_ENOMEM; goto fail; }
+      for (j = 0; j < ncb; j++)
+      {  /* column = 2 col + par (two classes) or col */
+         cb[j].base = (uint32_t)(m->nclass == 2 ? 2*j + cl : j); cb[j].parity = 0; cb[j].col = (uint32_t) j;
+      }
+   }
+   if (!inverse)
+   {
+      for (cl = 0; cl < (uint32_t) m->nclass; cl++)
+         if (mfft_sched_emit_sqrt2_cols(cs[cl], 0, n2, n1, w, trunc2, m->nclass == 2 ? (int) cl : -1, !m->fused) != 0) goto fail;
+      /* row FFTs on the valid rows, then the in-row relabel (2289-2303, 2341-2354) */
+      if (mfft_sched_emit(rs, MFFT_T_FFT, 0, 1, n1/2, w*n2, 0, 0, 0, 0) != 0) goto fail;
+      mfft_sched_revbin(rs, 0, 1, m->depth2);
+      for (i = 0; i < m->nrows; i++)
+      {
+         uint32_t slot = m->fused ? cs[0]->phys[m->rows[i]] : cs[0]->slot[m->rows[i]];
+         if (m->nclass == 2 && slot != (m->fused ? cs[1]->phys[m->rows[i]] : cs[1]->slot[m->rows[i]])) { rc = MPIRFFT_EINVAL; goto fail; }
+         rowb[i].base = (uint32_t)((slot % (2*n2)) * n1); rowb[i].parity = (uint32_t)(slot / (2*n2)); rowb[i].col = 0;
+      }
+      m->nmoves = (uint32_t) n1; m->ndst = m->nrows;
+      m->h_moves = mv = (mfft_move *) calloc(m->nmoves, sizeof(mfft_move));
+      m->h_dst_base = (uint32_t *) calloc(m->ndst, sizeof(uint32_t));
+      if (!mv || !m->h_dst_base) { rc = MPIRFFT_ENOMEM; goto fail; }
+      for (j = 0; j < n1; j++) { mv[j].src_slot = rs->slot[j]; mv[j].dst_pos = (uint32_t) j; }
+      for (i = 0; i < m->nrows; i++) m->h_dst_base[i] = (uint32_t)(m->rows[i] * n1);
+      m->dst_stride = 1;
+      last = rs;
+   } else
+   {
+      mfft_sched_revbin(rs, 0, 1, m->depth2);
+      if (mfft_sched_emit(rs, MFFT_T_IFFT, 0, 1, n1/2, w*n2, 0, 0, 0, 0) != 0) goto fail;
+      for (i = 0; i < m->nrows; i++) { rowb[i].base = (uint32_t)(m->rows[i] * n1); rowb[i].parity = 0; rowb[i].col = 0; }
+      for (cl = 0; cl < (uint32_t) m->nclass; cl++)
+      {
+         mfft_batch *cb = cl ? m->h_colb2 : m->h_colb; uint32_t ncb = cl ? m->ncolb2 : m->ncolb;
+         if (mfft_sched_emit_sqrt2_cols(cs[cl], 1, n2, n1, w, trunc2, m->nclass == 2 ? (int) cl : -1, !m->fused) != 0) goto fail;
+         for (j = 0; j < ncb; j++)
+         {  /* where the row pass left this column */
+            uint32_t c = cb[j].base, slot = m->fused ? rs->phys[c] : rs->slot[c];
+            cb[j].base = (uint32_t)(slot % n1); cb[j].parity = (uint32_t)(slot / n1);
+         }
+      }
+      /* outputs: logical positions 0 .. n2+trunc2-1 of every column -> dst block pos*n1 + column */
+      m->nmoves = m->nrows;
+      m->h_moves = mv = (mfft_move *) calloc(m->nmoves, sizeof(mfft_move));
+      if (!mv) { rc = MPIRFFT_ENOMEM; goto fail; }
+      for (i = 0; i < m->nmoves; i++)
+      {
+         mv[i].src_slot = cs[0]->slot[i]; mv[i].dst_pos = (uint32_t) i;
+         if (m->nclass == 2 && (cs[1]->slot[i] != cs[0]->slot[i] || cs[1]->phys[i] != cs[0]->phys[i])) { rc = MPIRFFT_EINVAL; goto fail; }
+      }
+      m->ndst = m->ncolb; m->h_dst_base = (uint32_t *) calloc(m->ndst, sizeof(uint32_t));
+      if (!m->h_dst_base) { rc = MPIRFFT_ENOMEM; goto fail; }
+      for (j = 0; j < m->ncolb; j++) m->h_dst_base[j] = (uint32_t)(m->nclass == 2 ? 2*j : j);
+      if (m->nclass == 2)
+      {
+         m->ndst2 = m->ncolb2; m->h_dst_base2 = (uint32_t *) calloc(m->ndst2, sizeof(uint32_t));
+         if (!m->h_dst_base2) { rc = MPIRFFT_ENOMEM; goto fail; }
+         for (j = 0; j < m->ncolb2; j++) m->h_dst_base2[j] = (uint32_t)(2*j + 1);
+      }
+      m->dst_stride = (uint32_t) n1;
+      last = cs[0];
+   }
+   if (m->fused)
+   {
+      uint32_t nout = m->nmoves, S = last->S;
+      uint32_t pmax = mfft_dev_tiles_max_npos(m->l);
+      uint8_t *live_first = NULL;
+      m->h_must_store = (uint8_t *) calloc(S, 1);
+      m->h_dstpos = (uint32_t *) malloc(sizeof(uint32_t) * S);
+      if (!m->h_must_store || !m->h_dstpos) { rc = MPIRFFT_ENOMEM; goto fail; }
+      for (k = 0; k < S; k++) m->h_dstpos[k] = MFFT_NONE;
+      if (m->final_shift)
+         for (cl = 0; cl < (uint32_t)(last == rs ? 1 : m->nclass); cl++)
+            for (k = 0; k < nout; k++)
+               mfft_sched_emit_op(last == rs ? rs : cs[cl], k, MFFT_NONE, k, 1, m->final_shift, 0, 0, MFFT_NONE, 0, 0, 0, 0);
+      for (k = 0; k < nout; k++) { m->h_must_store[last->phys[k]] = 1; m->h_dstpos[last->phys[k]] = k; }
+      if (!inverse)
+      {
+         live_first = (uint8_t *) calloc(cs[0]->S, 1);
+         if (!live_first) { rc = MPIRFFT_ENOMEM; goto fail; }
+         for (i = 0; i < m->nrows; i++) live_first[cs[0]->phys[m->rows[i]]] = 1;
+      }
+      rc = MPIRFFT_ENOMEM;
+      if (mfft_passes_build(&m->pcol, cs[0], pmax, last == rs ? NULL : m->h_must_store, last == rs ? live_first : m->h_must_store) != 0 ||
+          (m->nclass == 2 && mfft_passes_build(&m->pcol2, cs[1], pmax, last == rs ? NULL : m->h_must_store, last == rs ? live_first : m->h_must_store) != 0) ||
+          mfft_passes_build(&m->prow, rs, pmax, last == rs ? m->h_must_store : NULL, last == rs ? m->h_must_store : NULL) != 0)
+      { free(live_first); goto fail; }
+      free(live_first);
+      if (!inverse)
+         m->fuse_split_ok = passes_split_ok(&m->pcol, cs[0]->S) && (m->nclass == 1 || passes_split_ok(&m->pcol2, cs[1]->S));
+   }
+   if (mfft_sched_finish(cs[0]) != 0 || (m->nclass == 2 && mfft_sched_finish(cs[1]) != 0) || mfft_sched_finish(rs) != 0) { rc = MPIRFFT_ENOMEM; goto fail; }
+   return 0;
+fail:
+   mfft_mfa_free(m);
+   return rc;
+}
+
+int mfft_mfa_build_sqrt2(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
+                         uint32_t final_shift, int normalise)
+{
+   int rc = mfft_mfa_plan_sqrt2(m, inverse, n, w, n1, trunc, final_shift, normalise, 0);
+   if (rc != 0) return rc;
+   if ((rc = mfft_mfa_upload(m)) != 0) { mfft_mfa_free(m); return rc; }
+   return 0;
+}
+
 /* accessors for the CPU-side schedule tests (tests/schedsim.py) */
 mfft_mfa *mfft_mfa_debug_new(int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc)
 {
@@ -351,9 +525,17 @@ mfft_mfa *mfft_mfa_debug_new(int inverse, uint64_t n, uint64_t w, uint64_t n1, u
    return m;
 }
 void mfft_mfa_debug_free(mfft_mfa *m) { if (m) { mfft_mfa_free(m); free(m); } }
-mfft_sched *mfft_mfa_debug_sched(mfft_mfa *m, int which) { return which ? m->h_row : m->h_col; }
+mfft_mfa *mfft_mfa_debug_new_sqrt2(int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc)
+{
+   mfft_mfa *m = (mfft_mfa *) calloc(1, sizeof(*m));
+   if (m && mfft_mfa_plan_sqrt2(m, inverse, n, w, n1, trunc, 0, 0, 1) != 0) { free(m); return NULL; }
+   return m;
+}
+/* which: 0 column schedule (class 0), 1 row schedule, 2 column schedule of the odd columns (sqrt2, odd w) */
+mfft_sched *mfft_mfa_debug_sched(mfft_mfa *m, int which) { return which == 2 ? m->h_col2 : which ? m->h_row : m->h_col; }
 mfft_batch *mfft_mfa_debug_batch(mfft_mfa *m, int which, uint32_t *count)
-{ *count = which ? m->nrowb : m->ncolb; return which ? m->h_rowb : m->h_colb; }
+{ *count = which == 2 ? m->ncolb2 : which ? m->nrowb : m->ncolb; return which == 2 ? m->h_colb2 : which ? m->h_rowb : m->h_colb; }
+uint32_t *mfft_mfa_debug_dst_base2(mfft_mfa *m, uint32_t *count) { *count = m->ndst2; return m->h_dst_base2; }
 mfft_move *mfft_mfa_debug_moves(mfft_mfa *m, uint32_t *count, uint32_t *dst_stride)
 { *count = m->nmoves; *dst_stride = m->dst_stride; return m->h_moves; }
 uint32_t *mfft_mfa_debug_dst_base(mfft_mfa *m, uint32_t *count) { *count = m->ndst; return m->h_dst_base; }
@@ -365,12 +547,12 @@ uint32_t *mfft_mfa_debug_rows(mfft_mfa *m, uint32_t *count) { *count = m->nrows;
  * bytes / time is comparable across implementations */
 static double pass_bytes(const mfft_mfa *m)
 {
-   return 2.0 * (double) m->trunc_rows * (double) m->n1 * 8.0 * (m->l + 1);
+   return 2.0 * (double)(m->sqrt2 ? m->nrows : m->trunc_rows) * (double) m->n1 * 8.0 * (m->l + 1);
 }
 
 static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft_dpass *d, limb_t *slab,
                       const mfft_geom *g, const mfft_batch *d_batch, const mfft_batch *h_batch, uint32_t nbatch, limb_t *dst,
-                      const mfft_split *split, void *stream)
+                      const mfft_split *split, void *stream, const uint32_t *d_dst_base)
 {
    uint32_t i;
    for (i = 0; i < P->npasses; i++)
@@ -379,7 +561,7 @@ static int run_passes(const mfft_mfa *m, const mfft_passes *P, const struct mfft
       const int lastp = (i + 1 == P->npasses) && dst != NULL;
       mfft_dev_profile_bytes(pass_bytes(m));
       if (mfft_dev_run_tiles(slab, g, d[i].d_tiles, p->ntiles, d[i].d_pos, d[i].d_ops, p->max_npos, p->max_nops, d_batch, nbatch,
-                             lastp ? dst : NULL, m->d_dstpos, m->d_dst_base, m->dst_stride,
+                             lastp ? dst : NULL, m->d_dstpos, d_dst_base, m->dst_stride,
                              lastp ? m->normalise : 0, d[i].d_stoff, (5*p->nany > p->nops_total) || p->nr4, p->tiles, p->pos, p->stoff, h_batch, (i == 0) ? split : NULL, stream) != 0) return MPIRFFT_ENODEV;
    }
    return 0;
@@ -410,15 +592,19 @@ static int mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, const mfft_spl
    {
       if (!m->inverse)
       {
-         if ((rc = run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, NULL, split, stream)) != 0) return rc;
-         return run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, dst, NULL, stream);
+         if ((rc = run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, NULL, split, stream, NULL)) != 0) return rc;
+         if (m->nclass == 2 && (rc = run_passes(m, &m->pcol2, m->dcol2, slab, &m->gcol, m->d_colb2, m->h_colb2, m->ncolb2, NULL, split, stream, NULL)) != 0) return rc;
+         return run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, dst, NULL, stream, m->d_dst_base);
       }
-      if ((rc = run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, NULL, NULL, stream)) != 0) return rc;
-      return run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, dst, NULL, stream);
+      if ((rc = run_passes(m, &m->prow, m->drow, slab, &m->grow, m->d_rowb, m->h_rowb, m->nrowb, NULL, NULL, stream, NULL)) != 0) return rc;
+      if ((rc = run_passes(m, &m->pcol, m->dcol, slab, &m->gcol, m->d_colb, m->h_colb, m->ncolb, dst, NULL, stream, m->d_dst_base)) != 0) return rc;
+      if (m->nclass == 2) return run_passes(m, &m->pcol2, m->dcol2, slab, &m->gcol, m->d_colb2, m->h_colb2, m->ncolb2, dst, NULL, stream, m->d_dst_base2);
+      return 0;
    }
    if (!m->inverse)
    {
       if ((rc = mfft_dsched_run(&m->col, slab, &m->gcol, m->d_colb, m->ncolb, stream)) != 0) return rc;
+      if (m->nclass == 2 && (rc = mfft_dsched_run(&m->col2, slab, &m->gcol, m->d_colb2, m->ncolb2, stream)) != 0) return rc;
       if ((rc = mfft_dsched_run(&m->row, slab, &m->grow, m->d_rowb, m->nrowb, stream)) != 0) return rc;
       if (mfft_dev_finalize(dst, m->dst_stride, m->d_dst_base, slab, &m->grow, m->d_moves, m->nmoves,
                             m->d_rowb, m->nrowb, m->final_shift, m->normalise, stream) != 0) return MPIRFFT_ENODEV;
@@ -428,14 +614,20 @@ static int mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, const mfft_spl
       if ((rc = mfft_dsched_run(&m->col, slab, &m->gcol, m->d_colb, m->ncolb, stream)) != 0) return rc;
       if (mfft_dev_finalize(dst, m->dst_stride, m->d_dst_base, slab, &m->gcol, m->d_moves, m->nmoves,
                             m->d_colb, m->ncolb, m->final_shift, m->normalise, stream) != 0) return MPIRFFT_ENODEV;
+      if (m->nclass == 2)
+      {
+         if ((rc = mfft_dsched_run(&m->col2, slab, &m->gcol, m->d_colb2, m->ncolb2, stream)) != 0) return rc;
+         if (mfft_dev_finalize(dst, m->dst_stride, m->d_dst_base2, slab, &m->gcol, m->d_moves, m->nmoves,
+                               m->d_colb2, m->ncolb2, m->final_shift, m->normalise, stream) != 0) return MPIRFFT_ENODEV;
+      }
    }
    return 0;
 }
 
 uint64_t mfft_mfa_launches(const mfft_mfa *m)
 {
-   if (m->fused) return (uint64_t) m->pcol.npasses + m->prow.npasses;
-   return (uint64_t) m->col.s->nstages + m->row.s->nstages + 1;
+   if (m->fused) return (uint64_t) m->pcol.npasses + m->prow.npasses + m->pcol2.npasses;
+   return (uint64_t) m->col.s->nstages + m->row.s->nstages + 1 + (m->nclass == 2 ? m->col2.s->nstages + (m->inverse ? 1 : 0) : 0);
 }
 
 /* developer aid (no device needed): the pass structure of a fused MFA plan on stdout --

@@ -51,6 +51,13 @@ typedef struct {
    mfft_passes pcol, prow;
    struct mfft_dpass { mfft_tile *d_tiles; uint32_t *d_pos; mfft_tileop *d_ops; uint32_t *d_stoff; } *dcol, *drow;
    uint32_t *d_dstpos; uint8_t *h_must_store; uint32_t *h_dstpos;
+   /* sqrt2 transforms (FFT/IFFT_radix2_mfa_truncate_sqrt2): 4n coefficients, a column is 2*n2 positions
+      (first-half rows, then second-half rows); for odd w the even and the odd columns have their own
+      column schedules (class 0 = col/pcol/dcol/colb above, class 1 = the fields below) */
+   int sqrt2, nclass; uint64_t trunc2;
+   mfft_dsched col2; mfft_sched *h_col2; mfft_passes pcol2; struct mfft_dpass *dcol2;
+   mfft_batch *d_colb2, *h_colb2; uint32_t ncolb2;
+   uint32_t *d_dst_base2, *h_dst_base2; uint32_t ndst2;
    /* host copies of the tables (kept for the CPU-side schedule tests) */
    mfft_sched *h_col, *h_row;                  /* owned by col/row once uploaded */
    mfft_batch *h_colb, *h_rowb; mfft_move *h_moves; uint32_t *h_dst_base; uint32_t ndst;
@@ -67,6 +74,11 @@ int  mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1
 int  mfft_mfa_upload(mfft_mfa *m);
 int  mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
                     uint32_t final_shift, int normalise);
+/* the sqrt2 variant: transform length 4n, trunc in (2n, 4n] a multiple of 2*n1 */
+int  mfft_mfa_plan_sqrt2(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
+                         uint32_t final_shift, int normalise, int mode);
+int  mfft_mfa_build_sqrt2(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
+                          uint32_t final_shift, int normalise);
 void mfft_mfa_free(mfft_mfa *m);
 /* slab: 2N blocks, input in half 0 in reference order (ii[k] = block k); dst: N blocks */
 int  mfft_mfa_exec(const mfft_mfa *m, limb_t *slab, limb_t *dst, void *stream);

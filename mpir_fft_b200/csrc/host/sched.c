@@ -136,8 +136,14 @@ void mfft_sched_emit_op(mfft_sched *s, uint32_t posA, uint32_t posB,
    emit(s, posA, posB, pS, T(sSA, eSA, 0), T(sSB, eSB, 0), pT, T(sTA, eTA, 0), T(sTB, eTB, 0));
 }
 
-/* the walker's context: positions p0 + is*k, ring exponents mod M2, twist unit ws */
-typedef struct { mfft_sched *s; uint32_t is; uint64_t ws; } ctx;
+/* the walker's context: positions p0 + is*k, ring exponents mod M2, twist unit ws.  The column a
+   batch entry stands for is cmul*col + cadd (cmul = 1, cadd = 0 except for the sqrt2 transforms,
+   whose even and odd columns have different op lists and are run as two sub-batches) */
+typedef struct { mfft_sched *s; uint32_t is; uint64_t ws; uint64_t cmul, cadd; } ctx;
+
+/* a term 2^(x * column): constant part x*cadd, per-entry part x*cmul */
+static uint64_t mulmod64(uint64_t a, uint64_t b, uint64_t m) { return (uint64_t)(((unsigned __int128) a * b) % m); }
+#define CT(sign, x) T((sign), mulmod64((x) % c->s->M2, c->cadd, c->s->M2), mulmod64((x) % c->s->M2, c->cmul, c->s->M2))
 
 #define POS(k) ((uint32_t)(p0 + (uint64_t)c->is*(k)))
 #define NEG(e) ((c->s->M2 - ((e) % c->s->M2)) % c->s->M2)
@@ -169,8 +175,8 @@ static void fft_full(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, ui
             chunk-local in the tile executor, and each bit-granular twist then rotates one operand
             instead of two */
          emit(c->s, POS(0), POS(1), POS(0), T(1, 0, 0), T(1, 0, 0), POS(1), T(1, 0, 0), T(-1, 0, 0));
-         if (c1) emit(c->s, POS(0), MFFT_NONE, POS(0), T(1, 0, c1), T0, MFFT_NONE, T0, T0);
-         if (c2) emit(c->s, POS(1), MFFT_NONE, POS(1), T(1, 0, c2), T0, MFFT_NONE, T0, T0);
+         if (c1) emit(c->s, POS(0), MFFT_NONE, POS(0), CT(1, c1), T0, MFFT_NONE, T0, T0);
+         if (c2) emit(c->s, POS(1), MFFT_NONE, POS(1), CT(1, c2), T0, MFFT_NONE, T0, T0);
       }
       return;
    }
@@ -219,8 +225,8 @@ static void ifft_full(ctx *c, uint32_t p0, uint64_t n, uint64_t w, uint64_t r, u
       uint64_t c1 = (r % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
       uint64_t c2 = ((r + rs) % c->s->M2) * (c->ws % c->s->M2) % c->s->M2;
       /* the two rotations first, then an untwisted butterfly (see fft_full) */
-      if (c1) emit(c->s, POS(0), MFFT_NONE, POS(0), T(1, 0, NEG(c1)), T0, MFFT_NONE, T0, T0);
-      if (c2) emit(c->s, POS(1), MFFT_NONE, POS(1), T(1, 0, NEG(c2)), T0, MFFT_NONE, T0, T0);
+      if (c1) emit(c->s, POS(0), MFFT_NONE, POS(0), CT(1, NEG(c1)), T0, MFFT_NONE, T0, T0);
+      if (c2) emit(c->s, POS(1), MFFT_NONE, POS(1), CT(1, NEG(c2)), T0, MFFT_NONE, T0, T0);
       emit(c->s, POS(0), POS(1), POS(0), T(1, 0, 0), T(1, 0, 0), POS(1), T(1, 0, 0), T(-1, 0, 0));
       return;
    }
@@ -300,10 +306,105 @@ static void ifft_negacyclic(ctx *c, uint32_t p0, uint64_t n, uint64_t w)
    }
 }
 
+
+/* ---- the sqrt2 transforms: length 4n over Z/(2^(nw)+1) with the 4n-th root of unity
+ *      z1 = sqrt2^w,  sqrt2 = 2^(3nw/4) - 2^(nw/4)   (mul_fft.c:578-617, 959-1021) --------------------
+ * z1^j for even j is the power of two 2^((j/2) w); for odd j (w odd) it is
+ *      z1^j = 2^e (2^(nw/2) - 1),   e = (j w - 1)/2 + nw/4,
+ * i.e. one rotation followed by "x 2^(nw/2) - x", which is chunk-aligned.  The column schedule below
+ * covers positions 0..2 n2-1 of one MFA column (first half rows, then second half rows): the
+ * outermost layer between the halves (2240-2262 / 2700-2731), then the two column transforms.
+ * j = column + row*n1 has the parity of the column (n1 is even), so the op list depends on the
+ * column's parity: par = 0 / 1 builds the list of the even / odd columns (column = 2 col + par),
+ * par = -1 (even w: the root is the power of two 2^(w/2), 2264-2279) one list for all columns. */
+static void sq2_apply(ctx *c, uint32_t p)          /* x <- x 2^(NW/2) - x, in place */
+{
+   emit(c->s, p, p, p, T(1, c->s->NW/2, 0), T(-1, 0, 0), MFFT_NONE, T0, T0);
+}
+
+/* position dst <- src * z1^(+-j), j = column + row*n1, as one rotation (+ sq2_apply for odd j) */
+static void sqrt2_twiddle(ctx *c, uint32_t src, uint32_t dst, uint64_t row, uint64_t n1, uint64_t w, int par, int inverse, int pad)
+{
+   const uint64_t NW = c->s->NW, M2 = c->s->M2;
+   if (par < 0)
+   {  /* 2^(j w/2): constant part row*n1*w/2, per-column part w/2 */
+      uint64_t e0 = mulmod64(row % M2, (n1*(w/2)) % M2, M2), ec = (w/2) % M2;
+      if (inverse) { e0 = (M2 - e0) % M2; ec = (M2 - ec) % M2; }
+      emit(c->s, src, MFFT_NONE, dst, T(1, e0, ec), T0, MFFT_NONE, T0, T0);
+      return;
+   }
+   if (par == 0)
+   {  /* j even: 2^((j/2) w) = 2^(col w + row (n1/2) w) */
+      uint64_t e0 = mulmod64(row % M2, ((n1/2)*w) % M2, M2), ec = w % M2;
+      if (inverse) { e0 = (M2 - e0) % M2; ec = (M2 - ec) % M2; }
+      emit(c->s, src, MFFT_NONE, dst, T(1, e0, ec), T0, MFFT_NONE, T0, T0);
+      /* ping-pong view only: a copy where the odd columns apply (2^(NW/2) - 1), so that both classes
+         leave every position in the same slab half */
+      if (pad) emit(c->s, dst, MFFT_NONE, dst, T(1, 0, 0), T0, MFFT_NONE, T0, T0);
+      return;
+   }
+   {  /* j odd: (j w - 1)/2 = col w + (w-1)/2 + row (n1/2) w.  Forward exponent e = that + NW/4; the
+         inverse is z1^-j = 2^(2NW - (j w - 1)/2 - 1 + NW/4) (2^(NW/2) - 1)   (mul_fft.c:653-672) */
+      uint64_t h = (mulmod64(row % M2, ((n1/2)*w) % M2, M2) + (w - 1)/2) % M2, ec = w % M2, e0;
+      if (!inverse) e0 = (h + NW/4) % M2;
+      else { e0 = (2*M2 - h - 1 + NW/4) % M2; ec = (M2 - ec) % M2; }
+      emit(c->s, src, MFFT_NONE, dst, T(1, e0, ec), T0, MFFT_NONE, T0, T0);
+      sq2_apply(c, dst);
+   }
+}
+
+int mfft_sched_emit_sqrt2_cols(mfft_sched *s, int inverse, uint64_t n2, uint64_t n1, uint64_t w, uint64_t trunc2, int par, int pad)
+{
+   ctx cc, *c = &cc; uint64_t r, NW = s->NW, n = NW/w; uint32_t depth = 0, p0 = 0;
+   (void) p0;
+   c->s = s; c->is = 1; c->ws = w;
+   c->cmul = (par < 0) ? 1 : 2; c->cadd = (par < 0) ? 0 : (uint64_t) par;
+   if (n*w != NW || 2*n != n1*n2 || s->S != 2*n2 || (n1 & 1) || NW % 4) return -1;
+   if ((par < 0) != ((w & 1) == 0)) return -1;              /* parity classes exist iff w is odd */
+   if (trunc2 < 2 || trunc2 > n2 || (trunc2 & 1)) return -1;
+   while (((uint64_t)1 << depth) < n2) depth++;
+   if (!inverse)
+   {
+      for (r = 0; r < trunc2; r++)
+      {  /* [a, b] -> [a + b, z1^j (a - b)]   (FFT_radix2_butterfly(_sqrt2), 2244-2262) */
+         emit(s, (uint32_t) r, (uint32_t)(n2 + r), (uint32_t) r, T(1, 0, 0), T(1, 0, 0), (uint32_t)(n2 + r), T(1, 0, 0), T(-1, 0, 0));
+         sqrt2_twiddle(c, (uint32_t)(n2 + r), (uint32_t)(n2 + r), r, n1, w, par, 0, pad);
+      }
+      for (; r < n2; r++)     /* b = 0: second half row = z1^j a   (FFT_twiddle(_sqrt2), 2265-2271) */
+         sqrt2_twiddle(c, (uint32_t) r, (uint32_t)(n2 + r), r, n1, w, par, 0, pad);
+      /* the two column transforms with the z^(r c) twist (2283, 2337), then the row relabels */
+      { uint32_t p0 = 0; fft_full(c, p0, n2/2, w*n1, 0, 1); }
+      mfft_sched_revbin(s, 0, 1, depth);
+      { uint32_t p0 = (uint32_t) n2; fft_trunc1(c, p0, n2/2, w*n1, 0, 1, trunc2); }
+      mfft_sched_revbin(s, (uint32_t) n2, 1, depth);
+   } else
+   {
+      uint64_t j;
+      mfft_sched_revbin(s, 0, 1, depth);
+      { uint32_t p0 = 0; ifft_full(c, p0, n2/2, w*n1, 0, 1); }                                       /* 2629-2645 */
+      for (j = 0; j < trunc2; j++)                                                                   /* 2672-2681 */
+      {
+         uint64_t t = mfft_revbin(j, depth);
+         if (j < t) mfft_sched_swap(s, (uint32_t)(n2 + j), (uint32_t)(n2 + t));
+      }
+      for (r = trunc2; r < n2; r++)                                                                  /* 2683-2694 */
+         sqrt2_twiddle(c, (uint32_t) r, (uint32_t)(n2 + r), r, n1, w, par, 0, pad);
+      { uint32_t p0 = (uint32_t) n2; ifft_trunc1(c, p0, n2/2, w*n1, 0, 1, trunc2); }                  /* 2698 */
+      for (r = 0; r < trunc2; r++)
+      {  /* [a, b] -> [a + z1^-j b, a - z1^-j b]   (2702-2745) */
+         sqrt2_twiddle(c, (uint32_t)(n2 + r), (uint32_t)(n2 + r), r, n1, w, par, 1, pad);
+         emit(s, (uint32_t) r, (uint32_t)(n2 + r), (uint32_t) r, T(1, 0, 0), T(1, 0, 0), (uint32_t)(n2 + r), T(1, 0, 0), T(-1, 0, 0));
+      }
+      for (; r < n2; r++)     /* doubling of the first-half rows without a partner (2747-2748) */
+         emit(s, (uint32_t) r, MFFT_NONE, (uint32_t) r, T(1, 1, 0), T0, MFFT_NONE, T0, T0);
+   }
+   return 0;
+}
+
 int mfft_sched_emit(mfft_sched *s, mfft_transform_kind kind, uint32_t p0, uint32_t is,
                     uint64_t n, uint64_t w, uint64_t ws, uint64_t r, uint64_t rs, uint64_t trunc)
 {
-   ctx c; c.s = s; c.is = is; c.ws = ws;
+   ctx c; c.s = s; c.is = is; c.ws = ws; c.cmul = 1; c.cadd = 0;
    if (n == 0 || (n & (n - 1)) || n*w != s->NW) return -1;
    if ((uint64_t) p0 + (uint64_t) is*(2*n - 1) >= s->S) return -1;
    switch (kind)

@@ -48,6 +48,15 @@ void        mfft_sched_free(mfft_sched *s);
 int  mfft_sched_emit(mfft_sched *s, mfft_transform_kind kind, uint32_t p0, uint32_t is,
                      uint64_t n, uint64_t w, uint64_t ws, uint64_t r, uint64_t rs, uint64_t trunc);
 
+/* The column schedule of the sqrt2 MFA (FFT/IFFT_radix2_mfa_truncate_sqrt2, mul_fft.c:2212-2355,
+ * 2593-2750) over the 2*n2 positions of one column (first-half rows, then second-half rows, stride 1):
+ * the layer between the halves with the sqrt2^w twiddles, the two twisted column transforms (the
+ * second one truncated to trunc2 rows) and the row relabels.  par: 0 / 1 = the op list of the even /
+ * odd columns (w odd; batch entries carry col with column = 2 col + par), -1 = all columns (w even).
+ * pad: the even columns get a copy op where the odd ones have their extra op (ping-pong view: both
+ * classes must leave every position in the same slab half). */
+int  mfft_sched_emit_sqrt2_cols(mfft_sched *s, int inverse, uint64_t n2, uint64_t n1, uint64_t w, uint64_t trunc2, int par, int pad);
+
 /* Emit one explicit op: position pS <- sSA*A*2^eSA + sSB*B*2^eSB and (optionally) position
  * pT <- sTA*A*2^eTA + sTB*B*2^eTB, A/B = current contents of positions posA/posB (posB and pT
  * may be MFFT_NONE).  Exponents are bit counts mod 2*NW. */

@@ -209,3 +209,62 @@ def simulate_mfa(values, inverse, n, w, n1, trunc, shift=0):
         return out
     finally:
         L.mfft_mfa_debug_free(m)
+
+
+def simulate_mfa_sqrt2(values, inverse, n, w, n1, trunc, shift=0):
+    """the same for the sqrt2 MFA (4n blocks; two column classes when w is odd): {dst block: residue}"""
+    L = _setup()
+    L.mfft_mfa_debug_new_sqrt2.restype = C.c_void_p
+    L.mfft_mfa_debug_new_sqrt2.argtypes = [C.c_int] + [C.c_uint64] * 4
+    L.mfft_mfa_debug_free.argtypes = [C.c_void_p]
+    L.mfft_mfa_debug_sched.restype = C.POINTER(Sched)
+    L.mfft_mfa_debug_sched.argtypes = [C.c_void_p, C.c_int]
+    L.mfft_mfa_debug_batch.restype = C.POINTER(Batch)
+    L.mfft_mfa_debug_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]
+    L.mfft_mfa_debug_moves.restype = C.POINTER(Move)
+    L.mfft_mfa_debug_moves.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.mfft_mfa_debug_dst_base.restype = C.POINTER(C.c_uint32)
+    L.mfft_mfa_debug_dst_base.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    L.mfft_mfa_debug_dst_base2.restype = C.POINTER(C.c_uint32)
+    L.mfft_mfa_debug_dst_base2.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    m = L.mfft_mfa_debug_new_sqrt2(int(inverse), n, w, n1, trunc)
+    if not m:
+        raise ValueError("illegal sqrt2 MFA parameters")
+    try:
+        NW = n * w
+        p, M2, N, n2 = (1 << NW) + 1, 2 * NW, 4 * n, 2 * n // n1
+        cnt = C.c_uint32()
+        classes = [0, 2] if (w & 1) else [0]
+        cs = [L.mfft_mfa_debug_sched(m, k) for k in classes]
+        colb = []
+        for k in classes:
+            cb = L.mfft_mfa_debug_batch(m, k, C.byref(cnt))
+            colb.append([cb[i] for i in range(cnt.value)])
+        rs = L.mfft_mfa_debug_sched(m, 1)
+        rb = L.mfft_mfa_debug_batch(m, 1, C.byref(cnt)); rowb = [rb[i] for i in range(cnt.value)]
+        stride = C.c_uint32()
+        mv = L.mfft_mfa_debug_moves(m, C.byref(cnt), C.byref(stride)); moves = [mv[i] for i in range(cnt.value)]
+        db = L.mfft_mfa_debug_dst_base(m, C.byref(cnt)); dstb = [[db[i] for i in range(cnt.value)]]
+        if inverse and len(classes) == 2:
+            db2 = L.mfft_mfa_debug_dst_base2(m, C.byref(cnt)); dstb.append([db2[i] for i in range(cnt.value)])
+        mem = {i: v for i, v in enumerate(values)}
+        out = {}
+        if not inverse:
+            for c, b in zip(cs, colb):
+                _run_pass(mem, c, n1, N, b, p, M2)
+            _run_pass(mem, rs, 1, N, rowb, p, M2)
+            for mvi in moves:
+                for bi, b in enumerate(rowb):
+                    src = _block_index(n1, 1, N, mvi.src_slot, b)
+                    out[dstb[0][bi] + mvi.dst_pos * stride.value] = mem[src] * pow(2, shift % M2, p) % p
+        else:
+            _run_pass(mem, rs, 1, N, rowb, p, M2)
+            for c, b, d in zip(cs, colb, dstb):
+                _run_pass(mem, c, n1, N, b, p, M2)
+                for mvi in moves:
+                    for bi, be in enumerate(b):
+                        src = _block_index(2 * n2, n1, N, mvi.src_slot, be)
+                        out[d[bi] + mvi.dst_pos * stride.value] = mem[src] * pow(2, shift % M2, p) % p
+        return out
+    finally:
+        L.mfft_mfa_debug_free(m)

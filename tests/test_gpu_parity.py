@@ -411,3 +411,138 @@ def test_split_combine(lib, ref):
             Lb.FFT_combine_bits(ptr(r), s.ii, cl(length), cl(bits), cl(out), cl(total))
             outs.append(r)
         assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], limbs), ("combine", total, bits, out)
+
+
+# ---- the sqrt2 transforms and new_mpn_mul6 (mul_fft.c:591-700, 972, 2212, 2593, 3573) ----
+@pytest.mark.parametrize("case", [
+    # (n1, n2, depth, w, kinds): 2^(depth+1) < j1+j2-1 <= 2^(depth+2)
+    (60000, 60000, 11, 1, ("uniform", "uniform")),          # l = 32: odd w, stage-per-launch path
+    (60000, 60000, 10, 4, ("ones", "ones")),                # l = 64: fused tiles, even w
+    (700000, 650000, 13, 1, ("uniform", "runs")),           # l = 128: odd w, two column classes on the fused path
+    (3000000, 1700000, 14, 1, ("uniform", "uniform")),      # cfg3 sizes at l = 256 instead of 512
+    (3000000, 1700000, 14, 1, ("ones", "ones")),
+    (1 << 20, 1 << 20, 12, 6, ("uniform", "uniform")),      # l = 384, even w
+    (1700000, 1700000, 13, 3, ("uniform", "ones")),         # l = 384, odd w
+    (100000, 100000, 11, 3, ("runs", "uniform")), (123457, 65521, 11, 2, ("uniform", "ones")),
+])
+def test_new_mpn_mul6(lib, case):
+    n1, n2, depth, w, (k1, k2) = case
+    a, b = operand(k1, n1, 0x5EED0001), operand(k2, n2, 0x5EED0002)
+    got = M.new_mpn_mul6(a, b, depth, w)
+    want = oracle.gmp_mul(a, b)
+    assert first_diff(got, want) is None, "new_mpn_mul6 %s: (first,last,count)=%s" % (case, first_diff(got, want))
+
+
+def test_new_mpn_mul6_matches_reference(lib, ref):
+    """the reference's own big end-to-end test drives new_mpn_mul6 (mul_fft.c:5559)"""
+    n1, n2, depth, w = 50000, 45000, 10, 3
+    a, b = operand("uniform", n1, 1), operand("uniform", n2, 2)
+    want = np.zeros(n1 + n2, dtype=np.uint64)
+    ref.new_mpn_mul6(ptr(want), ptr(a), cl(n1), ptr(b), cl(n2), cul(depth), cul(w))
+    assert first_diff(M.new_mpn_mul6(a, b, depth, w), want) is None
+    assert first_diff(want, oracle.gmp_mul(a, b)) is None
+
+
+@pytest.mark.parametrize("n,w,n1,trunc", [(64, 1, 8, 144), (64, 3, 8, 176), (64, 2, 8, 208), (256, 1, 16, 672),
+                                          (2048, 2, 64, 4096 + 5 * 128), (4096, 1, 64, 8192 + 128), (8192, 1, 128, 4 * 8192)])
+def test_mfa_sqrt2(lib, ref, n, w, n1, trunc):
+    """FFT/IFFT_radix2_mfa_truncate_sqrt2 against the compiled reference (its tests: 4668, 4859)"""
+    rng = np.random.default_rng(n + trunc + w)
+    l, N = n * w // 64, 4 * n
+    n2, trunc2 = 2 * n // n1, (trunc - 2 * n) // n1
+    depth = n2.bit_length() - 1
+    rows = list(range(n2)) + [n2 + int(lib.mpir_revbin(s, depth)) for s in range(trunc2)]
+    for inverse in (0, 1):
+        data = rand_blocks(rng, N, l)
+        if not inverse:
+            data[trunc:] = 0
+        name = ("I" if inverse else "") + "FFT_radix2_mfa_truncate_sqrt2"
+        s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+        getattr(ref, name)(s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, cl(n1), cl(trunc))
+        getattr(lib, name)(s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, cl(n1), cl(trunc))
+        r1, r2 = residues(s1.all(), l), residues(s2.all(), l)
+        idx = [i * n1 + j for i in rows for j in range(n1)] if not inverse else list(range(trunc))
+        assert [r1[k] for k in idx] == [r2[k] for k in idx], name
+
+
+def test_sqrt2_butterflies(lib, ref):
+    rng = np.random.default_rng(19)
+    for (n, w) in [(256, 1), (256, 3), (64, 4 + 1), (1024, 1)]:
+        if (n * w) % 256:
+            continue
+        l = n * w // 64
+        for i in (1, 3, 5, n - 1, n + 1, 2 * n - 1, 2 * n + 1, 4 * n - 1):
+            blk = rand_blocks(rng, 2, l)
+            for name in ("FFT_radix2_butterfly_sqrt2", "FFT_radix2_inverse_butterfly_sqrt2"):
+                if name.startswith("FFT_radix2_inverse") and i >= 2 * n:
+                    continue                                   # the reference's exponent goes negative there (653)
+                outs = []
+                for Lb in (ref, lib):
+                    a, b = blk[0].copy(), blk[1].copy()
+                    s, t, tmp = np.zeros(l + 1, np.uint64), np.zeros(l + 1, np.uint64), np.zeros(2 * l + 2, np.uint64)
+                    getattr(Lb, name)(ptr(s), ptr(t), ptr(a), ptr(b), cl(i), cl(n), cul(w), ptr(tmp))
+                    outs.append((block_to_int(s, l), block_to_int(t, l)))
+                assert outs[0] == outs[1], (name, n, w, i)
+            outs = []
+            for Lb in (ref, lib):
+                a = blk[0].copy()
+                r, tmp = np.zeros(l + 1, np.uint64), np.zeros(2 * l + 2, np.uint64)
+                Lb.FFT_twiddle_sqrt2(ptr(r), ptr(a), cl(i), cl(n), cul(w), ptr(tmp))
+                outs.append(block_to_int(r, l))
+            assert outs[0] == outs[1], ("FFT_twiddle_sqrt2", n, w, i)
+
+
+# ---- direct-symbol checks of the entry points that were only reached through other paths ----
+@pytest.mark.parametrize("n,w", [(16, 8), (64, 2), (32, 64), (8, 256)])
+def test_negacyclic_symbols(lib, ref, n, w):
+    """FFT/IFFT_radix2_negacyclic (mul_fft.c:1290, 1861; even w) against the compiled reference"""
+    rng = np.random.default_rng(n * w + 1)
+    l, N = n * w // 64, 2 * n
+    for name in ("FFT_radix2_negacyclic", "IFFT_radix2_negacyclic"):
+        data = rand_blocks(rng, N, l)
+        s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+        getattr(ref, name)(s1.ii, cl(1), s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp)
+        getattr(lib, name)(s2.ii, cl(1), s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp)
+        assert residues(s1.all(), l) == residues(s2.all(), l), name
+
+
+@pytest.mark.parametrize("n,w,is_,twiddle", [(16, 8, 1, (1, 2, 3, 1)), (32, 4, 2, (2, 3, 5, 2)), (16, 16, 4, (4, 0, 7, 1))])
+def test_twiddle_symbols(lib, ref, n, w, is_, twiddle):
+    """FFT/IFFT_radix2_twiddle (mul_fft.c:1397, 1964; mul_fft.h:73-79), strided, with the z^(r c) twist"""
+    rng = np.random.default_rng(n + w + is_)
+    l, N = n * w // 64, 2 * n
+    ws, r, c, rs = twiddle
+    for name in ("FFT_radix2_twiddle", "IFFT_radix2_twiddle"):
+        data = rand_blocks(rng, N * is_, l)
+        s1, s2 = oracle.Slab(N * is_, l, data), oracle.Slab(N * is_, l, data)
+        getattr(ref, name)(s1.ii, cl(is_), cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, cl(ws), cl(r), cl(c), cl(rs))
+        getattr(lib, name)(s2.ii, cl(is_), cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, cl(ws), cl(r), cl(c), cl(rs))
+        r1, r2 = residues(s1.all(), l), residues(s2.all(), l)
+        assert [r1[k * is_] for k in range(N)] == [r2[k * is_] for k in range(N)], name
+        others = [k for k in range(N * is_) if k % is_]
+        assert [r2[k] for k in others] == [block_to_int(data[k], l) for k in others], name + ": untouched blocks"
+
+
+@pytest.mark.parametrize("n,w,n1,trunc", [(16384, 1, 128, 16640), (16384, 2, 128, 18432), (32768, 1, 128, 18432)])
+def test_mfa_at_bench_rings(lib, ref, n, w, n1, trunc):
+    """the fused tile passes at the cfg2 / cfg3 rings (l = 256, 512), pinned below product level:
+    FFT/IFFT_radix2_mfa_truncate against the compiled reference, limb for limb after normalisation"""
+    rng = np.random.default_rng(n + trunc)
+    l, N = n * w // 64, 2 * n
+    n2 = N // n1
+    depth = n2.bit_length() - 1
+    rows = [int(lib.mpir_revbin(s, depth)) for s in range(trunc // n1)]
+    for inverse in (0, 1):
+        data = rand_blocks(rng, N, l)
+        if not inverse:
+            data[trunc:] = 0
+        name = ("I" if inverse else "") + "FFT_radix2_mfa_truncate"
+        s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+        getattr(ref, name)(s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, cl(n1), cl(trunc))
+        getattr(lib, name)(s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, cl(n1), cl(trunc))
+        idx = [i * n1 + j for i in rows for j in range(n1)] if not inverse else list(range(trunc))
+        a1, a2 = s1.all(), s2.all()
+        for k in idx[::97] + idx[-3:]:
+            assert block_to_int(a1[k], l) == block_to_int(a2[k], l), (name, k)
+        sample = idx if len(idx) < 4000 else idx[::7]
+        assert [block_to_int(a1[k], l) for k in sample] == [block_to_int(a2[k], l) for k in sample], name
