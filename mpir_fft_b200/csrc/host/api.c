@@ -19,40 +19,65 @@ mp_limb_t mpir_revbin(mp_limb_t in, mp_bitcnt_t bits) { return (mp_limb_t) mfft_
 
 /* Run a schedule over S host blocks.  in[k] == NULL: position k starts as zero.  out[k] == NULL:
  * position k is not written back.  Takes ownership of s. */
+/* device (and host staging) scratch of the per-call entry points: one grow-only arena, so that a caller
+   which drives the single-block primitives in a loop (the reference's own tests do, thousands of
+   times) does not pay an allocation per call.  Used under the library lock only. */
+static unsigned char *g_arena = NULL; static size_t g_arena_bytes = 0;
+static limb_t *g_stage = NULL; static size_t g_stage_bytes = 0;
+
+static void *arena_take(size_t *off, size_t bytes)
+{
+   void *p = g_arena + *off;
+   *off += (bytes + 255) & ~(size_t) 255;
+   return p;
+}
+
 static void run_on_host_blocks(const char *fn, mfft_sched *s, uint32_t l, mp_limb_t **in, mp_limb_t **out,
                                uint32_t col, int normalise)
 {
    uint32_t S = s->S, k, pitch = l + 1, zero = 0;
-   size_t half = (size_t) S * pitch * sizeof(limb_t);
-   limb_t *stage = (limb_t *) calloc((size_t) S * pitch, sizeof(limb_t));
-   limb_t *d_slab = NULL, *d_dst = NULL; mfft_batch b, *d_b = NULL; mfft_move *mv = NULL, *d_mv = NULL;
-   uint32_t *d_base = NULL; mfft_dsched ds; mfft_geom g;
-   if (!stage) mfft_die(fn, "out of host memory");
+   size_t half = (size_t) S * pitch * sizeof(limb_t), need, off = 0, nops;
+   limb_t *stage, *d_slab, *d_dst; mfft_batch b, *d_b; mfft_move *mv, *d_mv;
+   uint32_t *d_base; mfft_dsched ds; mfft_geom g;
    mfft_lock();
    mfft_require_device(fn);
+   if (mfft_sched_finish(s) != 0) mfft_die(fn, "out of host memory");
+   nops = s->nops ? s->nops : 1;
+   need = 3*(half + 256) + sizeof(mfft_op)*nops + sizeof(mfft_move)*S + 4*256;
+   if (need > g_arena_bytes)
+   {
+      mfft_dev_free(g_arena);
+      g_arena_bytes = need + need/2;
+      g_arena = (unsigned char *) mfft_dev_alloc(g_arena_bytes);
+      if (!g_arena) { g_arena_bytes = 0; mfft_die(fn, "device allocation failed: %s", mfft_dev_last_error()); }
+   }
+   if (half + sizeof(mfft_move)*S > g_stage_bytes)
+   {
+      free(g_stage);
+      g_stage_bytes = 2*(half + sizeof(mfft_move)*S);
+      g_stage = (limb_t *) malloc(g_stage_bytes);
+      if (!g_stage) { g_stage_bytes = 0; mfft_die(fn, "out of host memory"); }
+   }
+   stage = g_stage; mv = (mfft_move *)((unsigned char *) g_stage + half);
+   d_slab = (limb_t *) arena_take(&off, 2*half); d_dst = (limb_t *) arena_take(&off, half);
+   d_b = (mfft_batch *) arena_take(&off, sizeof b); d_base = (uint32_t *) arena_take(&off, sizeof zero);
+   ds.s = s; ds.d_ops = (mfft_op *) arena_take(&off, sizeof(mfft_op)*nops);
+   d_mv = (mfft_move *) arena_take(&off, sizeof(mfft_move)*S);
+   memset(stage, 0, half);
    for (k = 0; k < S; k++) if (in[k]) memcpy(stage + (size_t) k*pitch, in[k], pitch*sizeof(limb_t));
-   d_slab = (limb_t *) mfft_dev_alloc(2*half); d_dst = (limb_t *) mfft_dev_alloc(half);
    b.base = 0; b.parity = 0; b.col = col; b.pad = 0;
-   d_b = (mfft_batch *) mfft_upload(&b, sizeof b);
-   d_base = (uint32_t *) mfft_upload(&zero, sizeof zero);
-   if (!d_slab || !d_dst || !d_b || !d_base) mfft_die(fn, "device allocation failed: %s", mfft_dev_last_error());
-   if (mfft_dsched_upload(&ds, s) != 0) mfft_die(fn, "schedule upload failed: %s", mfft_dev_last_error());
-   mv = (mfft_move *) malloc(sizeof(mfft_move) * S);
-   if (!mv) mfft_die(fn, "out of host memory");
    for (k = 0; k < S; k++) { mv[k].src_slot = s->slot[k]; mv[k].dst_pos = k; }
-   d_mv = (mfft_move *) mfft_upload(mv, sizeof(mfft_move) * S);
-   if (!d_mv) mfft_die(fn, "device allocation failed: %s", mfft_dev_last_error());
    g.S = S; g.slot_stride = 1; g.half_blocks = S; g.l = l; g.pitch = pitch;
-   if (mfft_dev_h2d(d_slab, stage, half, NULL) ||
+   if (mfft_dev_h2d(d_b, &b, sizeof b, NULL) || mfft_dev_h2d(d_base, &zero, sizeof zero, NULL) ||
+       mfft_dev_h2d(ds.d_ops, s->ops, sizeof(mfft_op)*s->nops, NULL) || mfft_dev_h2d(d_mv, mv, sizeof(mfft_move)*S, NULL) ||
+       mfft_dev_h2d(d_slab, stage, half, NULL) ||
        mfft_dsched_run(&ds, d_slab, &g, d_b, 1, NULL) ||
        mfft_dev_finalize(d_dst, 1, d_base, d_slab, &g, d_mv, S, d_b, 1, 0, normalise, NULL) ||
        mfft_dev_d2h(stage, d_dst, half, NULL) || mfft_dev_sync(NULL))
       mfft_die(fn, "device execution failed: %s", mfft_dev_last_error());
    for (k = 0; k < S; k++) if (out[k]) memcpy(out[k], stage + (size_t) k*pitch, pitch*sizeof(limb_t));
-   mfft_dsched_free(&ds);
-   mfft_dev_free(d_slab); mfft_dev_free(d_dst); mfft_dev_free(d_b); mfft_dev_free(d_base); mfft_dev_free(d_mv);
+   mfft_sched_free(s);
    mfft_unlock();
-   free(mv); free(stage);
 }
 
 static void check_ring(const char *fn, mp_size_t n, mp_bitcnt_t w)

@@ -458,7 +458,8 @@ int mfft_mfa_plan_sqrt2(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64
       for (i = 0; i < m->nmoves; i++)
       {
          mv[i].src_slot = cs[0]->slot[i]; mv[i].dst_pos = (uint32_t) i;
-         if (m->nclass == 2 && (cs[1]->slot[i] != cs[0]->slot[i] || cs[1]->phys[i] != cs[0]->phys[i])) { rc = MPIRFFT_EINVAL; goto fail; }
+         /* both column classes must leave their outputs in the same places (the view that is executed) */
+         if (m->nclass == 2 && (m->fused ? cs[1]->phys[i] != cs[0]->phys[i] : cs[1]->slot[i] != cs[0]->slot[i])) { rc = MPIRFFT_EINVAL; goto fail; }
       }
       m->ndst = m->ncolb; m->h_dst_base = (uint32_t *) calloc(m->ndst, sizeof(uint32_t));
       if (!m->h_dst_base) { rc = MPIRFFT_ENOMEM; goto fail; }

@@ -1,0 +1,72 @@
+"""The drop-in, proven the way INTEGRATION.md section 3 describes: the reference's OWN test functions
+(mul_fft.c:3671-5608, compiled unmodified into oracle/_ref/libmulfft_ref.so) run with every entry
+point they call bound to this library instead of the reference's implementation.
+
+Mechanism: the reference translation unit is a -fPIC shared object, so calls between its global
+functions go through the PLT; loading libmpirfft_b200.so first with RTLD_GLOBAL makes the dynamic
+linker resolve FFT_radix2, FFT_radix2_mfa_truncate_sqrt2, new_mpn_mul, mpn_normmod_2expp1, ... to OUR
+symbols when the reference's test_* functions call them.  A failing reference test abort()s, so each
+one runs in its own process.  `test_mul` is the tell-tale: it drives new_mpn_mul, which is wrong in
+the unpatched reference (mul_fft.c:3246, tests/test_oracle.py::test_reference_bug_3246) -- it can
+only pass here if this library's new_mpn_mul is the one being called.
+
+GPU: the product library.  CPU: the same flow on the CPU-emulated twin (tests/emu), small tests only.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.path.join(ROOT, "oracle", "_ref", "libmulfft_ref.so")          # the UNPATCHED reference
+OURS = os.path.join(ROOT, "mpir_fft_b200", "libmpirfft_b200.so")
+EMU = os.path.join(HERE, "emu", "libmpirfft_emu.so")
+
+DRIVER = r"""
+import ctypes as C, sys
+ours = C.CDLL(sys.argv[1], mode=C.RTLD_GLOBAL)        # first, globally: interposes the reference's implementation
+ref = C.CDLL(sys.argv[2], mode=C.RTLD_LOCAL)
+# the binding really is ours: the address the reference's PLT will use for a symbol equals our export
+for sym in ("FFT_radix2", "mpn_normmod_2expp1", "new_mpn_mul"):
+    assert C.cast(getattr(ours, sym), C.c_void_p).value is not None
+if len(sys.argv) > 4:
+    ours.mpirfft_init.argtypes = [C.c_int]; assert ours.mpirfft_init(int(sys.argv[4])) == 0
+getattr(ref, sys.argv[3])()
+ours.mpirfft_launch_count.restype = C.c_uint64
+assert ours.mpirfft_launch_count() > 0, "the reference test never reached this library's kernels"
+print("PASS", sys.argv[3], "kernel launches:", ours.mpirfft_launch_count())
+"""
+
+
+def run_reference_test(lib, name, timeout, device=None):
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref not built")
+    args = [sys.executable, "-c", DRIVER, lib, REF, name] + ([str(device)] if device is not None else [])
+    r = subprocess.run(args, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0 and ("PASS " + name) in r.stdout, (name, r.returncode, r.stdout[-800:], r.stderr[-800:])
+    assert "error" not in r.stdout.lower() and "wrong" not in r.stdout.lower(), r.stdout[-800:]
+
+
+# what each reference test drives (mul_fft.c line): single-block primitives, 1-D and MFA transforms incl.
+# the sqrt2 MFA pair, the mulmod recursion and the multiplication itself
+GPU_TESTS = [
+    ("test_norm", 3777), ("test_mul_2expmod", 3825), ("test_div_2expmod", 3973),
+    ("test_lshB_sumdiffmod", 4030), ("test_sumdiff_rshBmod", 4109), ("test_mulmod", 4224),
+    ("test_fft_ifft", 4276), ("test_fft_ifft_mfa", 4767), ("test_fft_ifft_mfa_sqrt2", 4859),
+    ("test_fft_ifft_mfa_truncate_sqrt2", 4668), ("test_mul", 5459),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,line", GPU_TESTS)
+def test_reference_test_passes_against_this_library(name, line):
+    run_reference_test(OURS, name, timeout=900, device=0)
+
+
+@pytest.mark.parametrize("name", ["test_norm", "test_lshB_sumdiffmod", "test_fft_ifft"])
+def test_reference_test_passes_against_the_emulated_library(name):
+    """the same flow without a GPU: kernel source compiled for the CPU emulator (tests/emu)"""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    run_reference_test(EMU, name, timeout=900)

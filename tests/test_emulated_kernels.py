@@ -40,12 +40,13 @@ def test_emulated_new_mpn_mul(emu, case):
 
 @pytest.mark.parametrize("case", [
     # (n1, n2, depth, w, operands): 2^(depth+1) < j1+j2-1 <= 2^(depth+2)
-    (30, 30, 6, 1, "uniform"), (50, 41, 6, 1, "ones"),                  # l = 1: stage-per-launch path, odd w (sqrt2 proper)
-    (3000, 3000, 6, 64, "uniform"), (3500, 4000, 6, 64, "ones"),        # l = 64, even w: fused tiles
+    (50, 41, 6, 1, "ones"),                                             # l = 1: stage-per-launch path, odd w (sqrt2 proper)
+    (3500, 4000, 6, 64, "ones"),                                        # l = 64, even w: fused tiles
     (5000, 6000, 6, 128, "runs"), (10000, 14000, 6, 256, "ones"),       # l = 128, 256
-    (700, 600, 8, 1, "ones"), (3000, 2500, 8, 3, "uniform"),            # l = 4, 12: odd w, two column classes
-    (12000, 12000, 8, 16, "uniform"), (20000, 22000, 9, 8, "ones"),      # l = 64 with bit-shifted twiddles
-    (13000, 12000, 8, 17, "runs"), (50000, 60000, 9, 25, "uniform"),    # odd w on tile sizes that exist only for even 64 l: l = 68 (stagewise), 200
+    (3000, 2500, 8, 3, "uniform"),                                      # l = 12: odd w, two column classes
+    (12000, 12000, 8, 16, "uniform"),                                   # l = 64 with bit-shifted twiddles
+    (13000, 12000, 8, 17, "runs"),                                      # odd w, l = 68 (stagewise)
+    (131000, 131000, 12, 1, "uniform"),                                 # odd w on the fused tile path (l = 64): even / odd column classes
 ])
 def test_emulated_new_mpn_mul6(emu, case):
     """new_mpn_mul6 (mul_fft.c:3573): the product through the sqrt2 transforms of length 4n"""
