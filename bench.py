@@ -313,6 +313,37 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * (n1 + n2) / (ms_per_step * 1e-3) / 1e6
 
+    # ---- the library's own parameter choice (mpirfft_mpn_mul: may pick the sqrt2 shape of new_mpn_mul6) ----
+    chooser = None
+    try:
+        cd, cw, csq = M.choose_params6(n1, n2)
+        if (cd, cw, csq) != (depth, w, False):
+            plan2 = M.MulPlan(n1, n2, cd, cw, sqrt2=csq)
+            r2 = torch.zeros(n1 + n2, dtype=torch.int64, device="cuda")
+            for _ in range(args.warmup):
+                plan2.exec_device(r2.data_ptr(), pa, pb, None)
+            torch.cuda.synchronize()
+            ok2 = bool(np.array_equal(r2.cpu().numpy().view(np.uint64), want)) if (rank == 0 and check is True) else None
+            ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for k in range(args.steps):
+                flush.zero_()
+                ev2[k][0].record()
+                plan2.exec_device(r2.data_ptr(), pa, pb, None)
+                ev2[k][1].record()
+            torch.cuda.synchronize()
+            ms2 = sum(a_.elapsed_time(b_) for a_, b_ in ev2) / args.steps
+            chooser = {"api": "mpirfft_mpn_mul / mpirfft_choose_params6", "depth": cd, "w": cw, "sqrt2_new_mpn_mul6": csq,
+                       "limbs_per_coefficient": plan2.params["limbs"], "coefficients": plan2.params["trunc"],
+                       "ms_per_step": ms2, "value": (n1 + n2) / (ms2 * 1e-3) / 1e6, "unit": UNIT, "bit_exact_vs_gmp": ok2,
+                       "launches_per_product": plan2.launches}
+            plan2.close()
+            del r2
+        else:
+            chooser = {"api": "mpirfft_mpn_mul / mpirfft_choose_params6", "depth": cd, "w": cw, "sqrt2_new_mpn_mul6": csq,
+                       "note": "same parameters as the workload"}
+    except Exception as e:
+        chooser = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- e2e: the drop-in C symbol with host buffers (pinned), copies inside the timed region ----
     ha = torch.from_numpy(splitmix64(0x5EED0001 + 1000 * rank, n1).view(np.int64)).pin_memory()
     hb = torch.from_numpy(splitmix64(0x5EED0002 + 1000 * rank, n2).view(np.int64)).pin_memory()
@@ -453,6 +484,7 @@ def main():
                              "api": "new_mpn_mul(r, i1, n1, i2, n2, depth, w) with malloc'ed (pageable) host buffers",
                              "bit_exact_vs_gmp": e2e_pg_check},
             "roofline": roofline, "roofline_pointwise": roofline_pw, "cpu_baseline": cpu, "phases": phases,
+            "library_parameter_choice": chooser,
             "bit_exact_vs_gmp": check, "wall_s_timed_region": wall,
             "step_ms_min_max": [min(step_ms), max(step_ms)],
         }

@@ -4,5 +4,5 @@ points of wbhart/mpir-fft.  The product is the C-ABI shared library libmpirfft_b
 """
 from ._lib import lib, build, LIB_PATH, MulParams  # noqa: F401
 from .api import (  # noqa: F401
-    new_mpn_mul, new_mpn_mul6, mpn_mul, mul_params, choose_params, MulPlan, mulmod_batch, have_gpu, init,
+    new_mpn_mul, new_mpn_mul6, mpn_mul, mul_params, choose_params, choose_params6, MulPlan, mulmod_batch, have_gpu, init,
 )

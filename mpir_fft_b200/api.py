@@ -32,6 +32,14 @@ def mul_params(n1, n2, depth, w):
     return {k: int(getattr(p, k)) for k, _ in MulParams._fields_}
 
 
+def choose_params6(n1, n2):
+    """(depth, w, sqrt2) of mpirfft_choose_params6: what mpirfft_mpn_mul uses"""
+    d, w, sq = C.c_uint64(), C.c_uint64(), C.c_int()
+    if lib().mpirfft_choose_params6(n1, n2, C.byref(d), C.byref(w), C.byref(sq)) != 0:
+        raise ValueError("no legal (depth, w) for %d x %d limbs" % (n1, n2))
+    return int(d.value), int(w.value), bool(sq.value)
+
+
 def choose_params(n1, n2):
     d, w = C.c_uint64(), C.c_uint64()
     if lib().mpirfft_choose_params(n1, n2, C.byref(d), C.byref(w)) != 0:
@@ -80,13 +88,21 @@ def mpn_mul(i1, i2):
 class MulPlan:
     """Device-resident multiplication plan (mpirfft_mul_plan_*)."""
 
-    def __init__(self, n1, n2, depth, w):
-        self.n1, self.n2, self.depth, self.w = n1, n2, depth, w
-        self.params = mul_params(n1, n2, depth, w)
+    def __init__(self, n1, n2, depth, w, sqrt2=False):
+        """sqrt2: the plan of new_mpn_mul6 (transform length 4n, mul_fft.c:3573)"""
+        self.n1, self.n2, self.depth, self.w, self.sqrt2 = n1, n2, depth, w, bool(sqrt2)
+        if sqrt2:
+            p = MulParams()
+            if lib().mpirfft_mul6_params_get(C.byref(p), n1, n2, depth, w) != 0:
+                raise ValueError("illegal new_mpn_mul6 parameters n1=%d n2=%d depth=%d w=%d" % (n1, n2, depth, w))
+            self.params = {k: int(getattr(p, k)) for k, _ in MulParams._fields_}
+        else:
+            self.params = mul_params(n1, n2, depth, w)
         h = C.c_void_p()
-        rc = lib().mpirfft_mul_plan_create(C.byref(h), n1, n2, depth, w)
+        create = lib().mpirfft_mul6_plan_create if sqrt2 else lib().mpirfft_mul_plan_create
+        rc = create(C.byref(h), n1, n2, depth, w)
         if rc != 0:
-            raise RuntimeError("mpirfft_mul_plan_create failed (%d): %s" % (rc, lib().mpirfft_last_error().decode()))
+            raise RuntimeError("mpirfft_mul%s_plan_create failed (%d): %s" % ("6" if sqrt2 else "", rc, lib().mpirfft_last_error().decode()))
         self.h = h
 
     def close(self):

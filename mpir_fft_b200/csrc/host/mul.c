@@ -322,11 +322,14 @@ int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i
    }
    /* the second operand travels while the first one is being split and transformed */
    rc = MPIRFFT_ENODEV;
-   if (mfft_dev_h2d(pl->d_i1, i1, b1, pl->s_copy) || mfft_dev_event_record(pl->ev1, pl->s_copy) ||
-       mfft_dev_h2d(pl->d_i2, i2, b2, pl->s_copy) || mfft_dev_event_record(pl->ev2, pl->s_copy)) goto done;
+   /* The first transform is launched BEFORE the second copy is issued: a copy from pageable memory
+      (what a caller that merely swaps libraries hands in) blocks the host while the driver stages it,
+      and the GPU should be busy with operand 1 meanwhile; with pinned buffers the order is immaterial. */
+   if (mfft_dev_h2d(pl->d_i1, i1, b1, pl->s_copy) || mfft_dev_event_record(pl->ev1, pl->s_copy)) goto done;
    if (mfft_dev_stream_wait(pl->s_comp, pl->ev1)) goto done;
    if ((rc = mpirfft_mul_exec_phase(pl, 0, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_comp)) != 0) goto done;
    rc = MPIRFFT_ENODEV;
+   if (mfft_dev_h2d(pl->d_i2, i2, b2, pl->s_copy) || mfft_dev_event_record(pl->ev2, pl->s_copy)) goto done;
    if (pl->X2)
    {  /* the second transform starts on its own stream as soon as its operand has arrived */
       if (mfft_dev_stream_wait(pl->s_fwd2, pl->ev2)) goto done;
