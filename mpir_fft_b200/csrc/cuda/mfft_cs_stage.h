@@ -49,20 +49,12 @@ k_cs_init(const limb_t *slab, int32_t *cw, mfft_geom g, const mfft_batch *__rest
    cw[idx * NCH + ch] = (ch == NCH - 1) ? (int32_t)(int64_t) slab[idx * g.pitch + g.l] : 0;
 }
 
-/* one layer: CTA = (op, batch entry), threads stride over the chunks */
-__global__ void __launch_bounds__(256)
-k_stage_cs(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict__ ops, uint32_t count,
-           const mfft_batch *__restrict__ batch, uint32_t nbatch)
+/* one op on carry-save blocks: reads A (and B), writes S (and T).  All reads go through the cs_blk
+   handles, so the operands may be shared-memory copies (in-place execution, k_stage_cs_ip) */
+__device__ __forceinline__ void cs_op_apply(const mfft_op &op, const cs_blk &A, const cs_blk &B, const cs_blk &S, const cs_blk &T,
+                                            const mfft_batch &b, const uint32_t NCH, const uint32_t NW)
 {
-   const uint32_t NCH = g.l / 2, NW = 64u * g.l;
-   const mfft_op op = ops[blockIdx.x / nbatch];
-   const mfft_batch b = batch[blockIdx.x % nbatch];
-   const cs_blk A = cs_block(slab, cw, g, op.inA, b);
-   const cs_blk B = (op.inB != MFFT_NONE) ? cs_block(slab, cw, g, op.inB, b) : A;
-   const cs_blk S = cs_block(slab, cw, g, op.outS, b);
-   const cs_blk T = (op.outT != MFFT_NONE) ? cs_block(slab, cw, g, op.outT, b) : S;
    const uint32_t yc = op.kparam & 0x7fffffffu, neg = op.kparam >> 31;
-   (void) count;
    switch (op.kind)
    {
    case MFFT_K_FWD:
@@ -178,6 +170,118 @@ k_stage_cs(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict__ o
       }
       break;
    }
+   }
+}
+
+/* one layer: CTA = (op, batch entry), threads stride over the chunks */
+__global__ void __launch_bounds__(256)
+k_stage_cs(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict__ ops, uint32_t count,
+           const mfft_batch *__restrict__ batch, uint32_t nbatch)
+{
+   const uint32_t NCH = g.l / 2, NW = 64u * g.l;
+   const mfft_op op = ops[blockIdx.x / nbatch];
+   const mfft_batch b = batch[blockIdx.x % nbatch];
+   const cs_blk A = cs_block(slab, cw, g, op.inA, b);
+   const cs_blk B = (op.inB != MFFT_NONE) ? cs_block(slab, cw, g, op.inB, b) : A;
+   const cs_blk S = cs_block(slab, cw, g, op.outS, b);
+   const cs_blk T = (op.outT != MFFT_NONE) ? cs_block(slab, cw, g, op.outT, b) : S;
+   (void) count;
+   cs_op_apply(op, A, B, S, T, b, NCH, NW);
+}
+
+/* The same IN PLACE on physical positions (pA, pB -> pS, pT of slab half 0): the operands are staged
+ * in shared memory first, so an output may overwrite an input.  For the few ops of a big-ring
+ * transform that are not slice-local (bit-granular twist rotations, halving, the final scaling);
+ * everything else runs in the multi-layer sliced passes (k_run_tiles_sliced).  Dynamic shared memory:
+ * two operands of l limbs + l/2 carry words. */
+__global__ void __launch_bounds__(256)
+k_stage_cs_ip(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict__ ops, uint32_t count,
+              const mfft_batch *__restrict__ batch, uint32_t nbatch)
+{
+   MFFT_DYN_SMEM(limb_t, sm);
+   const uint32_t NCH = g.l / 2, NW = 64u * g.l;
+   const mfft_op op = ops[blockIdx.x / nbatch];
+   const mfft_batch b = batch[blockIdx.x % nbatch];
+   const cs_blk Ag = cs_block(slab, cw, g, op.pA, b);
+   const bool hasB = (op.pB != MFFT_NONE) && (op.pB != op.pA);
+   const cs_blk Bg = hasB ? cs_block(slab, cw, g, op.pB, b) : Ag;
+   const cs_blk S = cs_block(slab, cw, g, op.pS, b);
+   const cs_blk T = (op.pT != MFFT_NONE) ? cs_block(slab, cw, g, op.pT, b) : S;
+   const uint32_t stride = g.l + g.l / 4;                 /* limbs per staged operand: body + carry words */
+   cs_blk A, B;
+   A.x = sm; A.c = reinterpret_cast<int32_t *>(sm + g.l);
+   B.x = hasB ? sm + stride : A.x; B.c = hasB ? reinterpret_cast<int32_t *>(sm + stride + g.l) : A.c;
+   (void) count;
+   for (uint32_t i = threadIdx.x; i < NCH; i += blockDim.x)
+   {
+      limb_t x0, x1;
+      ld2(x0, x1, Ag.x + 2 * i); st2(A.x + 2 * i, x0, x1); A.c[i] = Ag.c[i];
+      if (hasB) { ld2(x0, x1, Bg.x + 2 * i); st2(B.x + 2 * i, x0, x1); B.c[i] = Bg.c[i]; }
+   }
+   __syncthreads();
+   cs_op_apply(op, A, B, S, T, b, NCH, NW);
+}
+
+/* ---- multi-layer passes on chunk slices of big coefficients -------------------------------------
+ * All inner layers of a big-ring transform rotate by whole chunks, and by multiples of gs chunks:
+ * then the chunks { i0 + gs t } of every coefficient of a sub-transform form a closed system -- a
+ * coefficient of the ring with NCH/gs chunks (rotation by gs q chunks = rotation of the slice by q,
+ * the wrap-around negation included).  A CTA takes (tile of positions, batch entry, slice i0), loads
+ * those chunks and their carry words into shared memory, runs several layers there with the tile
+ * executor's chunk-local kinds, and stores chunks and carry words back in place: one read and one
+ * write of the slab per PASS instead of per layer.  (North-star: "several radix-2 layers ... inside
+ * one shared-memory tile"; the slice makes that possible when one coefficient is 16-64 KB.) */
+template <int NT, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, 2)
+k_run_tiles_sliced(limb_t *slab, int32_t *cw, mfft_geom g, uint32_t gs, const mfft_tile *__restrict__ tiles,
+                   const uint32_t *__restrict__ pos, const mfft_tileop *__restrict__ ops, const uint32_t *__restrict__ stoff,
+                   const mfft_batch *__restrict__ batch, uint32_t nbatch, uint32_t desc_bytes)
+{
+   MFFT_DYN_SMEM(limb_t, sm);
+   constexpr uint32_t NCHV = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP, CW = tile_cfg<NT>::CW;
+   const uint32_t i0 = blockIdx.x % gs, rest = blockIdx.x / gs, bi = rest % nbatch, tix = rest / nbatch;
+   const mfft_tile T = tiles[tix];
+   const mfft_batch b = batch[bi];
+   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NTHREADS >> 5;
+   const uint32_t NCH = g.l / 2;
+   mfft_tileop *sops = (mfft_tileop *) sm;
+   uint32_t *spos = (uint32_t *)(sops + T.nops);
+   uint32_t *sst = spos + T.npos;
+   limb_t *coef = sm + desc_bytes / 8;
+   {
+      const limb_t *src = (const limb_t *)(ops + T.op_off);
+      limb_t *d = (limb_t *) sops;
+      for (uint32_t k = tid; k < T.nops * (uint32_t)(sizeof(mfft_tileop) / 16); k += NTHREADS) cp_async16(d + 2 * k, src + 2 * k);
+      for (uint32_t k = tid; k < T.npos; k += NTHREADS) spos[k] = pos[T.pos_off + k];
+      for (uint32_t k = tid; k <= T.nstages; k += NTHREADS) sst[k] = stoff[T.pad + k];
+   }
+   __syncthreads();
+   for (uint32_t t = tid; t < T.npos * NCHV; t += NTHREADS)
+   {
+      const uint32_t p = t / NCHV, c = t % NCHV;
+      const uint32_t pp = spos[p];
+      if (!(pp & MFFT_TILE_LOAD)) continue;
+      const uint64_t idx = cs_block_index(g, pp & MFFT_TILE_POSMASK, b);
+      const uint32_t i = i0 + gs * c;
+      limb_t *d = coef + (size_t) p * SP;
+      cp_async16(d + 2 * c, slab + idx * g.pitch + 2 * i);
+      reinterpret_cast<int32_t *>(d + CW)[c] = cw[idx * NCH + i];
+   }
+   cp_async_wait_all();
+   __syncthreads();
+   tile_stages<NT, 1>(coef, sops, sst, T.nstages, b, warp, nwarps, lane, 0u, 0u);
+   for (uint32_t t = tid; t < T.npos * NCHV; t += NTHREADS)
+   {
+      const uint32_t p = t / NCHV, c = t % NCHV;
+      const uint32_t pp = spos[p];
+      if (!(pp & MFFT_TILE_STORE)) continue;
+      const uint64_t idx = cs_block_index(g, pp & MFFT_TILE_POSMASK, b);
+      const uint32_t i = i0 + gs * c;
+      const limb_t *d = coef + (size_t) p * SP;
+      limb_t x0, x1;
+      ld2(x0, x1, d + 2 * c);
+      st2(slab + idx * g.pitch + 2 * i, x0, x1);
+      cw[idx * NCH + i] = reinterpret_cast<const int32_t *>(d + CW)[c];
    }
 }
 

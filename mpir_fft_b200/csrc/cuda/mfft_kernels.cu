@@ -1631,6 +1631,58 @@ int mfft_dev_finalize_cs(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst
    return 0;
 }
 
+int mfft_dev_run_stage_cs_ip(limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
+                             const mfft_batch *d_batch, uint32_t nbatch, void *stream)
+{
+   if (!count || !nbatch) return 0;
+   const size_t sm = 2 * ((size_t) g->l * 8 + (size_t) g->l * 2);
+   if (sm > 227 * 1024) { snprintf(g_err, sizeof g_err, "run_stage_cs_ip: l=%u too large for in-place staging", g->l); return -2; }
+   PROF(PC_STAGE, stream);
+   CK(cudaFuncSetAttribute(k_stage_cs_ip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+   MFFT_LAUNCH(k_stage_cs_ip, (unsigned)((uint64_t) count * nbatch), 256, sm, (cudaStream_t) stream, slab, cw, *g, d_ops, count, d_batch, nbatch);
+   CKL();
+   return 0;
+}
+
+size_t mfft_dev_sliced_coeff_bytes(uint32_t nchv)
+{
+   switch (nchv) { case 32: case 64: case 96: case 128: case 192: case 256: return (size_t) nchv * 16 + 16 + (size_t) nchv * 4; default: return 0; }
+}
+
+int mfft_dev_run_tiles_sliced(limb_t *slab, int32_t *cw, const mfft_geom *g, uint32_t gs, uint32_t nchv,
+                              const mfft_tile *d_tiles, uint32_t ntiles, const uint32_t *d_pos, const mfft_tileop *d_ops,
+                              const uint32_t *d_stoff, uint32_t max_npos, uint32_t max_nops,
+                              const mfft_batch *d_batch, uint32_t nbatch, void *stream)
+{
+   if (!ntiles || !nbatch || !gs) return 0;
+   const size_t cb = mfft_dev_sliced_coeff_bytes(nchv);
+   if (!cb) { snprintf(g_err, sizeof g_err, "run_tiles_sliced: %u chunks per slice unsupported", nchv); return -2; }
+   const uint32_t desc = (uint32_t)(((size_t) max_nops * sizeof(mfft_tileop) + (size_t) max_npos * 4 + 4 * 64 + 15) & ~(size_t) 15);
+   const size_t smem = desc + (size_t) max_npos * cb;
+   const uint64_t grid = (uint64_t) ntiles * nbatch * gs;
+   cudaStream_t st = (cudaStream_t) stream;
+   if (smem > 227 * 1024 || grid > 0x7fffffffull) { snprintf(g_err, sizeof g_err, "run_tiles_sliced: launch too large"); return -2; }
+   PROF(PC_STAGE, st);
+#define RUN_SLICED(NN, TH)                                                                          \
+   do {                                                                                            \
+      CK(cudaFuncSetAttribute(k_run_tiles_sliced<NN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+      MFFT_LAUNCH((k_run_tiles_sliced<NN, TH>), (unsigned) grid, TH, smem, st, slab, cw, *g, gs, d_tiles, d_pos, d_ops, d_stoff, \
+                  d_batch, nbatch, desc);                                                          \
+   } while (0)
+   switch (nchv / 32)
+   {
+   case 1: RUN_SLICED(1, 256); break;
+   case 2: RUN_SLICED(2, 256); break;
+   case 3: RUN_SLICED(3, 256); break;
+   case 4: RUN_SLICED(4, 256); break;
+   case 6: RUN_SLICED(6, 256); break;
+   default: RUN_SLICED(8, 256); break;
+   }
+#undef RUN_SLICED
+   CKL();
+   return 0;
+}
+
 /* coefficient sizes the fused executor is instantiated for: l = 64*NT limbs */
 static int tiles_cfg(uint32_t l, int *NT)
 {

@@ -789,6 +789,34 @@ __device__ __forceinline__ void tile_stages(limb_t *coef, const mfft_tileop *sop
                   if (n) k = sub2(r0, r1, 0, 0, a0[tj], a1[tj]) - ca[tj];
                   st2(S + 2 * o, r0, r1); cwS[o] = k;
                }
+            } else if (op.kind == MFFT_K_2AMB)
+            {  /* S = 2A - B [, T = +-(A - B) 2^(128 yc)]  (1630-1631, 1639-1647): chunk-local like the doubling */
+#pragma unroll
+               for (int tj = 0; tj < NTS; tj++)
+               {
+                  const uint32_t i = (half + W * tj) * 32u + lane;
+                  ld2(a0[tj], a1[tj], A + 2 * i); ca[tj] = cwA[i];
+                  ld2(b0[tj], b1[tj], B + 2 * i); cb[tj] = cwB[i];
+               }
+               op_sync<W>(warp);
+#pragma unroll
+               for (int tj = 0; tj < NTS; tj++)
+               {
+                  const uint32_t i = (half + W * tj) * 32u + lane;
+                  limb_t r0, r1; int32_t k;
+                  const limb_t d0 = a0[tj] << 1, d1 = (a1[tj] << 1) | (a0[tj] >> 63);
+                  const int32_t dc = 2 * ca[tj] + (int32_t)(a1[tj] >> 63);
+                  k = sub2(r0, r1, d0, d1, b0[tj], b1[tj]);
+                  st2(S + 2 * i, r0, r1); cwS[i] = k + dc - cb[tj];
+                  if (hasT)
+                  {
+                     uint32_t o = i + yc, n = neg;
+                     if (o >= NCH) { o -= NCH; n ^= 1u; }
+                     if (n) k = sub2(r0, r1, b0[tj], b1[tj], a0[tj], a1[tj]) + cb[tj] - ca[tj];
+                     else   k = sub2(r0, r1, a0[tj], a1[tj], b0[tj], b1[tj]) + ca[tj] - cb[tj];
+                     st2(Tt + 2 * o, r0, r1); cwT[o] = k;
+                  }
+               }
             } else if (op.kind == MFFT_K_DBL)
             {  /* 2 (x + c B^2) = (2x mod B^2) + (2c + top bit of x) B^2: chunk-local */
 #pragma unroll

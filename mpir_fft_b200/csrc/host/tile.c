@@ -70,6 +70,13 @@ static void classify_op(mfft_tileop *d, uint64_t NW)
    if (!hasB && !hasT && d->sSA == 1 && d->eSA > 2*NW - 32 && d->eSA < 2*NW)
    { d->kind = MFFT_K_SHR; d->kparam = (uint32_t)(2*NW - d->eSA); return; }
    if (hasB && !hasT && d->sSA == 1 && d->sSB == 1 && d->eSA == 2*NW - 1 && d->eSB == 2*NW - 1) { d->kind = MFFT_K_HALF; return; }
+   if (hasB && d->sSA == 1 && d->eSA == 1 && d->sSB == -1 && d->eSB == 0)
+   {  /* S = 2A - B, optionally T = +-(A - B) rotated by whole chunks (1630-1631, 1639-1647) */
+      if (!hasT) { d->kind = MFFT_K_2AMB; return; }
+      if (d->sTA && d->sTB && !fold_term(d->sTA, d->eTA, NW, &yTA, &nTA) && !fold_term(d->sTB, d->eTB, NW, &yTB, &nTB) &&
+          yTA == yTB && nTA != nTB) { d->kind = MFFT_K_2AMB; d->kparam = yTA | (nTA << 31); }
+      return;
+   }
    if (fold_term(d->sSA, d->eSA, NW, &ySA, &nSA)) return;
    if (hasB) { if (!d->sSB || fold_term(d->sSB, d->eSB, NW, &ySB, &nSB)) return; }
    if (hasT)
@@ -350,5 +357,37 @@ int mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, co
 done:
    free(ops); free(par); free(scratch); free(st_off); free(last_read);
    if (rc != 0) mfft_passes_free(P);
+   return rc;
+}
+
+
+/* One pass from an explicit window of ops (sorted by pstage, all of them inside the window): used by
+ * the big-ring executor (bigpass.c), which cuts its own windows.  NW is the ring the ops' exponents
+ * refer to (a slice of a big coefficient is a small ring of its own).  Returns -1 if a connected
+ * component exceeds max_npos (the caller then shrinks the window), -2 on allocation failure. */
+int mfft_window_pass_build(mfft_pass *out, const mfft_op *ops, size_t nops, uint32_t S, uint32_t max_npos,
+                           uint64_t NW, const uint32_t *last_read, const uint8_t *live_out, const uint8_t *must_store)
+{
+   uint32_t *par, *sz, *scratch, p, s0, s1; size_t k; int rc = -2;
+   memset(out, 0, sizeof(*out));
+   if (!nops) return -2;
+   par = (uint32_t *) malloc(sizeof(uint32_t) * 2 * (size_t) S);
+   scratch = (uint32_t *) malloc(sizeof(uint32_t) * 6 * (size_t) S);
+   if (!par || !scratch) goto done;
+   sz = par + S;
+   for (p = 0; p < S; p++) { par[p] = p; sz[p] = 1; }
+   s0 = ops[0].pstage; s1 = ops[nops - 1].pstage;
+   for (k = 0; k < nops; k++)
+   {
+      const mfft_op *o = &ops[k]; uint32_t m = 1;
+      if (o->pB != MFFT_NONE) m = uf_union(par, sz, o->pA, o->pB);
+      m = uf_union(par, sz, o->pA, o->pS);
+      if (o->pT != MFFT_NONE) m = uf_union(par, sz, o->pA, o->pT);
+      if (m > max_npos) { rc = -1; goto done; }
+   }
+   rc = build_pass(out, ops, 0, nops, S, s0, max_npos, par, scratch, must_store, NW, s1, last_read, live_out) == 0 ? 0 : -2;
+   if (rc != 0) { free(out->tiles); free(out->pos); free(out->ops); free(out->stoff); memset(out, 0, sizeof(*out)); }
+done:
+   free(par); free(scratch);
    return rc;
 }

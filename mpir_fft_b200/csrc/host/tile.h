@@ -26,6 +26,9 @@ typedef struct { uint32_t npasses; mfft_pass *pass; } mfft_passes;
  * after the schedule; a position written by a pass is stored only if a later op reads it or it is live. */
 int  mfft_passes_build(mfft_passes *P, const mfft_sched *s, uint32_t max_npos, const uint8_t *must_store, const uint8_t *live_out);
 void mfft_passes_free(mfft_passes *P);
+/* one pass from an explicit window of ops (see tile.c); last_read[p] = latest pstage that reads position p */
+int  mfft_window_pass_build(mfft_pass *out, const mfft_op *ops, size_t nops, uint32_t S, uint32_t max_npos,
+                            uint64_t NW, const uint32_t *last_read, const uint8_t *live_out, const uint8_t *must_store);
 
 #ifdef __cplusplus
 }

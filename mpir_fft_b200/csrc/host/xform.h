@@ -8,6 +8,14 @@
 extern "C" {
 #endif
 
+/* one pass of the big-ring executor (rings above 512 limbs, in place on slab half 0) */
+typedef struct {
+   int sliced;                                    /* 1: multi-layer pass on chunk slices; 0: one stage, operands staged whole */
+   uint32_t gs, nchv;                             /* sliced: slice stride in chunks, chunks per slice */
+   mfft_pass pass; struct mfft_dpass d;           /* sliced: tile descriptors (virtual ring of nchv chunks) */
+   mfft_op *d_ops; uint32_t nops;                 /* whole: the stage's ops */
+} mfft_bigpass;
+
 typedef struct {
    mfft_geom g; int fused; uint32_t S, nbatch, nout, dst_stride, shift; int normalise;
    mfft_dsched ds;                                /* stagewise: uploaded schedule (owns s) */
@@ -15,6 +23,7 @@ typedef struct {
    mfft_passes P; struct mfft_dpass *dp;          /* fused passes */
    mfft_batch *d_batch, *h_batch; uint32_t *d_dst_base, *d_dstpos; mfft_move *d_moves;
    int cs; int32_t *d_cw;                         /* stagewise, carry-save kernel: carry words of both slab halves */
+   int big; mfft_bigpass *bp; uint32_t nbp;       /* carry-save, in place, multi-layer sliced passes (xform.c: big_build) */
 } mfft_xform;
 
 /* s: emitted (and relabelled) schedule over S positions; ownership passes to the xform.

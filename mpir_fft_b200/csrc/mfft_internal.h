@@ -99,7 +99,7 @@ typedef struct {            /* one op of a tile; a,b,s,t index the tile's positi
 #define MFFT_K_DBL   8u     /* S = 2 A           (the doubling steps of IFFT_radix2_truncate, 1788-1789) */
 #define MFFT_K_HALF  9u     /* S = (A + B) / 2   (the averaging steps of IFFT_radix2_truncate1, 1556-1560) */
 #define MFFT_K_SHR   10u    /* S = A / 2^s, 1 <= s <= 31 = kparam   (the final 2^-(depth+1) scaling, 3256-3258) */
-#define MFFT_K_2AMB  11u    /* S = 2A - B [, T = +-(A - B) * 2^(128 yc)]   (1630-1631, 1639-1647); stage kernel only */
+#define MFFT_K_2AMB  11u    /* S = 2A - B [, T = +-(A - B) * 2^(128 yc)]   (1630-1631, 1639-1647) */
 
 /* pad = offset of the tile's (nstages+1) stage offsets in the pass's stoff array (<= 63 stages) */
 typedef struct { uint32_t pos_off, npos, op_off, nops, nstages, pad; } mfft_tile;
@@ -157,6 +157,19 @@ int  mfft_dev_finalize_cs(limb_t *dst, uint32_t dst_stride, const uint32_t *d_ds
  * {src, nlimbs} (block k of slab half 0 = bits [k*bits, (k+1)*bits), zero for k >= ncoef;
  * FFT_split_bits, mul_fft.c:115-170 and the zero fill 3235-3236) instead of reading them from the slab */
 typedef struct { const limb_t *src; uint64_t nlimbs, bits, ncoef; } mfft_split;
+
+/* Big rings, in place on slab half 0 (position view).  run_stage_cs_ip: the ops of one stage, operands
+ * staged in shared memory (ops carry pA/pB/pS/pT and a kind).  run_tiles_sliced: several layers on the
+ * chunk slices { i0 + gs t } of the tile's coefficients (see mfft_cs_stage.h); the pass descriptors
+ * are those of the tile executor for the virtual ring of l/2/gs chunks. */
+int  mfft_dev_run_stage_cs_ip(limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
+                              const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+int  mfft_dev_run_tiles_sliced(limb_t *slab, int32_t *cw, const mfft_geom *g, uint32_t gs, uint32_t nchv,
+                               const mfft_tile *d_tiles, uint32_t ntiles, const uint32_t *d_pos, const mfft_tileop *d_ops,
+                               const uint32_t *d_stoff, uint32_t max_npos, uint32_t max_nops,
+                               const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+/* shared-memory bytes one coefficient of nchv chunks takes in a sliced tile; 0 if nchv is not built */
+size_t mfft_dev_sliced_coeff_bytes(uint32_t nchv);
 
 /* One fused pass: CTA (tile, batch entry) loads the tile's positions into shared memory, runs
  * all its stages there and stores the written positions back in place -- or, if dst != NULL,
