@@ -209,9 +209,13 @@ k_stage_cs_ip(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict_
    const cs_blk T = (op.pT != MFFT_NONE) ? cs_block(slab, cw, g, op.pT, b) : S;
    const uint32_t stride = g.l + g.l / 4;                 /* limbs per staged operand: body + carry words */
    cs_blk A, B;
+   (void) count;
+   /* no output overwrites an input (e.g. the rows a truncated transform synthesises from others,
+      1217-1220): nothing to stage */
+   if (op.pS != op.pA && op.pS != op.pB && (op.pT == MFFT_NONE || (op.pT != op.pA && op.pT != op.pB)))
+   { cs_op_apply(op, Ag, Bg, S, T, b, NCH, NW); return; }
    A.x = sm; A.c = reinterpret_cast<int32_t *>(sm + g.l);
    B.x = hasB ? sm + stride : A.x; B.c = hasB ? reinterpret_cast<int32_t *>(sm + stride + g.l) : A.c;
-   (void) count;
    for (uint32_t i = threadIdx.x; i < NCH; i += blockDim.x)
    {
       limb_t x0, x1;
@@ -233,13 +237,16 @@ k_stage_cs_ip(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict_
  * one shared-memory tile"; the slice makes that possible when one coefficient is 16-64 KB.) */
 template <int NT, int NTHREADS>
 __global__ void __launch_bounds__(NTHREADS, 2)
-k_run_tiles_sliced(limb_t *slab, int32_t *cw, mfft_geom g, uint32_t gs, const mfft_tile *__restrict__ tiles,
+k_run_tiles_sliced(limb_t *slab, int32_t *cw, mfft_geom g, uint32_t gs, uint32_t R, const mfft_tile *__restrict__ tiles,
                    const uint32_t *__restrict__ pos, const mfft_tileop *__restrict__ ops, const uint32_t *__restrict__ stoff,
                    const mfft_batch *__restrict__ batch, uint32_t nbatch, uint32_t desc_bytes)
 {
+   /* R adjacent slices i0 .. i0+R-1 per CTA: their chunks are contiguous in HBM (R x 16 bytes of body,
+      R x 4 bytes of carry words per step of gs chunks), which is what makes the sectors full */
    MFFT_DYN_SMEM(limb_t, sm);
    constexpr uint32_t NCHV = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP, CW = tile_cfg<NT>::CW;
-   const uint32_t i0 = blockIdx.x % gs, rest = blockIdx.x / gs, bi = rest % nbatch, tix = rest / nbatch;
+   const uint32_t nsl = gs / R;
+   const uint32_t i0 = (blockIdx.x % nsl) * R, rest = blockIdx.x / nsl, bi = rest % nbatch, tix = rest / nbatch;
    const mfft_tile T = tiles[tix];
    const mfft_batch b = batch[bi];
    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NTHREADS >> 5;
@@ -247,7 +254,7 @@ k_run_tiles_sliced(limb_t *slab, int32_t *cw, mfft_geom g, uint32_t gs, const mf
    mfft_tileop *sops = (mfft_tileop *) sm;
    uint32_t *spos = (uint32_t *)(sops + T.nops);
    uint32_t *sst = spos + T.npos;
-   limb_t *coef = sm + desc_bytes / 8;
+   limb_t *coef = sm + desc_bytes / 8;               /* slice r of position p: coef + (r * T.npos + p) * SP */
    {
       const limb_t *src = (const limb_t *)(ops + T.op_off);
       limb_t *d = (limb_t *) sops;
@@ -256,32 +263,45 @@ k_run_tiles_sliced(limb_t *slab, int32_t *cw, mfft_geom g, uint32_t gs, const mf
       for (uint32_t k = tid; k <= T.nstages; k += NTHREADS) sst[k] = stoff[T.pad + k];
    }
    __syncthreads();
-   for (uint32_t t = tid; t < T.npos * NCHV; t += NTHREADS)
+   /* a warp per coefficient: the block address is computed once, the lanes walk the slices' chunks
+      (16-byte chunk bodies and 4-byte carry words, both by asynchronous copies) */
+   for (uint32_t p = warp; p < T.npos; p += nwarps)
    {
-      const uint32_t p = t / NCHV, c = t % NCHV;
       const uint32_t pp = spos[p];
       if (!(pp & MFFT_TILE_LOAD)) continue;
       const uint64_t idx = cs_block_index(g, pp & MFFT_TILE_POSMASK, b);
-      const uint32_t i = i0 + gs * c;
-      limb_t *d = coef + (size_t) p * SP;
-      cp_async16(d + 2 * c, slab + idx * g.pitch + 2 * i);
-      reinterpret_cast<int32_t *>(d + CW)[c] = cw[idx * NCH + i];
+      const limb_t *src = slab + idx * g.pitch + 2 * (size_t) i0;
+      const int32_t *csrc = cw + idx * NCH + i0;
+#pragma unroll 4
+      for (uint32_t q = lane; q < NCHV * R; q += 32)
+      {
+         const uint32_t c = q / R, r = q % R;
+         limb_t *d = coef + ((size_t) r * T.npos + p) * SP;
+         cp_async16(d + 2 * c, src + 2 * ((size_t) gs * c + r));
+         cp_async4(reinterpret_cast<int32_t *>(d + CW) + c, csrc + (size_t) gs * c + r);
+      }
    }
    cp_async_wait_all();
    __syncthreads();
-   tile_stages<NT, 1>(coef, sops, sst, T.nstages, b, warp, nwarps, lane, 0u, 0u);
-   for (uint32_t t = tid; t < T.npos * NCHV; t += NTHREADS)
+   for (uint32_t r = 0; r < R; r++)
+      tile_stages<NT, 1>(coef + (size_t) r * T.npos * SP, sops, sst, T.nstages, b, warp, nwarps, lane, 0u, 0u);
+   for (uint32_t p = warp; p < T.npos; p += nwarps)
    {
-      const uint32_t p = t / NCHV, c = t % NCHV;
       const uint32_t pp = spos[p];
       if (!(pp & MFFT_TILE_STORE)) continue;
       const uint64_t idx = cs_block_index(g, pp & MFFT_TILE_POSMASK, b);
-      const uint32_t i = i0 + gs * c;
-      const limb_t *d = coef + (size_t) p * SP;
-      limb_t x0, x1;
-      ld2(x0, x1, d + 2 * c);
-      st2(slab + idx * g.pitch + 2 * i, x0, x1);
-      cw[idx * NCH + i] = reinterpret_cast<const int32_t *>(d + CW)[c];
+      limb_t *dstp = slab + idx * g.pitch + 2 * (size_t) i0;
+      int32_t *cdst = cw + idx * NCH + i0;
+#pragma unroll 4
+      for (uint32_t q = lane; q < NCHV * R; q += 32)
+      {
+         const uint32_t c = q / R, r = q % R;
+         const limb_t *d = coef + ((size_t) r * T.npos + p) * SP;
+         limb_t x0, x1;
+         ld2(x0, x1, d + 2 * c);
+         st2(dstp + 2 * ((size_t) gs * c + r), x0, x1);
+         cdst[(size_t) gs * c + r] = reinterpret_cast<const int32_t *>(d + CW)[c];
+      }
    }
 }
 

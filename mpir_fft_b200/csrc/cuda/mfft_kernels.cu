@@ -1649,24 +1649,25 @@ size_t mfft_dev_sliced_coeff_bytes(uint32_t nchv)
    switch (nchv) { case 32: case 64: case 96: case 128: case 192: case 256: return (size_t) nchv * 16 + 16 + (size_t) nchv * 4; default: return 0; }
 }
 
-int mfft_dev_run_tiles_sliced(limb_t *slab, int32_t *cw, const mfft_geom *g, uint32_t gs, uint32_t nchv,
+int mfft_dev_run_tiles_sliced(limb_t *slab, int32_t *cw, const mfft_geom *g, uint32_t gs, uint32_t nchv, uint32_t R,
                               const mfft_tile *d_tiles, uint32_t ntiles, const uint32_t *d_pos, const mfft_tileop *d_ops,
                               const uint32_t *d_stoff, uint32_t max_npos, uint32_t max_nops,
                               const mfft_batch *d_batch, uint32_t nbatch, void *stream)
 {
    if (!ntiles || !nbatch || !gs) return 0;
+   if (!R || gs % R) { snprintf(g_err, sizeof g_err, "run_tiles_sliced: %u slices per CTA do not divide the stride %u", R, gs); return -2; }
    const size_t cb = mfft_dev_sliced_coeff_bytes(nchv);
    if (!cb) { snprintf(g_err, sizeof g_err, "run_tiles_sliced: %u chunks per slice unsupported", nchv); return -2; }
    const uint32_t desc = (uint32_t)(((size_t) max_nops * sizeof(mfft_tileop) + (size_t) max_npos * 4 + 4 * 64 + 15) & ~(size_t) 15);
-   const size_t smem = desc + (size_t) max_npos * cb;
-   const uint64_t grid = (uint64_t) ntiles * nbatch * gs;
+   const size_t smem = desc + (size_t) max_npos * cb * R;
+   const uint64_t grid = (uint64_t) ntiles * nbatch * (gs / R);
    cudaStream_t st = (cudaStream_t) stream;
    if (smem > 227 * 1024 || grid > 0x7fffffffull) { snprintf(g_err, sizeof g_err, "run_tiles_sliced: launch too large"); return -2; }
    PROF(PC_STAGE, st);
 #define RUN_SLICED(NN, TH)                                                                          \
    do {                                                                                            \
       CK(cudaFuncSetAttribute(k_run_tiles_sliced<NN, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-      MFFT_LAUNCH((k_run_tiles_sliced<NN, TH>), (unsigned) grid, TH, smem, st, slab, cw, *g, gs, d_tiles, d_pos, d_ops, d_stoff, \
+      MFFT_LAUNCH((k_run_tiles_sliced<NN, TH>), (unsigned) grid, TH, smem, st, slab, cw, *g, gs, R, d_tiles, d_pos, d_ops, d_stoff, \
                   d_batch, nbatch, desc);                                                          \
    } while (0)
    switch (nchv / 32)

@@ -432,6 +432,15 @@ __device__ __forceinline__ void cp_async16(limb_t *sdst, const limb_t *gsrc)
    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
 #endif
 }
+__device__ __forceinline__ void cp_async4(int32_t *sdst, const int32_t *gsrc)
+{
+#ifdef MFFT_EMU
+   sdst[0] = gsrc[0];
+#else
+   const uint32_t sa = (uint32_t) __cvta_generic_to_shared(sdst);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(gsrc) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async_wait_all()
 {
 #ifndef MFFT_EMU

@@ -161,6 +161,27 @@ static int big_build(mfft_xform *x, const mfft_sched *s, uint32_t l, const uint8
             stage_g[cur] = 0;
             continue;
          }
+         {  /* adjacent slices per CTA: contiguous R x 16-byte runs in HBM (full sectors) as long as the
+               window's components still fit the tile */
+            uint32_t R; size_t n = st_off[best_e + 1] - st_off[cur], cb = mfft_dev_sliced_coeff_bytes(best_nchv);
+            bp->R = 1;
+            for (R = 8; R >= 2; R >>= 1)
+            {
+               uint32_t maxp = 4; mfft_pass cand;
+               if (best_gs % R || 4 * cb * R > budget) continue;
+               while (maxp * 2 * cb * R <= budget && maxp < 256) maxp *= 2;
+               for (k = 0; k < n; k++)
+               {
+                  mfft_op *o = &win[k]; *o = ops[st_off[cur] + k];
+                  o->eSA = scale_e(o->eSA, best_gs); o->eSB = scale_e(o->eSB, best_gs); o->eTA = scale_e(o->eTA, best_gs); o->eTB = scale_e(o->eTB, best_gs);
+               }
+               if (mfft_window_pass_build(&cand, win, n, S, maxp, 128ull * best_nchv, last_read, live_out, NULL) != 0) continue;
+               if (cand.nany) { free(cand.tiles); free(cand.pos); free(cand.ops); free(cand.stoff); continue; }
+               free(best.tiles); free(best.pos); free(best.ops); free(best.stoff);
+               best = cand; bp->R = R;
+               break;
+            }
+         }
          bp->sliced = 1; bp->gs = best_gs; bp->nchv = best_nchv; bp->pass = best;
          bp->d.d_tiles = (mfft_tile *) mfft_upload(best.tiles, sizeof(mfft_tile) * (best.ntiles ? best.ntiles : 1));
          bp->d.d_pos = (uint32_t *) mfft_upload(best.pos, sizeof(uint32_t) * (best.npos_total ? best.npos_total : 1));
@@ -300,8 +321,8 @@ int mfft_xform_build(mfft_xform *x, mfft_sched *s, uint32_t l, uint32_t slot_str
    {
       uint32_t q;
       for (q = 0; q < x->nbp; q++)
-         if (x->bp[q].sliced) fprintf(stderr, "   pass %u: sliced, stride %u chunks, %u chunks per slice, %u tiles of <= %u positions, %u stages\n",
-                                      q, x->bp[q].gs, x->bp[q].nchv, x->bp[q].pass.ntiles, x->bp[q].pass.max_npos, x->bp[q].pass.nstages);
+         if (x->bp[q].sliced) fprintf(stderr, "   pass %u: sliced, stride %u chunks, %u chunks per slice, %u slices per CTA, %u tiles of <= %u positions, %u stages\n",
+                                      q, x->bp[q].gs, x->bp[q].nchv, x->bp[q].R, x->bp[q].pass.ntiles, x->bp[q].pass.max_npos, x->bp[q].pass.nstages);
          else fprintf(stderr, "   pass %u: whole coefficients, %u ops\n", q, x->bp[q].nops);
    }
    return 0;
@@ -333,7 +354,7 @@ int mfft_xform_exec(const mfft_xform *x, limb_t *slab, limb_t *dst, void *stream
          const mfft_bigpass *b = &x->bp[i];
          if (b->sliced)
          {
-            if (mfft_dev_run_tiles_sliced(slab, x->d_cw, &x->g, b->gs, b->nchv, b->d.d_tiles, b->pass.ntiles, b->d.d_pos, b->d.d_ops,
+            if (mfft_dev_run_tiles_sliced(slab, x->d_cw, &x->g, b->gs, b->nchv, b->R, b->d.d_tiles, b->pass.ntiles, b->d.d_pos, b->d.d_ops,
                                           b->d.d_stoff, b->pass.max_npos, b->pass.max_nops, x->d_batch, x->nbatch, stream) != 0) return MPIRFFT_ENODEV;
          }
          else if (mfft_dev_run_stage_cs_ip(slab, x->d_cw, &x->g, b->d_ops, b->nops, x->d_batch, x->nbatch, stream) != 0) return MPIRFFT_ENODEV;

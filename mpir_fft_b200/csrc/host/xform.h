@@ -11,7 +11,7 @@ extern "C" {
 /* one pass of the big-ring executor (rings above 512 limbs, in place on slab half 0) */
 typedef struct {
    int sliced;                                    /* 1: multi-layer pass on chunk slices; 0: one stage, operands staged whole */
-   uint32_t gs, nchv;                             /* sliced: slice stride in chunks, chunks per slice */
+   uint32_t gs, nchv, R;                          /* sliced: slice stride in chunks, chunks per slice, adjacent slices per CTA */
    mfft_pass pass; struct mfft_dpass d;           /* sliced: tile descriptors (virtual ring of nchv chunks) */
    mfft_op *d_ops; uint32_t nops;                 /* whole: the stage's ops */
 } mfft_bigpass;
