@@ -154,6 +154,33 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_cpus(gpu):
+    """pin this process to the CPUs next to its GPU (NVML's ideal affinity): with one process per GPU the
+    host side of the end-to-end path -- staging copies, pinned buffers (first touch), launch threads --
+    otherwise piles up on one NUMA node (round 1: e2e weak-scaling efficiency 0.67 at 8 GPUs)"""
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        idx = gpu
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:
+            ids = [v.strip() for v in vis.split(",")]
+            if gpu < len(ids) and ids[gpu].isdigit():
+                idx = int(ids[gpu])
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = N.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1 and 64 * i + b < ncpu}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus)}
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+    return None
+
+
 def cpu_reference_product(n1, n2, depth, w, reps, seed=1):
     """time the compiled reference (fixed at mul_fft.c:3246) on this process's core"""
     from oracle import loader as oracle
@@ -245,6 +272,7 @@ def main():
     if not torch.cuda.is_available() or not M.have_gpu():
         raise SystemExit("bench.py: no CUDA device -- mpir_fft_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_cpus(local_rank)       # before any host buffer is allocated (first touch)
     M.init(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -474,7 +502,8 @@ def main():
                        "baseline_config_index": {"cfg1": 0, "cfg2": 1, "cfg3": 2, "big": None}[args.workload],
                        "coefficients": prm["trunc"], "limbs_per_coefficient": prm["limbs"],
                        "l2": "flushed between timed steps (256 MiB write)",
-                       "multi_gpu": "independent products per rank" if world > 1 else "single GPU"},
+                       "multi_gpu": "independent products per rank" if world > 1 else "single GPU",
+                       "host_affinity": numa},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * (n1 + n2),
                     "d2h_bytes_per_step": 8 * (n1 + n2), "ms_per_step": e2e_dt / e2e_steps * 1e3,
@@ -511,6 +540,15 @@ def main():
                 rec = sharded_leg(torch, dist, M, rank, world, lg, steps=2, peak_gbs=float(peaks.get("hbm_gbs", 6650.0)))
                 if rank == 0:
                     recs.append(rec)
+            if rank == 0 and world == 1 and not args.no_cpu_baseline and recs:
+                # the reference on one host core at a bounded sample of the same kind of workload
+                try:
+                    times, kind = cpu_reference_product(1 << 24, 1 << 24, 16, 1, 1)
+                    recs[0]["cpu_baseline"] = {"value": (2 << 24) / times[0] / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
+                                               "sample": "one 2^24 x 2^24-limb product (depth 16, w 1; a quarter of the operand size), "
+                                                         "%.1f s, 1 thread" % times[0], "cpu_model": _cpu_model(), "host_cores": os.cpu_count()}
+                except Exception as e:
+                    recs[0]["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": str(e)}
         except Exception as e:      # peers may now be waiting in a collective: the watchdog ends the run
             import traceback
             recs.append({"error": "%s: %s" % (type(e).__name__, e), "trace": traceback.format_exc()[-600:]})
@@ -641,13 +679,38 @@ def sharded_leg(torch, dist, M, rank, world, log2, steps=2, baseline_1gpu=True, 
     if world > 1:
         dist.all_reduce(pt, op=dist.ReduceOp.MAX)
     phases = {k: float(v) for k, v in zip(sorted(phases), pt.cpu().tolist())}
+    # end to end with HOST operands (pinned): every rank copies the operands in, the product runs, the
+    # rank's window of the result is copied out -- all inside the timed region (sizes that fit host memory)
+    e2e = None
+    if log2 <= 26:
+        ha = torch.empty(n, dtype=torch.int64).pin_memory(); ha.copy_(a)
+        hb = torch.empty(n, dtype=torch.int64).pin_memory(); hb.copy_(b)
+        hout = torch.empty(sm.out.numel(), dtype=torch.int64).pin_memory()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a.copy_(ha, non_blocking=True)
+        b.copy_(hb, non_blocking=True)
+        sm.multiply(a.data_ptr(), b.data_ptr())
+        hout.copy_(sm.out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": 2 * n / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": 16 * n,
+               "api": "ShardedMul.multiply (mpirfft_smul_* phases + NCCL) with pinned host operands copied to every rank "
+                      "and the result windows copied back"}
+        del ha, hb, hout
     a2a_bytes = int(lay.trunc_rows * lay.ncl * lay.block_limbs * 8)          # one rank's buffer per exchange
     sent = a2a_bytes * (world - 1) // world                                  # what actually leaves the GPU
     mem = torch.cuda.max_memory_allocated() / 1e9
     sm.close()
     del sm
     base = None
-    if baseline_1gpu and world > 1:
+    if baseline_1gpu and world > 1 and log2 <= 26:      # (the larger sizes do not fit one GPU's plan buffers)
         # the same product on rank 0 alone: strong-scaling denominator and world-size independence
         same = None
         if rank == 0:
@@ -689,6 +752,7 @@ def sharded_leg(torch, dist, M, rank, world, log2, steps=2, baseline_1gpu=True, 
                      "alg_bytes": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9, "unit": "GB/s",
                      "peak": (peak_gbs * world) if peak_gbs else None,
                      "frac": (b_alg / (ms * 1e-3) / 1e9 / (peak_gbs * world)) if peak_gbs else None},
+        "e2e": e2e,
         "bit_exact": bool(ok and (same is not False)),
         "check": {"residues": "a*b == r modulo the six 31-bit primes of mpir_fft_b200/residues.py (weights 2^(64k) mod p, "
                               "order of 2 > 3e8: position-sensitive), result limbs reduced where they live",
@@ -799,6 +863,22 @@ def run_cfg4(args, rank, local_rank, world, torch, dist, M):
     if rank == 0:
         inner_l = ((1 << d.value) * w.value) // 64
         mads = count * (2 << d.value) * 4 * inner_l ** 2
+        try:    # the product kernel against the integer multiply-add issue rate measured right here
+            Lb.mpirfft_measure_imad_rate.restype = C.c_double
+            imad_chain = float(Lb.mpirfft_measure_imad_rate(1))
+        except Exception:
+            imad_chain = 0.0
+        kara = inner_l in (128, 256)
+        school = mads / (phase_ms[2] * 1e-3)
+        issued = school * (0.75 if kara else 1.0)
+        cfg4_roofline = {"kernel": "k_pointwise (inner products mod 2^%d+1, %s block products)" % (
+                             64 * inner_l, "Karatsuba-split" if kara else "schoolbook"), "bound": "imad",
+                         "achieved": issued / 1e12, "unit": "Tmad32/s", "peak": (imad_chain / 1e12) if imad_chain > 0 else None,
+                         "frac": (issued / imad_chain) if imad_chain > 0 else None,
+                         "schoolbook_equivalent": school / 1e12,
+                         "schoolbook_equivalent_frac": (school / imad_chain) if imad_chain > 0 else None,
+                         "traffic": None, "share_of_step": phase_ms[2] / ms_per_step,
+                         "peak_source": "IMAD.WIDE.U32.X carry-chain rate measured in this run (csrc/cuda/imad_peak.cu)"}
         print(json.dumps({
             "metric": "fft_mulmod_2expp1 batch Mlimb/s", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -811,9 +891,7 @@ def run_cfg4(args, rank, local_rank, world, torch, dist, M):
             "e2e": {"value": world * count * l / e2e_dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * ha.nbytes,
                     "d2h_bytes_per_step": ha.nbytes, "ms_per_step": e2e_dt * 1e3,
                     "api": "mpirfft_mulmod_plan_exec on HBM blocks, pinned host blocks copied in and out every step"},
-            "roofline": {"kernel": "k_pointwise (inner products mod 2^%d+1)" % (64 * inner_l), "bound": "imad",
-                         "achieved": mads / (phase_ms[2] * 1e-3) / 1e12, "unit": "Tmad32/s", "peak": None, "frac": None,
-                         "traffic": None, "note": "see roofline_pointwise of the default workload for the measured IMAD rate"},
+            "roofline": cfg4_roofline,
             "cpu_baseline": cpu,
             "phases": {"split+forward a": phase_ms[0], "split+forward b": phase_ms[1], "pointwise": phase_ms[2],
                        "inverse": phase_ms[3], "finish": phase_ms[4], "unit": "ms per batch"},
