@@ -194,7 +194,7 @@ k_stage_cs(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict__ o
  * transform that are not slice-local (bit-granular twist rotations, halving, the final scaling);
  * everything else runs in the multi-layer sliced passes (k_run_tiles_sliced).  Dynamic shared memory:
  * two operands of l limbs + l/2 carry words. */
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_stage_cs_ip(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict__ ops, uint32_t count,
               const mfft_batch *__restrict__ batch, uint32_t nbatch)
 {
@@ -208,21 +208,25 @@ k_stage_cs_ip(limb_t *slab, int32_t *cw, mfft_geom g, const mfft_op *__restrict_
    const cs_blk S = cs_block(slab, cw, g, op.pS, b);
    const cs_blk T = (op.pT != MFFT_NONE) ? cs_block(slab, cw, g, op.pT, b) : S;
    const uint32_t stride = g.l + g.l / 4;                 /* limbs per staged operand: body + carry words */
-   cs_blk A, B;
+   /* only an operand that an output overwrites has to be staged (e.g. the rows a truncated transform
+      synthesises from others, 1217-1220, overwrite nothing: no staging at all) */
+   const bool stA = (op.pS == op.pA) || (op.pT == op.pA);
+   const bool stB = hasB && ((op.pS == op.pB) || (op.pT == op.pB));
+   cs_blk A = Ag, B = Bg;
    (void) count;
-   /* no output overwrites an input (e.g. the rows a truncated transform synthesises from others,
-      1217-1220): nothing to stage */
-   if (op.pS != op.pA && op.pS != op.pB && (op.pT == MFFT_NONE || (op.pT != op.pA && op.pT != op.pB)))
-   { cs_op_apply(op, Ag, Bg, S, T, b, NCH, NW); return; }
-   A.x = sm; A.c = reinterpret_cast<int32_t *>(sm + g.l);
-   B.x = hasB ? sm + stride : A.x; B.c = hasB ? reinterpret_cast<int32_t *>(sm + stride + g.l) : A.c;
-   for (uint32_t i = threadIdx.x; i < NCH; i += blockDim.x)
+   if (stA) { A.x = sm; A.c = reinterpret_cast<int32_t *>(sm + g.l); }
+   if (stB) { limb_t *q = sm + (stA ? stride : 0); B.x = q; B.c = reinterpret_cast<int32_t *>(q + g.l); }
+   if (!hasB) B = A;
+   if (stA || stB)
    {
-      limb_t x0, x1;
-      ld2(x0, x1, Ag.x + 2 * i); st2(A.x + 2 * i, x0, x1); A.c[i] = Ag.c[i];
-      if (hasB) { ld2(x0, x1, Bg.x + 2 * i); st2(B.x + 2 * i, x0, x1); B.c[i] = Bg.c[i]; }
+      for (uint32_t i = threadIdx.x; i < NCH; i += blockDim.x)
+      {
+         limb_t x0, x1;
+         if (stA) { ld2(x0, x1, Ag.x + 2 * i); st2(A.x + 2 * i, x0, x1); A.c[i] = Ag.c[i]; }
+         if (stB) { ld2(x0, x1, Bg.x + 2 * i); st2(B.x + 2 * i, x0, x1); B.c[i] = Bg.c[i]; }
+      }
+      __syncthreads();
    }
-   __syncthreads();
    cs_op_apply(op, A, B, S, T, b, NCH, NW);
 }
 

@@ -1632,14 +1632,17 @@ int mfft_dev_finalize_cs(limb_t *dst, uint32_t dst_stride, const uint32_t *d_dst
 }
 
 int mfft_dev_run_stage_cs_ip(limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
-                             const mfft_batch *d_batch, uint32_t nbatch, void *stream)
+                             const mfft_batch *d_batch, uint32_t nbatch, uint32_t nstaged, void *stream)
 {
    if (!count || !nbatch) return 0;
-   const size_t sm = 2 * ((size_t) g->l * 8 + (size_t) g->l * 2);
+   /* nstaged: how many operands an op of this stage has to stage at most (0..2) */
+   const size_t sm = (size_t)(nstaged > 2 ? 2 : nstaged) * ((size_t) g->l * 8 + (size_t) g->l * 2);
    if (sm > 227 * 1024) { snprintf(g_err, sizeof g_err, "run_stage_cs_ip: l=%u too large for in-place staging", g->l); return -2; }
+   /* big coefficients: few CTAs fit an SM, so each gets more threads to keep the loads in flight */
+   const unsigned threads = (sm > 96 * 1024) ? 1024u : (sm > 40 * 1024) ? 512u : 256u;
    PROF(PC_STAGE, stream);
    CK(cudaFuncSetAttribute(k_stage_cs_ip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-   MFFT_LAUNCH(k_stage_cs_ip, (unsigned)((uint64_t) count * nbatch), 256, sm, (cudaStream_t) stream, slab, cw, *g, d_ops, count, d_batch, nbatch);
+   MFFT_LAUNCH(k_stage_cs_ip, (unsigned)((uint64_t) count * nbatch), threads, sm, (cudaStream_t) stream, slab, cw, *g, d_ops, count, d_batch, nbatch);
    CKL();
    return 0;
 }

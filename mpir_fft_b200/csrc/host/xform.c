@@ -121,7 +121,14 @@ static int big_build(mfft_xform *x, const mfft_sched *s, uint32_t l, const uint8
       mfft_bigpass *bp = &x->bp[x->nbp];
       if (!stage_g[cur])
       {  /* one stage, operands staged whole */
-         bp->sliced = 0; bp->nops = (uint32_t)(st_off[cur + 1] - st_off[cur]);
+         bp->sliced = 0; bp->nops = (uint32_t)(st_off[cur + 1] - st_off[cur]); bp->nstaged = 0;
+         for (k = st_off[cur]; k < st_off[cur + 1]; k++)
+         {
+            const mfft_op *o = &ops[k];
+            const uint32_t hasB = (o->pB != MFFT_NONE && o->pB != o->pA);
+            const uint32_t ns = ((o->pS == o->pA || o->pT == o->pA) ? 1u : 0u) + ((hasB && (o->pS == o->pB || o->pT == o->pB)) ? 1u : 0u);
+            if (ns > bp->nstaged) bp->nstaged = ns;
+         }
          bp->d_ops = (mfft_op *) mfft_upload(ops + st_off[cur], sizeof(mfft_op) * (bp->nops ? bp->nops : 1));
          if (!bp->d_ops) goto done;
          x->nbp++; cur++;
@@ -357,7 +364,7 @@ int mfft_xform_exec(const mfft_xform *x, limb_t *slab, limb_t *dst, void *stream
             if (mfft_dev_run_tiles_sliced(slab, x->d_cw, &x->g, b->gs, b->nchv, b->R, b->d.d_tiles, b->pass.ntiles, b->d.d_pos, b->d.d_ops,
                                           b->d.d_stoff, b->pass.max_npos, b->pass.max_nops, x->d_batch, x->nbatch, stream) != 0) return MPIRFFT_ENODEV;
          }
-         else if (mfft_dev_run_stage_cs_ip(slab, x->d_cw, &x->g, b->d_ops, b->nops, x->d_batch, x->nbatch, stream) != 0) return MPIRFFT_ENODEV;
+         else if (mfft_dev_run_stage_cs_ip(slab, x->d_cw, &x->g, b->d_ops, b->nops, x->d_batch, x->nbatch, b->nstaged, stream) != 0) return MPIRFFT_ENODEV;
       }
       if (mfft_dev_finalize_cs(dst, x->dst_stride, x->d_dst_base, slab, x->d_cw, &x->g, x->d_moves, x->nout, x->d_batch,
                                x->nbatch, x->normalise, stream) != 0) return MPIRFFT_ENODEV;

@@ -13,7 +13,7 @@ typedef struct {
    int sliced;                                    /* 1: multi-layer pass on chunk slices; 0: one stage, operands staged whole */
    uint32_t gs, nchv, R;                          /* sliced: slice stride in chunks, chunks per slice, adjacent slices per CTA */
    mfft_pass pass; struct mfft_dpass d;           /* sliced: tile descriptors (virtual ring of nchv chunks) */
-   mfft_op *d_ops; uint32_t nops;                 /* whole: the stage's ops */
+   mfft_op *d_ops; uint32_t nops, nstaged;        /* whole: the stage's ops; operands an op stages at most (outputs that overwrite inputs) */
 } mfft_bigpass;
 
 typedef struct {

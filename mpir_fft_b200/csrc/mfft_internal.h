@@ -163,7 +163,7 @@ typedef struct { const limb_t *src; uint64_t nlimbs, bits, ncoef; } mfft_split;
  * chunk slices { i0 + gs t } of the tile's coefficients (see mfft_cs_stage.h); the pass descriptors
  * are those of the tile executor for the virtual ring of l/2/gs chunks; a CTA takes R adjacent slices. */
 int  mfft_dev_run_stage_cs_ip(limb_t *slab, int32_t *cw, const mfft_geom *g, const mfft_op *d_ops, uint32_t count,
-                              const mfft_batch *d_batch, uint32_t nbatch, void *stream);
+                              const mfft_batch *d_batch, uint32_t nbatch, uint32_t nstaged, void *stream);
 int  mfft_dev_run_tiles_sliced(limb_t *slab, int32_t *cw, const mfft_geom *g, uint32_t gs, uint32_t nchv, uint32_t R,
                                const mfft_tile *d_tiles, uint32_t ntiles, const uint32_t *d_pos, const mfft_tileop *d_ops,
                                const uint32_t *d_stoff, uint32_t max_npos, uint32_t max_nops,
