@@ -54,9 +54,16 @@ def run_reference_test(lib, name, timeout, device=None):
 GPU_TESTS = [
     ("test_norm", 3777), ("test_mul_2expmod", 3825), ("test_div_2expmod", 3973),
     ("test_lshB_sumdiffmod", 4030), ("test_sumdiff_rshBmod", 4109), ("test_mulmod", 4224),
-    ("test_fft_ifft", 4276), ("test_fft_ifft_mfa", 4767), ("test_fft_ifft_mfa_sqrt2", 4859),
-    ("test_fft_ifft_mfa_truncate_sqrt2", 4668), ("test_mul", 5459),
+    ("test_fft_ifft", 4276), ("test_fft_ifft_mfa", 4767), ("test_fft_ifft_mfa_sqrt2", 4859), ("test_mul", 5459),
 ]
+# Not in the list: test_fft_ifft_mfa_truncate_sqrt2 (4668) draws trunc as a random multiple of n1, not of 2*n1 as
+# the routine requires (2209-2211); with the GMP random stream of the shim the first draw gives an odd number of
+# second-half rows, on which the reference's own FFT_radix2_truncate1 recurses without end (1046, 786-827: no
+# n == 0 case) -- this library rejects such a trunc with a diagnostic.  The sqrt2 MFA pair is compared with the
+# reference on legal truncations in test_gpu_parity.py::test_mfa_sqrt2 and tests/test_schedule.py.  The tests
+# that iterate 100-1000 times over thousands of single-block calls (test_fft_truncate, test_fft_ifft_truncate,
+# test_fft_ifft_mfa_truncate) would take hours through a per-call device round trip and are covered by
+# test_truncated_1d / test_mfa instead.
 
 
 @pytest.mark.gpu
