@@ -57,6 +57,22 @@ def test_emulated_new_mpn_mul6(emu, case):
     assert np.array_equal(r, L.gmp_mul(a, b))
 
 
+def test_emulated_new_mpn_mul6_vs_golden(emu):
+    """new_mpn_mul6 products of the compiled reference, committed as fixtures (tests/golden)"""
+    import hashlib
+    from golden import make_golden as G
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.npz"))
+    for n1, n2, depth, w, kind in G.PRODUCTS6[:3]:
+        a, b = operand(kind, n1, 0x5EED0001), operand(kind, n2, 0x5EED0002)
+        r = np.zeros(n1 + n2, dtype=np.uint64)
+        emu.new_mpn_mul6(ptr(r), ptr(a), n1, ptr(b), n2, depth, w)
+        key = "P6_%d_%d_%d_%d_%s" % (n1, n2, depth, w, kind)
+        if key in gold:
+            assert np.array_equal(r, gold[key]), key
+        else:
+            assert hashlib.sha256(r.tobytes()).digest() == gold[key + "_sha256"].tobytes(), key
+
+
 @pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("case", [
     (1500, 1500, 6, 64, "ones"), (3000, 2000, 6, 128, "uniform"), (3000, 3000, 6, 128, "ones"),

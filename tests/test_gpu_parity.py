@@ -433,6 +433,21 @@ def test_new_mpn_mul6(lib, case):
     assert first_diff(got, want) is None, "new_mpn_mul6 %s: (first,last,count)=%s" % (case, first_diff(got, want))
 
 
+def test_new_mpn_mul6_vs_golden(lib):
+    """the committed new_mpn_mul6 fixtures (products of the compiled reference, tests/golden/make_golden.py)"""
+    import hashlib, os
+    from golden import make_golden as G
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.npz"))
+    for n1, n2, depth, w, kind in G.PRODUCTS6:
+        a, b = operand(kind, n1, 0x5EED0001), operand(kind, n2, 0x5EED0002)
+        r = M.new_mpn_mul6(a, b, depth, w)
+        key = "P6_%d_%d_%d_%d_%s" % (n1, n2, depth, w, kind)
+        if key in gold:
+            assert np.array_equal(r, gold[key]), key
+        else:
+            assert hashlib.sha256(r.tobytes()).digest() == gold[key + "_sha256"].tobytes(), key
+
+
 def test_new_mpn_mul6_matches_reference(lib, ref):
     """the reference's own big end-to-end test drives new_mpn_mul6 (mul_fft.c:5559)"""
     n1, n2, depth, w = 50000, 45000, 10, 3
