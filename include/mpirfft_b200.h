@@ -112,7 +112,7 @@ void IFFT_radix2_truncate_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_
 void IFFT_radix2_truncate1_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w,
                                    mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws,
                                    mp_size_t r, mp_size_t c, mp_size_t rs, mp_size_t trunc);
-/* mul_fft.c:1290, 1861  negacyclic transforms (even w; the odd-w sqrt2 path is out of scope) */
+/* mul_fft.c:1290, 1861  negacyclic transforms (even w: twist by powers of two; odd w: by powers of sqrt2^w) */
 void FFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                            mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
 void IFFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n,

@@ -172,13 +172,11 @@ void IFFT_radix2_truncate1_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp
 void FFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                            mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
 { (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  if (w & 1) mfft_die("FFT_radix2_negacyclic", "odd w needs the sqrt2 path, which is out of scope");
   transform_1d("FFT_radix2_negacyclic", MFFT_T_FFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); }
 
 void IFFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                             mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
 { (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  if (w & 1) mfft_die("IFFT_radix2_negacyclic", "odd w needs the sqrt2 path, which is out of scope");
   transform_1d("IFFT_radix2_negacyclic", MFFT_T_IFFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); }
 
 /* ------------------------------- MFA on host pointer tables -------------------------------- */

@@ -353,6 +353,42 @@ static void sqrt2_twiddle(ctx *c, uint32_t src, uint32_t dst, uint64_t row, uint
    }
 }
 
+/* position p <- p * z1^j, z1 = sqrt2^w the 4n-th root of unity (w odd), 0 <= j < 4n:
+   even j a power of two (FFT_twiddle, 926), odd j FFT_twiddle_sqrt2 (972) */
+static void z1pow(ctx *c, uint32_t p, uint64_t j, uint64_t w)
+{
+   const uint64_t NW = c->s->NW, M2 = c->s->M2;
+   if (!(j & 1)) { const uint64_t e = mulmod64((j/2) % M2, w % M2, M2); if (e) emit(c->s, p, MFFT_NONE, p, T(1, e, 0), T0, MFFT_NONE, T0, T0); return; }
+   emit(c->s, p, MFFT_NONE, p, T(1, ((mulmod64(j % (2*M2), w % (2*M2), 2*M2) - 1)/2 + NW/4) % M2, 0), T0, MFFT_NONE, T0, T0);
+   sq2_apply(c, p);
+}
+
+/* FFT_radix2_negacyclic / IFFT_radix2_negacyclic for odd w (1301-1343, 1892-1938): the twist by z1^p
+   needs sqrt2 at the odd positions */
+static void fft_negacyclic_odd(ctx *c, uint32_t p0, uint64_t n, uint64_t w)
+{
+   uint64_t i;
+   for (i = 0; i < n; i++)
+   {
+      z1pow(c, POS(i), i, w); z1pow(c, POS(n + i), n + i, w);
+      fwd_bfly(c, POS(i), POS(n + i), i*w);
+   }
+   fft_full(c, p0, n/2, 2*w, 0, 0);
+   fft_full(c, POS(n), n/2, 2*w, 0, 0);
+}
+
+static void ifft_negacyclic_odd(ctx *c, uint32_t p0, uint64_t n, uint64_t w)
+{
+   uint64_t i;
+   ifft_full(c, p0, n/2, 2*w, 0, 0);
+   ifft_full(c, POS(n), n/2, 2*w, 0, 0);
+   for (i = 0; i < n; i++)
+   {
+      inv_bfly(c, POS(i), POS(n + i), i*w);
+      z1pow(c, POS(i), (4*n - i) % (4*n), w); z1pow(c, POS(n + i), 3*n - i, w);
+   }
+}
+
 int mfft_sched_emit_sqrt2_cols(mfft_sched *s, int inverse, uint64_t n2, uint64_t n1, uint64_t w, uint64_t trunc2, int par, int pad)
 {
    ctx cc, *c = &cc; uint64_t r, NW = s->NW, n = NW/w; uint32_t depth = 0, p0 = 0;
@@ -420,11 +456,13 @@ int mfft_sched_emit(mfft_sched *s, mfft_transform_kind kind, uint32_t p0, uint32
       if (kind == MFFT_T_IFFT_TRUNC1) ifft_trunc1(&c, p0, n, w, r, rs, trunc);
       break;
    case MFFT_T_FFT_NEGACYCLIC:
-      if ((w & 1) || n < 2) return -1;
-      fft_negacyclic(&c, p0, n, w); break;
+      if (n < 2 || ((w & 1) && (s->NW % 4))) return -1;
+      if (w & 1) fft_negacyclic_odd(&c, p0, n, w); else fft_negacyclic(&c, p0, n, w);
+      break;
    case MFFT_T_IFFT_NEGACYCLIC:
-      if ((w & 1) || n < 2) return -1;
-      ifft_negacyclic(&c, p0, n, w); break;
+      if (n < 2 || ((w & 1) && (s->NW % 4))) return -1;
+      if (w & 1) ifft_negacyclic_odd(&c, p0, n, w); else ifft_negacyclic(&c, p0, n, w);
+      break;
    default: return -1;
    }
    return 0;

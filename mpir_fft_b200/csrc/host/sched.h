@@ -34,8 +34,8 @@ typedef enum {
    MFFT_T_IFFT,             /* IFFT_radix2 / IFFT_radix2_twiddle          mul_fft.c:1444, 1964 */
    MFFT_T_IFFT_TRUNC,       /* IFFT_radix2_truncate(_twiddle)            mul_fft.c:1674, 1733 */
    MFFT_T_IFFT_TRUNC1,      /* IFFT_radix2_truncate1(_twiddle)           mul_fft.c:1538, 1604 */
-   MFFT_T_FFT_NEGACYCLIC,   /* FFT_radix2_negacyclic (even w)            mul_fft.c:1290 */
-   MFFT_T_IFFT_NEGACYCLIC   /* IFFT_radix2_negacyclic (even w)           mul_fft.c:1861 */
+   MFFT_T_FFT_NEGACYCLIC,   /* FFT_radix2_negacyclic (even or odd w)     mul_fft.c:1290 */
+   MFFT_T_IFFT_NEGACYCLIC   /* IFFT_radix2_negacyclic (even or odd w)    mul_fft.c:1861 */
 } mfft_transform_kind;
 
 /* S = number of logical positions, NW = n*w of the ring */

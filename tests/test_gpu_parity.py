@@ -508,9 +508,10 @@ def test_sqrt2_butterflies(lib, ref):
 
 
 # ---- direct-symbol checks of the entry points that were only reached through other paths ----
-@pytest.mark.parametrize("n,w", [(16, 8), (64, 2), (32, 64), (8, 256)])
+@pytest.mark.parametrize("n,w", [(16, 8), (64, 2), (32, 64), (8, 256), (64, 1), (64, 3), (4096, 1), (1024, 5)])
 def test_negacyclic_symbols(lib, ref, n, w):
-    """FFT/IFFT_radix2_negacyclic (mul_fft.c:1290, 1861; even w) against the compiled reference"""
+    """FFT/IFFT_radix2_negacyclic (mul_fft.c:1290, 1861) against the compiled reference; odd w twists by
+    powers of sqrt2^w (the reference's test_fft_ifft_negacyclic runs depth 11, w 1)"""
     rng = np.random.default_rng(n * w + 1)
     l, N = n * w // 64, 2 * n
     for name in ("FFT_radix2_negacyclic", "IFFT_radix2_negacyclic"):
