@@ -78,6 +78,11 @@ void FFT_radix2_mfa_truncate_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, m
                                    mp_limb_t **t2, mp_limb_t **temp, mp_size_t n1, mp_size_t trunc);
 void IFFT_radix2_mfa_truncate_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
                                     mp_limb_t **t2, mp_limb_t **temp, mp_size_t n1, mp_size_t trunc);
+/* mul_fft.c:2078 / 2461  the untruncated pair (= trunc 4n) */
+void FFT_radix2_mfa_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                          mp_limb_t **temp, mp_size_t n1);
+void IFFT_radix2_mfa_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                           mp_limb_t **temp, mp_size_t n1);
 
 /* mul_fft.c:786 / 1444  length-2n radix-2 FFT (output bit-reversed) and its inverse (unscaled) */
 void FFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
@@ -93,6 +98,16 @@ void IFFT_radix2_truncate(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_
                           mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
 void IFFT_radix2_truncate1(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                            mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
+/* mul_fft.c:839, 1488, 1230, 1792  length-4n transforms with the 4n-th root of unity sqrt2^w (trunc even,
+ * in (2n, 4n]; even w falls back to the plain transforms with root 2^(w/2), as in the reference) */
+void FFT_radix2_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                      mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
+void IFFT_radix2_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                       mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
+void FFT_radix2_truncate_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                               mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
+void IFFT_radix2_truncate_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                                mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
 /* mul_fft.c:1397, 1964 (mul_fft.h:73-79), 1179, 1076, 1733, 1604  strided + twisted variants */
 void FFT_radix2_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
                         mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c,

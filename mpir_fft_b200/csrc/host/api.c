@@ -179,6 +179,39 @@ void IFFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_siz
 { (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
   transform_1d("IFFT_radix2_negacyclic", MFFT_T_IFFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); }
 
+/* 1-D transforms of length 4n with the root sqrt2^w (mul_fft.c:839, 1488, 1230, 1792) */
+static void transform_sqrt2_1d(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_size_t trunc)
+{
+   uint32_t S, k; mfft_sched *s; mp_limb_t **tab;
+   check_ring(fn, n, w);
+   S = (uint32_t)(4*n);
+   s = mfft_sched_new(S, (uint64_t) n*w);
+   tab = (mp_limb_t **) malloc(sizeof(mp_limb_t *) * S);
+   if (!s || !tab) mfft_die(fn, "out of host memory");
+   if (mfft_sched_emit_sqrt2_1d(s, inverse, (uint64_t) n, w, (uint64_t) trunc) != 0)
+      mfft_die(fn, "illegal transform parameters (n=%ld w=%lu trunc=%ld; trunc must be even, 2n < trunc <= 4n, 4 | n*w)",
+               (long) n, (unsigned long) w, (long) trunc);
+   for (k = 0; k < S; k++) tab[k] = ii[k];
+   run_on_host_blocks(fn, s, (uint32_t)((uint64_t) n*w/64), tab, tab, 0, 0);
+   free(tab);
+}
+
+void FFT_radix2_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                      mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp; transform_sqrt2_1d("FFT_radix2_sqrt2", 0, ii, n, w, 4*n); }
+
+void IFFT_radix2_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                       mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp; transform_sqrt2_1d("IFFT_radix2_sqrt2", 1, ii, n, w, 4*n); }
+
+void FFT_radix2_truncate_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                               mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp; transform_sqrt2_1d("FFT_radix2_truncate_sqrt2", 0, ii, n, w, trunc); }
+
+void IFFT_radix2_truncate_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
+                                mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
+{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp; transform_sqrt2_1d("IFFT_radix2_truncate_sqrt2", 1, ii, n, w, trunc); }
+
 /* ------------------------------- MFA on host pointer tables -------------------------------- */
 static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_size_t n1,
                      mp_size_t trunc, int truncated, int sqrt2)
@@ -330,6 +363,15 @@ void FFT_twiddle(mp_limb_t *r, mp_limb_t *i1, mp_size_t i, mp_size_t n, mp_bitcn
    l = (uint64_t) n*w/64; e = ((uint64_t) i % (2*(uint64_t) n)) * w;
    two_block_op("FFT_twiddle", (uint32_t) l, r, NULL, i1, NULL, 1, e, 0, 0, 0, 0, 0, 0, 0);
 }
+
+/* mul_fft.c:2078 / 2461: the untruncated pair is the truncated one at trunc = 4n */
+void FFT_radix2_mfa_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                          mp_limb_t **temp, mp_size_t n1)
+{ (void) t1; (void) t2; (void) temp; mfa_host("FFT_radix2_mfa_sqrt2", 0, ii, n, w, n1, 4*n, 1, 1); }
+
+void IFFT_radix2_mfa_sqrt2(mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1, mp_limb_t **t2,
+                           mp_limb_t **temp, mp_size_t n1)
+{ (void) t1; (void) t2; (void) temp; mfa_host("IFFT_radix2_mfa_sqrt2", 1, ii, n, w, n1, 4*n, 1, 1); }
 
 /* ---- sqrt2 butterflies (mul_fft.c:591, 673, 972): z1^i = 2^e (2^(nw/2) - 1), e = (i w - 1)/2 + nw/4 ---- */
 static void sqrt2_check(const char *fn, mp_size_t i, mp_size_t n, mp_bitcnt_t w)

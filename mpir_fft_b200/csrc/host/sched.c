@@ -389,6 +389,54 @@ static void ifft_negacyclic_odd(ctx *c, uint32_t p0, uint64_t n, uint64_t w)
    }
 }
 
+/* FFT_radix2_sqrt2 / FFT_radix2_truncate_sqrt2 / IFFT_radix2_sqrt2 / IFFT_radix2_truncate_sqrt2
+   (mul_fft.c:839, 1230, 1488, 1792): length 4n over positions 0..4n-1 (stride 1), root z1 = sqrt2^w.
+   trunc in (2n, 4n], even; outputs in the bit-reversed order of the two halves, like FFT_radix2. */
+int mfft_sched_emit_sqrt2_1d(mfft_sched *s, int inverse, uint64_t n, uint64_t w, uint64_t trunc)
+{
+   ctx cc, *c = &cc; uint64_t j, NW = s->NW, tr2; uint32_t p0 = 0;
+   c->s = s; c->is = 1; c->ws = 0; c->cmul = 1; c->cadd = 0;
+   if (n < 2 || (n & (n - 1)) || n*w != NW || s->S != 4*n || trunc <= 2*n || trunc > 4*n || (trunc & 1)) return -1;
+   if (!(w & 1))
+   {  /* the root is the power of two 2^(w/2): the plain transforms of length 2*(2n) (851-856, 1244-1248) */
+      if (trunc == 4*n) return mfft_sched_emit(s, inverse ? MFFT_T_IFFT : MFFT_T_FFT, 0, 1, 2*n, w/2, 0, 0, 0, 0);
+      return mfft_sched_emit(s, inverse ? MFFT_T_IFFT_TRUNC : MFFT_T_FFT_TRUNC, 0, 1, 2*n, w/2, 0, 0, 0, trunc);
+   }
+   if (NW % 4) return -1;
+   tr2 = trunc - 2*n;
+   if (!inverse)
+   {
+      for (j = 0; j < tr2; j++)
+      {
+         emit(s, (uint32_t) j, (uint32_t)(2*n + j), (uint32_t) j, T(1, 0, 0), T(1, 0, 0), (uint32_t)(2*n + j), T(1, 0, 0), T(-1, 0, 0));
+         z1pow(c, (uint32_t)(2*n + j), j, w);
+      }
+      for (; j < 2*n; j++)
+      {  /* the partner is zero: second half = z1^j * first half (1271-1278) */
+         emit(s, (uint32_t) j, MFFT_NONE, (uint32_t)(2*n + j), T(1, 0, 0), T0, MFFT_NONE, T0, T0);
+         z1pow(c, (uint32_t)(2*n + j), j, w);
+      }
+      fft_full(c, p0, n, w, 0, 0);
+      { uint32_t p0 = (uint32_t)(2*n); if (tr2 == 2*n) fft_full(c, p0, n, w, 0, 0); else fft_trunc1(c, p0, n, w, 0, 0, tr2); }
+   } else
+   {
+      ifft_full(c, p0, n, w, 0, 0);
+      for (j = tr2; j < 2*n; j++)
+      {
+         emit(s, (uint32_t) j, MFFT_NONE, (uint32_t)(2*n + j), T(1, 0, 0), T0, MFFT_NONE, T0, T0);
+         z1pow(c, (uint32_t)(2*n + j), j, w);
+      }
+      { uint32_t p0 = (uint32_t)(2*n); if (tr2 == 2*n) ifft_full(c, p0, n, w, 0, 0); else ifft_trunc1(c, p0, n, w, 0, 0, tr2); }
+      for (j = 0; j < tr2; j++)
+      {
+         z1pow(c, (uint32_t)(2*n + j), (4*n - j) % (4*n), w);
+         emit(s, (uint32_t) j, (uint32_t)(2*n + j), (uint32_t) j, T(1, 0, 0), T(1, 0, 0), (uint32_t)(2*n + j), T(1, 0, 0), T(-1, 0, 0));
+      }
+      for (; j < 2*n; j++) emit(s, (uint32_t) j, MFFT_NONE, (uint32_t) j, T(1, 1, 0), T0, MFFT_NONE, T0, T0);
+   }
+   return 0;
+}
+
 int mfft_sched_emit_sqrt2_cols(mfft_sched *s, int inverse, uint64_t n2, uint64_t n1, uint64_t w, uint64_t trunc2, int par, int pad)
 {
    ctx cc, *c = &cc; uint64_t r, NW = s->NW, n = NW/w; uint32_t depth = 0, p0 = 0;

@@ -57,6 +57,9 @@ int  mfft_sched_emit(mfft_sched *s, mfft_transform_kind kind, uint32_t p0, uint3
  * classes must leave every position in the same slab half). */
 int  mfft_sched_emit_sqrt2_cols(mfft_sched *s, int inverse, uint64_t n2, uint64_t n1, uint64_t w, uint64_t trunc2, int par, int pad);
 
+/* the 1-D transforms of length 4n with the root sqrt2^w (mul_fft.c:839, 1230, 1488, 1792); S = 4n */
+int  mfft_sched_emit_sqrt2_1d(mfft_sched *s, int inverse, uint64_t n, uint64_t w, uint64_t trunc);
+
 /* Emit one explicit op: position pS <- sSA*A*2^eSA + sSB*B*2^eSB and (optionally) position
  * pT <- sTA*A*2^eTA + sTB*B*2^eTB, A/B = current contents of positions posA/posB (posB and pT
  * may be MFFT_NONE).  Exponents are bit counts mod 2*NW. */

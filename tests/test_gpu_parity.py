@@ -471,10 +471,12 @@ def test_mfa_sqrt2(lib, ref, n, w, n1, trunc):
         data = rand_blocks(rng, N, l)
         if not inverse:
             data[trunc:] = 0
-        name = ("I" if inverse else "") + "FFT_radix2_mfa_truncate_sqrt2"
+        full = (trunc == 4 * n)         # the untruncated entry points (2078, 2461) take no trunc
+        name = ("I" if inverse else "") + ("FFT_radix2_mfa_sqrt2" if full else "FFT_radix2_mfa_truncate_sqrt2")
         s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
-        getattr(ref, name)(s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, cl(n1), cl(trunc))
-        getattr(lib, name)(s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, cl(n1), cl(trunc))
+        extra = () if full else (cl(trunc),)
+        getattr(ref, name)(s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, cl(n1), *extra)
+        getattr(lib, name)(s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, cl(n1), *extra)
         r1, r2 = residues(s1.all(), l), residues(s2.all(), l)
         idx = [i * n1 + j for i in rows for j in range(n1)] if not inverse else list(range(trunc))
         assert [r1[k] for k in idx] == [r2[k] for k in idx], name
@@ -562,3 +564,21 @@ def test_mfa_at_bench_rings(lib, ref, n, w, n1, trunc):
             assert block_to_int(a1[k], l) == block_to_int(a2[k], l), (name, k)
         sample = idx if len(idx) < 4000 else idx[::7]
         assert [block_to_int(a1[k], l) for k in sample] == [block_to_int(a2[k], l) for k in sample], name
+
+
+@pytest.mark.parametrize("n,w,trunc", [(64, 1, 256), (64, 1, 130), (64, 3, 192), (16, 4, 50), (1024, 1, 4096), (2048, 1, 2 * 2048 + 1234)])
+def test_sqrt2_1d_symbols(lib, ref, n, w, trunc):
+    """FFT/IFFT_radix2_sqrt2, FFT/IFFT_radix2_truncate_sqrt2 (mul_fft.c:839, 1488, 1230, 1792) vs the compiled reference"""
+    rng = np.random.default_rng(n + w + trunc)
+    l, N = n * w // 64, 4 * n
+    full = trunc == 4 * n
+    for inverse in (0, 1):
+        data = rand_blocks(rng, N, l)
+        if not inverse:
+            data[trunc:] = 0
+        name = ("I" if inverse else "") + ("FFT_radix2_sqrt2" if full else "FFT_radix2_truncate_sqrt2")
+        s1, s2 = oracle.Slab(N, l, data), oracle.Slab(N, l, data)
+        extra = () if full else (cl(trunc),)
+        getattr(ref, name)(s1.ii, cl(1), s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, *extra)
+        getattr(lib, name)(s2.ii, cl(1), s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, *extra)
+        assert residues(s1.all()[:trunc], l) == residues(s2.all()[:trunc], l), name
