@@ -432,6 +432,15 @@ __device__ __forceinline__ void cp_async16(limb_t *sdst, const limb_t *gsrc)
    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
 #endif
 }
+__device__ __forceinline__ void cp_async8(limb_t *sdst, const limb_t *gsrc)
+{
+#ifdef MFFT_EMU
+   sdst[0] = gsrc[0];
+#else
+   const uint32_t sa = (uint32_t) __cvta_generic_to_shared(sdst);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gsrc) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async4(int32_t *sdst, const int32_t *gsrc)
 {
 #ifdef MFFT_EMU
@@ -1055,7 +1064,8 @@ struct tile_params {
 template <int NT>
 __device__ __forceinline__ void tile_fill(limb_t *coef, const uint32_t *spos, uint32_t npos, limb_t *slab, const mfft_geom &g,
                                           const mfft_batch &b, const tile_params &TP, bool bulk_tile,
-                                          uint32_t tid, uint32_t nthreads, uint32_t warp, uint32_t nwarps, uint32_t lane)
+                                          uint32_t tid, uint32_t nthreads, uint32_t warp, uint32_t nwarps, uint32_t lane,
+                                          uint32_t bar_id, uint32_t bar_threads)
 {
    constexpr uint32_t L = tile_cfg<NT>::L, NCH = tile_cfg<NT>::NCH, SP = tile_cfg<NT>::SP;
    if (TP.split)
@@ -1065,6 +1075,42 @@ __device__ __forceinline__ void tile_fill(limb_t *coef, const uint32_t *spos, ui
          consecutive limbs, four coefficients are in flight per thread */
       const uint32_t blimbs = (uint32_t)((TP.split_bits + 63) >> 6);     /* limbs that receive bits */
       const limb_t lastmask = (TP.split_bits & 63) ? (((limb_t) 1 << (TP.split_bits & 63)) - 1) : ~(limb_t) 0;
+      if (2 * blimbs + 1 <= SP)
+      {  /* staged variant: the blimbs+1 raw operand limbs of every coefficient go by 8-byte asynchronous
+            copies into the upper end of the coefficient's own buffer (nobody waits on a register for
+            them), then they are shifted into place from shared memory, then the rest is zeroed */
+         const uint32_t raw = blimbs + 1, STG = SP - raw;
+         for (uint32_t t = tid; t < npos * raw; t += nthreads)
+         {
+            const uint32_t p = t / raw, k = t % raw, pp = spos[p];
+            if (!(pp & MFFT_TILE_LOAD)) continue;
+            const uint64_t i = (uint64_t) b.base + (uint64_t)(pp & MFFT_TILE_POSMASK) * g.slot_stride;
+            const uint64_t q = ((i * TP.split_bits) >> 6) + k;
+            limb_t *d = coef + (size_t) p * SP + STG + k;
+            if (i < TP.split_ncoef && q < TP.split_nlimbs) cp_async8(d, TP.split_src + q); else *d = 0;
+         }
+         cp_async_wait_all();
+         tile_sync(bar_id, bar_threads);
+         for (uint32_t t = tid; t < npos * blimbs; t += nthreads)
+         {
+            const uint32_t p = t / blimbs, k = t % blimbs, pp = spos[p];
+            if (!(pp & MFFT_TILE_LOAD)) continue;
+            const uint64_t i = (uint64_t) b.base + (uint64_t)(pp & MFFT_TILE_POSMASK) * g.slot_stride;
+            const uint32_t r = (uint32_t)((i * TP.split_bits) & 63);
+            const limb_t *st = coef + (size_t) p * SP + STG;
+            limb_t v = st[k] >> r;
+            if (r) v |= st[k + 1] << (64 - r);
+            if (k + 1 == blimbs) v &= lastmask;
+            coef[(size_t) p * SP + k] = v;
+         }
+         tile_sync(bar_id, bar_threads);
+         for (uint32_t t = tid; t < npos * (SP - blimbs); t += nthreads)
+         {
+            const uint32_t p = t / (SP - blimbs), k = blimbs + t % (SP - blimbs);
+            if (spos[p] & MFFT_TILE_LOAD) coef[(size_t) p * SP + k] = 0;
+         }
+      } else
+      {
       for (uint32_t p0 = 0; p0 < npos; p0 += 4)
       {
          uint64_t qb[4]; uint32_t rr[4]; bool ld[4], nz[4];
@@ -1106,6 +1152,7 @@ __device__ __forceinline__ void tile_fill(limb_t *coef, const uint32_t *spos, ui
       }
       for (uint32_t t = tid; t < npos * NCH; t += nthreads)
          if (spos[t / NCH] & MFFT_TILE_LOAD) reinterpret_cast<int32_t *>(coef + (size_t)(t / NCH) * SP + tile_cfg<NT>::CW)[t % NCH] = 0;
+      }
    } else
    if (bulk_tile)
    {  /* the block images are on their way; meanwhile zero the carry words (they live behind the image) */
@@ -1218,7 +1265,7 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
    const bool bulk_tile = al16 && !TP.split && g.pitch >= L + 2;      /* whole block images by bulk copy */
    if (warp == 0)     /* one warp issues the tile's copies */
       tile_issue<NT>(mbar, sops, coef, T, [&](uint32_t p) { return spos[p]; }, ops, slab, g, b, bulk_tile, lane);
-   tile_fill<NT>(coef, spos, T.npos, slab, g, b, TP, bulk_tile, tid, blockDim.x, warp, nwarps, lane);
+   tile_fill<NT>(coef, spos, T.npos, slab, g, b, TP, bulk_tile, tid, blockDim.x, warp, nwarps, lane, 0u, 0u);
    TILE_STAMP(1);
    mbar_wait(mbar, 0);
    if (bulk_tile)
@@ -1336,7 +1383,7 @@ k_run_tiles_p(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, co
          for (uint32_t q = gtid; q <= T.nstages; q += 128) sst[q] = stoff[T.pad + q];
       }
       tile_sync(1 + grp, 128);
-      tile_fill<NT>(coef, spos, T.npos, slab, g, b, TP, bulk_tile, gtid, 128, gwarp, 4, lane);
+      tile_fill<NT>(coef, spos, T.npos, slab, g, b, TP, bulk_tile, gtid, 128, gwarp, 4, lane, 1 + grp, 128);
       mbar_wait(mbar, use & 1u);
       if (bulk_tile)
       {  /* last carry word = the block's signed top limb, which arrived with the image */
