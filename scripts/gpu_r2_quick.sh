@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU check of a kernel change: parity tests, then the default bench line without the large sharded leg
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_sharded.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
 for wl in cfg2 cfg1 cfg3; do
 timeout 600 python bench.py --workload $wl --steps 20 --warmup 3 --no-sharded-leg --no-cpu-baseline > gpurun_out/bench_$wl.log 2> gpurun_out/bench_$wl.err; echo "bench $wl rc=$?"
