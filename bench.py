@@ -444,7 +444,7 @@ def main():
             achieved = (by[0] / ln[0]) / (avg_ms * 1e-3) / 1e9
             roofline = {"kernel": "k_run_tiles (one fused MFA pass: several radix-2 layers in shared memory)", "bound": "hbm",
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "traffic_source": "profiles/r01_ncu_tiles_summary.csv: mean dram read+write bytes "
+                        "traffic": traffic, "traffic_source": "profiles/r02_ncu_tiles_summary.csv: mean dram read+write bytes "
                         "per launch over the captured passes (ncu --set full, cold L2)" if traffic else None,
                         "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)",
                         "alg_bytes_per_launch": by[0] / ln[0], "avg_launch_us": avg_ms * 1e3,
