@@ -40,13 +40,26 @@ print("PASS", sys.argv[3], "kernel launches:", ours.mpirfft_launch_count())
 """
 
 
+def start_reference_test(lib, name, device=None):
+    args = [sys.executable, "-c", DRIVER, lib, REF, name] + ([str(device)] if device is not None else [])
+    return subprocess.Popen(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+def finish_reference_test(proc, name, timeout):
+    try:
+        out, err = proc.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+        out, err = proc.communicate()
+        raise AssertionError((name, "timeout", out[-400:], err[-400:]))
+    assert proc.returncode == 0 and ("PASS " + name) in out, (name, proc.returncode, out[-800:], err[-800:])
+    assert "error" not in out.lower() and "wrong" not in out.lower(), out[-800:]
+
+
 def run_reference_test(lib, name, timeout, device=None):
     if not os.path.exists(REF):
         pytest.skip("oracle/_ref not built")
-    args = [sys.executable, "-c", DRIVER, lib, REF, name] + ([str(device)] if device is not None else [])
-    r = subprocess.run(args, capture_output=True, text=True, timeout=timeout)
-    assert r.returncode == 0 and ("PASS " + name) in r.stdout, (name, r.returncode, r.stdout[-800:], r.stderr[-800:])
-    assert "error" not in r.stdout.lower() and "wrong" not in r.stdout.lower(), r.stdout[-800:]
+    finish_reference_test(start_reference_test(lib, name, device), name, timeout)
 
 
 # what each reference test drives (mul_fft.c line): single-block primitives, 1-D and MFA transforms incl.
@@ -66,10 +79,23 @@ GPU_TESTS = [
 # test_truncated_1d / test_mfa instead.
 
 
+@pytest.fixture(scope="module")
+def gpu_runs():
+    """all reference tests are started at once, each in its own process (they are host-bound: thousands
+    of small calls), and collected one by one"""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref not built")
+    procs = {name: start_reference_test(OURS, name, device=0) for name, _ in GPU_TESTS}
+    yield procs
+    for p in procs.values():
+        if p.poll() is None:
+            p.kill()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,line", GPU_TESTS)
-def test_reference_test_passes_against_this_library(name, line):
-    run_reference_test(OURS, name, timeout=900, device=0)
+def test_reference_test_passes_against_this_library(gpu_runs, name, line):
+    finish_reference_test(gpu_runs[name], name, timeout=900)
 
 
 @pytest.mark.parametrize("name", ["test_norm", "test_lshB_sumdiffmod", "test_fft_ifft"])
