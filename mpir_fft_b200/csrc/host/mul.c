@@ -159,11 +159,13 @@ static int plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, mp_bi
    if (sqrt2)
    {  /* FFT/IFFT_radix2_mfa_truncate_sqrt2 (3619, 3625, 3656); / 2^(depth+2) and the normalisation
          (3659-3663) folded into the last inverse pass */
+      mfft_mfa_promise_zero_inputs(pl->p.j1 > pl->p.j2 ? pl->p.j1 : pl->p.j2);     /* one plan serves both operands */
       if ((rc = mfft_mfa_build_sqrt2(&pl->fwd, 0, pl->p.n, w, pl->p.sqrt, pl->p.trunc, 0, 1)) != 0) goto fail;
       if ((rc = mfft_mfa_build_sqrt2(&pl->inv, 1, pl->p.n, w, pl->p.sqrt, pl->p.trunc,
                                      (uint32_t)(128ull*pl->l - (depth + 2)), 1)) != 0) goto fail;
    } else
    {
+   mfft_mfa_promise_zero_inputs(pl->p.j1 > pl->p.j2 ? pl->p.j1 : pl->p.j2);        /* one plan serves both operands */
    if ((rc = mfft_mfa_build(&pl->fwd, 0, pl->p.n, w, pl->p.sqrt, pl->p.trunc, 0, 1)) != 0) goto fail;
    /* the inverse is unscaled: fold / 2^(depth+1) and the normalisation into its last pass (3256-3260) */
    if ((rc = mfft_mfa_build(&pl->inv, 1, pl->p.n, w, pl->p.sqrt, pl->p.trunc,

@@ -132,6 +132,15 @@ int mfft_dsched_run(const mfft_dsched *ds, limb_t *slab, const mfft_geom *g,
    return 0;
 }
 
+/* consumed by the next forward plan (under the library lock) */
+#define MFFT_ZERO_PROMISE_DEFAULT 0
+static uint64_t g_promise_nz = 0;
+void mfft_mfa_promise_zero_inputs(uint64_t nz)
+{
+   const char *e = getenv("MPIRFFT_ZERO_PROMISE");       /* 0 / 1; see MFFT_ZERO_PROMISE_DEFAULT */
+   g_promise_nz = (e ? (e[0] != '0') : MFFT_ZERO_PROMISE_DEFAULT) ? nz : 0;
+}
+
 static uint32_t ilog2(uint64_t x) { uint32_t b = 0; while (((uint64_t)1 << b) < x) b++; return b; }
 
 static void dpass_free(struct mfft_dpass *d, uint32_t n)
@@ -224,6 +233,9 @@ int mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1,
 
    if (!inverse)
    {
+      /* rows that the split leaves zero (position-view plans only: the ping-pong view keeps every op) */
+      if (g_promise_nz && m->fused && (g_promise_nz + n1 - 1)/n1 < n2 && mfft_sched_zero_from(cs, (uint32_t)((g_promise_nz + n1 - 1)/n1)) != 0)
+      { rc = MPIRFFT_ENOMEM; goto fail; }
       /* column FFTs with the fused twist (2374-2379), then the row relabel (2380-2389) */
       if (mfft_sched_emit(cs, trunc ? MFFT_T_FFT_TRUNC : MFFT_T_FFT, 0, 1, n2/2, w*n1, w, 0, 1, m->trunc_rows) != 0) goto fail;
       mfft_sched_revbin(cs, 0, 1, m->depth1);
@@ -357,6 +369,7 @@ int mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1
                    uint32_t final_shift, int normalise)
 {
    int rc = mfft_mfa_plan(m, inverse, n, w, n1, trunc, final_shift, normalise, 0);
+   g_promise_nz = 0;
    if (rc != 0) return rc;
    if ((rc = mfft_mfa_upload(m)) != 0) { mfft_mfa_free(m); return rc; }
    return 0;
@@ -417,6 +430,9 @@ int mfft_mfa_plan_sqrt2(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64
    }
    if (!inverse)
    {
+      for (cl = 0; cl < (uint32_t) m->nclass; cl++)
+         if (g_promise_nz && m->fused && (g_promise_nz + n1 - 1)/n1 < 2*n2 && mfft_sched_zero_from(cs[cl], (uint32_t)((g_promise_nz + n1 - 1)/n1)) != 0)
+         { rc = MPIRFFT_ENOMEM; goto fail; }
       for (cl = 0; cl < (uint32_t) m->nclass; cl++)
          if (mfft_sched_emit_sqrt2_cols(cs[cl], 0, n2, n1, w, trunc2, m->nclass == 2 ? (int) cl : -1, !m->fused) != 0) goto fail;
       /* row FFTs on the valid rows, then the in-row relabel (2289-2303, 2341-2354) */
@@ -513,6 +529,7 @@ int mfft_mfa_build_sqrt2(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint6
                          uint32_t final_shift, int normalise)
 {
    int rc = mfft_mfa_plan_sqrt2(m, inverse, n, w, n1, trunc, final_shift, normalise, 0);
+   g_promise_nz = 0;
    if (rc != 0) return rc;
    if ((rc = mfft_mfa_upload(m)) != 0) { mfft_mfa_free(m); return rc; }
    return 0;

@@ -71,6 +71,9 @@ typedef struct {
  * allows (MPIRFFT_UNFUSED=1 in the environment overrides), 1 = one launch per radix-2 stage. */
 int  mfft_mfa_plan(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
                    uint32_t final_shift, int normalise, int mode);
+/* nz (forward transforms): only the first nz input coefficients (reference order) can be non-zero -- the
+ * split of an operand, mul_fft.c:3234-3236; 0 = no such promise.  Set before planning. */
+void mfft_mfa_promise_zero_inputs(uint64_t nz);
 int  mfft_mfa_upload(mfft_mfa *m);
 int  mfft_mfa_build(mfft_mfa *m, int inverse, uint64_t n, uint64_t w, uint64_t n1, uint64_t trunc,
                     uint32_t final_shift, int normalise);

@@ -48,13 +48,22 @@ void mfft_sched_free(mfft_sched *s)
 {
    if (!s) return;
    free(s->slot); free(s->wr_stage); free(s->rd_stage); free(s->ops); free(s->stage_off);
-   free(s->phys); free(s->pwr_stage); free(s->prd_stage); free(s);
+   free(s->phys); free(s->pwr_stage); free(s->prd_stage); free(s->zero); free(s);
+}
+
+int mfft_sched_zero_from(mfft_sched *s, uint32_t first)
+{
+   uint32_t k;
+   if (!s->zero && !(s->zero = (uint8_t *) calloc(s->S ? s->S : 1, 1))) return -1;
+   for (k = first; k < s->S; k++) s->zero[k] = 1;
+   return 0;
 }
 
 void mfft_sched_swap(mfft_sched *s, uint32_t a, uint32_t b)
 {
    uint32_t t = s->slot[a]; s->slot[a] = s->slot[b]; s->slot[b] = t;
    t = s->phys[a]; s->phys[a] = s->phys[b]; s->phys[b] = t;
+   if (s->zero) { uint8_t z = s->zero[a]; s->zero[a] = s->zero[b]; s->zero[b] = z; }
 }
 
 void mfft_sched_revbin(mfft_sched *s, uint32_t p0, uint32_t is, uint32_t bits)
@@ -80,6 +89,35 @@ static void emit(mfft_sched *s, uint32_t posA, uint32_t posB, uint32_t pS, term 
                  uint32_t pT, term ta, term tb)
 {
    mfft_op *op; uint32_t st = 0, S = s->S;
+   if (s->zero)
+   {  /* known zeros: drop zero operands; an output without a term left is zero and costs nothing */
+      int sz, tz;
+      if (posB != MFFT_NONE && s->zero[posB]) { posB = MFFT_NONE; sb = T0; tb = T0; }
+      if (s->zero[posA])
+      {
+         if (posB == MFFT_NONE) { s->zero[pS] = 1; if (pT != MFFT_NONE) s->zero[pT] = 1; return; }
+         posA = posB; sa = sb; ta = tb; posB = MFFT_NONE; sb = T0; tb = T0;      /* only B contributes */
+      }
+      if (posB == MFFT_NONE) { sb = T0; tb = T0; }
+      sz = (sa.sign == 0 && sb.sign == 0);
+      tz = (pT == MFFT_NONE) || (ta.sign == 0 && tb.sign == 0);
+      if (sz && tz) { s->zero[pS] = 1; if (pT != MFFT_NONE) s->zero[pT] = 1; return; }
+      if (sz) { s->zero[pS] = 1; pS = pT; sa = ta; sb = tb; pT = MFFT_NONE; ta = T0; tb = T0; }
+      else if (pT != MFFT_NONE && tz) { s->zero[pT] = 1; pT = MFFT_NONE; ta = T0; tb = T0; }
+      /* "x + 0" in place: no work, but the position keeps its place in the layer structure (its
+         in-place stage advances as if the op were there), so that the layers of the two halves of a
+         transform stay aligned and the pass windows keep their shape */
+      if (posB == MFFT_NONE && pS == posA && sa.sign == 1 && sa.e % s->M2 == 0 && sa.c % s->M2 == 0)
+      {
+         const uint32_t ph = s->phys[pS];
+         uint32_t g = umax(s->pwr_stage[ph], s->prd_stage[ph]) + 1;
+         s->pwr_stage[ph] = g; s->prd_stage[ph] = umax(s->prd_stage[ph], g);
+         if (g > s->npstages) s->npstages = g;
+         if (pT == MFFT_NONE) { s->zero[pS] = 0; return; }
+         pS = pT; sa = ta; pT = MFFT_NONE; ta = T0;            /* only the other output is work */
+      }
+      s->zero[pS] = 0; if (pT != MFFT_NONE) s->zero[pT] = 0;
+   }
    if (s->nops == s->cap)
    {
       s->cap *= 2; s->ops = (mfft_op *) realloc(s->ops, sizeof(mfft_op) * s->cap);

@@ -25,6 +25,9 @@ typedef struct {
    uint32_t *pwr_stage;  /* [S] last pstage that wrote the physical position */
    uint32_t *prd_stage;  /* [S] last pstage that read it */
    uint32_t  npstages;
+   /* known-zero tracking (optional): zero[k] != 0 = logical position k currently holds 0.  emit() then
+      drops zero operands, turns "x + 0 in place" into nothing and ops on zeros into zeros */
+   uint8_t  *zero;
 } mfft_sched;
 
 typedef enum {
@@ -66,6 +69,12 @@ int  mfft_sched_emit_sqrt2_1d(mfft_sched *s, int inverse, uint64_t n, uint64_t w
 void mfft_sched_emit_op(mfft_sched *s, uint32_t posA, uint32_t posB,
                         uint32_t pS, int sSA, uint64_t eSA, int sSB, uint64_t eSB,
                         uint32_t pT, int sTA, uint64_t eTA, int sTB, uint64_t eTB);
+
+/* Declare the logical positions first, first+1, ... as known zeros before emitting a transform: an
+ * operand of new_mpn_mul fills only about half of the truncated length (j1 of trunc coefficients,
+ * mul_fft.c:3234-3236 zero-fills the rest), so the first layers of the forward transform are mostly
+ * "x + 0" and "(x - 0) 2^e". */
+int  mfft_sched_zero_from(mfft_sched *s, uint32_t first);
 
 /* swap the slots of logical positions a and b (the reference's pointer swaps, e.g. 2380-2389) */
 void mfft_sched_swap(mfft_sched *s, uint32_t a, uint32_t b);
