@@ -89,7 +89,8 @@ void FFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bi
                 mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
 void IFFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                  mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp);
-/* mul_fft.c:1128, 1028, 1674, 1538  truncated variants (rr == ii, rs == 1 as in every caller) */
+/* mul_fft.c:1128, 1028, 1674, 1538  truncated variants.  (rr, rs): result k is written into the block
+ * rr[k*rs] points to (every caller of the reference passes rr == ii, rs == 1) */
 void FFT_radix2_truncate(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                          mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc);
 void FFT_radix2_truncate1(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,

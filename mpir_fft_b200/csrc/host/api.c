@@ -87,10 +87,17 @@ static void check_ring(const char *fn, mp_size_t n, mp_bitcnt_t w)
 }
 
 /* all 1-D transforms share this: positions k < 2n are ii[k*is] */
+/* where the results go for the entry points that take (rr, rs): result k into the block rr[k*rs] points
+   to (the reference stores the result pointers there, mul_fft.c:797-802, 821-826; every caller passes
+   rr == ii, rs == 1) */
+static mp_limb_t **g_rr = NULL; static mp_size_t g_rs = 1;
+
 static void transform_1d(const char *fn, mfft_transform_kind kind, mp_limb_t **ii, mp_size_t is, mp_size_t n,
                          mp_bitcnt_t w, mp_size_t ws, mp_size_t r, mp_size_t c, mp_size_t rs, mp_size_t trunc)
 {
-   uint32_t S, k; mfft_sched *s; mp_limb_t **tab;
+   uint32_t S, k; mfft_sched *s; mp_limb_t **tab, **otab = NULL;
+   mp_limb_t **rr = g_rr; const mp_size_t rrs = g_rs;
+   g_rr = NULL; g_rs = 1;
    check_ring(fn, n, w);
    if (is <= 0) mfft_die(fn, "illegal stride %ld", (long) is);
    S = (uint32_t)(2*n);
@@ -101,39 +108,46 @@ static void transform_1d(const char *fn, mfft_transform_kind kind, mp_limb_t **i
       mfft_die(fn, "illegal transform parameters (n=%ld w=%lu trunc=%ld; trunc must be even, 2 <= trunc <= 2n)",
                (long) n, (unsigned long) w, (long) trunc);
    for (k = 0; k < S; k++) tab[k] = ii[(size_t) k*is];
-   run_on_host_blocks(fn, s, (uint32_t)((uint64_t) n*w/64), tab, tab, (uint32_t) c, 0);
-   free(tab);
+   if (rr && (rr != ii || rrs != is))
+   {
+      if (rrs <= 0) mfft_die(fn, "illegal result stride %ld", (long) rrs);
+      otab = (mp_limb_t **) malloc(sizeof(mp_limb_t *) * S);
+      if (!otab) mfft_die(fn, "out of host memory");
+      for (k = 0; k < S; k++) otab[k] = rr[(size_t) k*rrs];
+   }
+   run_on_host_blocks(fn, s, (uint32_t)((uint64_t) n*w/64), tab, otab ? otab : tab, (uint32_t) c, 0);
+   free(tab); free(otab);
 }
 
 void FFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                 mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  transform_1d("FFT_radix2", MFFT_T_FFT, ii, 1, n, w, 0, 0, 0, 0, 0); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs;
+  transform_1d("FFT_radix2", MFFT_T_FFT, ii, 1, n, w, 0, 0, 0, 0, 0); mfft_unlock(); }
 
 void IFFT_radix2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                  mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  transform_1d("IFFT_radix2", MFFT_T_IFFT, ii, 1, n, w, 0, 0, 0, 0, 0); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs;
+  transform_1d("IFFT_radix2", MFFT_T_IFFT, ii, 1, n, w, 0, 0, 0, 0, 0); mfft_unlock(); }
 
 void FFT_radix2_truncate(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                          mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  transform_1d("FFT_radix2_truncate", MFFT_T_FFT_TRUNC, ii, 1, n, w, 0, 0, 0, 0, trunc); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs;
+  transform_1d("FFT_radix2_truncate", MFFT_T_FFT_TRUNC, ii, 1, n, w, 0, 0, 0, 0, trunc); mfft_unlock(); }
 
 void FFT_radix2_truncate1(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                           mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  transform_1d("FFT_radix2_truncate1", MFFT_T_FFT_TRUNC1, ii, 1, n, w, 0, 0, 0, 0, trunc); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs;
+  transform_1d("FFT_radix2_truncate1", MFFT_T_FFT_TRUNC1, ii, 1, n, w, 0, 0, 0, 0, trunc); mfft_unlock(); }
 
 void IFFT_radix2_truncate(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                           mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  transform_1d("IFFT_radix2_truncate", MFFT_T_IFFT_TRUNC, ii, 1, n, w, 0, 0, 0, 0, trunc); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs;
+  transform_1d("IFFT_radix2_truncate", MFFT_T_IFFT_TRUNC, ii, 1, n, w, 0, 0, 0, 0, trunc); mfft_unlock(); }
 
 void IFFT_radix2_truncate1(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                            mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  transform_1d("IFFT_radix2_truncate1", MFFT_T_IFFT_TRUNC1, ii, 1, n, w, 0, 0, 0, 0, trunc); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs;
+  transform_1d("IFFT_radix2_truncate1", MFFT_T_IFFT_TRUNC1, ii, 1, n, w, 0, 0, 0, 0, trunc); mfft_unlock(); }
 
 void FFT_radix2_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp_bitcnt_t w, mp_limb_t **t1,
                         mp_limb_t **t2, mp_limb_t **temp, mp_size_t ws, mp_size_t r, mp_size_t c, mp_size_t rs)
@@ -171,18 +185,20 @@ void IFFT_radix2_truncate1_twiddle(mp_limb_t **ii, mp_size_t is, mp_size_t n, mp
 
 void FFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                            mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  transform_1d("FFT_radix2_negacyclic", MFFT_T_FFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs;
+  transform_1d("FFT_radix2_negacyclic", MFFT_T_FFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); mfft_unlock(); }
 
 void IFFT_radix2_negacyclic(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                             mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp;
-  transform_1d("IFFT_radix2_negacyclic", MFFT_T_IFFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs;
+  transform_1d("IFFT_radix2_negacyclic", MFFT_T_IFFT_NEGACYCLIC, ii, 1, n, w, 0, 0, 0, 0, 0); mfft_unlock(); }
 
 /* 1-D transforms of length 4n with the root sqrt2^w (mul_fft.c:839, 1488, 1230, 1792) */
 static void transform_sqrt2_1d(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_size_t trunc)
 {
-   uint32_t S, k; mfft_sched *s; mp_limb_t **tab;
+   uint32_t S, k; mfft_sched *s; mp_limb_t **tab, **otab = NULL;
+   mp_limb_t **rr = g_rr; const mp_size_t rrs = g_rs;
+   g_rr = NULL; g_rs = 1;
    check_ring(fn, n, w);
    S = (uint32_t)(4*n);
    s = mfft_sched_new(S, (uint64_t) n*w);
@@ -192,25 +208,32 @@ static void transform_sqrt2_1d(const char *fn, int inverse, mp_limb_t **ii, mp_s
       mfft_die(fn, "illegal transform parameters (n=%ld w=%lu trunc=%ld; trunc must be even, 2n < trunc <= 4n, 4 | n*w)",
                (long) n, (unsigned long) w, (long) trunc);
    for (k = 0; k < S; k++) tab[k] = ii[k];
-   run_on_host_blocks(fn, s, (uint32_t)((uint64_t) n*w/64), tab, tab, 0, 0);
-   free(tab);
+   if (rr && (rr != ii || rrs != 1))
+   {
+      if (rrs <= 0) mfft_die(fn, "illegal result stride %ld", (long) rrs);
+      otab = (mp_limb_t **) malloc(sizeof(mp_limb_t *) * S);
+      if (!otab) mfft_die(fn, "out of host memory");
+      for (k = 0; k < S; k++) otab[k] = rr[(size_t) k*rrs];
+   }
+   run_on_host_blocks(fn, s, (uint32_t)((uint64_t) n*w/64), tab, otab ? otab : tab, 0, 0);
+   free(tab); free(otab);
 }
 
 void FFT_radix2_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                       mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp; transform_sqrt2_1d("FFT_radix2_sqrt2", 0, ii, n, w, 4*n); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs; transform_sqrt2_1d("FFT_radix2_sqrt2", 0, ii, n, w, 4*n); mfft_unlock(); }
 
 void IFFT_radix2_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                        mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp; transform_sqrt2_1d("IFFT_radix2_sqrt2", 1, ii, n, w, 4*n); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs; transform_sqrt2_1d("IFFT_radix2_sqrt2", 1, ii, n, w, 4*n); mfft_unlock(); }
 
 void FFT_radix2_truncate_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                                mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp; transform_sqrt2_1d("FFT_radix2_truncate_sqrt2", 0, ii, n, w, trunc); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs; transform_sqrt2_1d("FFT_radix2_truncate_sqrt2", 0, ii, n, w, trunc); mfft_unlock(); }
 
 void IFFT_radix2_truncate_sqrt2(mp_limb_t **rr, mp_size_t rs, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w,
                                 mp_limb_t **t1, mp_limb_t **t2, mp_limb_t **temp, mp_size_t trunc)
-{ (void) rr; (void) rs; (void) t1; (void) t2; (void) temp; transform_sqrt2_1d("IFFT_radix2_truncate_sqrt2", 1, ii, n, w, trunc); }
+{ (void) t1; (void) t2; (void) temp; mfft_lock(); g_rr = rr; g_rs = rs; transform_sqrt2_1d("IFFT_radix2_truncate_sqrt2", 1, ii, n, w, trunc); mfft_unlock(); }
 
 /* ------------------------------- MFA on host pointer tables -------------------------------- */
 static void mfa_host(const char *fn, int inverse, mp_limb_t **ii, mp_size_t n, mp_bitcnt_t w, mp_size_t n1,

@@ -178,3 +178,23 @@ def test_emulated_squaring_shortcut(emu):
     emu.mpirfft_memcpy_d2h(ptr(r), dr, r.nbytes, None)
     emu.mpirfft_mul_plan_destroy(h)
     assert np.array_equal(r, L.gmp_mul(a, a))
+
+
+def test_emulated_result_table_rr_rs(emu):
+    """FFT_radix2(rr, rs, ii, ...): results are delivered through rr with stride rs (mul_fft.c:786-827);
+    with rr != ii the inputs' blocks keep their contents"""
+    import ctypes as C
+    from common import rand_blocks, cl, cul, residues
+    n, w = 16, 8
+    l, N = n * w // 64, 2 * n
+    rng = np.random.default_rng(5)
+    data = rand_blocks(rng, N, l)
+    s1 = L.Slab(N, l, data)
+    emu.FFT_radix2(s1.ii, cl(1), s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp)
+    want = residues(s1.all(), l)
+    s2, out = L.Slab(N, l, data), L.Slab(2 * N, l)
+    emu.FFT_radix2(out.ii, cl(2), s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp)
+    got = residues(out.all(), l)
+    assert [got[2 * k] for k in range(N)] == want
+    assert all(v == 0 for v in got[1::2])
+    assert np.array_equal(s2.all(), data)
