@@ -46,7 +46,6 @@ def test_emulated_new_mpn_mul(emu, case):
     (3000, 2500, 8, 3, "uniform"),                                      # l = 12: odd w, two column classes
     (12000, 12000, 8, 16, "uniform"),                                   # l = 64 with bit-shifted twiddles
     (13000, 12000, 8, 17, "runs"),                                      # odd w, l = 68 (stagewise)
-    (131000, 131000, 12, 1, "uniform"),                                 # odd w on the fused tile path (l = 64): even / odd column classes
 ])
 def test_emulated_new_mpn_mul6(emu, case):
     """new_mpn_mul6 (mul_fft.c:3573): the product through the sqrt2 transforms of length 4n"""
@@ -156,7 +155,7 @@ def test_emulated_mulmod_long_ripple(emu, monkeypatch):
         assert np.array_equal(out[k], int_to_block(A[k] * B[k] % p, l)), k
 
 
-@pytest.mark.parametrize("n1,n2,kind", [(40000, 30000, "uniform"), (90000, 90000, "ones"), (9000, 3, "runs"), (150, 40, "uniform")])
+@pytest.mark.parametrize("n1,n2,kind", [(40000, 30000, "uniform"), (50000, 50000, "ones"), (9000, 3, "runs"), (150, 40, "uniform")])
 def test_emulated_mpn_mul_wrapper(emu, n1, n2, kind):
     """mpirfft_mpn_mul chooses (depth, w) itself (smallest fused ring that is legal)"""
     a, b = operand(kind, n1, 11), operand(kind, n2, 12)
@@ -198,3 +197,30 @@ def test_emulated_result_table_rr_rs(emu):
     assert [got[2 * k] for k in range(N)] == want
     assert all(v == 0 for v in got[1::2])
     assert np.array_equal(s2.all(), data)
+
+
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_emulated_sqrt2_mfa_odd_w_on_the_fused_path(emu, inverse):
+    """FFT/IFFT_radix2_mfa_truncate_sqrt2 with odd w on a ring the fused tile executor serves (l = 64, w = 1):
+    the even / odd column classes as two sub-batches of tile passes, against the compiled reference"""
+    from common import rand_blocks, cl, cul, residues
+    ref = L.load_ref(True)
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    n, w, n1 = 4096, 1, 64
+    trunc = 2 * n + 3 * 2 * n1
+    l, N = n * w // 64, 4 * n
+    n2, trunc2 = 2 * n // n1, (trunc - 2 * n) // n1
+    depth = n2.bit_length() - 1
+    rows = list(range(n2)) + [n2 + int(format(s, "0%db" % depth)[::-1], 2) for s in range(trunc2)]
+    rng = np.random.default_rng(77 + inverse)
+    data = rand_blocks(rng, N, l)
+    if not inverse:
+        data[trunc:] = 0
+    name = ("I" if inverse else "") + "FFT_radix2_mfa_truncate_sqrt2"
+    s1, s2 = L.Slab(N, l, data), L.Slab(N, l, data)
+    getattr(ref, name)(s1.ii, cl(n), cul(w), s1.pt1, s1.pt2, s1.ptmp, cl(n1), cl(trunc))
+    getattr(emu, name)(s2.ii, cl(n), cul(w), s2.pt1, s2.pt2, s2.ptmp, cl(n1), cl(trunc))
+    idx = [i * n1 + j for i in rows for j in range(n1)] if not inverse else list(range(trunc))
+    a1, a2 = s1.all(), s2.all()
+    assert residues([a1[k] for k in idx], l) == residues([a2[k] for k in idx], l)
