@@ -1546,6 +1546,8 @@ int mfft_dev_h2d_2d(void *d, size_t dpitch, const void *h, size_t hpitch, size_t
 { CK(cudaMemcpy2DAsync(d, dpitch, h, hpitch, width, rows, cudaMemcpyHostToDevice, (cudaStream_t) stream)); return 0; }
 int mfft_dev_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, void *stream)
 { CK(cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, rows, cudaMemcpyDeviceToHost, (cudaStream_t) stream)); return 0; }
+int mfft_dev_d2d(void *d, const void *s, size_t bytes, void *stream)
+{ if (bytes) CK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t) stream)); return 0; }
 int mfft_dev_memset0(void *d, size_t bytes, void *stream)
 { CK(cudaMemsetAsync(d, 0, bytes, (cudaStream_t) stream)); return 0; }
 int mfft_dev_sync(void *stream)

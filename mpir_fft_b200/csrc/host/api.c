@@ -35,15 +35,24 @@ static void *arena_take(size_t *off, size_t bytes)
 static void run_on_host_blocks(const char *fn, mfft_sched *s, uint32_t l, mp_limb_t **in, mp_limb_t **out,
                                uint32_t col, int normalise)
 {
-   uint32_t S = s->S, k, pitch = l + 1, zero = 0;
-   size_t half = (size_t) S * pitch * sizeof(limb_t), need, off = 0, nops;
-   limb_t *stage, *d_slab, *d_dst; mfft_batch b, *d_b; mfft_move *mv, *d_mv;
+   /* One packed upload per call: [batch | dst base | ops | moves | slab half 0] lie in this order both in
+      the pinned host staging buffer and in the device arena, followed on the device by slab half 1 and the
+      result blocks.  A call is one copy in, the schedule's launches, one copy out. */
+   uint32_t S = s->S, k, pitch = l + 1;
+   size_t half = (size_t) S * pitch * sizeof(limb_t), need, off = 0, nops, o_b, o_base, o_ops, o_mv, o_slab, up;
+   unsigned char *st; limb_t *stage, *d_slab, *d_dst; mfft_batch *b, *d_b; mfft_move *mv, *d_mv;
    uint32_t *d_base; mfft_dsched ds; mfft_geom g;
    mfft_lock();
    mfft_require_device(fn);
    if (mfft_sched_finish(s) != 0) mfft_die(fn, "out of host memory");
    nops = s->nops ? s->nops : 1;
-   need = 3*(half + 256) + sizeof(mfft_op)*nops + sizeof(mfft_move)*S + 4*256;
+   o_b = off;    (void) arena_take(&off, sizeof *b);
+   o_base = off; (void) arena_take(&off, sizeof(uint32_t));
+   o_ops = off;  (void) arena_take(&off, sizeof(mfft_op)*nops);
+   o_mv = off;   (void) arena_take(&off, sizeof(mfft_move)*S);
+   o_slab = off; (void) arena_take(&off, 2*half);
+   up = o_slab + half;
+   need = off + half + 256;
    if (need > g_arena_bytes)
    {
       mfft_dev_free(g_arena);
@@ -51,26 +60,27 @@ static void run_on_host_blocks(const char *fn, mfft_sched *s, uint32_t l, mp_lim
       g_arena = (unsigned char *) mfft_dev_alloc(g_arena_bytes);
       if (!g_arena) { g_arena_bytes = 0; mfft_die(fn, "device allocation failed: %s", mfft_dev_last_error()); }
    }
-   if (half + sizeof(mfft_move)*S > g_stage_bytes)
+   if (up > g_stage_bytes)
    {
-      free(g_stage);
-      g_stage_bytes = 2*(half + sizeof(mfft_move)*S);
-      g_stage = (limb_t *) malloc(g_stage_bytes);
-      if (!g_stage) { g_stage_bytes = 0; mfft_die(fn, "out of host memory"); }
+      mfft_host_free_pinned(g_stage);
+      g_stage_bytes = 2*up;
+      g_stage = (limb_t *) mfft_host_alloc_pinned(g_stage_bytes);
+      if (!g_stage) { g_stage_bytes = 0; mfft_die(fn, "out of (pinned) host memory"); }
    }
-   stage = g_stage; mv = (mfft_move *)((unsigned char *) g_stage + half);
-   d_slab = (limb_t *) arena_take(&off, 2*half); d_dst = (limb_t *) arena_take(&off, half);
-   d_b = (mfft_batch *) arena_take(&off, sizeof b); d_base = (uint32_t *) arena_take(&off, sizeof zero);
-   ds.s = s; ds.d_ops = (mfft_op *) arena_take(&off, sizeof(mfft_op)*nops);
-   d_mv = (mfft_move *) arena_take(&off, sizeof(mfft_move)*S);
-   memset(stage, 0, half);
-   for (k = 0; k < S; k++) if (in[k]) memcpy(stage + (size_t) k*pitch, in[k], pitch*sizeof(limb_t));
-   b.base = 0; b.parity = 0; b.col = col; b.pad = 0;
+   st = (unsigned char *) g_stage;
+   b = (mfft_batch *)(st + o_b); mv = (mfft_move *)(st + o_mv); stage = (limb_t *)(st + o_slab);
+   d_b = (mfft_batch *)(g_arena + o_b); d_base = (uint32_t *)(g_arena + o_base);
+   ds.s = s; ds.d_ops = (mfft_op *)(g_arena + o_ops); d_mv = (mfft_move *)(g_arena + o_mv);
+   d_slab = (limb_t *)(g_arena + o_slab); d_dst = (limb_t *)(g_arena + off);
+   b->base = 0; b->parity = 0; b->col = col; b->pad = 0;
+   *(uint32_t *)(st + o_base) = 0;
+   if (s->nops) memcpy(st + o_ops, s->ops, sizeof(mfft_op)*s->nops);
    for (k = 0; k < S; k++) { mv[k].src_slot = s->slot[k]; mv[k].dst_pos = k; }
+   for (k = 0; k < S; k++)
+      if (in[k]) memcpy(stage + (size_t) k*pitch, in[k], pitch*sizeof(limb_t));
+      else memset(stage + (size_t) k*pitch, 0, pitch*sizeof(limb_t));
    g.S = S; g.slot_stride = 1; g.half_blocks = S; g.l = l; g.pitch = pitch;
-   if (mfft_dev_h2d(d_b, &b, sizeof b, NULL) || mfft_dev_h2d(d_base, &zero, sizeof zero, NULL) ||
-       mfft_dev_h2d(ds.d_ops, s->ops, sizeof(mfft_op)*s->nops, NULL) || mfft_dev_h2d(d_mv, mv, sizeof(mfft_move)*S, NULL) ||
-       mfft_dev_h2d(d_slab, stage, half, NULL) ||
+   if (mfft_dev_h2d(g_arena, st, up, NULL) ||
        mfft_dsched_run(&ds, d_slab, &g, d_b, 1, NULL) ||
        mfft_dev_finalize(d_dst, 1, d_base, d_slab, &g, d_mv, S, d_b, 1, 0, normalise, NULL) ||
        mfft_dev_d2h(stage, d_dst, half, NULL) || mfft_dev_sync(NULL))

@@ -23,6 +23,9 @@ struct mpirfft_mul_plan {
    mfft_mfa fwd, inv;
    limb_t *X, *Z, *Y;          /* 2N, 2N, N blocks */
    limb_t *X2;                 /* work slab of the second forward transform (runs concurrently with the first) */
+   mpirfft_smul_plan *big;     /* coefficient rings above 512 limbs: the sharded plan on one rank (multi-layer sliced
+                                  passes, pointwise products through the negacyclic recursion) with local copies for
+                                  the exchanges */
    void *s_fwd2, *ev_fork, *ev_join;
    uint32_t *d_pw_blocks; uint32_t npw;
    void *combine_work;
@@ -123,6 +126,7 @@ int mpirfft_choose_params6(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_bi
 void mpirfft_mul_plan_destroy(mpirfft_mul_plan *pl)
 {
    if (!pl) return;
+   if (pl->big) mpirfft_smul_plan_destroy(pl->big);
    mfft_lock();
    mfft_mfa_free(&pl->fwd); mfft_mfa_free(&pl->inv);
    mfft_dev_free(pl->X); mfft_dev_free(pl->Z); mfft_dev_free(pl->Y); mfft_dev_free(pl->X2);
@@ -152,6 +156,19 @@ static int plan_create(mpirfft_mul_plan **out, mp_size_t n1, mp_size_t n2, mp_bi
    pl->n1 = n1; pl->n2 = n2; pl->depth = depth; pl->w = w; pl->sqrt2 = sqrt2;
    rc = sqrt2 ? mpirfft_mul6_params_get(&pl->p, n1, n2, depth, w) : mpirfft_mul_params_get(&pl->p, n1, n2, depth, w);
    if (rc != 0) { free(pl); return rc; }
+   if (!sqrt2 && pl->p.limbs > 512 && pl->p.limbs % 64 == 0)
+   {  /* no shared-memory tile holds such a coefficient: run the plan of the sharded multiplication with
+         world size 1 (smul.c) -- its transforms work in place on chunk slices, its pointwise products
+         recurse (fft_mulmod_2expp1, mul_fft.c:3125) */
+      const char *e = getenv("MPIRFFT_BIG_PLAN");
+      if (!(e && e[0] == '0') && mpirfft_smul_plan_create(&pl->big, n1, n2, depth, w, 0, 1) == 0)
+      {
+         pl->l = (uint32_t) pl->p.limbs; pl->pitch = mfft_pitch(pl->l);
+         *out = pl;
+         return 0;
+      }
+      pl->big = NULL;
+   }
    mfft_lock();
    if ((rc = mfft_try_device()) != 0) goto fail;
    pl->l = (uint32_t) pl->p.limbs; pl->pitch = mfft_pitch(pl->l);
@@ -212,10 +229,11 @@ fail:
    return rc;
 }
 
-size_t mpirfft_mul_plan_device_bytes(const mpirfft_mul_plan *pl) { return pl->dev_bytes; }
+size_t mpirfft_mul_plan_device_bytes(const mpirfft_mul_plan *pl) { return pl->dev_bytes; }   /* (0 for the big-ring plan: its buffers belong to the smul plan) */
 
 uint64_t mpirfft_mul_plan_launches(const mpirfft_mul_plan *pl)
 {
+   if (pl->big) return 0;     /* not tabulated for the big-ring plan */
    /* 2 x (split + fwd) + pointwise + inv + combine (4 kernels) */
    return 2*((mfft_mfa_can_fuse_split(&pl->fwd) ? 0 : 1) + mfft_mfa_launches(&pl->fwd)) + 1 + mfft_mfa_launches(&pl->inv) + 4;
 }
@@ -230,6 +248,7 @@ int mpirfft_mul_exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, cons
                            const mp_limb_t *d_i2, void *stream)
 {
    int rc;
+   if (pl->big) return MPIRFFT_EINVAL;        /* the big-ring plan runs as a whole (mpirfft_mul_exec_device) */
    mfft_lock();
    rc = mfft_try_device();
    if (rc == 0) rc = exec_phase(pl, phase, d_r, d_i1, d_i2, stream);
@@ -274,12 +293,37 @@ static int exec_phase(mpirfft_mul_plan *pl, int phase, mp_limb_t *d_r, const mp_
    return rc;
 }
 
+/* the sharded plan on one rank: the three exchanges are local copies, the carry hand-off has nobody to
+   hand to (what leaves limb n1+n2-1 is zero) */
+static int exec_big(mpirfft_mul_plan *pl, mp_limb_t *d_r, const mp_limb_t *d_i1, const mp_limb_t *d_i2, void *stream)
+{
+   mpirfft_smul_layout lay; int which, rc; size_t tr;
+   if ((rc = mpirfft_smul_info(pl->big, &lay)) != 0) return rc;
+   tr = (size_t) lay.trunc_rows * lay.ncl * lay.block_limbs * sizeof(limb_t);
+   for (which = 0; which < 2; which++)
+   {
+      if ((rc = mpirfft_smul_phase(pl->big, 0, which, which ? d_i2 : d_i1, stream)) != 0) return rc;
+      if (mfft_dev_d2d(lay.recv, lay.send, tr, stream)) return MPIRFFT_ENODEV;
+      if ((rc = mpirfft_smul_phase(pl->big, 1, which, NULL, stream)) != 0) return rc;
+   }
+   if ((rc = mpirfft_smul_phase(pl->big, 2, 0, NULL, stream)) != 0) return rc;
+   if ((rc = mpirfft_smul_phase(pl->big, 3, 0, NULL, stream)) != 0) return rc;
+   if (mfft_dev_d2d(lay.work, lay.send, tr, stream)) return MPIRFFT_ENODEV;
+   if ((rc = mpirfft_smul_phase(pl->big, 4, 0, NULL, stream)) != 0) return rc;
+   if (mfft_dev_d2d(lay.recv, lay.send, tr, stream)) return MPIRFFT_ENODEV;
+   if ((rc = mpirfft_smul_phase(pl->big, 5, 0, NULL, stream)) != 0) return rc;
+   if ((rc = mpirfft_smul_phase(pl->big, 6, 0, NULL, stream)) != 0) return rc;
+   if (mfft_dev_d2d(d_r, lay.out, (size_t)(lay.limb_hi - lay.limb_lo) * sizeof(limb_t), stream)) return MPIRFFT_ENODEV;
+   return 0;
+}
+
 int mpirfft_mul_exec_device(mpirfft_mul_plan *pl, mp_limb_t *d_r, const mp_limb_t *d_i1,
                             const mp_limb_t *d_i2, void *stream)
 {
    int ph, rc;
    mfft_lock();
    if ((rc = mfft_try_device()) != 0) goto done;
+   if (pl->big) { rc = exec_big(pl, d_r, d_i1, d_i2, stream); goto done; }
    if (d_i1 == d_i2 && pl->n1 == pl->n2)
    {  /* squaring: one forward transform, the spectrum multiplied by itself */
       if ((rc = exec_phase(pl, 0, d_r, d_i1, d_i2, stream)) != 0) goto done;
@@ -324,6 +368,16 @@ int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i
    }
    /* the second operand travels while the first one is being split and transformed */
    rc = MPIRFFT_ENODEV;
+   if (pl->big)
+   {
+      rc = MPIRFFT_ENODEV;
+      if (mfft_dev_h2d(pl->d_i1, i1, b1, pl->s_comp) || mfft_dev_h2d(pl->d_i2, i2, b2, pl->s_comp)) goto done;
+      if ((rc = exec_big(pl, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_comp)) != 0) goto done;
+      rc = MPIRFFT_ENODEV;
+      if (mfft_dev_d2h(r, pl->d_r, b1 + b2, pl->s_comp) || mfft_dev_sync(pl->s_comp)) goto done;
+      rc = 0;
+      goto done;
+   }
    /* The first transform is launched BEFORE the second copy is issued: a copy from pageable memory
       (what a caller that merely swaps libraries hands in) blocks the host while the driver stages it,
       and the GPU should be busy with operand 1 meanwhile; with pinned buffers the order is immaterial. */

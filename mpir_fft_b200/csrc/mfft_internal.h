@@ -127,6 +127,7 @@ int  mfft_dev_h2d(void *d, const void *h, size_t bytes, void *stream);
 int  mfft_dev_d2h(void *h, const void *d, size_t bytes, void *stream);
 int  mfft_dev_h2d_2d(void *d, size_t dpitch, const void *h, size_t hpitch, size_t width, size_t rows, void *stream);
 int  mfft_dev_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, void *stream);
+int  mfft_dev_d2d(void *d, const void *s, size_t bytes, void *stream);
 int  mfft_dev_memset0(void *d, size_t bytes, void *stream);
 int  mfft_dev_sync(void *stream);
 void *mfft_dev_stream_create(void);                   /* non-blocking stream; NULL on failure */

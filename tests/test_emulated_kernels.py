@@ -38,6 +38,25 @@ def test_emulated_new_mpn_mul(emu, case):
     assert np.array_equal(r, L.gmp_mul(a, b))
 
 
+@pytest.mark.parametrize("case", [(2000, 1500, 6, 1024, "uniform"), (5000, 6000, 5, 2048, "runs")])
+def test_emulated_new_mpn_mul_big_ring(emu, case, monkeypatch):
+    """Coefficient rings above 512 limbs: new_mpn_mul runs the sharded plan on one rank (mul.c: exec_big --
+    sliced in-place transforms, pointwise products through the recursion); MPIRFFT_BIG_PLAN=0 keeps the
+    layer-per-launch path with the schoolbook pointwise kernel.  Both must equal GMP."""
+    n1, n2, depth, w, kind = case
+    a, b = operand(kind, n1, 1), operand(kind, n2, 2)
+    want = L.gmp_mul(a, b)
+    r = np.zeros(n1 + n2, dtype=np.uint64)
+    emu.new_mpn_mul(ptr(r), ptr(a), n1, ptr(b), n2, depth, w)
+    assert np.array_equal(r, want)
+    if w == 1024:
+        monkeypatch.setenv("MPIRFFT_BIG_PLAN", "0")
+        a2 = operand(kind, n1 - 1, 1)                      # another plan-cache key: the switch is read at plan creation
+        r2 = np.zeros(n1 - 1 + n2, dtype=np.uint64)
+        emu.new_mpn_mul(ptr(r2), ptr(a2), n1 - 1, ptr(b), n2, depth, w)
+        assert np.array_equal(r2, L.gmp_mul(a2, b))
+
+
 @pytest.mark.parametrize("case", [
     # (n1, n2, depth, w, operands): 2^(depth+1) < j1+j2-1 <= 2^(depth+2)
     (50, 41, 6, 1, "ones"),                                             # l = 1: stage-per-launch path, odd w (sqrt2 proper)

@@ -82,6 +82,18 @@ def test_odd_sizes(lib, case):
     check_mul(*case)
 
 
+@pytest.mark.parametrize("case", [
+    (30000, 28000, 6, 1024, "uniform"), (20000, 7, 6, 1024, "ones"), (5000, 6000, 5, 2048, "runs"),
+    (1 << 22, 1 << 22, 16, 1, "uniform"),                  # 4M x 4M limbs in the ring of 1024 limbs
+    (3000000, 2000001, 14, 8, "ones"),                     # ring of 2048 limbs, 2^14 x 2 coefficients
+])
+def test_big_ring_through_the_dropin_symbol(lib, case):
+    """Rings above 512 limbs: new_mpn_mul runs the plan of the sharded multiplication on one rank
+    (mul.c: exec_big)."""
+    n1, n2, depth, w, kind = case
+    check_mul(n1, n2, depth, w, kind, kind)
+
+
 def test_size_independent_properties_cfg2(lib):
     """at full size: commutativity, and (a*b) mod small primes from the inputs alone"""
     n = 1 << 20
