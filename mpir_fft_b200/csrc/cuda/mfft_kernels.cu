@@ -363,8 +363,14 @@ __device__ __forceinline__ void suffix_block_sums(uint32_t (&S)[C + 1], const ui
  * block); b0+b1 is recomputed after every rotation (the complement of a wrapped block is not the
  * complement of its half-sum).  The additions go to the ALU pipe, next to the IMAD pipe the products
  * keep busy. */
-template <int C, bool KARA, int UNR>
-__global__ void __launch_bounds__(128, 1)
+/* MAXR = 224: nine warps per SM instead of eight (three CTAs of 96 threads) -- one wave less at cfg2 */
+#ifdef MFFT_EMU
+#define PW_MAXNREG(r)
+#else
+#define PW_MAXNREG(r) __maxnreg__(r)
+#endif
+template <int C, bool KARA, int UNR, int MAXR>
+__global__ void PW_MAXNREG(MAXR)
 k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
             uint32_t nblk, uint32_t l, uint32_t pitch)
 {
@@ -1923,8 +1929,13 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
    const int u = (unr == 0 && l == 512) ? 1 : unr;   /* l = 512: 252 registers already, unrolling only adds spills (measured: no gain) */
 #define PW_LAUNCH(CC, KA) do { \
       const size_t sm__ = (size_t) 4 * 32 * ((KA) ? (CC + CC / 2 + 1) : CC) * 4; \
-      if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 1>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); \
-      else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 4>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
+      if (w9) { const unsigned grid9 = (nblk + 2) / 3; const size_t sm9 = sm__ / 4 * 3; \
+         if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 1, 224>), grid9, 96, sm9, st, a, b, d_blocks, nblk, l, pitch); \
+         else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 4, 224>), grid9, 96, sm9, st, a, b, d_blocks, nblk, l, pitch); } \
+      else if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 1, 255>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); \
+      else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 4, 255>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
+   static int w9 = -1;         /* MPIRFFT_PW_WARPS=9: nine warps per SM (224 registers per thread) */
+   if (w9 < 0) { const char *e = getenv("MPIRFFT_PW_WARPS"); w9 = (e && atoi(e) == 9) ? 1 : 0; }
    const bool kara = (g_pw_mode == 2) || (g_pw_mode == 0 && PW_KARA_DEFAULT(l));
    if (l == 64)       { if (kara) PW_LAUNCH(4, true); else PW_LAUNCH(4, false); }
    else if (l == 128) { if (kara) PW_LAUNCH(8, true); else PW_LAUNCH(8, false); }
