@@ -363,21 +363,91 @@ __device__ __forceinline__ void suffix_block_sums(uint32_t (&S)[C + 1], const ui
  * block); b0+b1 is recomputed after every rotation (the complement of a wrapped block is not the
  * complement of its half-sum).  The additions go to the ALU pipe, next to the IMAD pipe the products
  * keep busy. */
-/* MAXR = 224: nine warps per SM instead of eight (three CTAs of 96 threads) -- one wave less at cfg2 */
-#ifdef MFFT_EMU
-#define PW_MAXNREG(r)
-#else
-#define PW_MAXNREG(r) __maxnreg__(r)
-#endif
-template <int C, bool KARA, int UNR, int MAXR>
-__global__ void PW_MAXNREG(MAXR)
+/* One level of Karatsuba on 2Q-word operands, accumulated over the steps of a sweep (the building block of the
+ * two-level variant, KARA == 2): L = x0 y0, Hh = x1 y1, M = (x0+x1)(y0+y1) in three accumulator sets, the carry
+ * bits of the two sums in UV / n2 exactly as in the one-level code.  reduce() turns the sets into the 4Q+1
+ * canonical words of sum_s X_s Y_s (< 32 * 2^(128 Q)). */
+template <int Q>
+struct kara_acc
+{
+   uint32_t eL[2 * Q + 2], oL[2 * Q + 2], kL[Q + 2], eM[2 * Q + 2], oM[2 * Q + 2], kM[Q + 2],
+            eH[2 * Q + 2], oH[2 * Q + 2], kH[Q + 2], UV[Q + 1], n2;
+   __device__ __forceinline__ void zero()
+   {
+#pragma unroll
+      for (int i = 0; i < 2 * Q + 2; i++) { eL[i] = 0; oL[i] = 0; eM[i] = 0; oM[i] = 0; eH[i] = 0; oH[i] = 0; }
+#pragma unroll
+      for (int i = 0; i < Q + 2; i++) { kL[i] = 0; kM[i] = 0; kH[i] = 0; }
+#pragma unroll
+      for (int i = 0; i <= Q; i++) UV[i] = 0;
+      n2 = 0;
+   }
+   /* X: x0 | x1 (2Q words, shared memory), XS: x0 + x1 (Q words) and its carry; y: y0 | y1 in registers */
+   __device__ __forceinline__ void step(const uint32_t *X, const uint32_t *XS, const uint32_t (&y)[2 * Q])
+   {
+      uint32_t x[Q], yy[Q];
+#pragma unroll
+      for (int i = 0; i < Q; i++) { x[i] = X[i]; yy[i] = y[i]; }
+      mac_block<Q>(eL, oL, kL, x, yy);
+#pragma unroll
+      for (int i = 0; i < Q; i++) { x[i] = X[Q + i]; yy[i] = y[Q + i]; }
+      mac_block<Q>(eH, oH, kH, x, yy);
+      uint64_t cy = 0;
+#pragma unroll
+      for (int i = 0; i < Q; i++)
+      {
+         const uint64_t v = (uint64_t) y[i] + y[Q + i] + cy;
+         yy[i] = (uint32_t) v; cy = v >> 32;
+         x[i] = XS[i];
+      }
+      const uint32_t cb = (uint32_t) cy, ca = XS[Q];
+      mac_block<Q>(eM, oM, kM, x, yy);
+      const uint32_t ma = 0u - ca, mb = 0u - cb;
+      cy = 0;
+#pragma unroll
+      for (int i = 0; i < Q; i++)
+      {
+         const uint64_t v = (uint64_t) UV[i] + (yy[i] & ma) + (x[i] & mb) + cy;
+         UV[i] = (uint32_t) v; cy = v >> 32;
+      }
+      UV[Q] += (uint32_t) cy;
+      n2 += ca & cb;
+   }
+   /* V[0 .. 4Q] = L + (M + UV W + n2 W^2 - L - Hh) W + Hh W^2,  W = 2^(32 Q) */
+   __device__ __forceinline__ void reduce(uint32_t *V) const
+   {
+      int64_t cy = 0;
+#pragma unroll
+      for (int k = 0; k <= 4 * Q; k++)
+      {
+         int64_t v = cy + mac_word<Q>(eL, oL, kL, k);
+         if (k >= Q) v += mac_word<Q>(eM, oM, kM, k - Q) - mac_word<Q>(eL, oL, kL, k - Q) - mac_word<Q>(eH, oH, kH, k - Q);
+         if (k >= 2 * Q) v += mac_word<Q>(eH, oH, kH, k - 2 * Q);
+         if (k >= 2 * Q && k - 2 * Q <= Q) v += (int64_t)(uint64_t) UV[k - 2 * Q];
+         if (k == 3 * Q) v += (int64_t)(uint64_t) n2;
+         V[k] = (uint32_t) v; cy = v >> 32;
+      }
+   }
+};
+
+/* (Nine warps per SM -- 224 registers, three CTAs of 96 threads -- were measured: 36 % SLOWER.  The kernel is
+   bound by the IMAD pipe of each scheduler, and 9 warps spread 3/2/2/2 over the four schedulers.) */
+/* KARA: 0 schoolbook blocks, 1 one level of Karatsuba (two sweeps at C = 32), 2 two levels: the three
+ * half-size products L, Hh, M of the first level are accumulated in sweeps of their own (L and Hh together when
+ * MERGE), each with one more level inside the lane (kara_acc): 9 Q^2 = 2.25 H^2 multiply-adds per step. */
+template <int C, int KARA, int UNR, bool MERGE = false>
+__global__ void __launch_bounds__(128, (KARA == 2 && C == 16 && !MERGE) ? 3 : 1)      /* one form per sweep: 12 warps per SM fit */
 k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ blocks,
             uint32_t nblk, uint32_t l, uint32_t pitch)
 {
    pdl_wait();
    MFFT_DYN_SMEM(uint32_t, smem);
    constexpr int H = C / 2;
-   constexpr int WSM = KARA ? 32 * (C + H + 1) : 32 * C;       /* shared words per warp */
+   constexpr int Q = H / 2;
+   constexpr bool TWOSWEEP = (KARA == 1) && (C >= 32);          /* three accumulator sets do not fit the registers */
+   constexpr int PARK = 2 * (2 * H + 1) + 1;                    /* words of L and Hh parked per lane (odd stride) */
+   constexpr int WSM = KARA == 2 ? 32 * (C + H + 1 + 3 * (Q + 1) + PARK)
+                     : KARA ? 32 * (C + H + 1) + (TWOSWEEP ? 32 * PARK : 0) : 32 * C;       /* shared words per warp */
    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const uint64_t wid = (uint64_t) blockIdx.x * (blockDim.x >> 5) + wib;
    if (wid >= nblk) return;
@@ -428,12 +498,222 @@ k_pointwise(limb_t *a_slab, const limb_t *b_slab, const uint32_t *__restrict__ b
          sAs[lane * (H + 1) + i] = (uint32_t) v; cy = v >> 32;
       }
       sAs[lane * (H + 1) + H] = (uint32_t) cy;
+      if constexpr (KARA == 2)
+      {  /* second level: x0 + x1 (Q words and a carry) of the three forms a0, a1, a0 + a1 of this lane's block */
+         uint32_t *sQ = sAs + 32 * (H + 1) + lane * 3 * (Q + 1);
+#pragma unroll
+         for (int f = 0; f < 3; f++)
+         {
+            uint64_t c2 = 0;
+#pragma unroll
+            for (int i = 0; i < Q; i++)
+            {
+               const uint32_t lo = f == 0 ? a[i] : f == 1 ? a[H + i] : sAs[lane * (H + 1) + i];
+               const uint32_t hi = f == 0 ? a[Q + i] : f == 1 ? a[H + Q + i] : sAs[lane * (H + 1) + Q + i];
+               const uint64_t v = (uint64_t) lo + hi + c2;
+               sQ[f * (Q + 1) + i] = (uint32_t) v; c2 = v >> 32;
+            }
+            sQ[f * (Q + 1) + Q] = (uint32_t) c2;
+         }
+      }
    }
    __syncwarp();
 
    uint32_t acc[2 * C + 1];
    const uint32_t m0 = (lane == 0) ? 0xffffffffu : 0u;
-   if constexpr (KARA)
+   if constexpr (KARA == 2)
+   {
+      constexpr int NV = 2 * H + 1;                              /* words of a half-size product summed over the steps */
+      const uint32_t *sQ = sAs + 32 * (H + 1);
+      uint32_t *park = sAs + 32 * (H + 1) + 32 * 3 * (Q + 1) + lane * PARK;
+      const uint32_t src = (lane + 31) & 31;
+      if constexpr (MERGE)
+      {
+         kara_acc<Q> A0, A1;
+         A0.zero(); A1.zero();
+#pragma unroll UNR
+         for (uint32_t s = 0; s < 32; s++)
+         {
+            uint32_t y[H];
+#pragma unroll
+            for (int i = 0; i < H; i++) y[i] = b[i];
+            A0.step(sA + s * C, sQ + (s * 3 + 0) * (Q + 1), y);
+#pragma unroll
+            for (int i = 0; i < H; i++) y[i] = b[H + i];
+            A1.step(sA + s * C + H, sQ + (s * 3 + 1) * (Q + 1), y);
+#pragma unroll
+            for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src) ^ m0;
+         }
+         A0.reduce(park); A1.reduce(park + NV);
+      } else
+      {
+#pragma unroll 1
+         for (int f = 0; f < 2; f++)
+         {
+            kara_acc<Q> A0;
+            A0.zero();
+#pragma unroll UNR
+            for (uint32_t s = 0; s < 32; s++)
+            {
+               uint32_t y[H];
+#pragma unroll
+               for (int i = 0; i < H; i++) y[i] = f ? b[H + i] : b[i];
+               A0.step(sA + s * C + f * H, sQ + (s * 3 + f) * (Q + 1), y);
+#pragma unroll
+               for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src) ^ m0;
+            }
+            A0.reduce(park + f * NV);
+            /* after 32 rotations every B block has been complemented exactly once */
+#pragma unroll
+            for (int i = 0; i < C; i++) b[i] = ~b[i];
+         }
+      }
+      if constexpr (MERGE)
+      {
+#pragma unroll
+         for (int i = 0; i < C; i++) b[i] = ~b[i];
+      }
+      uint32_t V2[NV], UV[H + 1], n2 = 0;
+      {
+         kara_acc<Q> A2;
+         A2.zero();
+#pragma unroll
+         for (int i = 0; i <= H; i++) UV[i] = 0;
+#pragma unroll UNR
+         for (uint32_t s = 0; s < 32; s++)
+         {
+            uint32_t y[H];
+            uint64_t cy = 0;
+#pragma unroll
+            for (int i = 0; i < H; i++)
+            {
+               const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
+               y[i] = (uint32_t) v; cy = v >> 32;
+            }
+            const uint32_t cb = (uint32_t) cy, ca = sAs[s * (H + 1) + H];
+            A2.step(sAs + s * (H + 1), sQ + (s * 3 + 2) * (Q + 1), y);
+            const uint32_t ma = 0u - ca, mb = 0u - cb;
+            cy = 0;
+#pragma unroll
+            for (int i = 0; i < H; i++)
+            {
+               const uint64_t v = (uint64_t) UV[i] + (y[i] & ma) + (sAs[s * (H + 1) + i] & mb) + cy;
+               UV[i] = (uint32_t) v; cy = v >> 32;
+            }
+            UV[H] += (uint32_t) cy;
+            n2 += ca & cb;
+#pragma unroll
+            for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src) ^ m0;
+         }
+         A2.reduce(V2);
+      }
+      uint32_t S[C + 1];
+      suffix_block_sums<C>(S, sA + lane * C, lane);
+      int64_t cy = 0;
+#pragma unroll
+      for (int k = 0; k <= 2 * C; k++)
+      {
+         int64_t v = cy;
+         if (k <= 2 * H) v += (int64_t)(uint64_t) park[k];
+         if (k >= H && k - H <= 2 * H) v += (int64_t)(uint64_t) V2[k - H] - (int64_t)(uint64_t) park[k - H] - (int64_t)(uint64_t) park[NV + k - H];
+         if (k >= C && k - C <= 2 * H) v += (int64_t)(uint64_t) park[NV + k - C];
+         if (k >= C && k - C <= H) v += (int64_t)(uint64_t) UV[k - C];
+         if (k == 3 * H) v += (int64_t)(uint64_t) n2;
+         if (k <= C) v += (int64_t)(uint64_t) S[k];
+         if (k >= C) v -= (int64_t)(uint64_t) S[k - C];
+         acc[k] = (uint32_t) v; cy = v >> 32;
+      }
+   } else
+   if constexpr (TWOSWEEP)
+   {
+      /* Sweep 1 accumulates L and Hh over the 32 steps, reduces them to 2H+1 canonical words each and parks
+         them in shared memory; after 32 rotations every B block has been complemented exactly once, so one
+         more complement restores B.  Sweep 2 accumulates M (and the carry terms UV, n2) and combines. */
+      uint32_t *park = sAs + 32 * (H + 1) + lane * PARK;
+      {
+         uint32_t eL[2 * H + 2], oL[2 * H + 2], kL[H + 2], eH[2 * H + 2], oH[2 * H + 2], kH[H + 2];
+#pragma unroll
+         for (int i = 0; i < 2 * H + 2; i++) { eL[i] = 0; oL[i] = 0; eH[i] = 0; oH[i] = 0; }
+#pragma unroll
+         for (int i = 0; i < H + 2; i++) { kL[i] = 0; kH[i] = 0; }
+#pragma unroll UNR
+         for (uint32_t s = 0; s < 32; s++)
+         {
+            uint32_t x[H], y[H];
+#pragma unroll
+            for (int i = 0; i < H; i++) { x[i] = sA[s * C + i]; y[i] = b[i]; }
+            mac_block<H>(eL, oL, kL, x, y);
+#pragma unroll
+            for (int i = 0; i < H; i++) { x[i] = sA[s * C + H + i]; y[i] = b[H + i]; }
+            mac_block<H>(eH, oH, kH, x, y);
+            const uint32_t src = (lane + 31) & 31;
+#pragma unroll
+            for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src) ^ m0;
+         }
+         int64_t cl = 0, ch = 0;
+#pragma unroll
+         for (int k = 0; k <= 2 * H; k++)
+         {
+            const int64_t vl = cl + mac_word<H>(eL, oL, kL, k), vh = ch + mac_word<H>(eH, oH, kH, k);
+            park[k] = (uint32_t) vl; cl = vl >> 32;
+            park[2 * H + 1 + k] = (uint32_t) vh; ch = vh >> 32;
+         }
+      }
+#pragma unroll
+      for (int i = 0; i < C; i++) b[i] = ~b[i];
+      uint32_t eM[2 * H + 2], oM[2 * H + 2], kM[H + 2], UV[H + 1], n2 = 0;
+#pragma unroll
+      for (int i = 0; i < 2 * H + 2; i++) { eM[i] = 0; oM[i] = 0; }
+#pragma unroll
+      for (int i = 0; i < H + 2; i++) kM[i] = 0;
+#pragma unroll
+      for (int i = 0; i <= H; i++) UV[i] = 0;
+#pragma unroll UNR
+      for (uint32_t s = 0; s < 32; s++)
+      {
+         uint32_t x[H], y[H];
+         uint64_t cy = 0;
+#pragma unroll
+         for (int i = 0; i < H; i++)
+         {
+            const uint64_t v = (uint64_t) b[i] + b[H + i] + cy;
+            y[i] = (uint32_t) v; cy = v >> 32;
+            x[i] = sAs[s * (H + 1) + i];
+         }
+         const uint32_t cb = (uint32_t) cy, ca = sAs[s * (H + 1) + H];
+         mac_block<H>(eM, oM, kM, x, y);
+         const uint32_t ma = 0u - ca, mb = 0u - cb;
+         cy = 0;
+#pragma unroll
+         for (int i = 0; i < H; i++)
+         {
+            const uint64_t v = (uint64_t) UV[i] + (y[i] & ma) + (x[i] & mb) + cy;
+            UV[i] = (uint32_t) v; cy = v >> 32;
+         }
+         UV[H] += (uint32_t) cy;
+         n2 += ca & cb;
+         const uint32_t src = (lane + 31) & 31;
+#pragma unroll
+         for (int i = 0; i < C; i++) b[i] = __shfl_sync(FULL, b[i], src) ^ m0;
+      }
+      uint32_t S[C + 1];
+      suffix_block_sums<C>(S, sA + lane * C, lane);
+      int64_t cy = 0;
+#pragma unroll
+      for (int k = 0; k <= 2 * C; k++)
+      {
+         int64_t v = cy;
+         if (k <= 2 * H) v += (int64_t)(uint64_t) park[k];
+         if (k >= H) v += mac_word<H>(eM, oM, kM, k - H);
+         if (k >= H && k - H <= 2 * H) v -= (int64_t)(uint64_t) park[k - H] + (int64_t)(uint64_t) park[2 * H + 1 + k - H];
+         if (k >= C && k - C <= 2 * H) v += (int64_t)(uint64_t) park[2 * H + 1 + k - C];
+         if (k >= C && k - C <= H) v += (int64_t)(uint64_t) UV[k - C];
+         if (k == 3 * H) v += (int64_t)(uint64_t) n2;
+         if (k <= C) v += (int64_t)(uint64_t) S[k];
+         if (k >= C) v -= (int64_t)(uint64_t) S[k - C];
+         acc[k] = (uint32_t) v; cy = v >> 32;
+      }
+   } else if constexpr (KARA)
    {
       uint32_t eL[2 * H + 2], oL[2 * H + 2], kL[H + 2], eM[2 * H + 2], oM[2 * H + 2], kM[H + 2],
                eH[2 * H + 2], oH[2 * H + 2], kH[H + 2], UV[H + 1], n2 = 0;
@@ -1882,8 +2162,8 @@ int mfft_dev_normalise(limb_t *slab, uint32_t l, uint32_t pitch, uint64_t nblk, 
 }
 
 static limb_t *g_pw_scratch = NULL; static size_t g_pw_scratch_bytes = 0;
-static int g_pw_mode = -1;     /* 0 auto, 1 nested SS, 2 Karatsuba-split blocks, 3 schoolbook blocks */
-#define PW_KARA_DEFAULT(l) ((l) == 256 || (l) == 128)
+static int g_pw_mode = -1;     /* 0 auto, 1 nested SS, 2 Karatsuba-split blocks, 3 schoolbook blocks, 4 / 5 two Karatsuba levels */
+#define PW_KARA_DEFAULT(l) ((l) == 512 || (l) == 256 || (l) == 128)
 void mfft_dev_pointwise_mode(int mode) { g_pw_mode = mode; }
 
 int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uint32_t nblk,
@@ -1900,7 +2180,7 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
          slower, 0.91 ms: ptxas never emits IMAD.WIDE with a non-zero 64-bit addend on sm_100a, it
          splits every mad.wide.u32 into IMAD.WIDE(.., RZ) + IADD3 + IADD3.X, so the real ceiling for
          32x32->64 multiply-ADDs is the ~31/clk/SM of the IMAD.WIDE.U32.X chains used here.) */
-      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = !e ? 0 : e[0] == 's' ? 1 : e[0] == 'k' ? 2 : e[0] == 'd' ? 3 : 0; }
+      if (g_pw_mode < 0) { const char *e = getenv("MPIRFFT_POINTWISE"); g_pw_mode = !e ? 0 : e[0] == 's' ? 1 : e[0] == 'k' ? 2 : e[0] == 'd' ? 3 : e[0] == '2' ? 4 : e[0] == 'm' ? 5 : 0; }
       uint32_t np = 0, lp = 0;
       if (g_pw_mode == 1)
       {
@@ -1926,21 +2206,34 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
    }
    static int unr = -1;        /* step-loop unroll factor (tuning aid): MPIRFFT_PW_UNROLL = 1 or 4; default 4 */
    if (unr < 0) { const char *e = getenv("MPIRFFT_PW_UNROLL"); unr = e ? atoi(e) : 0; }
-   const int u = (unr == 0 && l == 512) ? 1 : unr;   /* l = 512: 252 registers already, unrolling only adds spills (measured: no gain) */
+   const bool kara = (g_pw_mode == 2) || ((g_pw_mode == 0 || g_pw_mode >= 4) && PW_KARA_DEFAULT(l));
+   const int u = (unr == 0 && l == 512 && !kara) ? 1 : unr;   /* schoolbook blocks at l = 512: 252 registers already, unrolling only adds spills */
+#define PW_SMEM(CC, KA) ((size_t) 4 * 32 * ((KA) == 2 ? (CC) + (CC) / 2 + 1 + 3 * ((CC) / 4 + 1) + 2 * (CC) + 3 \
+                                              : (KA) ? (CC) + (CC) / 2 + 1 + ((CC) >= 32 ? 2 * (CC) + 3 : 0) : (CC)) * 4)
 #define PW_LAUNCH(CC, KA) do { \
-      const size_t sm__ = (size_t) 4 * 32 * ((KA) ? (CC + CC / 2 + 1) : CC) * 4; \
-      if (w9) { const unsigned grid9 = (nblk + 2) / 3; const size_t sm9 = sm__ / 4 * 3; \
-         if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 1, 224>), grid9, 96, sm9, st, a, b, d_blocks, nblk, l, pitch); \
-         else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 4, 224>), grid9, 96, sm9, st, a, b, d_blocks, nblk, l, pitch); } \
-      else if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 1, 255>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); \
-      else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 4, 255>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
-   static int w9 = -1;         /* MPIRFFT_PW_WARPS=9: nine warps per SM (224 registers per thread) */
-   if (w9 < 0) { const char *e = getenv("MPIRFFT_PW_WARPS"); w9 = (e && atoi(e) == 9) ? 1 : 0; }
-   const bool kara = (g_pw_mode == 2) || (g_pw_mode == 0 && PW_KARA_DEFAULT(l));
-   if (l == 64)       { if (kara) PW_LAUNCH(4, true); else PW_LAUNCH(4, false); }
-   else if (l == 128) { if (kara) PW_LAUNCH(8, true); else PW_LAUNCH(8, false); }
-   else if (l == 256) { if (kara) PW_LAUNCH(16, true); else PW_LAUNCH(16, false); }
-   else if (l == 512) PW_LAUNCH(32, false);
+      const size_t sm__ = PW_SMEM(CC, KA); \
+      if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 1>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); \
+      else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 4>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
+#define PW_LAUNCH2(CC, MG) do { \
+      const size_t sm__ = PW_SMEM(CC, 2); \
+      if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, 2, 1, MG>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); \
+      else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, 2, 4, MG>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
+   static bool attr = false;
+   if (!attr)
+   {  /* the kernels with parked words need more than the default 48 KB per CTA */
+      CK(cudaFuncSetAttribute(k_pointwise<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PW_SMEM(32, 1)));
+      CK(cudaFuncSetAttribute(k_pointwise<32, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PW_SMEM(32, 1)));
+      CK(cudaFuncSetAttribute(k_pointwise<32, 2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PW_SMEM(32, 2)));
+      CK(cudaFuncSetAttribute(k_pointwise<32, 2, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PW_SMEM(32, 2)));
+      attr = true;
+   }
+   const int kara2 = (g_pw_mode == 4) ? 1 : (g_pw_mode == 5) ? 2 : 0;     /* two levels; 2: L and Hh in one sweep */
+   if (kara2 && l == 256) { if (kara2 == 2) PW_LAUNCH2(16, true); else PW_LAUNCH2(16, false); }
+   else if (kara2 && l == 512) PW_LAUNCH2(32, false);
+   else if (l == 64)  { if (kara) PW_LAUNCH(4, 1); else PW_LAUNCH(4, 0); }
+   else if (l == 128) { if (kara) PW_LAUNCH(8, 1); else PW_LAUNCH(8, 0); }
+   else if (l == 256) { if (kara) PW_LAUNCH(16, 1); else PW_LAUNCH(16, 0); }
+   else if (l == 512) { if (kara) PW_LAUNCH(32, 1); else PW_LAUNCH(32, 0); }
    else
    {
       const size_t need = (size_t) nblk * 3 * l * sizeof(limb_t);

@@ -110,10 +110,12 @@ def test_emulated_new_mpn_mul_product_kernels(emu, case, mode):
     assert np.array_equal(r, L.gmp_mul(a, b))
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("l", [1, 3, 24, 64, 128, 256, 512])
 def test_emulated_mulmod_adversarial(emu, l, mode):
-    emu.mpirfft_set_pointwise_mode(mode)        # 0: default, 1: nested SS kernel, 2: Karatsuba blocks, 3: schoolbook blocks
+    if mode >= 4 and l not in (256, 512):
+        pytest.skip("two Karatsuba levels exist at 256 and 512 limbs")
+    emu.mpirfft_set_pointwise_mode(mode)        # 0: default, 1: nested SS kernel, 2: Karatsuba blocks, 3: schoolbook blocks, 4 / 5: two Karatsuba levels
     random.seed(l)
     NW = 64 * l
     p = (1 << NW) + 1
