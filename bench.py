@@ -462,8 +462,8 @@ def main():
             pw_ms = phases["pointwise"]["ms_per_product"]
             if pw_ms > 0 and imad_chain > 0:
                 school = phases["pointwise_mad32_per_product"] / (pw_ms * 1e-3)
-                # l = 128 / 256: every block product is split once (Karatsuba): 3/4 of the multiply-adds are issued
-                kara = prm["limbs"] in (128, 256) and os.environ.get("MPIRFFT_POINTWISE", "") in ("", "k")
+                # l = 128 / 256 / 512: every block product is split once (Karatsuba): 3/4 of the multiply-adds are issued
+                kara = prm["limbs"] in (128, 256, 512) and os.environ.get("MPIRFFT_POINTWISE", "") in ("", "k")
                 issued = school * (0.75 if kara else 1.0)
                 roofline_pw = {"kernel": "k_pointwise (%s block products, 32x32->64 multiply-add carry chains)" % (
                                    "Karatsuba-split" if kara else "schoolbook"), "bound": "imad",
@@ -868,7 +868,7 @@ def run_cfg4(args, rank, local_rank, world, torch, dist, M):
             imad_chain = float(Lb.mpirfft_measure_imad_rate(1))
         except Exception:
             imad_chain = 0.0
-        kara = inner_l in (128, 256)
+        kara = inner_l in (128, 256, 512)
         school = mads / (phase_ms[2] * 1e-3)
         issued = school * (0.75 if kara else 1.0)
         cfg4_roofline = {"kernel": "k_pointwise (inner products mod 2^%d+1, %s block products)" % (

@@ -484,12 +484,12 @@ mp_size_t FFT_split(mp_limb_t **poly, mp_limb_t *limbs, mp_size_t total_limbs, m
 { return FFT_split_bits(poly, limbs, total_limbs, 64*coeff_limbs, output_limbs); }
 
 /* Blocks are read as output_limbs+1 limbs (the reference adds the carry limb too when the
- * coefficient is bit-shifted, mul_fft.c:231-232); res is overwritten (the reference requires it
- * zeroed on entry, 203-204). */
+ * coefficient is bit-shifted, mul_fft.c:231-232).  Like the reference (185, 229-233) the sum is ADDED to
+ * what res holds on entry (which its contract wants zeroed, 203-204), modulo 2^(64 total_limbs). */
 void FFT_combine_bits(mp_limb_t *res, mp_limb_t **poly, mp_size_t length, mp_size_t bits, mp_size_t output_limbs, mp_size_t total_limbs)
 {
    uint32_t l = (uint32_t) output_limbs + 1, pitch = l; uint64_t k;
-   limb_t *d_res, *d_slab, *stage; void *work;
+   limb_t *d_res, *d_slab, *stage, *sum; void *work; unsigned cy = 0;
    if (length < 0 || bits <= 0 || output_limbs <= 0 || total_limbs <= 0)
       mfft_die("FFT_combine_bits", "illegal sizes length=%ld bits=%ld output_limbs=%ld total=%ld", (long) length, (long) bits, (long) output_limbs, (long) total_limbs);
    mfft_lock();
@@ -498,13 +498,20 @@ void FFT_combine_bits(mp_limb_t *res, mp_limb_t **poly, mp_size_t length, mp_siz
    d_slab = (limb_t *) mfft_dev_alloc((size_t)(length ? length : 1)*pitch*8);
    work = mfft_dev_alloc(mfft_dev_combine_work((uint64_t) total_limbs));
    stage = (limb_t *) malloc((size_t)(length ? length : 1)*pitch*8);
-   if (!d_res || !d_slab || !work || !stage) mfft_die("FFT_combine_bits", "allocation failed: %s", mfft_dev_last_error());
+   sum = (limb_t *) malloc((size_t) total_limbs*8);
+   if (!d_res || !d_slab || !work || !stage || !sum) mfft_die("FFT_combine_bits", "allocation failed: %s", mfft_dev_last_error());
    for (k = 0; k < (uint64_t) length; k++) memcpy(stage + k*pitch, poly[k], pitch*8);
    if (mfft_dev_h2d(d_slab, stage, (size_t) length*pitch*8, NULL) ||
        mfft_dev_combine(d_res, (uint64_t) total_limbs, d_slab, l, pitch, (uint64_t) bits, (uint64_t) length, work, NULL) ||
-       mfft_dev_d2h(res, d_res, (size_t) total_limbs*8, NULL) || mfft_dev_sync(NULL))
+       mfft_dev_d2h(sum, d_res, (size_t) total_limbs*8, NULL) || mfft_dev_sync(NULL))
       mfft_die("FFT_combine_bits", "device execution failed: %s", mfft_dev_last_error());
-   mfft_dev_free(d_res); mfft_dev_free(d_slab); mfft_dev_free(work); free(stage);
+   for (k = 0; k < (uint64_t) total_limbs; k++)
+   {
+      const limb_t a = res[k], t = a + sum[k], u = t + cy;
+      cy = (unsigned)((t < a) | (u < t));
+      res[k] = u;
+   }
+   mfft_dev_free(d_res); mfft_dev_free(d_slab); mfft_dev_free(work); free(stage); free(sum);
    mfft_unlock();
 }
 
@@ -513,7 +520,7 @@ void FFT_combine(mp_limb_t *res, mp_limb_t **poly, mp_size_t length, mp_size_t c
    /* the limb-aligned variant adds exactly output_limbs limbs per coefficient (mul_fft.c:188);
       clear the carry limbs of a private copy so that both variants share one kernel */
    mp_size_t k; mp_limb_t **tab, *copy; size_t sz = (size_t) output_limbs + 1;
-   if (length <= 0) { memset(res, 0, (size_t) total_limbs*8); return; }
+   if (length <= 0) return;
    tab = (mp_limb_t **) malloc(sizeof(mp_limb_t *) * (size_t) length);
    copy = (mp_limb_t *) malloc(sz*8*(size_t) length);
    if (!tab || !copy) mfft_die("FFT_combine", "out of host memory");

@@ -245,3 +245,25 @@ def test_emulated_sqrt2_mfa_odd_w_on_the_fused_path(emu, inverse):
     idx = [i * n1 + j for i in rows for j in range(n1)] if not inverse else list(range(trunc))
     a1, a2 = s1.all(), s2.all()
     assert residues([a1[k] for k in idx], l) == residues([a2[k] for k in idx], l)
+
+
+@pytest.mark.parametrize("total,bits,out", [(100, 29, 1), (300, 640, 12), (50, 64, 3)])
+def test_emulated_combine_adds_to_res(emu, total, bits, out):
+    """FFT_combine_bits / FFT_combine add the shifted coefficients to what res holds on entry
+    (mul_fft.c:185, 229-233), modulo 2^(64 total_limbs)."""
+    rng = np.random.default_rng(total)
+    length = (64 * total - 1) // bits + 1
+    s = L.Slab(length, out)
+    coef = []
+    for k in range(length):
+        v = int(rng.integers(0, 2 ** 62)) % (1 << min(bits, 62))
+        s.mem[k * (out + 1)] = v
+        coef.append(v)
+    r0 = rng.integers(0, 2 ** 64, total, dtype=np.uint64)
+    r = r0.copy()
+    cl = C.c_long
+    emu.FFT_combine_bits.restype = None
+    emu.FFT_combine_bits(ptr(r), s.ii, cl(length), cl(bits), cl(out), cl(total))
+    want = (sum(int(x) << (64 * i) for i, x in enumerate(r0)) + sum(v << (bits * k) for k, v in enumerate(coef))) % (1 << (64 * total))
+    got = sum(int(x) << (64 * i) for i, x in enumerate(r))
+    assert got == want

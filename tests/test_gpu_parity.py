@@ -423,6 +423,15 @@ def test_split_combine(lib, ref):
             Lb.FFT_combine_bits(ptr(r), s.ii, cl(length), cl(bits), cl(out), cl(total))
             outs.append(r)
         assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], limbs), ("combine", total, bits, out)
+        # both ADD to what res holds on entry (mul_fft.c:185, 229-233); small addends, so that no carry leaves
+        # one of the reference's per-coefficient windows
+        outs = []
+        for Lb in (ref, lib):
+            s = oracle.Slab(length, out, res[0] >> np.uint64(1))
+            r = (limbs >> np.uint64(2)).copy()
+            Lb.FFT_combine_bits(ptr(r), s.ii, cl(length), cl(bits), cl(out), cl(total))
+            outs.append(r)
+        assert np.array_equal(outs[0], outs[1]), ("combine adds to res", total, bits, out)
 
 
 # ---- the sqrt2 transforms and new_mpn_mul6 (mul_fft.c:591-700, 972, 2212, 2593, 3573) ----
