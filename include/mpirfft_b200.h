@@ -206,7 +206,10 @@ int  mpirfft_choose_params6(mp_size_t n1, mp_size_t n2, mp_bitcnt_t *depth, mp_b
  * reference leaves as a FIXME (mul_fft.c:3177-3178).  Host pointers; aborts like new_mpn_mul. */
 void mpirfft_mpn_mul(mp_limb_t *r, mp_limb_t *i1, mp_size_t n1, mp_limb_t *i2, mp_size_t n2);
 
-/* A multiplication plan owns the schedules and the HBM slabs for one (n1, n2, depth, w). */
+/* A multiplication plan owns the schedules and the HBM slabs for one (n1, n2, depth, w).  With a
+ * coefficient ring above 512 limbs (2^depth * w > 32768) the plan is the plan of the sharded
+ * multiplication on one rank (mpirfft_smul_*, below): it executes as a whole -- mpirfft_mul_exec_phase
+ * returns MPIRFFT_EINVAL, the byte and launch counters read 0. */
 typedef struct mpirfft_mul_plan mpirfft_mul_plan;
 int  mpirfft_mul_plan_create(mpirfft_mul_plan **plan, mp_size_t n1, mp_size_t n2, mp_bitcnt_t depth,
                              mp_bitcnt_t w);
