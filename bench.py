@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
             row = [str(gpu), sm, mx, "", hex(bits)] + ["Active" if bits & m else "Not Active" for _, m in self.NVML_REASONS]
             if self.marking:
                 self.rows.append([str(x) for x in row])
-            time.sleep(0.0005)
+            time.sleep(0.002)      # a handful of samples per 20 ms of timed region; NVML queries take a driver lock
 
     def run(self):
         try:
@@ -516,6 +516,7 @@ def main():
             "library_parameter_choice": chooser,
             "bit_exact_vs_gmp": check, "wall_s_timed_region": wall,
             "step_ms_min_max": [min(step_ms), max(step_ms)],
+            "step_ms_median": sorted(step_ms)[len(step_ms) // 2], "slowest_step_index": step_ms.index(max(step_ms)),
         }
 
     # ---- the collective path: ONE large product sharded over all ranks (strong scaling) ----

@@ -1267,7 +1267,9 @@ k_run_tiles(limb_t *slab, mfft_geom g, const mfft_tile *__restrict__ tiles, cons
       tile_issue<NT>(mbar, sops, coef, T, [&](uint32_t p) { return spos[p]; }, ops, slab, g, b, bulk_tile, lane);
    tile_fill<NT>(coef, spos, T.npos, slab, g, b, TP, bulk_tile, tid, blockDim.x, warp, nwarps, lane, 0u, 0u);
    TILE_STAMP(1);
-   mbar_wait(mbar, 0);
+   /* one warp polls the mbarrier; the others sleep in the hardware barrier below instead of spending issue
+      slots on try_wait loops next to CTAs that are computing (TP.debug & 4: every warp polls, for A/B) */
+   if (warp == 0 || (TP.debug & 4u)) mbar_wait(mbar, 0);
    if (bulk_tile)
    {  /* last carry word = the block's signed top limb, which arrived with the image */
       __syncthreads();
