@@ -1848,6 +1848,13 @@ void *mfft_dev_event_create(void)
 void mfft_dev_event_destroy(void *e) { if (e) cudaEventDestroy((cudaEvent_t) e); }
 int mfft_dev_event_record(void *e, void *stream) { CK(cudaEventRecord((cudaEvent_t) e, (cudaStream_t) stream)); return 0; }
 int mfft_dev_stream_wait(void *stream, void *e) { CK(cudaStreamWaitEvent((cudaStream_t) stream, (cudaEvent_t) e, 0)); return 0; }
+int mfft_dev_event_sync(void *e) { return cudaEventSynchronize((cudaEvent_t) e) == cudaSuccess ? 0 : -1; }   /* called from worker threads: no g_err */
+int mfft_dev_host_is_pinned(const void *p)
+{
+   cudaPointerAttributes at;
+   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+   return at.type != cudaMemoryTypeUnregistered;
+}
 
 static int pick_m(uint32_t l)
 {

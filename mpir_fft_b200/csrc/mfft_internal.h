@@ -136,6 +136,8 @@ void *mfft_dev_event_create(void);
 void mfft_dev_event_destroy(void *e);
 int  mfft_dev_event_record(void *e, void *stream);
 int  mfft_dev_stream_wait(void *stream, void *e);      /* stream waits for the event */
+int  mfft_dev_event_sync(void *e);                     /* the calling host thread waits for the event */
+int  mfft_dev_host_is_pinned(const void *p);           /* 1: page-locked / registered (or device) memory, 0: pageable */
 const char *mfft_dev_last_error(void);
 
 /* run ops[first .. first+count) (one stage) over nbatch batch entries */

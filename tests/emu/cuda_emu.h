@@ -63,6 +63,12 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered, cudaMemoryTypeHost, cudaMemoryTypeDevice, cudaMemoryTypeManaged };
+struct cudaPointerAttributes { cudaMemoryType type; };
+/* the emulator has no pinned memory: everything counts as pageable unless EMU_ALL_PINNED is set (tests both paths) */
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *)
+{ a->type = getenv("EMU_ALL_PINNED") ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered; return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 
 /* ---- fibers ---- */

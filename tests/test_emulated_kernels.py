@@ -6,6 +6,7 @@ import ctypes as C
 import os
 import random
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -267,3 +268,33 @@ def test_emulated_combine_adds_to_res(emu, total, bits, out):
     want = (sum(int(x) << (64 * i) for i, x in enumerate(r0)) + sum(v << (bits * k) for k, v in enumerate(coef))) % (1 << (64 * total))
     got = sum(int(x) << (64 * i) for i, x in enumerate(r))
     assert got == want
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_emulated_host_copy_paths(pinned):
+    """new_mpn_mul with operands in pageable memory goes through the worker threads and the pinned staging
+    buffer (hostcopy.c; many small chunks here), with pinned operands straight to the device; both in a
+    fresh process because the switches are read once."""
+    code = r'''
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from oracle import loader as L
+from common import operand, ptr
+from mpir_fft_b200._lib import bind
+emu = bind(C.CDLL(%r, mode=C.RTLD_LOCAL))
+for n1, n2, depth, w in [(6000, 6000, 6, 256), (6000, 10, 6, 256), (3000, 2000, 6, 128), (3000, 3000, 7, 96)]:
+    for rep in range(3):
+        a, b = operand("uniform", n1, 10 + rep), operand("runs", n2, 20 + rep)
+        r = np.zeros(n1 + n2, dtype=np.uint64)
+        emu.new_mpn_mul(ptr(r), ptr(a), n1, ptr(b), n2, depth, w)
+        assert np.array_equal(r, L.gmp_mul(a, b)), (n1, n2, rep)
+print("ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+       os.path.join(EMU_DIR, "libmpirfft_emu.so"))
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    env = dict(os.environ, MPIRFFT_COPY_THREADS="3", MPIRFFT_COPY_CHUNK="4096", MPIRFFT_COPY_MIN="0")
+    if pinned:
+        env["EMU_ALL_PINNED"] = "1"
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, (out.stdout[-500:], out.stderr[-800:])
