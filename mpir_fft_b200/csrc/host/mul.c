@@ -451,16 +451,6 @@ int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i
    }
    /* the second operand travels while the first one is being split and transformed */
    rc = MPIRFFT_ENODEV;
-   if (pl->big)
-   {
-      rc = MPIRFFT_ENODEV;
-      if (mfft_dev_h2d(pl->d_i1, i1, b1, pl->s_comp) || mfft_dev_h2d(pl->d_i2, i2, b2, pl->s_comp)) goto done;
-      if ((rc = exec_big(pl, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_comp)) != 0) goto done;
-      rc = MPIRFFT_ENODEV;
-      if (mfft_dev_d2h(r, pl->d_r, b1 + b2, pl->s_comp) || mfft_dev_sync(pl->s_comp)) goto done;
-      rc = 0;
-      goto done;
-   }
    {
       /* Pageable operands (what a caller that merely swaps libraries hands in): a plain copy blocks the host
          while the driver stages it at 10-13 GB/s.  Worker threads copy 1 MB chunks into the pinned staging
@@ -486,6 +476,18 @@ int mpirfft_mul_exec_host(mpirfft_mul_plan *pl, mp_limb_t *r, const mp_limb_t *i
          const size_t off = k*STAGE_CHUNK, len = ji.bytes[w] - off < STAGE_CHUNK ? ji.bytes[w] - off : STAGE_CHUNK; \
          while (!__atomic_load_n(&ji.ready[(w ? ji.nch[0] : 0) + k], __ATOMIC_ACQUIRE)) sched_yield();          \
          if (mfft_dev_h2d((unsigned char *)(dptr) + off, pl->h_stage + (w ? b1 : 0) + off, len, pl->s_copy)) goto fail_in; \
+      }
+      if (pl->big)
+      {  /* rings above 512 limbs: the sharded plan on one rank runs as a whole behind both copies */
+         if (in_staged) { STAGED_H2D(0, pl->d_i1) STAGED_H2D(1, pl->d_i2) mfft_hc_end(nin); free(ji.ready); ji.ready = NULL; }
+         else if (mfft_dev_h2d(pl->d_i1, i1, b1, pl->s_copy) || mfft_dev_h2d(pl->d_i2, i2, b2, pl->s_copy)) goto fail_in;
+         if (mfft_dev_event_record(pl->ev1, pl->s_copy) || mfft_dev_stream_wait(pl->s_comp, pl->ev1)) goto fail_in;
+         if ((rc = exec_big(pl, (mp_limb_t *) pl->d_r, (const mp_limb_t *) pl->d_i1, (const mp_limb_t *) pl->d_i2, pl->s_comp)) != 0) goto done;
+         if (out_staged) { rc = staged_result(pl, r, b1 + b2, pl->s_comp); goto done; }
+         rc = MPIRFFT_ENODEV;
+         if (mfft_dev_d2h(r, pl->d_r, b1 + b2, pl->s_comp) || mfft_dev_sync(pl->s_comp)) goto done;
+         rc = 0;
+         goto done;
       }
       /* The first transform is launched BEFORE the second copy is issued: the GPU should be busy with operand 1
          while operand 2 is on its way */

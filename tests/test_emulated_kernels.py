@@ -283,7 +283,7 @@ from oracle import loader as L
 from common import operand, ptr
 from mpir_fft_b200._lib import bind
 emu = bind(C.CDLL(%r, mode=C.RTLD_LOCAL))
-for n1, n2, depth, w in [(6000, 6000, 6, 256), (6000, 10, 6, 256), (3000, 2000, 6, 128), (3000, 3000, 7, 96)]:
+for n1, n2, depth, w in [(6000, 6000, 6, 256), (6000, 10, 6, 256), (3000, 3000, 7, 96), (2000, 1500, 6, 1024)]:
     for rep in range(2):
         a, b = operand("uniform", n1, 10 + rep), operand("runs", n2, 20 + rep)
         r = np.zeros(n1 + n2, dtype=np.uint64)
