@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag, self.proc = gpu, [], False, None
-        self.ready, self.marking = False, True
+        self.ready, self.marking, self.error = False, True, None
 
     NVML_REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
                     ("sw_power_cap", 0x4))
@@ -84,6 +84,8 @@ class ClockSampler(threading.Thread):
     def _run_nvml(self):
         """in-process NVML polling (about 1 ms per sample): the timed region of one cfg2 run is tens
         of milliseconds, shorter than nvidia-smi's start-up"""
+        if os.environ.get("MPIRFFT_BENCH_NO_NVML"):        # test aid: exercise the nvidia-smi fallback
+            raise RuntimeError("NVML disabled by MPIRFFT_BENCH_NO_NVML")
         import pynvml as N
         N.nvmlInit()
         gpu = self.gpu
@@ -96,32 +98,36 @@ class ClockSampler(threading.Thread):
         mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
         self.ready = True
         while not self.stop_flag:
-            sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
             try:
-                bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
-            except Exception:
-                bits = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-            row = [str(gpu), sm, mx, "", hex(bits)] + ["Active" if bits & m else "Not Active" for _, m in self.NVML_REASONS]
-            if self.marking:
-                self.rows.append([str(x) for x in row])
-            time.sleep(0.002)      # a handful of samples per 20 ms of timed region; NVML queries take a driver lock
+                sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                try:
+                    bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    bits = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                row = [str(gpu), sm, mx, "", hex(bits)] + ["Active" if bits & m else "Not Active" for _, m in self.NVML_REASONS]
+                if self.marking:
+                    self.rows.append([str(x) for x in row])
+            except Exception as e:         # one failed query must not end the sampling
+                self.error = repr(e)
+            time.sleep(0.001)      # about ten samples per 20 ms of timed region; NVML queries take a driver lock
 
     def run(self):
         try:
             self._run_nvml()
             return
-        except Exception:
-            self.ready = True
+        except Exception as e:
+            self.error = repr(e)
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.ready = True
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
                 if self.stop_flag:
                     break
         except Exception:
-            pass
+            self.ready = True
 
     def begin(self):
         """wait for the first sample source to be up; samples count from here"""
@@ -149,7 +155,18 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            # nothing arrived during the timed region (NVML unavailable, nvidia-smi too slow to start): one query
+            # right behind it, while the clocks have not yet dropped
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=20).stdout.strip().splitlines()
+                r = [x.strip() for x in out[0].split(",")]
+                reasons = sorted(name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9])
+                                 if v.lower().startswith("active"))
+                return {"sm_mhz": float(r[1]), "sm_max_mhz": float(r[2]), "reasons": reasons, "samples": 1,
+                        "note": "one nvidia-smi query right after the timed region (no sample arrived during it)", "sampler_error": self.error}
+            except Exception as e:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "sampler_error": "%s; %r" % (self.error, e)}
         busy = sorted(sm)[len(sm) // 2:]
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
