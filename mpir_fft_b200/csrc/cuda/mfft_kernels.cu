@@ -2173,6 +2173,26 @@ static int g_pw_mode = -1;     /* 0 auto, 1 nested SS, 2 Karatsuba-split blocks,
 #define PW_KARA_DEFAULT(l) ((l) == 512 || (l) == 256 || (l) == 128)
 void mfft_dev_pointwise_mode(int mode) { g_pw_mode = mode; }
 
+/* warps of a product kernel (launched as four-warp CTAs with `smem` bytes each) that are resident on the
+   device at once; a multiple of 4 */
+static unsigned pw_capacity(const void *kern, size_t smem)
+{
+   static const void *fk[16]; static unsigned fv[16]; static int nf = 0;
+   for (int i = 0; i < nf; i++) if (fk[i] == kern) return fv[i];
+   unsigned cap = 0;
+#ifdef MFFT_EMU
+   (void) smem;
+   { const char *e = getenv("MPIRFFT_PW_TAIL_TEST"); cap = e ? 8u : 0u; }      /* tests: two "SMs" of one CTA */
+#else
+   int nb = 0, dev = 0, nsm = 0;
+   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, smem) != cudaSuccess) { cudaGetLastError(); nb = 0; }
+   cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+   if (nb > 0 && nsm > 0) cap = (unsigned) nb * 4u * (unsigned) nsm;
+#endif
+   if (nf < 16) { fk[nf] = kern; fv[nf] = cap; nf++; }
+   return cap;
+}
+
 int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uint32_t nblk,
                        uint32_t l, uint32_t pitch, void *stream)
 {
@@ -2217,14 +2237,29 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
    const int u = (unr == 0 && l == 512 && !kara) ? 1 : unr;   /* schoolbook blocks at l = 512: 252 registers already, unrolling only adds spills */
 #define PW_SMEM(CC, KA) ((size_t) 4 * 32 * ((KA) == 2 ? (CC) + (CC) / 2 + 1 + 3 * ((CC) / 4 + 1) + 2 * (CC) + 3 \
                                               : (KA) ? (CC) + (CC) / 2 + 1 + ((CC) >= 32 ? 2 * (CC) + 3 : 0) : (CC)) * 4)
+   /* The last, partly filled wave of a launch costs as much as a full one (the kernel is bound per scheduler:
+      two warps share each IMAD pipe).  When the remainder is small it goes into a second launch of one-warp
+      CTAs, which spread over the SMs and have a pipe each: about half the time of a shared wave
+      (MPIRFFT_PW_TAIL=0: one launch). */
+   static int tailsplit = -1;
+   if (tailsplit < 0) { const char *e = getenv("MPIRFFT_PW_TAIL"); tailsplit = e ? atoi(e) : 1; }
+#define PW_LAUNCH_K(KERN, SM4) do { \
+      const size_t sm__ = (SM4); \
+      const unsigned cap__ = tailsplit ? pw_capacity((const void *) KERN, sm__) : 0u; \
+      const uint32_t tail__ = (cap__ && nblk > cap__) ? nblk % cap__ : 0u; \
+      if (tail__ && tail__ <= cap__ / 4) \
+      { \
+         MFFT_LAUNCH_PDL(pdl_on(), (KERN), (nblk - tail__) / 4, 128, sm__, st, a, b, d_blocks, nblk - tail__, l, pitch); \
+         MFFT_LAUNCH_PDL(pdl_on(), (KERN), tail__, 32, sm__ / 4, st, a, b, d_blocks + (nblk - tail__), tail__, l, pitch); \
+         g_launches++;        /* CKL() below counts one launch per call */ \
+      } \
+      else MFFT_LAUNCH_PDL(pdl_on(), (KERN), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
 #define PW_LAUNCH(CC, KA) do { \
-      const size_t sm__ = PW_SMEM(CC, KA); \
-      if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 1>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); \
-      else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, KA, 4>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
+      if (u == 1) PW_LAUNCH_K((k_pointwise<CC, KA, 1>), PW_SMEM(CC, KA)); \
+      else PW_LAUNCH_K((k_pointwise<CC, KA, 4>), PW_SMEM(CC, KA)); } while (0)
 #define PW_LAUNCH2(CC, MG) do { \
-      const size_t sm__ = PW_SMEM(CC, 2); \
-      if (u == 1) MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, 2, 1, MG>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); \
-      else MFFT_LAUNCH_PDL(pdl_on(), (k_pointwise<CC, 2, 4, MG>), grid, 128, sm__, st, a, b, d_blocks, nblk, l, pitch); } while (0)
+      if (u == 1) PW_LAUNCH_K((k_pointwise<CC, 2, 1, MG>), PW_SMEM(CC, 2)); \
+      else PW_LAUNCH_K((k_pointwise<CC, 2, 4, MG>), PW_SMEM(CC, 2)); } while (0)
    static bool attr = false;
    if (!attr)
    {  /* the kernels with parked words need more than the default 48 KB per CTA */

@@ -298,3 +298,37 @@ print("ok")
         env["EMU_ALL_PINNED"] = "1"
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, (out.stdout[-500:], out.stderr[-800:])
+
+
+def test_emulated_pointwise_tail_launch():
+    """the remainder of the last wave of the product kernel goes into a second launch of one-warp CTAs
+    (mfft_dev_pointwise: PW_LAUNCH_K); the emulator pretends that eight warps fill the device"""
+    code = r'''
+import ctypes as C, os, random, sys
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from common import ptr, int_to_block
+from mpir_fft_b200._lib import bind
+emu = bind(C.CDLL(%r, mode=C.RTLD_LOCAL))
+for l in (128, 256, 512):
+    for count in (9, 10, 18):
+        random.seed(l + count)
+        NW = 64 * l; p = (1 << NW) + 1
+        A = [random.getrandbits(NW) for _ in range(count - 2)] + [p - 1, p - 2]
+        B = [random.getrandbits(NW) for _ in range(count - 2)] + [p - 2, p - 2]
+        a = np.stack([int_to_block(v, l) for v in A]); b = np.stack([int_to_block(v, l) for v in B])
+        da, db = emu.mpirfft_malloc_device(a.nbytes), emu.mpirfft_malloc_device(b.nbytes)
+        emu.mpirfft_memcpy_h2d(da, ptr(a), a.nbytes, None); emu.mpirfft_memcpy_h2d(db, ptr(b), b.nbytes, None)
+        emu.mpirfft_launch_count_reset()
+        assert emu.mpirfft_mulmod_batch_device(da, db, count, l, l + 1, None) == 0
+        assert emu.mpirfft_launch_count() == 2, emu.mpirfft_launch_count()
+        out = np.empty_like(a); emu.mpirfft_memcpy_d2h(ptr(out), da, a.nbytes, None)
+        for k in range(count):
+            assert np.array_equal(out[k], int_to_block(A[k] * B[k] %% p, l)), (l, count, k)
+print("ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+       os.path.join(EMU_DIR, "libmpirfft_emu.so"))
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MPIRFFT_PW_TAIL_TEST="1"),
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, (out.stdout[-500:], out.stderr[-800:])
