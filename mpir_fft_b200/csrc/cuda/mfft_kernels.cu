@@ -2237,12 +2237,12 @@ int mfft_dev_pointwise(limb_t *a, const limb_t *b, const uint32_t *d_blocks, uin
    const int u = (unr == 0 && l == 512 && !kara) ? 1 : unr;   /* schoolbook blocks at l = 512: 252 registers already, unrolling only adds spills */
 #define PW_SMEM(CC, KA) ((size_t) 4 * 32 * ((KA) == 2 ? (CC) + (CC) / 2 + 1 + 3 * ((CC) / 4 + 1) + 2 * (CC) + 3 \
                                               : (KA) ? (CC) + (CC) / 2 + 1 + ((CC) >= 32 ? 2 * (CC) + 3 : 0) : (CC)) * 4)
-   /* The last, partly filled wave of a launch costs as much as a full one (the kernel is bound per scheduler:
-      two warps share each IMAD pipe).  When the remainder is small it goes into a second launch of one-warp
-      CTAs, which spread over the SMs and have a pipe each: about half the time of a shared wave
-      (MPIRFFT_PW_TAIL=0: one launch). */
+   /* Experiment kept as an opt-in (MPIRFFT_PW_TAIL=1): the remainder of the last, partly filled wave in a
+      second launch of one-warp CTAs, which spread over the SMs and have an IMAD pipe each.  Measured at cfg2
+      (16 640 products = 14.05 waves): SLOWER, 0.528 -> 0.546 ms -- the partly filled wave already overlaps the
+      start of the next pass, and the second launch puts one product's full latency behind the first. */
    static int tailsplit = -1;
-   if (tailsplit < 0) { const char *e = getenv("MPIRFFT_PW_TAIL"); tailsplit = e ? atoi(e) : 1; }
+   if (tailsplit < 0) { const char *e = getenv("MPIRFFT_PW_TAIL"); tailsplit = e ? atoi(e) : 0; }
 #define PW_LAUNCH_K(KERN, SM4) do { \
       const size_t sm__ = (SM4); \
       const unsigned cap__ = tailsplit ? pw_capacity((const void *) KERN, sm__) : 0u; \

@@ -301,8 +301,8 @@ print("ok")
 
 
 def test_emulated_pointwise_tail_launch():
-    """the remainder of the last wave of the product kernel goes into a second launch of one-warp CTAs
-    (mfft_dev_pointwise: PW_LAUNCH_K); the emulator pretends that eight warps fill the device"""
+    """opt-in (MPIRFFT_PW_TAIL=1): the remainder of the last wave of the product kernel goes into a second launch
+    of one-warp CTAs (mfft_dev_pointwise: PW_LAUNCH_K); the emulator pretends that eight warps fill the device"""
     code = r'''
 import ctypes as C, os, random, sys
 import numpy as np
@@ -329,6 +329,6 @@ print("ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
        os.path.join(EMU_DIR, "libmpirfft_emu.so"))
     subprocess.check_call(["make", "-s", "-C", EMU_DIR])
-    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MPIRFFT_PW_TAIL_TEST="1"),
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MPIRFFT_PW_TAIL_TEST="1", MPIRFFT_PW_TAIL="1"),
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, (out.stdout[-500:], out.stderr[-800:])
