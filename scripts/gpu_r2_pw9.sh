@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B of the pointwise kernel's occupancy: 8 warps per SM (240/252 registers) vs 9 (224, MPIRFFT_PW_WARPS=9)
+# (record of a finished experiment: the MPIRFFT_PW_WARPS switch it drives was removed after this run -- nine warps per SM were 36 % slower)
 mkdir -p gpurun_out
 MPIRFFT_PW_WARPS=9 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mulmod or cfg or odd_sizes or mul6" > gpurun_out/pytest_pw9.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_pw9.log
 for v in 8 9; do
